@@ -1,0 +1,324 @@
+// dv_device.cuh -- the arithmetic of the hot path as __device__ functions.
+//
+// PARITY RULES.  The CPU reference is built without FMA
+// contraction, so every translation unit that includes this file is compiled
+// with -fmad=false and IEEE division / square root (nvcc defaults).  Anything
+// that feeds an index, a sample count or the transmittance stop test
+// (t, position, grid coordinate, sigma lerps, alpha, T) follows the reference
+// operation by operation; citations are file:line under /root/reference.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "dv_types.h"
+
+namespace dv {
+
+// ---------------------------------------------------------------------------
+// ray generation -- hotpath/src/cpu/ray_cpu.cpp:189-216
+// ---------------------------------------------------------------------------
+struct Ray { float ox, oy, oz, dx, dy, dz; };
+
+// Unnormalised pinhole direction pieces, kept for the camera adjoint.
+struct RayAux { float qx, qy, qz, inv_len; };
+
+__device__ __forceinline__ Ray make_ray(const CameraParams& c, uint32_t px, uint32_t py, RayAux* aux = nullptr) {
+    const float u = static_cast<float>(px) + 0.5f;
+    const float v = static_cast<float>(py) + 0.5f;
+    float qx = (u - c.cx) / c.fx;
+    float qy = (v - c.cy) / c.fy;
+    const float qz = 1.0f;
+    if (c.ortho) { qx = 0.0f; qy = 0.0f; }
+    float wx = c.r00 * qx + c.r01 * qy + c.r02 * qz;
+    float wy = c.r10 * qx + c.r11 * qy + c.r12 * qz;
+    float wz = c.r20 * qx + c.r21 * qy + c.r22 * qz;
+    const float len_sq = wx * wx + wy * wy + wz * wz;
+    const float inv_len = 1.0f / sqrtf(fmaxf(len_sq, FLT_MIN));
+    Ray r;
+    r.dx = wx * inv_len; r.dy = wy * inv_len; r.dz = wz * inv_len;
+    r.ox = c.ox; r.oy = c.oy; r.oz = c.oz;
+    if (aux) { aux->qx = qx; aux->qy = qy; aux->qz = qz; aux->inv_len = inv_len; }
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// stratified jitter -- hotpath/src/cpu/samp_cpu.cpp:21-35
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t s) {
+    s = (s ^ (s >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    s = (s ^ (s >> 27)) * 0x94d049bb133111ebULL;
+    return s ^ (s >> 31);
+}
+
+// The reference divides a 52-bit integer by 2^52 in double and rounds to float.
+// Rounding the integer straight to float and scaling by the exact power of two
+// is the same single rounding, without fp64.
+__device__ __forceinline__ float jitter_unit(uint64_t seed, uint64_t ray_index, uint32_t step) {
+    const uint64_t s = mix64(seed ^ (ray_index << 32) ^ static_cast<uint64_t>(step));
+    return __ull2float_rn(s & 0x000fffffffffffffULL) * 0x1p-52f;
+}
+
+// ---------------------------------------------------------------------------
+// one iteration of the marching loop -- hotpath/src/cpu/samp_cpu.cpp:226-244
+// returns 0 = emit sample, 1 = skip (continue), 2 = stop (break)
+// ---------------------------------------------------------------------------
+template <bool kStratified>
+__device__ __forceinline__ int march_step(float tn, float tf, float dts, uint64_t seed, uint64_t ray_index,
+                                          uint32_t step, float& t_out, float& dt_out) {
+    const float base = tn + static_cast<float>(step) * dts;
+    if (base >= tf) return 2;
+    float jit = 0.5f;
+    if (kStratified) {
+        jit = jitter_unit(seed, ray_index, step);
+        jit = jit < 0.0f ? 0.0f : (jit > 1.0f ? 1.0f : jit);
+    }
+    float t = base + jit * dts;
+    if (t >= tf) t = nextafterf(tf, tn);
+    const float seg_end = fminf(base + dts, tf);
+    const float dta = seg_end - base;
+    if (!(dta > 0.0f)) return 1;
+    t_out = t;
+    dt_out = dta;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// dense grid -- hotpath/src/cpu/grid_dense_cpu.cpp:56-119,143-175
+// World bounds are the unit cube (hp_runtime.cpp:289-294), so the reference's
+// (p - 0) / 1 is the identity bit for bit and is not spelled out.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float lerp_ref(float a, float b, float t) { return a + (b - a) * t; }
+
+struct Cell {
+    int32_t x0, y0, z0, x1, y1, z1;
+    float tx, ty, tz;
+};
+
+// Returns false when the query contributes nothing (outside + ZERO policy).
+__device__ __forceinline__ bool grid_coords(float px, float py, float pz, bool clamp_oob, int32_t nx, int32_t ny,
+                                            int32_t nz, float& fx, float& fy, float& fz) {
+    const bool outside = (px < 0.0f || px > 1.0f) || (py < 0.0f || py > 1.0f) || (pz < 0.0f || pz > 1.0f);
+    if (clamp_oob) {
+        px = px < 0.0f ? 0.0f : (px > 1.0f ? 1.0f : px);
+        py = py < 0.0f ? 0.0f : (py > 1.0f ? 1.0f : py);
+        pz = pz < 0.0f ? 0.0f : (pz > 1.0f ? 1.0f : pz);
+    } else if (outside) {
+        return false;
+    }
+    fx = px * static_cast<float>(nx - 1);
+    fy = py * static_cast<float>(ny - 1);
+    fz = pz * static_cast<float>(nz - 1);
+    return true;
+}
+
+__device__ __forceinline__ Cell make_cell(float fx, float fy, float fz, int32_t nx, int32_t ny, int32_t nz) {
+    Cell c;
+    c.x0 = static_cast<int32_t>(floorf(fx));
+    c.y0 = static_cast<int32_t>(floorf(fy));
+    c.z0 = static_cast<int32_t>(floorf(fz));
+    c.x1 = min(c.x0 + 1, nx - 1);
+    c.y1 = min(c.y0 + 1, ny - 1);
+    c.z1 = min(c.z0 + 1, nz - 1);
+    c.tx = fx - static_cast<float>(c.x0);
+    c.ty = fy - static_cast<float>(c.y0);
+    c.tz = fz - static_cast<float>(c.z0);
+    return c;
+}
+
+__device__ __forceinline__ float trilerp(float c000, float c100, float c010, float c110, float c001, float c101,
+                                         float c011, float c111, float tx, float ty, float tz) {
+    const float c00 = lerp_ref(c000, c100, tx);
+    const float c10 = lerp_ref(c010, c110, tx);
+    const float c01 = lerp_ref(c001, c101, tx);
+    const float c11 = lerp_ref(c011, c111, tx);
+    const float c0 = lerp_ref(c00, c10, ty);
+    const float c1 = lerp_ref(c01, c11, ty);
+    return lerp_ref(c0, c1, tz);
+}
+
+__device__ __forceinline__ size_t voxel_index(int32_t x, int32_t y, int32_t z, int32_t nx, int32_t ny) {
+    return (static_cast<size_t>(z) * static_cast<size_t>(ny) + static_cast<size_t>(y)) * static_cast<size_t>(nx) +
+           static_cast<size_t>(x);
+}
+
+// Packed {r,g,b,sigma} gather: 8 x 16-byte loads through the read-only path.
+template <bool kLinear, bool kClamp>
+__device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+                                                float px, float py, float pz) {
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kLinear) {
+        const int32_t ix = static_cast<int32_t>(roundf(fx));
+        const int32_t iy = static_cast<int32_t>(roundf(fy));
+        const int32_t iz = static_cast<int32_t>(roundf(fz));
+        return __ldg(g + voxel_index(ix, iy, iz, nx, ny));
+    }
+    const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
+    const size_t row00 = voxel_index(0, c.y0, c.z0, nx, ny);
+    const size_t row10 = voxel_index(0, c.y1, c.z0, nx, ny);
+    const size_t row01 = voxel_index(0, c.y0, c.z1, nx, ny);
+    const size_t row11 = voxel_index(0, c.y1, c.z1, nx, ny);
+    const float4 v000 = __ldg(g + row00 + c.x0), v100 = __ldg(g + row00 + c.x1);
+    const float4 v010 = __ldg(g + row10 + c.x0), v110 = __ldg(g + row10 + c.x1);
+    const float4 v001 = __ldg(g + row01 + c.x0), v101 = __ldg(g + row01 + c.x1);
+    const float4 v011 = __ldg(g + row11 + c.x0), v111 = __ldg(g + row11 + c.x1);
+    float4 o;
+    o.x = trilerp(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, c.tx, c.ty, c.tz);
+    o.y = trilerp(v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y, c.tx, c.ty, c.tz);
+    o.z = trilerp(v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z, c.tx, c.ty, c.tz);
+    o.w = trilerp(v000.w, v100.w, v010.w, v110.w, v001.w, v101.w, v011.w, v111.w, c.tx, c.ty, c.tz);
+    return o;
+}
+
+// Generic single-grid query (separate sigma / colour arrays with their own
+// resolution and policies, as hp_samp allows).  `ch` selects the channel.
+__device__ __forceinline__ float sample_plain(const GridParams& g, float px, float py, float pz, int ch) {
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, g.clamp != 0, g.nx, g.ny, g.nz, fx, fy, fz)) return 0.0f;
+    const float* __restrict__ d = g.data;
+    const size_t cs = static_cast<size_t>(g.channels);
+    if (!g.linear) {
+        const int32_t ix = static_cast<int32_t>(roundf(fx));
+        const int32_t iy = static_cast<int32_t>(roundf(fy));
+        const int32_t iz = static_cast<int32_t>(roundf(fz));
+        return __ldg(d + voxel_index(ix, iy, iz, g.nx, g.ny) * cs + ch);
+    }
+    const Cell c = make_cell(fx, fy, fz, g.nx, g.ny, g.nz);
+    auto at = [&](int32_t x, int32_t y, int32_t z) { return __ldg(d + voxel_index(x, y, z, g.nx, g.ny) * cs + ch); };
+    return trilerp(at(c.x0, c.y0, c.z0), at(c.x1, c.y0, c.z0), at(c.x0, c.y1, c.z0), at(c.x1, c.y1, c.z0),
+                   at(c.x0, c.y0, c.z1), at(c.x1, c.y0, c.z1), at(c.x0, c.y1, c.z1), at(c.x1, c.y1, c.z1), c.tx,
+                   c.ty, c.tz);
+}
+
+// sigma and rgb of one position for an arbitrary field pair -> {r,g,b,sigma}
+__device__ __forceinline__ float4 sample_fields(const FieldPair& f, float px, float py, float pz) {
+    if (f.packed != nullptr) {
+        const bool lin = f.sigma.linear != 0, clampo = f.sigma.clamp != 0;
+        const int32_t nx = f.sigma.nx, ny = f.sigma.ny, nz = f.sigma.nz;
+        if (lin) {
+            return clampo ? sample_packed<true, true>(f.packed, nx, ny, nz, px, py, pz)
+                          : sample_packed<true, false>(f.packed, nx, ny, nz, px, py, pz);
+        }
+        return clampo ? sample_packed<false, true>(f.packed, nx, ny, nz, px, py, pz)
+                      : sample_packed<false, false>(f.packed, nx, ny, nz, px, py, pz);
+    }
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f.sigma.present) o.w = sample_plain(f.sigma, px, py, pz, 0);
+    if (f.color.present) {
+        o.x = sample_plain(f.color, px, py, pz, 0);
+        o.y = sample_plain(f.color, px, py, pz, 1);
+        o.z = sample_plain(f.color, px, py, pz, 2);
+    }
+    return o;
+}
+
+// ---------------------------------------------------------------------------
+// alpha -- hotpath/src/cpu/int_cpu.cpp:98-109 (+ the call-site clamp :188)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float alpha_of(float sigma, float dt) {
+    const float od = sigma * dt;
+    if (od <= 0.0f) return 0.0f;
+    if (od < 1e-4f) {
+        const float half = 0.5f * od;
+        return od * (1.0f - half);
+    }
+    double a = -expm1(-static_cast<double>(od));
+    a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
+    return static_cast<float>(a);
+}
+
+// ---------------------------------------------------------------------------
+// per-ray emission-absorption scan -- hotpath/src/cpu/int_cpu.cpp:181-215
+// ---------------------------------------------------------------------------
+struct RayAccum {
+    float T = 1.0f, depth_w = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t_cursor = 0.0f;
+};
+
+// Returns true when the ray stops (T <= 1e-4 after this sample).
+__device__ __forceinline__ bool integrate_sample(RayAccum& s, float dtv, float4 rgbs, float& alpha_out,
+                                                 float& weight_out, float& T_before_out) {
+    const float alpha = alpha_of(rgbs.w, dtv);
+    const float T_before = s.T;
+    const float w = T_before * alpha;
+    s.cr += w * rgbs.x;
+    s.cg += w * rgbs.y;
+    s.cb += w * rgbs.z;
+    const float mid = s.t_cursor + 0.5f * dtv;
+    s.depth_w += w * mid;
+    s.T = T_before * fmaxf(1.0f - alpha, 0.0f);
+    s.t_cursor += dtv;
+    alpha_out = alpha; weight_out = w; T_before_out = T_before;
+    return s.T <= kStopThreshold;
+}
+
+__device__ __forceinline__ void finish_ray(const RayAccum& s, float plan_t_far, float& opacity, float& depth) {
+    opacity = 1.0f - s.T;
+    depth = opacity > 1e-6f ? s.depth_w / opacity : plan_t_far;
+}
+
+// ---------------------------------------------------------------------------
+// reverse adjoint of one sample -- hotpath/src/cpu/diff_cpu.cpp:170-194
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void adjoint_sample(float dot_gc, float alpha, float T_prev, float dtv, float& adj_T,
+                                               float& dsigma) {
+    const float adj_alpha = dot_gc * T_prev - adj_T * T_prev;
+    const float adj_prev = dot_gc * alpha + adj_T * (1.0f - alpha);
+    dsigma = adj_alpha * (dtv * (1.0f - alpha));
+    adj_T = adj_prev;
+}
+
+// ---------------------------------------------------------------------------
+// sample -> grid scatter -- src/fields/dense_grid.cpp:206-306
+// g = {d r, d g, d b, d sigma} of the sample.  One 16-byte red per corner.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void red_add4(float4* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+__device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px, float py, float pz, float4 g) {
+    const float ex = sp.bmax[0] - sp.bmin[0], ey = sp.bmax[1] - sp.bmin[1], ez = sp.bmax[2] - sp.bmin[2];
+    float lx = ex != 0.0f ? (px - sp.bmin[0]) / ex : 0.0f;
+    float ly = ey != 0.0f ? (py - sp.bmin[1]) / ey : 0.0f;
+    float lz = ez != 0.0f ? (pz - sp.bmin[2]) / ez : 0.0f;
+    const bool outside = lx < 0.0f || lx > 1.0f || ly < 0.0f || ly > 1.0f || lz < 0.0f || lz > 1.0f;
+    if (outside) {
+        if (!sp.clamp) return;
+        lx = fmaxf(0.0f, fminf(1.0f, lx));
+        ly = fmaxf(0.0f, fminf(1.0f, ly));
+        lz = fmaxf(0.0f, fminf(1.0f, lz));
+    }
+    const int32_t nx = sp.nx, ny = sp.ny, nz = sp.nz;
+    const float gx = lx * static_cast<float>(max(nx - 1, 1));
+    const float gy = ly * static_cast<float>(max(ny - 1, 1));
+    const float gz = lz * static_cast<float>(max(nz - 1, 1));
+    if (sp.nearest || nx == 1 || ny == 1 || nz == 1) {
+        const int32_t ix = static_cast<int32_t>(roundf(gx));
+        const int32_t iy = static_cast<int32_t>(roundf(gy));
+        const int32_t iz = static_cast<int32_t>(roundf(gz));
+        if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
+        red_add4(sp.grad + voxel_index(ix, iy, iz, nx, ny), g);
+        return;
+    }
+    const Cell c = make_cell(gx, gy, gz, nx, ny, nz);
+    const float ux = 1.0f - c.tx, uy = 1.0f - c.ty, uz = 1.0f - c.tz;
+    const int32_t xs[2] = {c.x0, c.x1}, ys[2] = {c.y0, c.y1}, zs[2] = {c.z0, c.z1};
+    const float wx[2] = {ux, c.tx}, wy[2] = {uy, c.ty}, wz[2] = {uz, c.tz};
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dz = 0; dz < 2; ++dz) {
+                const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
+                if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
+                const float w = wx[dx] * wy[dy] * wz[dz];
+                red_add4(sp.grad + voxel_index(ix, iy, iz, nx, ny),
+                         make_float4(g.x * w, g.y * w, g.z * w, g.w * w));
+            }
+}
+
+}  // namespace dv

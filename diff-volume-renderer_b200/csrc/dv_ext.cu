@@ -1,0 +1,437 @@
+// dv_ext.cu -- hp_b200.h: packed device grids, per-plan frame workspaces, the
+// lean forward / backward entry points and CUDA-graph capture; plus the
+// hp_graph_* entry points of hp.h built on the same machinery.
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "dv_objects.h"
+
+using namespace dv;
+
+#define DV_TRY(expr)                                     \
+    do {                                                 \
+        const hp_status dv_st__ = (expr);                \
+        if (dv_st__ != HP_STATUS_SUCCESS) return dv_st__; \
+    } while (0)
+
+namespace {
+
+constexpr size_t kCameraFloats = 16;
+constexpr size_t kStageVoxels = size_t(1) << 25;  // 32 Mi voxels per staging chunk (512 MiB)
+
+hp_status grid_alloc(hpx_grid* g) {
+    DV_CUDA(cudaMalloc(&g->d_values, std::max<size_t>(g->voxels, 1) * sizeof(float4)));
+    return HP_STATUS_SUCCESS;
+}
+
+hp_status grid_ensure_grad(hpx_grid* g) {
+    if (g->d_grad != nullptr) return HP_STATUS_SUCCESS;
+    const size_t floats = g->voxels * 4 + kCameraFloats;
+    DV_CUDA(cudaMalloc(&g->d_grad, floats * sizeof(float)));
+    DV_CUDA(cudaMemsetAsync(g->d_grad, 0, floats * sizeof(float), g->ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
+PackedGrid packed_view(const hpx_grid& g) {
+    PackedGrid p;
+    p.values = g.d_values;
+    p.nx = g.nx; p.ny = g.ny; p.nz = g.nz;
+    p.linear = g.linear;
+    p.clamp = g.clamp;
+    return p;
+}
+
+void set_bbox(hpx_grid* g, const float bmin[3], const float bmax[3]) {
+    for (int i = 0; i < 3; ++i) {
+        g->bmin[i] = bmin ? bmin[i] : 0.0f;
+        g->bmax[i] = bmax ? bmax[i] : 1.0f;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+// =============================================================================
+// hpx_grid
+// =============================================================================
+HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp_field* fc, const float bbox_min[3],
+                                 const float bbox_max[3], hpx_grid** out_grid) {
+    if (ctx == nullptr || out_grid == nullptr || (fs == nullptr && fc == nullptr)) return HP_STATUS_INVALID_ARGUMENT;
+    if ((fs && fs->kind != FieldKind::kDenseSigma) || (fc && fc->kind != FieldKind::kDenseColor))
+        return HP_STATUS_INVALID_ARGUMENT;
+    const hp_field* ref = fs ? fs : fc;
+    if (fs && fc) {
+        // one packed voxel serves both lookups only if they index identically
+        if (fs->nx != fc->nx || fs->ny != fc->ny || fs->nz != fc->nz || fs->interp != fc->interp ||
+            fs->oob != fc->oob || fc->channels != 3)
+            return HP_STATUS_UNSUPPORTED;
+    }
+    DV_TRY(ensure_device(ctx));
+    hpx_grid* g = new (std::nothrow) hpx_grid();
+    if (g == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    g->ctx = ctx;
+    g->nx = ref->nx; g->ny = ref->ny; g->nz = ref->nz;
+    g->linear = ref->interp == HP_INTERP_LINEAR;
+    g->clamp = ref->oob == HP_OOB_CLAMP;
+    g->voxels = static_cast<size_t>(g->nx) * g->ny * g->nz;
+    set_bbox(g, bbox_min, bbox_max);
+    hp_status st = grid_alloc(g);
+    if (st == HP_STATUS_SUCCESS) {
+        const cudaError_t e = launch_pack_grid(ctx->stream, fs ? fs->d_data : nullptr, fc ? fc->d_data : nullptr,
+                                               g->d_values, g->voxels, false);
+        if (e != cudaSuccess) st = cuda_fail(e, "pack_grid");
+    }
+    if (st != HP_STATUS_SUCCESS) {
+        hpx_grid_release(g);
+        return st;
+    }
+    *out_grid = g;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* color, hp_memspace memspace) {
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (sigma == nullptr && color == nullptr) return HP_STATUS_SUCCESS;
+    DV_TRY(ensure_device(g->ctx));
+    cudaStream_t s = g->ctx->stream;
+    if (memspace == HP_MEMSPACE_DEVICE) {
+        DV_CUDA(launch_pack_grid(s, sigma, color, g->d_values, g->voxels, true));
+        return HP_STATUS_SUCCESS;
+    }
+    // HOST: stream the arrays through a bounded staging buffer and interleave on the device
+    const size_t chunk = std::min<size_t>(g->voxels, kStageVoxels);
+    DeviceScratch scratch;
+    float* d_sig = sigma ? static_cast<float*>(scratch.take(chunk * 4)) : nullptr;
+    float* d_col = color ? static_cast<float*>(scratch.take(chunk * 12)) : nullptr;
+    if ((sigma && !d_sig) || (color && !d_col)) return HP_STATUS_OUT_OF_MEMORY;
+    for (size_t off = 0; off < g->voxels; off += chunk) {
+        const size_t n = std::min(chunk, g->voxels - off);
+        if (sigma) DV_CUDA(cudaMemcpyAsync(d_sig, sigma + off, n * 4, cudaMemcpyHostToDevice, s));
+        if (color) DV_CUDA(cudaMemcpyAsync(d_col, color + 3 * off, n * 12, cudaMemcpyHostToDevice, s));
+        DV_CUDA(launch_pack_grid(s, d_sig, d_col, g->d_values + off, n, true));
+    }
+    DV_CUDA(cudaStreamSynchronize(s));  // the caller may free its buffers; scratch is released
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, int32_t nz, const float* sigma,
+                                     const float* color, hp_memspace memspace, uint32_t interp, uint32_t oob,
+                                     const float bbox_min[3], const float bbox_max[3], hpx_grid** out_grid) {
+    if (ctx == nullptr || out_grid == nullptr || nx <= 0 || ny <= 0 || nz <= 0) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(ctx));
+    hpx_grid* g = new (std::nothrow) hpx_grid();
+    if (g == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    g->ctx = ctx;
+    g->nx = nx; g->ny = ny; g->nz = nz;
+    g->linear = interp != static_cast<uint32_t>(HP_INTERP_NEAREST);
+    g->clamp = oob == static_cast<uint32_t>(HP_OOB_CLAMP);
+    g->voxels = static_cast<size_t>(nx) * ny * nz;
+    set_bbox(g, bbox_min, bbox_max);
+    hp_status st = grid_alloc(g);
+    if (st == HP_STATUS_SUCCESS) {
+        const cudaError_t e = cudaMemsetAsync(g->d_values, 0, g->voxels * sizeof(float4), ctx->stream);
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMemsetAsync(grid)");
+    }
+    if (st == HP_STATUS_SUCCESS) st = hpx_grid_update(g, sigma, color, memspace);
+    if (st != HP_STATUS_SUCCESS) {
+        hpx_grid_release(g);
+        return st;
+    }
+    *out_grid = g;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_zero_grad(hpx_grid* g) {
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(g->ctx));
+    if (g->d_grad == nullptr) return grid_ensure_grad(g);
+    DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), g->ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_grad_buffer(hpx_grid* g, float** out_device_ptr, size_t* out_floats) {
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(g->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    if (out_device_ptr) *out_device_ptr = g->d_grad;
+    if (out_floats) *out_floats = g->voxels * 4 + kCameraFloats;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color_grad, float* camera16,
+                                    hp_memspace memspace) {
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(g->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    cudaStream_t s = g->ctx->stream;
+    const float4* packed = reinterpret_cast<const float4*>(g->d_grad);
+    if (memspace == HP_MEMSPACE_DEVICE) {
+        DV_CUDA(launch_unpack_grad(s, packed, sigma_grad, color_grad, g->voxels));
+        if (camera16) DV_CUDA(cudaMemcpyAsync(camera16, g->d_grad + g->voxels * 4, kCameraFloats * sizeof(float),
+                                              cudaMemcpyDeviceToDevice, s));
+        return HP_STATUS_SUCCESS;
+    }
+    // HOST: un-interleave chunk by chunk through a bounded staging buffer
+    const size_t chunk = std::min<size_t>(g->voxels, kStageVoxels);
+    DeviceScratch scratch;
+    float* d_sig = sigma_grad ? static_cast<float*>(scratch.take(chunk * 4)) : nullptr;
+    float* d_col = color_grad ? static_cast<float*>(scratch.take(chunk * 12)) : nullptr;
+    if ((sigma_grad && !d_sig) || (color_grad && !d_col)) return HP_STATUS_OUT_OF_MEMORY;
+    for (size_t off = 0; off < g->voxels && (sigma_grad || color_grad); off += chunk) {
+        const size_t n = std::min(chunk, g->voxels - off);
+        DV_CUDA(launch_unpack_grad(s, packed + off, d_sig, d_col, n));
+        if (sigma_grad) DV_CUDA(cudaMemcpyAsync(sigma_grad + off, d_sig, n * 4, cudaMemcpyDeviceToHost, s));
+        if (color_grad) DV_CUDA(cudaMemcpyAsync(color_grad + 3 * off, d_col, n * 12, cudaMemcpyDeviceToHost, s));
+    }
+    if (camera16) DV_CUDA(cudaMemcpyAsync(camera16, g->d_grad + g->voxels * 4, kCameraFloats * sizeof(float),
+                                          cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API void hpx_grid_release(hpx_grid* g) {
+    if (g == nullptr) return;
+    if (g->ctx != nullptr && g->ctx->ready) cudaSetDevice(g->ctx->device);
+    cudaFree(g->d_values);
+    cudaFree(g->d_grad);
+    delete g;
+}
+
+// =============================================================================
+// hpx_frame: the per-plan workspace planner
+// =============================================================================
+static void* frame_take(hpx_frame* f, size_t bytes, hp_status* st) {
+    if (*st != HP_STATUS_SUCCESS) return nullptr;
+    void* p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) {
+        *st = cuda_fail(e, "cudaMalloc(frame)");
+        return nullptr;
+    }
+    f->allocations.push_back(p);
+    f->device_bytes += bytes;
+    return p;
+}
+
+HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
+    if (plan == nullptr || out_frame == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (!plan->gap_free) {
+        set_last_error("plan skips marching steps (dt below float resolution); use the materialising hp_* path");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_TRY(ensure_device(plan->ctx));
+    hpx_frame* f = new (std::nothrow) hpx_frame();
+    if (f == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    f->plan = plan;
+    f->ctx = plan->ctx;
+    f->h_params = frame_params_from_plan(*plan);
+    const hp_plan_desc& d = plan->desc;
+    const size_t pixels = static_cast<size_t>(d.width) * d.height;
+    const size_t rays = static_cast<size_t>(d.roi.width) * d.roi.height;
+    f->rays = rays;
+    f->samples = static_cast<uint64_t>(rays) * plan->uniform_count;
+    const size_t segments = (plan->uniform_count + kSegment - 1) / kSegment;
+    hp_status st = HP_STATUS_SUCCESS;
+    f->d_params = static_cast<FrameParams*>(frame_take(f, sizeof(FrameParams), &st));
+    f->buf.image = static_cast<float*>(frame_take(f, pixels * 12, &st));
+    f->buf.trans = static_cast<float*>(frame_take(f, pixels * 4, &st));
+    f->buf.opacity = static_cast<float*>(frame_take(f, pixels * 4, &st));
+    f->buf.depth = static_cast<float*>(frame_take(f, pixels * 4, &st));
+    f->buf.hitmask = static_cast<uint32_t*>(frame_take(f, pixels * 4, &st));
+    f->buf.live = static_cast<uint32_t*>(frame_take(f, rays * 4, &st));
+    f->buf.ckpt_stride = (rays + 31) & ~static_cast<size_t>(31);
+    f->buf.ckpt = static_cast<float*>(frame_take(f, segments * f->buf.ckpt_stride * 4, &st));
+    f->buf.live_total = static_cast<unsigned long long*>(frame_take(f, sizeof(unsigned long long), &st));
+    f->d_dL_dI = static_cast<float*>(frame_take(f, rays * 12, &st));
+    f->d_cam_partials = static_cast<double*>(frame_take(f, static_cast<size_t>(lean_block_count(f->h_params.roi)) * 16 * 8, &st));
+    if (st == HP_STATUS_SUCCESS) {
+        const cudaError_t e = cudaMallocHost(&f->h_pinned, sizeof(FrameParams) + sizeof(unsigned long long));
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMallocHost(frame)");
+    }
+    if (st != HP_STATUS_SUCCESS) {
+        hpx_frame_release(f);
+        return st;
+    }
+    f->params_dirty = true;
+    *out_frame = f;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API size_t hpx_frame_bytes(const hpx_frame* f) { return f ? f->device_bytes : 0; }
+
+HP_API hp_status hpx_frame_set_view(hpx_frame* f, const hp_camera_desc* camera, uint64_t seed,
+                                    uint64_t ray_index_base) {
+    if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (camera != nullptr) {
+        hp_plan_desc tmp = f->plan->desc;   // apply the plan-time camera defaults to the new camera too
+        tmp.camera = *camera;
+        DV_TRY(resolve_plan_desc(&tmp));
+        f->h_params.cam = camera_params(tmp.camera);
+    }
+    f->h_params.march.seed = seed;
+    f->h_params.march.ray_index_base = ray_index_base;
+    f->params_dirty = true;
+    return HP_STATUS_SUCCESS;
+}
+
+static hp_status frame_push_params(hpx_frame* f) {
+    if (!f->params_dirty) return HP_STATUS_SUCCESS;
+    // the pinned staging copy must not be rewritten while an earlier copy is still in flight
+    DV_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    *f->h_pinned = f->h_params;
+    DV_CUDA(cudaMemcpyAsync(f->d_params, f->h_pinned, sizeof(FrameParams), cudaMemcpyHostToDevice, f->ctx->stream));
+    f->params_dirty = false;
+    return HP_STATUS_SUCCESS;
+}
+
+static hp_status frame_check_grid(const hpx_frame* f, const hpx_grid* g) {
+    if (f == nullptr || g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (f->ctx != g->ctx && (f->ctx->device != g->ctx->device)) return HP_STATUS_INVALID_ARGUMENT;
+    return HP_STATUS_SUCCESS;
+}
+
+static hp_status enqueue_forward(hpx_frame* f, const hpx_grid* g) {
+    cudaStream_t s = f->ctx->stream;
+    DV_CUDA(cudaMemsetAsync(f->buf.live_total, 0, sizeof(unsigned long long), s));
+    const RoiParams& roi = f->h_params.roi;
+    const bool partial = roi.w != roi.img_w || roi.h != roi.img_h;
+    DV_CUDA(launch_lean_forward(s, f->d_params, f->h_params, packed_view(*g), f->buf, partial));
+    return HP_STATUS_SUCCESS;
+}
+
+static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_dI, uint32_t flags) {
+    cudaStream_t s = f->ctx->stream;
+    if (flags & HPX_BACKWARD_ZERO)
+        DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), s));
+    if (flags & HPX_BACKWARD_GRID)
+        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf));
+    if (flags & HPX_BACKWARD_CAMERA)
+        DV_CUDA(launch_camera_adjoint(s, f->d_params, f->h_params, packed_view(*g), d_dL_dI, f->buf.live,
+                                      f->d_cam_partials, g->d_grad + g->voxels * 4));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_forward(hpx_frame* f, const hpx_grid* g) {
+    DV_TRY(frame_check_grid(f, g));
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(frame_push_params(f));
+    DV_TRY(enqueue_forward(f, g));
+    f->forward_done = true;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags) {
+    DV_TRY(frame_check_grid(f, g));
+    if (dL_dI == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (!f->forward_done) {
+        set_last_error("hpx_backward needs the checkpoints of a preceding hpx_forward on the same frame");
+        return HP_STATUS_INVALID_ARGUMENT;
+    }
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    DV_TRY(frame_push_params(f));
+    const float* d_g = dL_dI;
+    if (memspace == HP_MEMSPACE_HOST) {
+        DV_CUDA(cudaMemcpyAsync(f->d_dL_dI, dL_dI, f->rays * 12, cudaMemcpyHostToDevice, f->ctx->stream));
+        d_g = f->d_dL_dI;
+    }
+    return enqueue_backward(f, g, d_g, flags);
+}
+
+HP_API hp_status hpx_frame_image(const hpx_frame* f, hp_img_t* out) {
+    if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    const hp_plan_desc& d = f->plan->desc;
+    const int64_t w = d.width, h = d.height;
+    shape_tensor(out->image, HP_DTYPE_F32, HP_MEMSPACE_DEVICE, 3, h, w, 3);
+    shape_tensor(out->trans, HP_DTYPE_F32, HP_MEMSPACE_DEVICE, 2, h, w);
+    shape_tensor(out->opacity, HP_DTYPE_F32, HP_MEMSPACE_DEVICE, 2, h, w);
+    shape_tensor(out->depth, HP_DTYPE_F32, HP_MEMSPACE_DEVICE, 2, h, w);
+    shape_tensor(out->hitmask, HP_DTYPE_U32, HP_MEMSPACE_DEVICE, 2, h, w);
+    out->image.data = f->buf.image;
+    out->trans.data = f->buf.trans;
+    out->opacity.data = f->buf.opacity;
+    out->depth.data = f->buf.depth;
+    out->hitmask.data = f->buf.hitmask;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_read(hpx_frame* f, float* image, float* trans, float* opacity, float* depth,
+                                uint32_t* hitmask) {
+    if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    cudaStream_t s = f->ctx->stream;
+    const size_t pixels = static_cast<size_t>(f->plan->desc.width) * f->plan->desc.height;
+    if (image) DV_CUDA(cudaMemcpyAsync(image, f->buf.image, pixels * 12, cudaMemcpyDeviceToHost, s));
+    if (trans) DV_CUDA(cudaMemcpyAsync(trans, f->buf.trans, pixels * 4, cudaMemcpyDeviceToHost, s));
+    if (opacity) DV_CUDA(cudaMemcpyAsync(opacity, f->buf.opacity, pixels * 4, cudaMemcpyDeviceToHost, s));
+    if (depth) DV_CUDA(cudaMemcpyAsync(depth, f->buf.depth, pixels * 4, cudaMemcpyDeviceToHost, s));
+    if (hitmask) DV_CUDA(cudaMemcpyAsync(hitmask, f->buf.hitmask, pixels * 4, cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_counts(hpx_frame* f, hpx_counts* out) {
+    if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    auto* h_live = reinterpret_cast<unsigned long long*>(f->h_pinned + 1);
+    DV_CUDA(cudaMemcpyAsync(h_live, f->buf.live_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            f->ctx->stream));
+    DV_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    out->rays = f->rays;
+    out->samples = f->samples;
+    out->live_samples = *h_live;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_grad_input(hpx_frame* f, float** out) {
+    if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    *out = f->d_dL_dI;
+    return HP_STATUS_SUCCESS;
+}
+
+// Real capture: every node is a kernel or memset on the context's stream; no
+// allocation, no synchronisation and no host read inside the captured region.
+HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_flags) {
+    DV_TRY(frame_check_grid(f, g));
+    DV_TRY(ensure_device(f->ctx));
+    if (backward_flags != 0) DV_TRY(grid_ensure_grad(g));
+    DV_TRY(frame_push_params(f));
+    cudaStream_t s = f->ctx->stream;
+    DV_CUDA(cudaStreamSynchronize(s));
+    if (f->graph_exec) { cudaGraphExecDestroy(f->graph_exec); f->graph_exec = nullptr; }
+    if (f->graph) { cudaGraphDestroy(f->graph); f->graph = nullptr; }
+    DV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    hp_status st = enqueue_forward(f, g);
+    if (st == HP_STATUS_SUCCESS && backward_flags != 0) st = enqueue_backward(f, g, f->d_dL_dI, backward_flags);
+    const cudaError_t e = cudaStreamEndCapture(s, &f->graph);
+    if (st != HP_STATUS_SUCCESS) return st;
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+    DV_CUDA(cudaGraphInstantiate(&f->graph_exec, f->graph, nullptr, nullptr, 0));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_replay(hpx_frame* f) {
+    if (f == nullptr || f->graph_exec == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(frame_push_params(f));
+    DV_CUDA(cudaGraphLaunch(f->graph_exec, f->ctx->stream));
+    f->forward_done = true;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API void hpx_frame_release(hpx_frame* f) {
+    if (f == nullptr) return;
+    if (f->ctx != nullptr && f->ctx->ready) {
+        cudaSetDevice(f->ctx->device);
+        cudaStreamSynchronize(f->ctx->stream);
+    }
+    if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+    if (f->graph) cudaGraphDestroy(f->graph);
+    for (void* p : f->allocations) cudaFree(p);
+    if (f->h_pinned) cudaFreeHost(f->h_pinned);
+    delete f;
+}
+
+}  // extern "C"

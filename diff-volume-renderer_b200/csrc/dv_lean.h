@@ -1,0 +1,45 @@
+// dv_lean.h -- host-side launch interface of the non-materialising kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "dv_types.h"
+
+namespace dv {
+
+// Packed {r,g,b,sigma} grid resident in HBM.
+struct PackedGrid {
+    const float4* values = nullptr;
+    int32_t nx = 0, ny = 0, nz = 0;
+    bool linear = true;
+    bool clamp = false;
+};
+
+// Device buffers one frame reads and writes (all owned by hpx_frame).
+struct LeanBuffers {
+    float* image = nullptr;        // [H][W][3]
+    float* trans = nullptr;        // [H][W]
+    float* opacity = nullptr;      // [H][W]
+    float* depth = nullptr;        // [H][W]
+    uint32_t* hitmask = nullptr;   // [H][W]
+    uint32_t* live = nullptr;      // [rays] samples integrated before the stop
+    float* ckpt = nullptr;         // [ceil(K / kSegment)][ckpt_stride] transmittance at segment starts
+    size_t ckpt_stride = 0;
+    unsigned long long* live_total = nullptr;
+};
+
+uint32_t lean_block_count(const RoiParams& roi);
+
+cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
+                                const PackedGrid& grid, const LeanBuffers& out, bool fill_background);
+
+cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
+                                 const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
+                                 const LeanBuffers& state);
+
+// d_partials: [lean_block_count][16] doubles of scratch; d_cam16 is accumulated into.
+cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
+                                  const PackedGrid& grid, const float* d_dL_dI, const uint32_t* d_live,
+                                  double* d_partials, float* d_cam16);
+
+}  // namespace dv

@@ -1,0 +1,139 @@
+// dv_objects.h -- the opaque handles behind hp.h / hp_b200.h and small host helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "dv_lean.h"
+#include "dv_staged.h"
+#include "dv_types.h"
+#include "hotpath/hp.h"
+#include "hotpath/hp_b200.h"
+
+// ---- handles ---------------------------------------------------------------
+// Context: which GPU, which stream.  Device state is created on first use so
+// that hp_ctx_create / hp_plan_create (pure host logic, reference
+// hp_runtime.cpp:15-146) work on machines without a GPU; every compute entry
+// point fails with HP_STATUS_UNSUPPORTED there.
+struct hp_ctx {
+    hp_ctx_desc desc{};
+    std::string device_name;      // owned copy of desc.preferred_device
+    hp_version version{HP_VERSION_MAJOR, HP_VERSION_MINOR, HP_VERSION_PATCH};
+    int requested_ordinal = -1;
+    cudaStream_t user_stream = nullptr;
+    bool has_user_stream = false;
+    // lazily initialised
+    mutable bool ready = false;
+    mutable bool failed = false;
+    mutable int device = 0;
+    mutable cudaStream_t stream = nullptr;
+    mutable bool owns_stream = false;
+    mutable uint32_t* d_status = nullptr;            // device status word for kernels
+    mutable unsigned long long* d_total = nullptr;   // device sample total
+    mutable uint32_t* h_status = nullptr;            // pinned mirrors
+    mutable unsigned long long* h_total = nullptr;
+};
+
+struct hp_plan {
+    hp_plan_desc desc{};
+    const hp_ctx* ctx = nullptr;
+    uint32_t uniform_count = 0;   // samples a generated ray emits
+    bool gap_free = true;         // emitted samples are steps 0..uniform_count-1
+};
+
+enum class FieldKind : uint32_t { kDenseSigma = 0, kDenseColor = 1 };
+
+// Dense-grid field.  The reference keeps a view of the caller's HOST tensor
+// (hp_runtime.cpp:259-339); this library snapshots it into HBM at creation.
+struct hp_field {
+    FieldKind kind = FieldKind::kDenseSigma;
+    const hp_ctx* ctx = nullptr;
+    hp_tensor source{};           // the caller's view, kept for hp_plan-style introspection
+    hp_interp_mode interp = HP_INTERP_LINEAR;
+    hp_oob_policy oob = HP_OOB_ZERO;
+    int32_t nx = 0, ny = 0, nz = 0, channels = 1;
+    float* d_data = nullptr;      // [nz][ny][nx][channels]
+    bool owns_data = true;
+    // lazily built packed partner cache (sigma field only): packed grid for (this, partner)
+    mutable const hp_field* packed_partner = nullptr;
+    mutable float4* d_packed = nullptr;
+};
+
+struct hpx_grid {
+    const hp_ctx* ctx = nullptr;
+    int32_t nx = 0, ny = 0, nz = 0;
+    bool linear = true, clamp = false;
+    float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {1.f, 1.f, 1.f};
+    float4* d_values = nullptr;   // [V] {r,g,b,sigma}
+    float* d_grad = nullptr;      // [4V + 16]: packed gradient grid, then camera gradient
+    size_t voxels = 0;
+};
+
+struct hpx_frame {
+    const hp_plan* plan = nullptr;
+    const hp_ctx* ctx = nullptr;
+    dv::FrameParams h_params{};
+    dv::FrameParams* d_params = nullptr;
+    dv::FrameParams* h_pinned = nullptr;
+    bool params_dirty = true;
+    dv::LeanBuffers buf{};
+    float* d_dL_dI = nullptr;     // [rays][3]
+    double* d_cam_partials = nullptr;
+    size_t device_bytes = 0;
+    uint64_t rays = 0, samples = 0;
+    bool forward_done = false;
+    // captured graph
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<void*> allocations;
+};
+
+namespace dv {
+
+// ---- errors ----------------------------------------------------------------
+void set_last_error(const std::string& what);
+const char* last_error_text();
+hp_status cuda_fail(cudaError_t err, const char* what);  // records text, maps to hp_status
+
+#define DV_CUDA(call)                                                   \
+    do {                                                                \
+        const cudaError_t dv_err__ = (call);                            \
+        if (dv_err__ != cudaSuccess) return dv::cuda_fail(dv_err__, #call); \
+    } while (0)
+
+// Makes ctx's device current and creates its stream on first use.
+hp_status ensure_device(const hp_ctx* ctx);
+
+// ---- plan helpers -----------------------------------------------------------
+hp_status resolve_plan_desc(hp_plan_desc* desc);   // reference hp_runtime.cpp:54-142
+void emitted_samples(const hp_plan_desc& desc, uint32_t* count, bool* gap_free);
+FrameParams frame_params_from_plan(const hp_plan& plan);
+CameraParams camera_params(const hp_camera_desc& cam);
+
+// ---- tensors ----------------------------------------------------------------
+void shape_tensor(hp_tensor& t, hp_dtype dtype, hp_memspace ms, uint32_t rank, int64_t d0, int64_t d1 = 0,
+                  int64_t d2 = 0);
+
+// Bump allocator over the caller's workspace (reference workspace.hpp:6-33).
+struct Bump {
+    char* ptr;
+    size_t remaining;
+    Bump(void* base, size_t bytes) : ptr(static_cast<char*>(base)), remaining(base ? bytes : 0) {}
+    void* take(size_t bytes, size_t alignment = 4);
+};
+
+// Scratch device allocations freed on scope exit.
+struct DeviceScratch {
+    std::vector<void*> ptrs;
+    ~DeviceScratch();
+    void* take(size_t bytes);   // nullptr on failure (error text recorded)
+};
+
+FieldPair field_pair(const hp_field* fs, const hp_field* fc);
+ScatterParams scatter_params(const hpx_grid& grid);
+
+}  // namespace dv

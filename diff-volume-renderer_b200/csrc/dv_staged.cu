@@ -1,0 +1,489 @@
+// dv_staged.cu -- materialising kernels behind the hp.h entry points.
+//
+// These honour the reference's buffer contracts (per-sample positions / dt /
+// sigma / colour, prefix offsets, aux rows) so existing callers of hp_ray,
+// hp_samp, hp_int, hp_samp_int_fused, hp_diff and hp_img keep working on
+// DEVICE tensors.  They share every arithmetic routine with the lean kernels
+// (dv_device.cuh), so staged == fused bit for bit (reference test
+// hotpath/tests/runner/hp_runner.cpp:1737-1760).
+//
+// Compiled with -fmad=false: see dv_device.cuh.
+#include "dv_staged.h"
+
+#include "dv_device.cuh"
+
+namespace dv {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+inline uint32_t blocks_for(size_t n, int threads) { return static_cast<uint32_t>((n + threads - 1) / threads); }
+
+// ---- K1: rays (reference hotpath/src/cpu/ray_cpu.cpp:183-226) ---------------
+__global__ void rays_kernel(FrameParams p, RayArrays out, uint32_t n_rays) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    const uint32_t lx = i % p.roi.w, ly = i / p.roi.w;
+    const uint32_t px = p.roi.x + lx, py = p.roi.y + ly;
+    const Ray r = make_ray(p.cam, px, py);
+    out.origins[3 * i + 0] = r.ox; out.origins[3 * i + 1] = r.oy; out.origins[3 * i + 2] = r.oz;
+    out.directions[3 * i + 0] = r.dx; out.directions[3 * i + 1] = r.dy; out.directions[3 * i + 2] = r.dz;
+    out.t_near[i] = p.march.t_near;
+    out.t_far[i] = p.march.t_far;
+    out.pixel_ids[i] = py * p.roi.img_w + px;
+}
+
+// ---- sample counts + exclusive scan ----------------------------------------
+__device__ __forceinline__ uint32_t ray_sample_count(const MarchParams& mp, float tn, float tf) {
+    if (!(tf > tn)) return 0;
+    uint32_t n = 0;
+    for (uint32_t step = 0; step < mp.max_steps; ++step) {
+        float t, dtv;
+        const int r = march_step<false>(tn, tf, mp.dt, 0, 0, step, t, dtv);
+        if (r == 2) break;
+        if (r == 0) ++n;
+    }
+    return n;
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__global__ void count_kernel(MarchParams mp, RayArrays rays, uint32_t n_rays, uint32_t* counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rays) return;
+    counts[i] = ray_sample_count(mp, rays.t_near[i], rays.t_far[i]);
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint32_t* counts, uint32_t n,
+                                                                      unsigned long long* tile_sums) {
+    __shared__ unsigned long long warp_sums[kScanThreads / 32];
+    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile;
+    unsigned long long s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const size_t i = base + static_cast<size_t>(k) * kScanThreads + threadIdx.x;
+        if (i < n) s += counts[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += warp_sums[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// one block: exclusive scan of the tile sums in place, grand total to *total
+__global__ void __launch_bounds__(1024) scan_spine_kernel(unsigned long long* tile_sums, uint32_t tiles,
+                                                          unsigned long long* total) {
+    __shared__ unsigned long long warp_part[32];
+    __shared__ unsigned long long carry, chunk_total;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long v = i < tiles ? tile_sums[i] : 0ULL;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (lane == 31) warp_part[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const unsigned long long w = warp_part[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += up;
+            }
+            warp_part[lane] = wi - w;  // exclusive offset of each warp inside the chunk
+            if (lane == 31) chunk_total = wi;
+        }
+        __syncthreads();
+        if (i < tiles) tile_sums[i] = carry + warp_part[warp] + (incl - v);
+        __syncthreads();
+        if (threadIdx.x == 0) carry += chunk_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* counts, uint32_t n,
+                                                                  const unsigned long long* tile_offsets,
+                                                                  const unsigned long long* total,
+                                                                  uint32_t* ray_offset) {
+    // blocked arrangement: thread t owns items [t*4, t*4+4) of the tile
+    __shared__ uint32_t warp_tot[kScanThreads / 32];
+    const size_t base = static_cast<size_t>(blockIdx.x) * kScanTile + static_cast<size_t>(threadIdx.x) * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? counts[base + k] : 0u;
+        local += v[k];
+    }
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += up;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0;
+    for (int w = 0; w < static_cast<int>(threadIdx.x >> 5); ++w) warp_base += warp_tot[w];
+    // the reference keeps offsets in u32 (static_cast<uint32_t>(total_samples), samp_cpu.cpp:208)
+    uint32_t run = static_cast<uint32_t>(tile_offsets[blockIdx.x]) + warp_base + (incl - local);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) ray_offset[base + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) ray_offset[n] = static_cast<uint32_t>(*total);
+}
+
+// offsets of a plan whose rays all emit the same number of samples (graph path: no host read-back)
+__global__ void uniform_offsets_kernel(uint32_t* ray_offset, uint32_t n_rays, uint32_t per_ray) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i <= n_rays) ray_offset[i] = static_cast<uint32_t>(i * per_ray);
+}
+
+// ---- K2: sampler, optionally with the integrator inline --------------------
+template <bool kStratified, bool kIntegrate>
+__global__ void __launch_bounds__(kThreads)
+sample_kernel(MarchParams mp, float plan_t_near, float plan_t_far, FieldPair fields, RayArrays rays, uint32_t n_rays,
+              SampleArrays samp, IntegralArrays intl, bool aux_aligned) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const float ox = rays.origins[3 * ray], oy = rays.origins[3 * ray + 1], oz = rays.origins[3 * ray + 2];
+    const float dx = rays.directions[3 * ray], dy = rays.directions[3 * ray + 1], dz = rays.directions[3 * ray + 2];
+    const float tn = rays.t_near[ray], tf = rays.t_far[ray];
+    const uint64_t ray_index = mp.ray_index_base + ray;
+    size_t idx = samp.ray_offset[ray];
+    RayAccum acc;
+    acc.t_cursor = plan_t_near;
+    bool stopped = false;
+    if (tf > tn) {
+        for (uint32_t step = 0; step < mp.max_steps; ++step) {
+            float t, dtv;
+            const int r = march_step<kStratified>(tn, tf, mp.dt, mp.seed, ray_index, step, t, dtv);
+            if (r == 2) break;
+            if (r == 1) continue;
+            const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+            const float4 v = sample_fields(fields, px, py, pz);
+            samp.positions[3 * idx] = px; samp.positions[3 * idx + 1] = py; samp.positions[3 * idx + 2] = pz;
+            samp.dt[idx] = dtv;
+            samp.sigma[idx] = v.w;
+            samp.color[3 * idx] = v.x; samp.color[3 * idx + 1] = v.y; samp.color[3 * idx + 2] = v.z;
+            if (kIntegrate) {
+                float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!stopped) {
+                    float a, w, tb;
+                    stopped = integrate_sample(acc, dtv, v, a, w, tb);
+                    row = make_float4(a, w, tb, logf(fmaxf(tb, 1e-30f)));
+                }
+                if (aux_aligned) {
+                    reinterpret_cast<float4*>(intl.aux)[idx] = row;
+                } else {
+                    float* a4 = intl.aux + 4 * idx;
+                    a4[0] = row.x; a4[1] = row.y; a4[2] = row.z; a4[3] = row.w;
+                }
+            }
+            ++idx;
+        }
+    }
+    if (kIntegrate) {
+        float opacity, depth;
+        finish_ray(acc, plan_t_far, opacity, depth);
+        intl.radiance[3 * ray] = acc.cr; intl.radiance[3 * ray + 1] = acc.cg; intl.radiance[3 * ray + 2] = acc.cb;
+        intl.transmittance[ray] = acc.T;
+        intl.opacity[ray] = opacity;
+        intl.depth[ray] = depth;
+    }
+}
+
+// ---- K4: integrator over materialised samples (int_cpu.cpp:160-226) ---------
+__global__ void __launch_bounds__(kThreads)
+integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_t n_rays, uint32_t n_samples,
+                 IntegralArrays intl, bool aux_aligned, uint32_t* status) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const uint32_t b = samp.ray_offset[ray], e = samp.ray_offset[ray + 1];
+    RayAccum acc;
+    acc.t_cursor = plan_t_near;
+    if (e < b || e > n_samples) {
+        atomicOr(status, kErrBadOffsets);
+    } else {
+        bool stopped = false;
+        for (uint32_t i = b; i < e; ++i) {
+            float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!stopped) {
+                const float4 v = make_float4(samp.color[3 * size_t(i)], samp.color[3 * size_t(i) + 1],
+                                             samp.color[3 * size_t(i) + 2], samp.sigma[i]);
+                float a, w, tb;
+                stopped = integrate_sample(acc, samp.dt[i], v, a, w, tb);
+                row = make_float4(a, w, tb, logf(fmaxf(tb, 1e-30f)));
+            }
+            if (intl.aux != nullptr) {
+                if (aux_aligned) {
+                    reinterpret_cast<float4*>(intl.aux)[i] = row;
+                } else {
+                    float* a4 = intl.aux + 4 * size_t(i);
+                    a4[0] = row.x; a4[1] = row.y; a4[2] = row.z; a4[3] = row.w;
+                }
+            }
+        }
+    }
+    float opacity, depth;
+    finish_ray(acc, plan_t_far, opacity, depth);
+    intl.radiance[3 * ray] = acc.cr; intl.radiance[3 * ray + 1] = acc.cg; intl.radiance[3 * ray + 2] = acc.cb;
+    intl.transmittance[ray] = acc.T;
+    intl.opacity[ray] = opacity;
+    intl.depth[ray] = depth;
+}
+
+// ---- K5: per-sample backward (diff_cpu.cpp:156-195) -------------------------
+__global__ void __launch_bounds__(kThreads)
+diff_kernel(const float* __restrict__ dL_dI, int64_t stride_ray, int64_t stride_c, SampleArrays samp,
+            const float* __restrict__ aux, uint32_t n_rays, uint32_t n_samples, float* grad_sigma, float* grad_color,
+            uint32_t* status) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const uint32_t b = samp.ray_offset[ray], e = samp.ray_offset[ray + 1];
+    if (e < b || e > n_samples) {
+        atomicOr(status, kErrBadOffsets);
+        return;
+    }
+    const float* gp = dL_dI + static_cast<int64_t>(ray) * stride_ray;
+    const float g0 = gp[0], g1 = gp[stride_c], g2 = gp[2 * stride_c];
+    float adj_T = 0.0f;
+    for (uint32_t i = e; i-- > b;) {
+        const float alpha = aux[4 * size_t(i)], w = aux[4 * size_t(i) + 1], T_prev = aux[4 * size_t(i) + 2];
+        const float c0 = samp.color[3 * size_t(i)], c1 = samp.color[3 * size_t(i) + 1],
+                    c2 = samp.color[3 * size_t(i) + 2];
+        const float dot = g0 * c0 + g1 * c1 + g2 * c2;
+        float dsigma;
+        adjoint_sample(dot, alpha, T_prev, samp.dt[i], adj_T, dsigma);
+        grad_color[3 * size_t(i)] = g0 * w;
+        grad_color[3 * size_t(i) + 1] = g1 * w;
+        grad_color[3 * size_t(i) + 2] = g2 * w;
+        grad_sigma[i] = dsigma;
+    }
+}
+
+// ---- K7: image composition (img_cpu.cpp:148-185) ----------------------------
+__global__ void background_planes_kernel(ImagePlanes img, size_t pixels, float t_far) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < pixels;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        img.image[3 * i] = 0.f; img.image[3 * i + 1] = 0.f; img.image[3 * i + 2] = 0.f;
+        img.trans[i] = 1.0f;
+        img.opacity[i] = 0.0f;
+        img.depth[i] = t_far;
+        img.hitmask[i] = 0u;
+    }
+}
+
+// Unique-pixel fast path.  A second ray on an already-claimed pixel raises
+// kFlagDuplicatePixel and the host re-runs the order-preserving kernel below.
+__global__ void compose_kernel(ImagePlanes img, size_t pixels, const uint32_t* __restrict__ pixel_ids,
+                               IntegralArrays intl, uint32_t n_rays, uint32_t* status) {
+    const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ray >= n_rays) return;
+    const uint32_t pid = pixel_ids != nullptr ? pixel_ids[ray] : 0u;
+    if (pid >= pixels) {
+        atomicOr(status, kErrBadPixel);
+        return;
+    }
+    if (atomicExch(&img.hitmask[pid], 1u) != 0u) {
+        atomicOr(status, kFlagDuplicatePixel);
+        return;
+    }
+    img.image[3 * size_t(pid)] = intl.radiance[3 * ray];
+    img.image[3 * size_t(pid) + 1] = intl.radiance[3 * ray + 1];
+    img.image[3 * size_t(pid) + 2] = intl.radiance[3 * ray + 2];
+    img.trans[pid] = intl.transmittance[ray];
+    img.opacity[pid] = intl.opacity[ray];
+    img.depth[pid] = intl.depth[ray];
+}
+
+// Repeated pixel ids (override rays): ray order matters for the float sums and
+// products, so one thread walks the rays in order, exactly like the reference.
+__global__ void compose_sequential_kernel(ImagePlanes img, size_t pixels, const uint32_t* __restrict__ pixel_ids,
+                                          IntegralArrays intl, uint32_t n_rays) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (uint32_t ray = 0; ray < n_rays; ++ray) {
+        const uint32_t pid = pixel_ids != nullptr ? pixel_ids[ray] : 0u;
+        if (pid >= pixels) return;
+        if (img.hitmask[pid] == 0u) {
+            img.image[3 * size_t(pid)] = intl.radiance[3 * ray];
+            img.image[3 * size_t(pid) + 1] = intl.radiance[3 * ray + 1];
+            img.image[3 * size_t(pid) + 2] = intl.radiance[3 * ray + 2];
+            img.trans[pid] = intl.transmittance[ray];
+            img.opacity[pid] = intl.opacity[ray];
+            img.depth[pid] = intl.depth[ray];
+            img.hitmask[pid] = 1u;
+        } else {
+            img.image[3 * size_t(pid)] += intl.radiance[3 * ray];
+            img.image[3 * size_t(pid) + 1] += intl.radiance[3 * ray + 1];
+            img.image[3 * size_t(pid) + 2] += intl.radiance[3 * ray + 2];
+            img.trans[pid] *= intl.transmittance[ray];
+            img.opacity[pid] = 1.0f - img.trans[pid];
+            img.depth[pid] = fminf(img.depth[pid], intl.depth[ray]);
+        }
+    }
+}
+
+// ---- sample -> grid scatter on materialised samples -------------------------
+__global__ void scatter_kernel(ScatterParams sp, const float* __restrict__ positions,
+                               const float* __restrict__ grad_sigma, const float* __restrict__ grad_color,
+                               size_t n_samples) {
+    const size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_samples) return;
+    scatter_sample(sp, positions[3 * i], positions[3 * i + 1], positions[3 * i + 2],
+                   make_float4(grad_color[3 * i], grad_color[3 * i + 1], grad_color[3 * i + 2], grad_sigma[i]));
+}
+
+// ---- K8: pack / unpack -------------------------------------------------------
+__global__ void pack_grid_kernel(const float* __restrict__ sigma, const float* __restrict__ color,
+                                 float4* __restrict__ packed, size_t voxels, bool keep_missing) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (keep_missing && (sigma == nullptr || color == nullptr)) v = packed[i];
+        if (color != nullptr) { v.x = color[3 * i]; v.y = color[3 * i + 1]; v.z = color[3 * i + 2]; }
+        if (sigma != nullptr) v.w = sigma[i];
+        packed[i] = v;
+    }
+}
+
+__global__ void unpack_grad_kernel(const float4* __restrict__ packed, float* __restrict__ sigma_grad,
+                                   float* __restrict__ color_grad, size_t voxels) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = packed[i];
+        if (sigma_grad != nullptr) sigma_grad[i] = v.w;
+        if (color_grad != nullptr) { color_grad[3 * i] = v.x; color_grad[3 * i + 1] = v.y; color_grad[3 * i + 2] = v.z; }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_rays(cudaStream_t s, const FrameParams& p, const RayArrays& out, uint32_t n_rays) {
+    if (n_rays == 0) return cudaSuccess;
+    rays_kernel<<<blocks_for(n_rays, 256), 256, 0, s>>>(p, out, n_rays);
+    return cudaGetLastError();
+}
+
+size_t scan_scratch_bytes(uint32_t n_rays) {
+    const size_t tiles = (static_cast<size_t>(n_rays) + kScanTile - 1) / kScanTile + 1;
+    return static_cast<size_t>(n_rays) * sizeof(uint32_t) + 16 + tiles * sizeof(unsigned long long);
+}
+
+cudaError_t launch_count_and_scan(cudaStream_t s, const MarchParams& mp, const RayArrays& rays, uint32_t n_rays,
+                                  uint32_t* ray_offset, unsigned long long* d_total, void* scratch) {
+    if (n_rays == 0) {
+        cudaMemsetAsync(ray_offset, 0, sizeof(uint32_t), s);
+        return cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s);
+    }
+    uint32_t* counts = static_cast<uint32_t*>(scratch);
+    const size_t counts_bytes = (static_cast<size_t>(n_rays) * sizeof(uint32_t) + 15) & ~size_t(15);
+    auto* tile_sums = reinterpret_cast<unsigned long long*>(static_cast<char*>(scratch) + counts_bytes);
+    const uint32_t tiles = blocks_for(n_rays, kScanTile);
+    count_kernel<<<blocks_for(n_rays, 256), 256, 0, s>>>(mp, rays, n_rays, counts);
+    scan_tile_sums_kernel<<<tiles, kScanThreads, 0, s>>>(counts, n_rays, tile_sums);
+    scan_spine_kernel<<<1, 1024, 0, s>>>(tile_sums, tiles, d_total);
+    scan_apply_kernel<<<tiles, kScanThreads, 0, s>>>(counts, n_rays, tile_sums, d_total, ray_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_uniform_offsets(cudaStream_t s, uint32_t* ray_offset, uint32_t n_rays, uint32_t per_ray) {
+    uniform_offsets_kernel<<<blocks_for(static_cast<size_t>(n_rays) + 1, 256), 256, 0, s>>>(ray_offset, n_rays, per_ray);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample(cudaStream_t s, const MarchParams& mp, float plan_t_near, float plan_t_far,
+                          const FieldPair& fields, const RayArrays& rays, uint32_t n_rays, const SampleArrays& samp,
+                          bool integrate, const IntegralArrays& intl) {
+    if (n_rays == 0) return cudaSuccess;
+    const uint32_t blocks = blocks_for(n_rays, kThreads);
+    const bool al = (reinterpret_cast<uintptr_t>(intl.aux) & 15u) == 0;
+    if (mp.stratified) {
+        if (integrate) sample_kernel<true, true><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+        else           sample_kernel<true, false><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+    } else {
+        if (integrate) sample_kernel<false, true><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+        else           sample_kernel<false, false><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_integrate(cudaStream_t s, float plan_t_near, float plan_t_far, const SampleArrays& samp,
+                             uint32_t n_rays, uint32_t n_samples, const IntegralArrays& intl, uint32_t* d_status) {
+    if (n_rays == 0) return cudaSuccess;
+    const bool aligned = (reinterpret_cast<uintptr_t>(intl.aux) & 15u) == 0;
+    integrate_kernel<<<blocks_for(n_rays, kThreads), kThreads, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays,
+                                                                       n_samples, intl, aligned, d_status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diff(cudaStream_t s, const float* dL_dI, int64_t stride_ray, int64_t stride_c,
+                        const SampleArrays& samp, const float* aux, uint32_t n_rays, uint32_t n_samples,
+                        float* grad_sigma, float* grad_color, uint32_t* d_status) {
+    if (n_rays == 0 || n_samples == 0) return cudaSuccess;
+    diff_kernel<<<blocks_for(n_rays, kThreads), kThreads, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays,
+                                                                  n_samples, grad_sigma, grad_color, d_status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_background(cudaStream_t s, const ImagePlanes& img, size_t pixels, float t_far) {
+    if (pixels == 0) return cudaSuccess;
+    const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (pixels + 255) / 256));
+    background_planes_kernel<<<blocks, 256, 0, s>>>(img, pixels, t_far);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compose(cudaStream_t s, const ImagePlanes& img, size_t pixels, const uint32_t* pixel_ids,
+                           const IntegralArrays& intl, uint32_t n_rays, uint32_t* d_status) {
+    if (n_rays == 0) return cudaSuccess;
+    compose_kernel<<<blocks_for(n_rays, 256), 256, 0, s>>>(img, pixels, pixel_ids, intl, n_rays, d_status);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compose_sequential(cudaStream_t s, const ImagePlanes& img, size_t pixels,
+                                      const uint32_t* pixel_ids, const IntegralArrays& intl, uint32_t n_rays) {
+    compose_sequential_kernel<<<1, 32, 0, s>>>(img, pixels, pixel_ids, intl, n_rays);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(cudaStream_t s, const ScatterParams& sp, const float* positions, const float* grad_sigma,
+                           const float* grad_color, size_t n_samples) {
+    if (n_samples == 0) return cudaSuccess;
+    scatter_kernel<<<blocks_for(n_samples, 256), 256, 0, s>>>(sp, positions, grad_sigma, grad_color, n_samples);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* color, float4* packed, size_t voxels,
+                             bool keep_missing) {
+    if (voxels == 0) return cudaSuccess;
+    const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (voxels + 255) / 256));
+    pack_grid_kernel<<<blocks, 256, 0, s>>>(sigma, color, packed, voxels, keep_missing);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad,
+                               size_t voxels) {
+    if (voxels == 0) return cudaSuccess;
+    const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (voxels + 255) / 256));
+    unpack_grad_kernel<<<blocks, 256, 0, s>>>(packed, sigma_grad, color_grad, voxels);
+    return cudaGetLastError();
+}
+
+}  // namespace dv

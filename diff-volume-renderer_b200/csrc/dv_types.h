@@ -1,0 +1,80 @@
+// dv_types.h -- POD parameter blocks shared by host and device code.
+//
+// Everything a kernel needs travels in one of these structs.  Values that can
+// change between launches of a captured CUDA graph (camera, seed, ray-index
+// base) live in FrameParams, which kernels read through a device pointer.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <vector_types.h>
+
+namespace dv {
+
+// Pinhole / orthographic camera as the reference's hp_camera_desc resolves it
+// (reference hotpath/src/cpu/ray_cpu.cpp:158-176).
+struct CameraParams {
+    float fx, fy, cx, cy;
+    float r00, r01, r02, r10, r11, r12, r20, r21, r22;
+    float ox, oy, oz;
+    uint32_t ortho;
+};
+
+// Marching parameters (reference hotpath/src/cpu/samp_cpu.cpp:197-199).
+struct MarchParams {
+    float t_near, t_far, dt;
+    uint32_t max_steps;
+    uint32_t stratified;
+    uint32_t uniform_count;  // samples every generated ray emits (host-computed)
+    uint64_t seed;
+    uint64_t ray_index_base; // added to the plan-local ray index in the jitter hash
+};
+
+struct RoiParams {
+    uint32_t x, y, w, h;     // region marched
+    uint32_t img_w, img_h;   // full frame
+};
+
+struct FrameParams {
+    CameraParams cam;
+    MarchParams march;
+    RoiParams roi;
+};
+
+// One dense grid as a field of the reference holds it
+// (reference hotpath/src/runtime/hp_internal.hpp:24-31, grid_dense_cpu.cpp:17-36).
+struct GridParams {
+    const float* data;       // [nz][ny][nx][channels]
+    int32_t nx, ny, nz, channels;
+    uint32_t linear;         // HP_INTERP_LINEAR
+    uint32_t clamp;          // HP_OOB_CLAMP
+    uint32_t present;
+};
+
+// sigma + colour fields of one call.  `packed` (float4 {r,g,b,sigma} per voxel)
+// is non-null when both grids have the same resolution / interpolation / OOB.
+struct FieldPair {
+    GridParams sigma;
+    GridParams color;
+    const float4* packed;
+};
+
+// Scatter target: packed gradient grid with the DenseGridField's bbox mapping
+// (reference src/fields/dense_grid.cpp:198-230).
+struct ScatterParams {
+    float4* grad;            // [nz][ny][nx] {d r, d g, d b, d sigma}
+    int32_t nx, ny, nz;
+    uint32_t nearest;        // interp == NEAREST
+    uint32_t clamp;
+    float bmin[3], bmax[3];
+};
+
+constexpr int kSegment = 8;        // samples between transmittance checkpoints
+constexpr int kTileW = 8;          // warp tile = 8 x 4 pixels
+constexpr int kTileH = 4;
+constexpr int kWarpsX = 2;         // CTA tile = 16 x 8 pixels (4 warps)
+constexpr int kWarpsY = 2;
+constexpr int kLeanThreads = 32 * kWarpsX * kWarpsY;
+constexpr float kStopThreshold = 1e-4f;
+
+}  // namespace dv

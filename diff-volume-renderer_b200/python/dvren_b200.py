@@ -1,0 +1,254 @@
+"""ctypes front end of the product library libdvren_hp.so (hp.h + hp_b200.h).
+
+No fallback of any kind lives here: if the library is missing, fails to load or
+reports no CUDA device, the call raises.  Reference-side counterparts of the
+classes below: dvren::Context / Plan / DenseGridField / Renderer
+(reference include/dvren/**), which libdvren.so re-implements in C++ on the
+same C ABI; this module is the Python door used by tests and bench.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import numpy as np
+
+import hp_abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(PKG_DIR, "libdvren_hp.so")
+
+HPX_CTX_EXT_MAGIC = 0x42323030
+HPX_BACKWARD_GRID, HPX_BACKWARD_CAMERA, HPX_BACKWARD_ZERO = 1, 2, 4
+
+
+class hpx_ctx_ext(C.Structure):
+    _fields_ = [("magic", C.c_uint32), ("device_ordinal", C.c_int32), ("stream", C.c_void_p)]
+
+
+class hpx_counts(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("samples", C.c_uint64), ("live_samples", C.c_uint64)]
+
+
+P = C.POINTER
+f3 = C.c_float * 3
+HPX_FUNCTIONS = {
+    "hpx_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "hpx_ctx_device": (C.c_int, [C.c_void_p, P(C.c_int32), P(C.c_void_p)]),
+    "hpx_last_error": (C.c_char_p, []),
+    "hpx_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hpx_grid_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(f3), P(f3), P(C.c_void_p)]),
+    "hpx_grid_create_raw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                      C.c_int, C.c_uint32, C.c_uint32, P(f3), P(f3), P(C.c_void_p)]),
+    "hpx_grid_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hpx_grid_zero_grad": (C.c_int, [C.c_void_p]),
+    "hpx_grid_grad_buffer": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]),
+    "hpx_grid_read_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hpx_grid_release": (None, [C.c_void_p]),
+    "hpx_frame_create": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
+    "hpx_frame_bytes": (C.c_size_t, [C.c_void_p]),
+    "hpx_frame_set_view": (C.c_int, [C.c_void_p, P(A.hp_camera_desc), C.c_uint64, C.c_uint64]),
+    "hpx_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
+    "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
+    "hpx_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hpx_frame_counts": (C.c_int, [C.c_void_p, P(hpx_counts)]),
+    "hpx_frame_capture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "hpx_frame_replay": (C.c_int, [C.c_void_p]),
+    "hpx_frame_grad_input": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
+    "hpx_frame_release": (None, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    """Load and bind the product library.  Raises if it is not built."""
+    global _lib
+    if _lib is None or path is not None:
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise RuntimeError(f"{p} is not built; run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = C.CDLL(p)
+        A.bind(lib)
+        A.bind(lib, HPX_FUNCTIONS)
+        if path is not None:
+            return lib
+        _lib = lib
+    return _lib
+
+
+class DvrenError(RuntimeError):
+    def __init__(self, what: str, status: int, detail: str = ""):
+        name = A.STATUS_NAMES[status] if 0 <= status < len(A.STATUS_NAMES) else str(status)
+        super().__init__(f"{what} -> {name}" + (f" ({detail})" if detail else ""))
+        self.status = status
+
+
+def check(what: str, status: int):
+    if status != A.HP_STATUS_SUCCESS:
+        detail = load().hpx_last_error()
+        raise DvrenError(what, status, detail.decode() if detail else "")
+
+
+def _vec3(v):
+    return None if v is None else f3(*[float(x) for x in v])
+
+
+class Context:
+    """hp_ctx bound to a device ordinal and (optionally) a caller stream."""
+
+    def __init__(self, device: int = -1, stream: int = 0):
+        self.lib = load()
+        self._ext = hpx_ctx_ext(HPX_CTX_EXT_MAGIC, device, stream or None)
+        desc = A.hp_ctx_desc(0, None, C.cast(C.pointer(self._ext), C.c_void_p))
+        self.handle = C.c_void_p()
+        check("hp_ctx_create", self.lib.hp_ctx_create(C.byref(desc), C.byref(self.handle)))
+
+    def synchronize(self):
+        check("hpx_ctx_synchronize", self.lib.hpx_ctx_synchronize(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.lib.hp_ctx_release(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Plan:
+    def __init__(self, ctx: Context, desc: A.hp_plan_desc):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.handle = C.c_void_p()
+        check("hp_plan_create", self.lib.hp_plan_create(ctx.handle, C.byref(desc), C.byref(self.handle)))
+        self.desc = A.hp_plan_desc()
+        check("hp_plan_get_desc", self.lib.hp_plan_get_desc(self.handle, C.byref(self.desc)))
+
+    @property
+    def n_rays(self) -> int:
+        return self.desc.roi.width * self.desc.roi.height
+
+    def close(self):
+        if self.handle:
+            self.lib.hp_plan_release(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Grid:
+    """hpx_grid: packed {r,g,b,sigma} device grid + gradient block."""
+
+    def __init__(self, ctx: Context, sigma, color, interp=A.HP_INTERP_LINEAR, oob=A.HP_OOB_ZERO,
+                 bbox_min=None, bbox_max=None, device_shape=None):
+        """sigma (nz,ny,nx) / color (nz,ny,nx,3): numpy arrays (HOST), or raw device pointers
+        (ints) together with device_shape=(nx,ny,nz)."""
+        self.ctx, self.lib = ctx, ctx.lib
+        self.handle = C.c_void_p()
+        lo, hi = _vec3(bbox_min), _vec3(bbox_max)
+        if device_shape is None:
+            sig = np.ascontiguousarray(sigma, np.float32)
+            col = np.ascontiguousarray(color, np.float32)
+            nz, ny, nx = sig.shape
+            assert col.shape == (nz, ny, nx, 3)
+            ms, ps, pc = A.HP_MEMSPACE_HOST, sig.ctypes.data, col.ctypes.data
+        else:
+            nx, ny, nz = device_shape
+            ms, ps, pc = A.HP_MEMSPACE_DEVICE, int(sigma), int(color)
+        self.shape = (nx, ny, nz)
+        self.voxels = nx * ny * nz
+        check("hpx_grid_create_raw",
+              self.lib.hpx_grid_create_raw(ctx.handle, nx, ny, nz, ps, pc, ms, interp, oob,
+                                           C.byref(lo) if lo else None, C.byref(hi) if hi else None,
+                                           C.byref(self.handle)))
+
+    def zero_grad(self):
+        check("hpx_grid_zero_grad", self.lib.hpx_grid_zero_grad(self.handle))
+
+    def grad_buffer(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check("hpx_grid_grad_buffer", self.lib.hpx_grid_grad_buffer(self.handle, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def read_grad(self):
+        sg = np.zeros(self.voxels, np.float32)
+        cg = np.zeros(self.voxels * 3, np.float32)
+        cam = np.zeros(16, np.float32)
+        check("hpx_grid_read_grad", self.lib.hpx_grid_read_grad(self.handle, sg.ctypes.data, cg.ctypes.data,
+                                                                cam.ctypes.data, A.HP_MEMSPACE_HOST))
+        return sg, cg, cam
+
+    def update(self, sigma=None, color=None):
+        s = np.ascontiguousarray(sigma, np.float32) if sigma is not None else None
+        c = np.ascontiguousarray(color, np.float32) if color is not None else None
+        check("hpx_grid_update", self.lib.hpx_grid_update(self.handle, s.ctypes.data if s is not None else None,
+                                                          c.ctypes.data if c is not None else None,
+                                                          A.HP_MEMSPACE_HOST))
+
+    def close(self):
+        if self.handle:
+            self.lib.hpx_grid_release(self.handle)
+            self.handle = C.c_void_p()
+
+
+class Frame:
+    """hpx_frame: per-plan device workspace; forward / backward / graph replay."""
+
+    def __init__(self, plan: Plan):
+        self.plan, self.lib = plan, plan.lib
+        self.handle = C.c_void_p()
+        check("hpx_frame_create", self.lib.hpx_frame_create(plan.handle, C.byref(self.handle)))
+
+    def set_view(self, camera: Optional[A.hp_camera_desc], seed: int, ray_index_base: int = 0):
+        check("hpx_frame_set_view", self.lib.hpx_frame_set_view(
+            self.handle, C.byref(camera) if camera is not None else None, seed, ray_index_base))
+
+    def forward(self, grid: Grid):
+        check("hpx_forward", self.lib.hpx_forward(self.handle, grid.handle))
+
+    def backward(self, grid: Grid, dL_dI, flags=HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO, device=False):
+        if device:
+            ptr, ms = int(dL_dI), A.HP_MEMSPACE_DEVICE
+        else:
+            self._g = np.ascontiguousarray(dL_dI, np.float32)
+            assert self._g.size == self.plan.n_rays * 3
+            ptr, ms = self._g.ctypes.data, A.HP_MEMSPACE_HOST
+        check("hpx_backward", self.lib.hpx_backward(self.handle, grid.handle, ptr, ms, flags))
+
+    def read(self):
+        d = self.plan.desc
+        h, w = d.height, d.width
+        o = {"image": np.zeros((h, w, 3), np.float32), "trans": np.zeros((h, w), np.float32),
+             "opacity": np.zeros((h, w), np.float32), "depth": np.zeros((h, w), np.float32),
+             "hitmask": np.zeros((h, w), np.uint32)}
+        check("hpx_frame_read", self.lib.hpx_frame_read(self.handle, o["image"].ctypes.data, o["trans"].ctypes.data,
+                                                        o["opacity"].ctypes.data, o["depth"].ctypes.data,
+                                                        o["hitmask"].ctypes.data))
+        return o
+
+    def counts(self):
+        c = hpx_counts()
+        check("hpx_frame_counts", self.lib.hpx_frame_counts(self.handle, C.byref(c)))
+        return {"rays": c.rays, "samples": c.samples, "live_samples": c.live_samples}
+
+    def capture(self, grid: Grid, backward_flags: int = 0):
+        check("hpx_frame_capture", self.lib.hpx_frame_capture(self.handle, grid.handle, backward_flags))
+
+    def replay(self):
+        check("hpx_frame_replay", self.lib.hpx_frame_replay(self.handle))
+
+    def grad_input_ptr(self) -> int:
+        p = C.c_void_p()
+        check("hpx_frame_grad_input", self.lib.hpx_frame_grad_input(self.handle, C.byref(p)))
+        return p.value
+
+    def image_ptrs(self):
+        v = A.hp_img_t()
+        check("hpx_frame_image", self.lib.hpx_frame_image(self.handle, C.byref(v)))
+        return v
+
+    def bytes(self) -> int:
+        return self.lib.hpx_frame_bytes(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.hpx_frame_release(self.handle)
+            self.handle = C.c_void_p()

@@ -56,6 +56,10 @@ def smooth_volume(n, blobs: int = 4, seed: int = 7, peak: float = 6.0):
         sigma += peak * rng.uniform(0.5, 1.0) * g
         color += g[..., None] * rng.uniform(0.2, 1.0, 3)
     color = color / max(color.max(), 1e-6)
+    # density must vanish on the cube faces: with the OOB-zero policy a non-zero face value makes
+    # the rendered loss discontinuous in the camera, and finite differences meaningless
+    window = (np.sin(np.pi * x) * np.sin(np.pi * y) * np.sin(np.pi * z)) ** 2
+    sigma = sigma * window
     return sigma.astype(np.float32), np.ascontiguousarray(color.astype(np.float32))
 
 

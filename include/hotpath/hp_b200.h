@@ -1,0 +1,125 @@
+/*
+ * hotpath/hp_b200.h -- additive B200 entry points next to hotpath/hp.h.
+ *
+ * hp.h (reference hotpath/include/hotpath/hp.h) fixes the drop-in surface; it
+ * materialises every sample (32 B + 16 B aux each), returns per-sample
+ * gradients only, has no device ordinal / stream, and creates fields from HOST
+ * tensors only (reference hp_runtime.cpp:271-274).  The entry points below add
+ * what a device-resident training loop needs without touching that surface
+ * (SURVEY section 8b "additive extensions"):
+ *
+ *   hpx_ctx_ext     device ordinal + caller stream, passed via hp_ctx_desc.reserved
+ *   hpx_grid        sigma+RGB packed {r,g,b,sigma} float4 grid in HBM, plus its
+ *                   packed gradient grid and the 16-float camera gradient
+ *   hpx_frame       per-plan device workspace (the Plan workspace planner):
+ *                   image planes, per-ray state, transmittance checkpoints
+ *   hpx_forward     ray generation + marching + integration + image compose in
+ *                   ONE kernel, no per-sample global traffic
+ *                   (replaces hp_ray -> hp_samp_int_fused -> hp_img,
+ *                   reference src/render/renderer.cpp:259-365)
+ *   hpx_backward    reverse march with recompute, warp-level scatter into the
+ *                   packed gradient grid, optional camera adjoint
+ *                   (replaces hp_diff + DenseGridField::AccumulateSampleGradients,
+ *                   reference src/render/renderer.cpp:415-427,
+ *                   src/fields/dense_grid.cpp:171-309)
+ *   hpx_frame_capture / hpx_frame_replay   real CUDA-graph capture of the above
+ *
+ * All functions return hp_status; none blocks the host unless documented.
+ * Work is enqueued on the context's stream.
+ */
+#ifndef DVREN_HOTPATH_HP_B200_H_
+#define DVREN_HOTPATH_HP_B200_H_
+
+#include "hotpath/hp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPX_CTX_EXT_MAGIC 0x42323030u /* "B200" */
+
+/* Optional extension of hp_ctx_desc (pass its address in .reserved). */
+typedef struct hpx_ctx_ext {
+    uint32_t magic;          /* HPX_CTX_EXT_MAGIC */
+    int32_t  device_ordinal; /* -1: take it from preferred_device / current device */
+    void*    stream;         /* cudaStream_t to enqueue on; NULL: library-owned stream */
+} hpx_ctx_ext;
+
+typedef struct hpx_grid  hpx_grid;
+typedef struct hpx_frame hpx_frame;
+
+/* flags for hpx_backward / hpx_frame_capture */
+#define HPX_BACKWARD_GRID    0x1u /* accumulate d/d sigma, d/d rgb into the grid's gradient */
+#define HPX_BACKWARD_CAMERA  0x2u /* accumulate d/d c2w[12], d/d {fx,fy,cx,cy}               */
+#define HPX_BACKWARD_ZERO    0x4u /* zero the gradient buffers first                         */
+
+/* Per-frame counters (valid after the stream has been synchronised). */
+typedef struct hpx_counts {
+    uint64_t rays;          /* rays marched                                        */
+    uint64_t samples;       /* reference sample_count: every emitted sample        */
+    uint64_t live_samples;  /* samples integrated before the T <= 1e-4 stop        */
+} hpx_counts;
+
+/* ---- context helpers ---------------------------------------------------- */
+HP_API hp_status hpx_ctx_synchronize(const hp_ctx* ctx);
+HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream);
+/* Blocking device-to-host copy on the context's stream, for binding languages without a CUDA
+ * runtime of their own (reading back the DEVICE views hp_graph_execute / hpx_frame_image return). */
+HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void* device_src, size_t bytes);
+/* Last CUDA/runtime error text recorded on this thread ("" if none). */
+HP_API const char* hpx_last_error(void);
+
+/* ---- packed device grid -------------------------------------------------- */
+/* Build from two dense-grid fields of equal resolution, interpolation and OOB
+ * policy (what DenseGridField creates).  bbox_* (NULL = unit cube) is used by
+ * the backward scatter only, like the reference (SURVEY finding 8). */
+HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp_field* fc,
+                                 const float bbox_min[3], const float bbox_max[3],
+                                 hpx_grid** out_grid);
+/* Build from raw arrays: sigma[nz][ny][nx], color[nz][ny][nx][3] in `memspace`. */
+HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, int32_t nz,
+                                     const float* sigma, const float* color, hp_memspace memspace,
+                                     uint32_t interp, uint32_t oob, const float bbox_min[3],
+                                     const float bbox_max[3], hpx_grid** out_grid);
+/* Replace the values (parameter update); either pointer may be NULL to keep it. */
+HP_API hp_status hpx_grid_update(hpx_grid* grid, const float* sigma, const float* color,
+                                 hp_memspace memspace);
+HP_API hp_status hpx_grid_zero_grad(hpx_grid* grid);
+/* Device view of the contiguous gradient block [4*V grid floats {r,g,b,sigma} | 16 camera floats]
+ * -- the buffer a data-parallel caller all-reduces. */
+HP_API hp_status hpx_grid_grad_buffer(hpx_grid* grid, float** out_device_ptr, size_t* out_floats);
+/* Un-interleave into the reference layout sigma_grad[V], color_grad[3V] (+camera[16], may be NULL)
+ * in `memspace`.  Blocks until done when the destination is HOST. */
+HP_API hp_status hpx_grid_read_grad(hpx_grid* grid, float* sigma_grad, float* color_grad,
+                                    float* camera16, hp_memspace memspace);
+HP_API void      hpx_grid_release(hpx_grid* grid);
+
+/* ---- per-plan frame workspace ------------------------------------------- */
+HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame);
+/* Bytes of device memory the frame owns (workspace accounting). */
+HP_API size_t    hpx_frame_bytes(const hpx_frame* frame);
+/* Change camera / seed / global ray-index base without re-planning (graph friendly:
+ * the values live in a device parameter block that captured kernels re-read). */
+HP_API hp_status hpx_frame_set_view(hpx_frame* frame, const hp_camera_desc* camera, uint64_t seed,
+                                    uint64_t ray_index_base);
+HP_API hp_status hpx_forward(hpx_frame* frame, const hpx_grid* grid);
+/* dL_dI: (rays,3) f32 per ray in plan order, HOST (copied on the stream) or DEVICE. */
+HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_dI,
+                              hp_memspace memspace, uint32_t flags);
+/* Device views of the composed frame (shapes as hp_img_t). */
+HP_API hp_status hpx_frame_image(const hpx_frame* frame, hp_img_t* out_views);
+/* Copy the composed frame to HOST buffers (any may be NULL); synchronises. */
+HP_API hp_status hpx_frame_read(hpx_frame* frame, float* image, float* trans, float* opacity,
+                                float* depth, uint32_t* hitmask);
+HP_API hp_status hpx_frame_counts(hpx_frame* frame, hpx_counts* out_counts);
+/* Capture forward (+ backward when flags != 0, reading dL/dI from the frame's own
+ * device buffer, see hpx_frame_grad_input) into a CUDA graph; replay launches it. */
+HP_API hp_status hpx_frame_capture(hpx_frame* frame, hpx_grid* grid, uint32_t backward_flags);
+HP_API hp_status hpx_frame_replay(hpx_frame* frame);
+HP_API hp_status hpx_frame_grad_input(hpx_frame* frame, float** out_device_dL_dI);
+HP_API void      hpx_frame_release(hpx_frame* frame);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVREN_HOTPATH_HP_B200_H_ */
