@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- Msamples/s of the dvren hot path (fused forward + backward to the dense grid).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3]
+
+A "step" is one pass of the hot path over one batch of synthetic input: ray generation ->
+fused march / integrate / compose -> reverse-march backward with grid scatter (-> NCCL all-reduce
+of the packed gradient block when N > 1).  Default workload = BASELINE.json configs[1]:
+256^3 grid, 1024x1024, stratified sampling, 512 steps (537 M samples), on one B200.  For N > 1
+every rank renders its own view of an N-view batch against a replicated grid (weak scaling) and
+the ranks all-reduce the gradients; `value` counts the samples of all ranks.
+
+Prints ONE JSON line (see README / DESIGN.md section "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(REPO, "diff-volume-renderer_b200", "python")]
+
+CONFIGS = {
+    # name: grid n, image W, steps, stratified, description
+    "c1": dict(grid=64, width=512, steps=256, stratified=False,
+               workload="BASELINE configs[0] shape: 64^3 grid, 512x512, fixed, 256 steps"),
+    "c2": dict(grid=256, width=1024, steps=512, stratified=True,
+               workload="BASELINE configs[1]: 256^3 dense grid, 1024x1024, stratified, 512 steps, fused fwd + sigma/color bwd"),
+    "c3": dict(grid=512, width=2048, steps=1024, stratified=False,
+               workload="BASELINE configs[2]: 512^3 dense grid, 2048x2048, fixed, 1024 steps, fwd+bwd"),
+}
+METRIC = "Msamples/s fwd+bwd (fused forward + backward adjoint to the dense sigma/color grid)"
+UNIT = "Msamples/s"
+# algorithmic bytes per live sample: 8 corners x 16 B gathered; + 8 x 16 B gradient reds
+BYTES_FWD_PER_SAMPLE = 128
+BYTES_BWD_PER_SAMPLE = 256
+
+
+def read_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1])); mx = float(p[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the upper half: the sampler also sees idle gaps between steps
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class CudaArrayView:
+    """Exposes a raw device pointer to torch (zero copy) via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dvren_b200 as D
+    import synth as S
+
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    sigma, color = S.hashed_volume(n, "thin")       # no early termination: live samples == samples
+    ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank, views=max(world, 1)))
+    grid = D.Grid(ctx, sigma, color)
+    del sigma, color
+    frame = D.Frame(plan)
+    n_rays = plan.n_rays
+    g_host = torch.from_numpy(S.hashed_image_grad(n_rays)).pin_memory()
+    g_dev = g_host.to(dev, non_blocking=True)
+    grad_ptr, grad_floats = grid.grad_buffer()
+    grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
+    img = frame.image_ptrs()
+    pixels = W * W
+    planes = [torch.as_tensor(CudaArrayView(img.image.data, pixels * 3), device=dev),
+              torch.as_tensor(CudaArrayView(img.trans.data, pixels), device=dev),
+              torch.as_tensor(CudaArrayView(img.opacity.data, pixels), device=dev),
+              torch.as_tensor(CudaArrayView(img.depth.data, pixels), device=dev)]
+    planes_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in planes]
+    grad_host = torch.empty(grad_floats, dtype=torch.float32).pin_memory()
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+
+    def step_resident():
+        frame.forward(grid)
+        frame.backward(grid, g_dev.data_ptr(), flags, device=True)
+        if world > 1:
+            dist.all_reduce(grad_view)
+
+    def step_e2e():
+        # what dvren::Renderer::Forward/Backward move per step (reference renderer.hpp:50-66):
+        # dL/dI host->device; image planes and the full gradient block device->host
+        g_dev.copy_(g_host, non_blocking=True)
+        frame.forward(grid)
+        for h, d in zip(planes_host, planes):
+            h.copy_(d, non_blocking=True)
+        frame.backward(grid, g_dev.data_ptr(), flags, device=True)
+        if world > 1:
+            dist.all_reduce(grad_view)
+        grad_host.copy_(grad_view, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(k):
+            fn()
+        b.record(stream)
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = frame.counts()
+    samples, live = counts["samples"], counts["live_samples"]
+    e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 1))
+    # kernel-level timing for the roofline lines (same stream, CUDA events, after the runs above)
+    fwd_ms = timed(lambda: frame.forward(grid), args.steps, 1)
+    bwd_ms = timed(lambda: frame.backward(grid, g_dev.data_ptr(), D.HPX_BACKWARD_GRID, device=True), args.steps, 1)
+
+    ms_per_step = total_ms / args.steps
+    value = world * samples / (ms_per_step * 1e-3) / 1e6
+    e2e_value = world * samples / (e2e_ms / args.steps * 1e-3) / 1e6
+    peak, peak_src = read_peaks()
+    bwd_bytes = BYTES_BWD_PER_SAMPLE * live + 12 * n_rays
+    fwd_bytes = BYTES_FWD_PER_SAMPLE * live + 24 * n_rays
+    bwd_gbs = bwd_bytes / (bwd_ms / args.steps * 1e-3) / 1e9
+    fwd_gbs = fwd_bytes / (fwd_ms / args.steps * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.config, {}).get("lean_backward_kernel")
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
+                   "rays_per_gpu": n_rays, "samples_per_gpu_step": samples, "live_samples_per_gpu_step": live,
+                   "parallelism": f"ray-tile data parallel x{world}, grid replicated, NCCL all-reduce of gradients" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (packed grid %d MB + gradient grid %d MB vs 126 MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(g_host.numel() * 4),
+                "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + grad_floats * 4),
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": 2 * args.steps,
+        "clocks": clocks,
+        "fwd": {"ms": fwd_ms / args.steps, "msamples_s": samples / (fwd_ms / args.steps * 1e-3) / 1e6},
+        "bwd": {"ms": bwd_ms / args.steps, "msamples_s": samples / (bwd_ms / args.steps * 1e-3) / 1e6},
+        "roofline": {"bound": "hbm", "kernel": "lean_backward_kernel", "achieved": bwd_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bwd_bytes,
+                     "note": "algorithmic bytes are gather/scatter bytes at L1/L2 level (256 B per live sample); "
+                             "compulsory HBM bytes are far smaller, see DESIGN.md",
+                     "forward_kernel": {"kernel": "lean_forward_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
+                                        "algorithmic_bytes_per_launch": fwd_bytes}},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    frame.close(); grid.close(); plan.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, rows: int, threads: int):
+    """The reference's own CPU implementation (oracle/_ref, unmodified, via dvren::Renderer) -- or the
+    oracle port when that library is absent -- timed on a band of `rows` image rows per thread."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import numpy as np
+
+    import oracle as O
+    import synth as S
+
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    sigma, color = S.hashed_volume(n, "thin")
+    use_ref = O.ref_available()
+    if not use_ref:
+        O.build_oracle()
+    results = [None] * threads
+    y_start = (W - rows * threads) // 2
+
+    def work(t):
+        y0 = y_start + t * rows
+        desc = S.bench_plan(W, W, steps, stratified=cfg["stratified"], roi=(0, y0, W, rows))
+        dl = S.hashed_image_grad(W * rows)
+        t0 = time.perf_counter()
+        if use_ref:
+            r = O.ref_render(desc, sigma, color, dl)
+            assert r["status"] == 0, r["status"]
+            ms = r["forward_ms"] + r["backward_ms"]
+            cnt = r["sample_count"]
+        else:
+            st, rd = O.plan_resolve(desc)
+            gs, gc = O.make_grid(sigma, 1), O.make_grid(color, 3)
+            r = O.render(rd, gs, gc, dl, per_ray=False, frames=True)
+            ms = (time.perf_counter() - t0) * 1e3
+            cnt = r["sample_count"]
+        results[t] = (cnt, ms, (time.perf_counter() - t0) * 1e3)
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in results)
+    # throughput of the hot path itself: samples / (forward + backward time), slowest thread
+    busy_ms = max(r[1] for r in results)
+    return {"value": total / (busy_ms * 1e-3) / 1e6, "unit": UNIT, "cores": threads,
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{threads} band(s) of {rows} rows x {W} px x {steps} steps = {total} samples, "
+                      f"Renderer::Forward+Backward time {busy_ms:.0f} ms (wall incl. setup {wall:.1f} s)"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    threads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(cfg, rows=1, threads=threads)
+    t0 = time.perf_counter()
+    vals = [cpu_baseline(cfg, rows=args.cpu_rows_ref, threads=threads) for _ in range(args.steps)]
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    v = sum(x["value"] for x in vals) / len(vals)
+    base = vals[-1]
+    base["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)"},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-rows", type=int, default=32, help="image rows of the cpu_baseline sample")
+    ap.add_argument("--cpu-rows-ref", type=int, default=8, help="rows per thread per step for --impl reference")
+    ap.add_argument("--cpu-threads", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -139,13 +139,28 @@ __device__ __forceinline__ float trilerp(float c000, float c100, float c010, flo
     return lerp_ref(c0, c1, tz);
 }
 
+// Colour channels never feed an index, a count or the transmittance stop test, so the lean
+// kernels may contract their lerps (results stay within 1 ulp per lerp of the reference's).
+__device__ __forceinline__ float lerp_fma(float a, float b, float t) { return __fmaf_rn(b - a, t, a); }
+
+__device__ __forceinline__ float trilerp_fma(float c000, float c100, float c010, float c110, float c001, float c101,
+                                             float c011, float c111, float tx, float ty, float tz) {
+    const float c00 = lerp_fma(c000, c100, tx);
+    const float c10 = lerp_fma(c010, c110, tx);
+    const float c01 = lerp_fma(c001, c101, tx);
+    const float c11 = lerp_fma(c011, c111, tx);
+    const float c0 = lerp_fma(c00, c10, ty);
+    const float c1 = lerp_fma(c01, c11, ty);
+    return lerp_fma(c0, c1, tz);
+}
+
 __device__ __forceinline__ size_t voxel_index(int32_t x, int32_t y, int32_t z, int32_t nx, int32_t ny) {
     return (static_cast<size_t>(z) * static_cast<size_t>(ny) + static_cast<size_t>(y)) * static_cast<size_t>(nx) +
            static_cast<size_t>(x);
 }
 
 // Packed {r,g,b,sigma} gather: 8 x 16-byte loads through the read-only path.
-template <bool kLinear, bool kClamp>
+template <bool kLinear, bool kClamp, bool kExactColor = true>
 __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                 float px, float py, float pz) {
     float fx, fy, fz;
@@ -166,9 +181,16 @@ __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, in
     const float4 v001 = __ldg(g + row01 + c.x0), v101 = __ldg(g + row01 + c.x1);
     const float4 v011 = __ldg(g + row11 + c.x0), v111 = __ldg(g + row11 + c.x1);
     float4 o;
-    o.x = trilerp(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, c.tx, c.ty, c.tz);
-    o.y = trilerp(v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y, c.tx, c.ty, c.tz);
-    o.z = trilerp(v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z, c.tx, c.ty, c.tz);
+    if (kExactColor) {
+        o.x = trilerp(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, c.tx, c.ty, c.tz);
+        o.y = trilerp(v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y, c.tx, c.ty, c.tz);
+        o.z = trilerp(v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z, c.tx, c.ty, c.tz);
+    } else {
+        o.x = trilerp_fma(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, c.tx, c.ty, c.tz);
+        o.y = trilerp_fma(v000.y, v100.y, v010.y, v110.y, v001.y, v101.y, v011.y, v111.y, c.tx, c.ty, c.tz);
+        o.z = trilerp_fma(v000.z, v100.z, v010.z, v110.z, v001.z, v101.z, v011.z, v111.z, c.tx, c.ty, c.tz);
+    }
+    // sigma decides alpha, T and the stop test: always the reference's operation order
     o.w = trilerp(v000.w, v100.w, v010.w, v110.w, v001.w, v101.w, v011.w, v111.w, c.tx, c.ty, c.tz);
     return o;
 }
@@ -216,6 +238,34 @@ __device__ __forceinline__ float4 sample_fields(const FieldPair& f, float px, fl
 }
 
 // ---------------------------------------------------------------------------
+// Conservative parameter interval in which a ray can be inside the unit cube.  With the OOB-zero
+// policy every sample outside [0,1]^3 has sigma = rgb = 0 exactly (grid_dense_cpu.cpp:147-149), i.e.
+// alpha = w = 0 and T unchanged: such samples only advance the depth cursor.  The interval is
+// widened by far more than the rounding error of o + d*t so that no sample the reference evaluates
+// inside the cube is ever skipped; samples inside the widened shell take the ordinary path.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cube_interval(const Ray& r, float& t_in, float& t_out) {
+    t_in = -CUDART_INF_F;
+    t_out = CUDART_INF_F;
+    const float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (fabsf(d[i]) > 1e-12f) {
+            const float inv = 1.0f / d[i];
+            const float a = (0.0f - o[i]) * inv, b = (1.0f - o[i]) * inv;
+            t_in = fmaxf(t_in, fminf(a, b));
+            t_out = fminf(t_out, fmaxf(a, b));
+        } else if (o[i] < -1e-3f || o[i] > 1.001f) {
+            t_in = CUDART_INF_F;   // parallel to the slab and clearly outside it: never inside
+            t_out = -CUDART_INF_F;
+        }
+    }
+    const float pad_in = 1e-3f * (1.0f + fabsf(t_in)), pad_out = 1e-3f * (1.0f + fabsf(t_out));
+    t_in -= pad_in;
+    t_out += pad_out;
+}
+
+// ---------------------------------------------------------------------------
 // alpha -- hotpath/src/cpu/int_cpu.cpp:98-109 (+ the call-site clamp :188)
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ float alpha_of(float sigma, float dt) {
@@ -237,17 +287,26 @@ struct RayAccum {
     float T = 1.0f, depth_w = 0.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f, t_cursor = 0.0f;
 };
 
-// Returns true when the ray stops (T <= 1e-4 after this sample).
+// Returns true when the ray stops (T <= 1e-4 after this sample).  kExact = false contracts the
+// radiance / depth accumulations (they feed no decision); alpha, w and T never change.
+template <bool kExact = true>
 __device__ __forceinline__ bool integrate_sample(RayAccum& s, float dtv, float4 rgbs, float& alpha_out,
                                                  float& weight_out, float& T_before_out) {
     const float alpha = alpha_of(rgbs.w, dtv);
     const float T_before = s.T;
     const float w = T_before * alpha;
-    s.cr += w * rgbs.x;
-    s.cg += w * rgbs.y;
-    s.cb += w * rgbs.z;
     const float mid = s.t_cursor + 0.5f * dtv;
-    s.depth_w += w * mid;
+    if (kExact) {
+        s.cr += w * rgbs.x;
+        s.cg += w * rgbs.y;
+        s.cb += w * rgbs.z;
+        s.depth_w += w * mid;
+    } else {
+        s.cr = __fmaf_rn(w, rgbs.x, s.cr);
+        s.cg = __fmaf_rn(w, rgbs.y, s.cg);
+        s.cb = __fmaf_rn(w, rgbs.z, s.cb);
+        s.depth_w = __fmaf_rn(w, mid, s.depth_w);
+    }
     s.T = T_before * fmaxf(1.0f - alpha, 0.0f);
     s.t_cursor += dtv;
     alpha_out = alpha; weight_out = w; T_before_out = T_before;

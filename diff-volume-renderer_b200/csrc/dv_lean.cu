@@ -63,6 +63,8 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
     bool alive = px.inside;
     uint32_t live = 0;
     const uint32_t count = mp.uniform_count;
+    float t_in = -CUDART_INF_F, t_out = CUDART_INF_F;
+    if (!kClamp) cube_interval(ray, t_in, t_out);
 
     for (uint32_t step = 0; step < count; ++step) {
         if (!__any_sync(0xffffffffu, alive)) break;
@@ -70,15 +72,21 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
             out.ckpt[static_cast<size_t>(step / kSegment) * out.ckpt_stride + px.ray] = acc.T;
         }
         if (alive) {
+            ++live;
+            const float base = mp.t_near + static_cast<float>(step) * mp.dt;
+            if (!kClamp && (base > t_out || base + mp.dt < t_in)) {
+                // whole step outside the cube: sigma = 0, only the depth cursor moves (same dt arithmetic)
+                acc.t_cursor += fminf(base + mp.dt, mp.t_far) - base;
+                continue;
+            }
             float t, dtv;
             march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, step, t, dtv);
             const float pxw = ray.ox + ray.dx * t;
             const float pyw = ray.oy + ray.dy * t;
             const float pzw = ray.oz + ray.dz * t;
-            const float4 v = sample_packed<kLinear, kClamp>(grid, nx, ny, nz, pxw, pyw, pzw);
+            const float4 v = sample_packed<kLinear, kClamp, false>(grid, nx, ny, nz, pxw, pyw, pzw);
             float a, w, tb;
-            ++live;
-            if (integrate_sample(acc, dtv, v, a, w, tb)) alive = false;
+            if (integrate_sample<false>(acc, dtv, v, a, w, tb)) alive = false;
         }
     }
 
@@ -104,14 +112,28 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
     }
 }
 
+// Per-sample state of one segment, stashed in shared memory between the forward recompute and the
+// reverse sweep: [sample][field][thread] so that a warp touches 32 consecutive banks.  Keeping the
+// two loops rolled (dynamic index into shared memory instead of unrolled register arrays) keeps the
+// kernel body small: the fully unrolled form stalled on instruction fetch (ncu: no_instruction).
+struct SegmentStash {
+    float alpha[kSegment][kLeanThreads];
+    float T_prev[kSegment][kLeanThreads];
+    float dot[kSegment][kLeanThreads];
+    float t[kSegment][kLeanThreads];
+    float dt[kSegment][kLeanThreads];
+};
+
 template <bool kLinear, bool kClamp, bool kStratified>
 __global__ void __launch_bounds__(kLeanThreads)
 lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
                      int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st) {
+    __shared__ SegmentStash stash;
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
     const RoiParams roi = P->roi;
     const TilePixel px = tile_pixel(roi);
+    const uint32_t tid = threadIdx.x;
 
     const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
     const uint64_t ray_index = mp.ray_index_base + px.ray;
@@ -124,47 +146,54 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
         g1 = dL_dI[static_cast<size_t>(px.ray) * 3 + 1];
         g2 = dL_dI[static_cast<size_t>(px.ray) * 3 + 2];
     }
-    uint32_t nseg = (live + kSegment - 1) / kSegment;
+    const uint32_t nseg = (live + kSegment - 1) / kSegment;
     uint32_t warp_nseg = nseg;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_nseg = max(warp_nseg, __shfl_xor_sync(0xffffffffu, warp_nseg, o));
 
+    float t_in = -CUDART_INF_F, t_out = CUDART_INF_F;
+    const bool skippable = !kClamp && sp.unit_bbox != 0u;   // outside samples touch neither T nor the grid
+    if (skippable) cube_interval(ray, t_in, t_out);
+
     float adj_T = 0.0f;
+    // all lanes of a warp walk the same segment index in the same iteration: the warp's gathers and
+    // scatters of one iteration stay inside one thin slab of the grid
     for (uint32_t seg = warp_nseg; seg-- > 0;) {
         if (seg >= nseg) continue;
-        float T = st.ckpt[static_cast<size_t>(seg) * st.ckpt_stride + px.ray];
-        float s_alpha[kSegment], s_Tprev[kSegment], s_dot[kSegment], s_t[kSegment], s_dt[kSegment];
         const uint32_t first = seg * kSegment;
-        // forward part: recompute the segment from its checkpoint
-#pragma unroll
-        for (int j = 0; j < kSegment; ++j) {
-            const uint32_t k = first + j;
-            float t = 0.f, dtv = 0.f;
-            march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, k, t, dtv);
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < live) {
-                v = sample_packed<kLinear, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
-                                                   ray.oz + ray.dz * t);
+        const uint32_t count = min(static_cast<uint32_t>(kSegment), live - first);
+        float T = st.ckpt[static_cast<size_t>(seg) * st.ckpt_stride + px.ray];
+        // forward part: recompute the segment from its transmittance checkpoint
+#pragma unroll 1
+        for (uint32_t j = 0; j < count; ++j) {
+            const float base = mp.t_near + static_cast<float>(first + j) * mp.dt;
+            if (skippable && (base > t_out || base + mp.dt < t_in)) {
+                stash.alpha[j][tid] = -1.0f;   // marker: no contribution, adj_T unchanged
+                continue;
             }
+            float t, dtv;
+            march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j, t, dtv);
+            const float4 v = sample_packed<kLinear, kClamp, false>(grid, nx, ny, nz, ray.ox + ray.dx * t,
+                                                                   ray.oy + ray.dy * t, ray.oz + ray.dz * t);
             const float a = alpha_of(v.w, dtv);
-            s_alpha[j] = a;
-            s_Tprev[j] = T;
-            s_dot[j] = g0 * v.x + g1 * v.y + g2 * v.z;
-            s_t[j] = t;
-            s_dt[j] = dtv;
+            stash.alpha[j][tid] = a;
+            stash.T_prev[j][tid] = T;
+            stash.dot[j][tid] = g0 * v.x + g1 * v.y + g2 * v.z;
+            stash.t[j][tid] = t;
+            stash.dt[j][tid] = dtv;
             T = T * fmaxf(1.0f - a, 0.0f);
         }
         // reverse part: the reference's adjoint recurrence, then the grid scatter
-#pragma unroll
-        for (int j = kSegment - 1; j >= 0; --j) {
-            if (first + j < live) {
-                const float w = s_Tprev[j] * s_alpha[j];
-                float dsigma;
-                adjoint_sample(s_dot[j], s_alpha[j], s_Tprev[j], s_dt[j], adj_T, dsigma);
-                const float t = s_t[j];
-                scatter_sample(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t,
-                               make_float4(g0 * w, g1 * w, g2 * w, dsigma));
-            }
+#pragma unroll 1
+        for (uint32_t j = count; j-- > 0;) {
+            const float a = stash.alpha[j][tid], Tp = stash.T_prev[j][tid];
+            if (a < 0.0f) continue;
+            const float w = Tp * a;
+            float dsigma;
+            adjoint_sample(stash.dot[j][tid], a, Tp, stash.dt[j][tid], adj_T, dsigma);
+            const float t = stash.t[j][tid];
+            scatter_sample(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t,
+                           make_float4(g0 * w, g1 * w, g2 * w, dsigma));
         }
     }
 }

@@ -236,7 +236,12 @@ ScatterParams scatter_params(const hpx_grid& g) {
     sp.nx = g.nx; sp.ny = g.ny; sp.nz = g.nz;
     sp.nearest = g.linear ? 0u : 1u;
     sp.clamp = g.clamp ? 1u : 0u;
-    for (int i = 0; i < 3; ++i) { sp.bmin[i] = g.bmin[i]; sp.bmax[i] = g.bmax[i]; }
+    sp.unit_bbox = 1u;
+    for (int i = 0; i < 3; ++i) {
+        sp.bmin[i] = g.bmin[i];
+        sp.bmax[i] = g.bmax[i];
+        if (g.bmin[i] != 0.0f || g.bmax[i] != 1.0f) sp.unit_bbox = 0u;
+    }
     return sp;
 }
 

@@ -66,6 +66,7 @@ struct ScatterParams {
     int32_t nx, ny, nz;
     uint32_t nearest;        // interp == NEAREST
     uint32_t clamp;
+    uint32_t unit_bbox;      // bbox == [0,1]^3: the scatter sees the cube the forward pass sees
     float bmin[3], bmax[3];
 };
 

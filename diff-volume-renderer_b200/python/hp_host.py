@@ -147,19 +147,21 @@ class HpHostPipeline:
         return b
 
     def fused(self, plan, fs, fc, rays, capacity: int):
+        """hp_samp_int_fused the way the reference's Renderer calls it (renderer.cpp:276-311): every
+        output pointer NULL, one workspace sized for samples (capacity) + integrator outputs."""
         n = rays["t_near"].shape[0]
-        sb = self._samp_buffers(capacity, n)
-        ss = self._samp_struct(sb)
-        ib = self._intl_buffers(n, capacity)
-        istr = self._intl_struct(ib)
+        need = capacity * 32 + (n + 1) * 4 + n * 24 + capacity * 16
+        ws = np.zeros(need + 16, np.uint8)
+        ss, istr = A.hp_samp_t(), A.hp_intl_t()
         rs = self._rays_struct(rays)
-        ws = np.zeros(64, np.uint8)  # the fused entry point insists on a non-null workspace
         _check("hp_samp_int_fused",
                self.lib.hp_samp_int_fused(plan, fs, fc, C.byref(rs), C.byref(ss), C.byref(istr),
-                                          ws.ctypes.data, ws.nbytes))
-        samp = self._trim_samp(sb, ss)
-        ib["aux"] = ib["aux"][:samp["count"]]
-        return samp, ib
+                                          ws.ctypes.data, need))
+        self._keep_ws = ws
+        samp = {k: A.host_array(getattr(ss, k)) for k in ("positions", "dt", "ray_offset", "sigma", "color")}
+        samp["count"] = int(ss.dt.shape[0])
+        intl = {k: A.host_array(getattr(istr, k)) for k in ("radiance", "transmittance", "opacity", "depth", "aux")}
+        return samp, intl
 
     def img(self, plan, desc: A.hp_plan_desc, intl, rays):
         h, w = desc.height, desc.width

@@ -103,16 +103,17 @@ def test_lean_backward_accumulates_and_is_linear(ctx):
     dl = S.hashed_image_grad(n)
     a = run_lean(ctx, desc, sig, col, 1, 0, None, None, dl)
     b = run_lean(ctx, desc, sig, col, 1, 0, None, None, 2.0 * dl)
-    # scaling dL/dI by 2 is exact in binary floating point on every product of the adjoint
-    U.assert_close(b["sigma_grad"], 2.0 * a["sigma_grad"], 2e-6, "linearity sigma")
-    U.assert_close(b["color_grad"], 2.0 * a["color_grad"], 2e-6, "linearity color")
+    # scaling dL/dI by 2 is exact on every product of the adjoint; what remains is the order of the
+    # float atomics in the scatter, which differs from run to run -> the gradient tolerance applies
+    U.assert_close(b["sigma_grad"], 2.0 * a["sigma_grad"], U.GRAD_RTOL, "linearity sigma")
+    U.assert_close(b["color_grad"], 2.0 * a["color_grad"], U.GRAD_RTOL, "linearity color")
     # without HPX_BACKWARD_ZERO gradients accumulate (DenseGridField semantics, dense_grid.cpp:166-169)
     plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
     frame.forward(grid)
     frame.backward(grid, dl, D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO)
     frame.backward(grid, dl, D.HPX_BACKWARD_GRID)
     sg, cg, _ = grid.read_grad()
-    U.assert_close(sg, 2.0 * a["sigma_grad"], 1e-5, "accumulate sigma")
+    U.assert_close(sg, 2.0 * a["sigma_grad"], U.GRAD_RTOL, "accumulate sigma")
     frame.close(); grid.close(); plan.close()
 
 
@@ -136,8 +137,8 @@ def test_lean_roi_tiles_reproduce_full_frame(ctx):
         sg += part["sigma_grad"]; cg += part["color_grad"]
     U.assert_bits(image, full["image"], "tiled image")
     U.assert_bits(depth, full["depth"], "tiled depth")
-    U.assert_close(sg, full["sigma_grad"], 1e-5, "tiled sigma_grad")
-    U.assert_close(cg, full["color_grad"], 1e-5, "tiled color_grad")
+    U.assert_close(sg, full["sigma_grad"], U.GRAD_RTOL, "tiled sigma_grad")
+    U.assert_close(cg, full["color_grad"], U.GRAD_RTOL, "tiled color_grad")
 
 
 def test_lean_forward_is_deterministic_and_graph_replay_matches(ctx):
@@ -161,8 +162,8 @@ def test_lean_forward_is_deterministic_and_graph_replay_matches(ctx):
     for k in a:
         U.assert_bits(a[k], c[k], "graph " + k)
     assert ca == cc
-    U.assert_close(sg_c, sg_a, 1e-5, "graph sigma_grad")
-    U.assert_close(cg_c, cg_a, 1e-5, "graph color_grad")
+    U.assert_close(sg_c, sg_a, U.GRAD_RTOL, "graph sigma_grad")
+    U.assert_close(cg_c, cg_a, U.GRAD_RTOL, "graph color_grad")
     frame.close(); grid.close(); plan.close()
 
 

@@ -18,6 +18,12 @@ GOLDEN_DIR = os.path.join(REPO, "tests", "golden")
 IMAGE_RTOL = 1e-5
 GRAD_RTOL = 1e-4
 FLOOR_FRAC = 1e-3
+# Grid gradients are float32 sums of signed terms; the GPU adds them with float atomics in an
+# arbitrary order, the reference in sample order.  Two orders of the same sum differ by about
+# eps * sum|terms|, so entries far below the largest gradient are compared against a floor of 1e-2
+# of the largest magnitude (absolute 1e-6 * max|ref|; the reference's own determinism gate is an
+# absolute 1e-6, hp_runner.cpp:2580-2594, and its CPU<->CUDA gradient gate 1e-3 relative).
+GRAD_FLOOR_FRAC = 1e-2
 
 
 def golden_cases():
@@ -51,8 +57,10 @@ def assert_bits(a, b, what):
                              f"{a.reshape(-1)[diff[:5]]} vs {b.reshape(-1)[diff[:5]]}")
 
 
-def assert_close(got, ref, rtol, what, floor_frac=FLOOR_FRAC):
+def assert_close(got, ref, rtol, what, floor_frac=None):
     """|got - ref| <= rtol * max(|ref|, floor_frac * max|ref|)  (SURVEY 8d)."""
+    if floor_frac is None:
+        floor_frac = GRAD_FLOOR_FRAC if rtol >= GRAD_RTOL else FLOOR_FRAC
     got = np.asarray(got, np.float64)
     ref = np.asarray(ref, np.float64)
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"

@@ -34,7 +34,9 @@ def run(n_grid, W, steps, strat, kind, iters=5):
     frame.close(); grid.close(); plan.close(); ctx.close()
 
 if __name__ == "__main__":
+  with torch.cuda.stream(torch.cuda.Stream()):
     run(64, 512, 256, False, "thin")
     run(64, 512, 256, False, "dense")
     run(256, 1024, 512, True, "thin")
     run(256, 1024, 512, True, "dense")
+    run(256, 1024, 512, False, "thin")
