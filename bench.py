@@ -50,49 +50,43 @@ def read_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.err = index, False, [], set(), None, None
+        self.thread = None
+
+    def _run(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            while not self.stop_flag:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                mask = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report it, never fake a clock
+            self.err = repr(e)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ln in self.lines:
-            p = [x.strip() for x in ln.split(",")]
-            if len(p) < 8:
-                continue
-            try:
-                sm.append(float(p[1])); mx = float(p[2])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        # median over the upper half: the sampler also sees idle gaps between steps
-        busy = sm[len(sm) // 2:] if sm else []
-        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=2.0)
+        sm = sorted(self.sm)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(sm)}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 class CudaArrayView:
@@ -143,7 +137,6 @@ def run_ours(args):
               torch.as_tensor(CudaArrayView(img.opacity.data, pixels), device=dev),
               torch.as_tensor(CudaArrayView(img.depth.data, pixels), device=dev)]
     planes_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in planes]
-    grad_host = torch.empty(grad_floats, dtype=torch.float32).pin_memory()
     flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
 
     def step_resident():
@@ -152,17 +145,27 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(grad_view)
 
+    # e2e: the same step through the C ABI with HOST buffers (pinned), i.e. what dvren::Renderer
+    # Forward/Backward move per step (reference renderer.hpp:50-66): dL/dI host->device; image planes
+    # and the un-interleaved sigma / colour gradient grids device->host.  Both read calls block.
+    import ctypes as C
+    import hp_abi as A
+    lib = ctx.lib
+    sg_host = torch.empty(grid.voxels, dtype=torch.float32).pin_memory()
+    cg_host = torch.empty(grid.voxels * 3, dtype=torch.float32).pin_memory()
+    cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    mask_host = torch.empty(pixels, dtype=torch.int32).pin_memory()
+
     def step_e2e():
-        # what dvren::Renderer::Forward/Backward move per step (reference renderer.hpp:50-66):
-        # dL/dI host->device; image planes and the full gradient block device->host
-        g_dev.copy_(g_host, non_blocking=True)
-        frame.forward(grid)
-        for h, d in zip(planes_host, planes):
-            h.copy_(d, non_blocking=True)
-        frame.backward(grid, g_dev.data_ptr(), flags, device=True)
+        D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
+        D.check("hpx_frame_read", lib.hpx_frame_read(frame.handle, planes_host[0].data_ptr(), planes_host[1].data_ptr(),
+                                                     planes_host[2].data_ptr(), planes_host[3].data_ptr(),
+                                                     mask_host.data_ptr()))
+        D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
         if world > 1:
             dist.all_reduce(grad_view)
-        grad_host.copy_(grad_view, non_blocking=True)
+        D.check("hpx_grid_read_grad", lib.hpx_grid_read_grad(grid.handle, sg_host.data_ptr(), cg_host.data_ptr(),
+                                                             cam_host.data_ptr(), A.HP_MEMSPACE_HOST))
 
     def barrier():
         if world > 1:
@@ -219,7 +222,7 @@ def run_ours(args):
                    "parallelism": f"ray-tile data parallel x{world}, grid replicated, NCCL all-reduce of gradients" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (packed grid %d MB + gradient grid %d MB vs 126 MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(g_host.numel() * 4),
-                "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + grad_floats * 4),
+                "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4 + grad_floats * 4),
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,

@@ -173,12 +173,16 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
                                               cudaMemcpyDeviceToDevice, s));
         return HP_STATUS_SUCCESS;
     }
-    // HOST: un-interleave chunk by chunk through a bounded staging buffer
+    // HOST: un-interleave chunk by chunk through a staging buffer the grid keeps (no per-call malloc)
     const size_t chunk = std::min<size_t>(g->voxels, kStageVoxels);
-    DeviceScratch scratch;
-    float* d_sig = sigma_grad ? static_cast<float*>(scratch.take(chunk * 4)) : nullptr;
-    float* d_col = color_grad ? static_cast<float*>(scratch.take(chunk * 12)) : nullptr;
-    if ((sigma_grad && !d_sig) || (color_grad && !d_col)) return HP_STATUS_OUT_OF_MEMORY;
+    if (g->d_unpacked == nullptr || g->unpacked_voxels < chunk) {
+        cudaFree(g->d_unpacked);
+        g->d_unpacked = nullptr;
+        DV_CUDA(cudaMalloc(&g->d_unpacked, chunk * 16));
+        g->unpacked_voxels = chunk;
+    }
+    float* d_sig = sigma_grad ? g->d_unpacked : nullptr;
+    float* d_col = color_grad ? g->d_unpacked + chunk : nullptr;
     for (size_t off = 0; off < g->voxels && (sigma_grad || color_grad); off += chunk) {
         const size_t n = std::min(chunk, g->voxels - off);
         DV_CUDA(launch_unpack_grad(s, packed + off, d_sig, d_col, n));
@@ -191,11 +195,41 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
     return HP_STATUS_SUCCESS;
 }
 
+HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* g, const float* positions, const float* grad_sigma,
+                                             const float* grad_color, size_t count, hp_memspace memspace) {
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (count == 0) return HP_STATUS_SUCCESS;
+    if (positions == nullptr || grad_sigma == nullptr || grad_color == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(g->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    cudaStream_t s = g->ctx->stream;
+    if (memspace == HP_MEMSPACE_DEVICE) {
+        DV_CUDA(launch_scatter(s, scatter_params(*g), positions, grad_sigma, grad_color, count));
+        return HP_STATUS_SUCCESS;
+    }
+    const size_t chunk = std::min<size_t>(count, size_t(1) << 24);
+    DeviceScratch scratch;
+    float* d_pos = static_cast<float*>(scratch.take(chunk * 12));
+    float* d_gs = static_cast<float*>(scratch.take(chunk * 4));
+    float* d_gc = static_cast<float*>(scratch.take(chunk * 12));
+    if (!d_pos || !d_gs || !d_gc) return HP_STATUS_OUT_OF_MEMORY;
+    for (size_t off = 0; off < count; off += chunk) {
+        const size_t n = std::min(chunk, count - off);
+        DV_CUDA(cudaMemcpyAsync(d_pos, positions + 3 * off, n * 12, cudaMemcpyHostToDevice, s));
+        DV_CUDA(cudaMemcpyAsync(d_gs, grad_sigma + off, n * 4, cudaMemcpyHostToDevice, s));
+        DV_CUDA(cudaMemcpyAsync(d_gc, grad_color + 3 * off, n * 12, cudaMemcpyHostToDevice, s));
+        DV_CUDA(launch_scatter(s, scatter_params(*g), d_pos, d_gs, d_gc, n));
+    }
+    DV_CUDA(cudaStreamSynchronize(s));
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API void hpx_grid_release(hpx_grid* g) {
     if (g == nullptr) return;
     if (g->ctx != nullptr && g->ctx->ready) cudaSetDevice(g->ctx->device);
     cudaFree(g->d_values);
     cudaFree(g->d_grad);
+    cudaFree(g->d_unpacked);
     delete g;
 }
 

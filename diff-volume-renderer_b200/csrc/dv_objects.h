@@ -70,6 +70,8 @@ struct hpx_grid {
     float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {1.f, 1.f, 1.f};
     float4* d_values = nullptr;   // [V] {r,g,b,sigma}
     float* d_grad = nullptr;      // [4V + 16]: packed gradient grid, then camera gradient
+    float* d_unpacked = nullptr;  // [V + 3V] staging for un-interleaved read-back (lazily allocated)
+    size_t unpacked_voxels = 0;
     size_t voxels = 0;
 };
 

@@ -326,6 +326,30 @@ HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void*
     return HP_STATUS_SUCCESS;
 }
 
+HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_device_ptr) {
+    if (out_device_ptr == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    const hp_status st = ensure_device(ctx);
+    if (st != HP_STATUS_SUCCESS) return st;
+    DV_CUDA(cudaMalloc(out_device_ptr, bytes ? bytes : 16));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API void hpx_device_free(const hp_ctx* ctx, void* device_ptr) {
+    if (device_ptr == nullptr || ctx == nullptr || !ctx->ready) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(device_ptr);
+}
+
+HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const void* host_src, size_t bytes) {
+    if (device_dst == nullptr || host_src == nullptr) return bytes == 0 ? HP_STATUS_SUCCESS : HP_STATUS_INVALID_ARGUMENT;
+    const hp_status st = ensure_device(ctx);
+    if (st != HP_STATUS_SUCCESS) return st;
+    DV_CUDA(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    DV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream) {
     const hp_status st = ensure_device(ctx);
     if (st != HP_STATUS_SUCCESS) return st;

@@ -1,0 +1,290 @@
+// renderer.cpp -- dvren::Renderer with device-resident internals (reference src/render/renderer.cpp).
+//
+//   fused  (use_fused_path, default)  hpx_forward / hpx_backward on one hpx_frame: no per-sample
+//          buffers at all; with enable_graph the forward is a replayed CUDA graph.
+//   staged (use_fused_path = false)   hp_ray -> hp_samp -> hp_int -> hp_img and hp_diff + grid scatter
+//          on DEVICE tensors with capacity-sized workspaces, i.e. the reference's staged call
+//          sequence (renderer.cpp:259-365,415-427) executed by the materialising GPU kernels.
+// Either way the only host traffic is what ForwardResult / BackwardResult hold.
+#include "dvren/render/renderer.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <string>
+
+namespace dvren {
+
+namespace {
+
+using Clock = std::chrono::steady_clock;
+
+double MsSince(Clock::time_point t0) { return std::chrono::duration<double, std::milli>(Clock::now() - t0).count(); }
+
+hp_tensor DeviceTensor(void* data) {
+    hp_tensor t{};
+    t.data = data;
+    t.memspace = HP_MEMSPACE_DEVICE;
+    t.dtype = HP_DTYPE_F32;
+    return t;
+}
+
+Status Fail(hp_status st, const char* what) {
+    return Status::FromHotpath(st, std::string(what) + " failed: " + hpx_last_error());
+}
+
+}  // namespace
+
+struct Renderer::Impl {
+    const hp_ctx* ctx{nullptr};
+    hpx_frame* frame{nullptr};
+    bool graph_captured{false};
+    const hpx_grid* graph_grid{nullptr};
+    // staged path: device buffers sized from the plan's capacities
+    void* d_rays{nullptr};
+    void* d_ws{nullptr};
+    void* d_img{nullptr};
+    void* d_grads{nullptr};
+    void* d_dl{nullptr};
+    size_t rays_bytes{0}, ws_bytes{0}, img_bytes{0}, grads_bytes{0}, dl_bytes{0};
+    hp_rays_t rays{};
+    hp_samp_t samp{};
+    hp_intl_t intl{};
+
+    ~Impl() {
+        if (frame) hpx_frame_release(frame);
+        for (void* p : {d_rays, d_ws, d_img, d_grads, d_dl}) hpx_device_free(ctx, p);
+    }
+
+    Status Ensure(void*& ptr, size_t& have, size_t want) {
+        if (ptr != nullptr && have >= want) return Status::Ok();
+        hpx_device_free(ctx, ptr);
+        ptr = nullptr;
+        const hp_status st = hpx_device_alloc(ctx, want, &ptr);
+        if (st != HP_STATUS_SUCCESS) return Fail(st, "device allocation");
+        have = want;
+        return Status::Ok();
+    }
+};
+
+Renderer::Renderer(const Context& ctx, const Plan& plan, RenderOptions options)
+    : ctx_(&ctx), plan_(&plan), options_(options), impl_(new Impl()) {
+    impl_->ctx = ctx.handle();
+}
+
+Renderer::~Renderer() { delete impl_; }
+
+Status Renderer::EnsureFrame() {
+    if (impl_->frame != nullptr) return Status::Ok();
+    const hp_status st = hpx_frame_create(plan_->handle(), &impl_->frame);
+    if (st != HP_STATUS_SUCCESS) return Fail(st, "hpx_frame_create");
+    return Status::Ok();
+}
+
+Status Renderer::ForwardFused(const DenseGridField& field, RenderStats& stats) {
+    Status st = EnsureFrame();
+    if (!st.ok()) return st;
+    const auto t0 = Clock::now();
+    hp_status hs;
+    if (options_.enable_graph) {
+        if (!impl_->graph_captured || impl_->graph_grid != field.device_grid()) {
+            hs = hpx_frame_capture(impl_->frame, field.device_grid(), 0);
+            if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_frame_capture");
+            impl_->graph_captured = true;
+            impl_->graph_grid = field.device_grid();
+            stats.notes.emplace_back("graph_forward_captured");
+        }
+        hs = hpx_frame_replay(impl_->frame);
+    } else {
+        hs = hpx_forward(impl_->frame, field.device_grid());
+    }
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_forward");
+    hpx_counts counts{};
+    hs = hpx_frame_counts(impl_->frame, &counts);   // synchronises the stream
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_frame_counts");
+    stats.sample_ms = MsSince(t0);                  // ray generation, marching and integration are one kernel
+    last_ray_count_ = static_cast<size_t>(counts.rays);
+    last_sample_count_ = static_cast<size_t>(counts.samples);
+    live_samples_ = static_cast<size_t>(counts.live_samples);
+    return Status::Ok();
+}
+
+Status Renderer::ForwardStaged(const DenseGridField& field, RenderStats& stats) {
+    const hp_plan_desc& d = plan_->descriptor();
+    const size_t n = static_cast<size_t>(d.roi.width) * d.roi.height;
+    const size_t cap = d.max_samples;
+    const size_t pixels = static_cast<size_t>(d.width) * d.height;
+    Status st = impl_->Ensure(impl_->d_rays, impl_->rays_bytes, n * 36);
+    if (!st.ok()) return st;
+    // samples (capacity sized, reference samp_cpu.cpp:111-136) then the integrator's outputs
+    st = impl_->Ensure(impl_->d_ws, impl_->ws_bytes, cap * 32 + (n + 1) * 4 + n * 24 + cap * 16 + 64);
+    if (!st.ok()) return st;
+    st = impl_->Ensure(impl_->d_img, impl_->img_bytes, pixels * 28);
+    if (!st.ok()) return st;
+
+    char* rb = static_cast<char*>(impl_->d_rays);
+    impl_->rays = hp_rays_t{};
+    impl_->rays.origins = DeviceTensor(rb);
+    impl_->rays.directions = DeviceTensor(rb + n * 12);
+    impl_->rays.t_near = DeviceTensor(rb + n * 24);
+    impl_->rays.t_far = DeviceTensor(rb + n * 28);
+    impl_->rays.pixel_ids = DeviceTensor(rb + n * 32);
+    auto t0 = Clock::now();
+    hp_status hs = hp_ray(plan_->handle(), nullptr, &impl_->rays, nullptr, 0);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_ray");
+    stats.ray_ms = MsSince(t0);
+    last_ray_count_ = impl_->rays.t_near.rank >= 1 ? static_cast<size_t>(impl_->rays.t_near.shape[0]) : 0;
+
+    const size_t samp_bytes = cap * 32 + (n + 1) * 4;
+    impl_->samp = hp_samp_t{};
+    impl_->intl = hp_intl_t{};
+    t0 = Clock::now();
+    hs = hp_samp(plan_->handle(), field.sigma_field(), field.color_field(), &impl_->rays, &impl_->samp, impl_->d_ws,
+                 samp_bytes);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_samp");
+    stats.sample_ms = MsSince(t0);
+    t0 = Clock::now();
+    hs = hp_int(plan_->handle(), &impl_->samp, &impl_->intl, static_cast<char*>(impl_->d_ws) + samp_bytes,
+                impl_->ws_bytes - samp_bytes);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_int");
+    stats.integrate_ms = MsSince(t0);
+    last_sample_count_ = impl_->samp.dt.rank >= 1 ? static_cast<size_t>(impl_->samp.dt.shape[0]) : 0;
+    live_samples_ = 0;   // not tracked by the staged entry points
+    return Status::Ok();
+}
+
+Status Renderer::Forward(const DenseGridField& field, ForwardResult& out) {
+    if (!field.valid() || field.device_grid() == nullptr) return Status(StatusCode::kInvalidArgument, "field is invalid");
+    if (plan_ == nullptr || ctx_ == nullptr || !plan_->valid())
+        return Status(StatusCode::kInvalidArgument, "renderer is not bound to a context/plan");
+    RenderStats stats{};
+    const auto total0 = Clock::now();
+    const bool fused = options_.use_fused_path;
+    if (options_.enable_graph) stats.notes.emplace_back("graph_capture_enabled");
+    stats.notes.emplace_back(fused ? "forward_mode=fused" : "forward_mode=staged");
+
+    const hp_plan_desc& d = plan_->descriptor();
+    const size_t pixels = static_cast<size_t>(d.width) * d.height;
+    Status st = fused ? ForwardFused(field, stats) : ForwardStaged(field, stats);
+    if (!st.ok()) return st;
+    last_forward_staged_ = !fused;
+    if (!fused && options_.enable_graph) {
+        // keep the lean frame around too: the graph path owns its workspace (accounting, test_core.cpp:163)
+        st = EnsureFrame();
+        if (!st.ok()) return st;
+    }
+    if (last_ray_count_ == 0) {
+        out = ForwardResult{};
+        stats.total_ms = MsSince(total0);
+        out.stats = stats;
+        return Status::Ok();
+    }
+
+    const auto img0 = Clock::now();
+    out.image.resize(pixels * 3);
+    out.transmittance.resize(pixels);
+    out.opacity.resize(pixels);
+    out.depth.resize(pixels);
+    out.hitmask.resize(pixels);
+    if (fused) {
+        const hp_status hs = hpx_frame_read(impl_->frame, out.image.data(), out.transmittance.data(),
+                                            out.opacity.data(), out.depth.data(), out.hitmask.data());
+        if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_frame_read");
+    } else {
+        char* ib = static_cast<char*>(impl_->d_img);
+        hp_img_t img{};
+        img.image = DeviceTensor(ib);
+        img.trans = DeviceTensor(ib + pixels * 12);
+        img.opacity = DeviceTensor(ib + pixels * 16);
+        img.depth = DeviceTensor(ib + pixels * 20);
+        img.hitmask = DeviceTensor(ib + pixels * 24);
+        hp_status hs = hp_img(plan_->handle(), &impl_->intl, &impl_->rays, &img, nullptr, 0);
+        if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_img");
+        const hp_ctx* c = ctx_->handle();
+        hs = hpx_copy_to_host(c, out.image.data(), img.image.data, pixels * 12);
+        if (hs == HP_STATUS_SUCCESS) hs = hpx_copy_to_host(c, out.transmittance.data(), img.trans.data, pixels * 4);
+        if (hs == HP_STATUS_SUCCESS) hs = hpx_copy_to_host(c, out.opacity.data(), img.opacity.data, pixels * 4);
+        if (hs == HP_STATUS_SUCCESS) hs = hpx_copy_to_host(c, out.depth.data(), img.depth.data, pixels * 4);
+        if (hs == HP_STATUS_SUCCESS) hs = hpx_copy_to_host(c, out.hitmask.data(), img.hitmask.data, pixels * 4);
+        if (hs != HP_STATUS_SUCCESS) return Fail(hs, "image read-back");
+    }
+    stats.compose_ms = MsSince(img0);
+    out.ray_count = last_ray_count_;
+    out.sample_count = last_sample_count_;
+    stats.total_ms = MsSince(total0);
+    out.stats = std::move(stats);
+    return Status::Ok();
+}
+
+Status Renderer::BackwardStaged(DenseGridField& field, std::span<const float> dL_dI) {
+    const size_t n = last_ray_count_, m = last_sample_count_;
+    Status st = impl_->Ensure(impl_->d_dl, impl_->dl_bytes, n * 12);
+    if (!st.ok()) return st;
+    st = impl_->Ensure(impl_->d_grads, impl_->grads_bytes, m * 16 + 64);
+    if (!st.ok()) return st;
+    const hp_ctx* c = ctx_->handle();
+    hp_status hs = hpx_copy_to_device(c, impl_->d_dl, dL_dI.data(), n * 12);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "dL/dI upload");
+    hp_tensor g = DeviceTensor(impl_->d_dl);
+    g.rank = 2;
+    g.shape[0] = static_cast<int64_t>(n);
+    g.shape[1] = 3;
+    g.stride[0] = 3;
+    g.stride[1] = 1;
+    char* gb = static_cast<char*>(impl_->d_grads);
+    hp_grads_t grads{};
+    grads.sigma = DeviceTensor(gb);
+    grads.color = DeviceTensor(gb + m * 4);
+    grads.camera = DeviceTensor(gb + m * 16);
+    hs = hp_diff(plan_->handle(), &g, &impl_->samp, &impl_->intl, &grads, nullptr, 0);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_diff");
+    field.ZeroGradients();
+    hs = hpx_grid_accumulate_samples(field.device_grid(), static_cast<const float*>(impl_->samp.positions.data),
+                                     static_cast<const float*>(grads.sigma.data),
+                                     static_cast<const float*>(grads.color.data), m, HP_MEMSPACE_DEVICE);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "gradient scatter");
+    return Status::Ok();
+}
+
+Status Renderer::Backward(DenseGridField& field, std::span<const float> dL_dI, BackwardResult& out) {
+    if (!field.valid() || field.device_grid() == nullptr) return Status(StatusCode::kInvalidArgument, "field is invalid");
+    if (last_ray_count_ == 0 || last_sample_count_ == 0)
+        return Status(StatusCode::kInvalidArgument, "forward pass not executed or produced zero samples");
+    if (dL_dI.size() != last_ray_count_ * 3) return Status(StatusCode::kInvalidArgument, "dL/dI size mismatch");
+
+    if (last_forward_staged_) {
+        const Status st = BackwardStaged(field, dL_dI);
+        if (!st.ok()) return st;
+    } else {
+        uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
+        if (options_.camera_gradients) flags |= HPX_BACKWARD_CAMERA;
+        const hp_status hs = hpx_backward(impl_->frame, field.device_grid(), dL_dI.data(), HP_MEMSPACE_HOST, flags);
+        if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_backward");
+    }
+    field.MarkGradientsStale();
+    out.sigma = field.sigma_gradients();   // full-grid copies: what the reference's API returns (renderer.cpp:441-442)
+    out.color = field.color_gradients();
+    out.camera.fill(0.0f);
+    intrinsics_grad_.fill(0.0f);
+    if (options_.camera_gradients && !last_forward_staged_) {
+        for (int i = 0; i < 12; ++i) out.camera[static_cast<size_t>(i)] = field.camera_grad_[static_cast<size_t>(i)];
+        for (int i = 0; i < 4; ++i) intrinsics_grad_[static_cast<size_t>(i)] = field.camera_grad_[static_cast<size_t>(12 + i)];
+    }
+    out.sample_count = last_sample_count_;
+    return Status::Ok();
+}
+
+WorkspaceInfo Renderer::workspace_info() const {
+    WorkspaceInfo info{};
+    const hp_plan_desc& d = plan_->descriptor();
+    const size_t pixels = static_cast<size_t>(d.width) * d.height;
+    info.ray_buffer_bytes = impl_->rays_bytes;
+    info.sample_buffer_bytes = impl_->ws_bytes;
+    info.integration_buffer_bytes = 0;   // carved out of the sample workspace, like the reference's fused call
+    info.image_buffer_bytes = impl_->img_bytes + (impl_->frame ? pixels * 28 : 0);
+    info.gradient_buffer_bytes = impl_->grads_bytes + impl_->dl_bytes;
+    const size_t frame_bytes = impl_->frame ? hpx_frame_bytes(impl_->frame) : 0;
+    info.workspace_buffer_bytes = frame_bytes > pixels * 28 ? frame_bytes - pixels * 28 : 0;
+    return info;
+}
+
+}  // namespace dvren

@@ -66,6 +66,10 @@ HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** 
 /* Blocking device-to-host copy on the context's stream, for binding languages without a CUDA
  * runtime of their own (reading back the DEVICE views hp_graph_execute / hpx_frame_image return). */
 HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void* device_src, size_t bytes);
+/* Plain device memory on the context's GPU for callers that do not link a CUDA runtime. */
+HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_device_ptr);
+HP_API void      hpx_device_free(const hp_ctx* ctx, void* device_ptr);
+HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const void* host_src, size_t bytes);
 /* Last CUDA/runtime error text recorded on this thread ("" if none). */
 HP_API const char* hpx_last_error(void);
 
@@ -92,6 +96,11 @@ HP_API hp_status hpx_grid_grad_buffer(hpx_grid* grid, float** out_device_ptr, si
  * in `memspace`.  Blocks until done when the destination is HOST. */
 HP_API hp_status hpx_grid_read_grad(hpx_grid* grid, float* sigma_grad, float* color_grad,
                                     float* camera16, hp_memspace memspace);
+/* DenseGridField::AccumulateSampleGradients on the GPU (reference src/fields/dense_grid.cpp:171-309):
+ * scatter per-sample gradients (positions (M,3), grad_sigma (M), grad_color (M,3) in `memspace`)
+ * into the packed gradient grid with the grid's bbox / interpolation / OOB policy. */
+HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* grid, const float* positions, const float* grad_sigma,
+                                             const float* grad_color, size_t count, hp_memspace memspace);
 HP_API void      hpx_grid_release(hpx_grid* grid);
 
 /* ---- per-plan frame workspace ------------------------------------------- */

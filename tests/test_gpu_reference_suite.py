@@ -1,0 +1,43 @@
+"""Drop-in acceptance: the reference's OWN test executables, compiled unmodified against this
+repository's headers and libraries by oracle/build_ref_tests.sh, must pass on the GPU.
+
+  hp_runner              21 in-scope contract cases of hotpath/tests/runner/hp_runner.cpp
+  dvren_core_tests       staged / fused / graph agreement (tests/core/test_core.cpp)
+  dvren_smoke_forward    32^2 smoke volume vs an independent per-pixel integrator + device ABI path
+  dvren_smoke_highres    960x720 probes, dvren_sdf_sphere 800^2 SDF shell, dvren_smoke_animation 120 frames
+"""
+import json
+import os
+import subprocess
+
+import pytest
+
+import util as U
+
+pytestmark = pytest.mark.gpu
+BIN = os.path.join(U.REPO, "oracle", "_ref", "bin")
+
+
+def _run(name, *args, timeout=900, cwd=None):
+    exe = os.path.join(BIN, name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built (needs /root/reference at build time)")
+    return subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, cwd=cwd)
+
+
+def test_reference_hp_runner_contract_cases(tmp_path):
+    r = _run("hp_runner", os.path.join(U.REPO, "tests", "hp_runner_manifest.yaml"), cwd=tmp_path)
+    start = r.stdout.find("{")
+    board = json.loads(r.stdout[start:r.stdout.rfind("}") + 1])
+    cases = {c["name"]: c for c in board["cases"]}
+    bad = {n: c for n, c in cases.items() if c["status"] != "pass"}
+    assert len(cases) == 21, sorted(cases)
+    assert not bad, bad
+    assert r.returncode == 0
+
+
+@pytest.mark.parametrize("name", ["dvren_core_tests", "dvren_smoke_forward", "dvren_smoke_highres",
+                                  "dvren_sdf_sphere", "dvren_smoke_animation"])
+def test_reference_dvren_executables(name, tmp_path):
+    r = _run(name, cwd=tmp_path)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
