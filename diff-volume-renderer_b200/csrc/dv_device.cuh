@@ -275,9 +275,13 @@ __device__ __forceinline__ float alpha_of(float sigma, float dt) {
         const float half = 0.5f * od;
         return od * (1.0f - half);
     }
+#ifdef DV_EXP_FLOAT_EXPM1   // timing experiment only: cost of the fp64 expm1
+    return fminf(fmaxf(-expm1f(-od), 0.0f), 1.0f);
+#else
     double a = -expm1(-static_cast<double>(od));
     a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
     return static_cast<float>(a);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -334,6 +338,9 @@ __device__ __forceinline__ void adjoint_sample(float dot_gc, float alpha, float 
 // g = {d r, d g, d b, d sigma} of the sample.  One 16-byte red per corner.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void red_add4(float4* addr, float4 v) {
+#ifdef DV_EXP_NORED   // timing experiment only (tools/quick_time.py): everything but the reds
+    if (v.x != 1234.56789f) return;
+#endif
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }

@@ -1,0 +1,132 @@
+"""N > 1 path on CPU: world_size-2 `gloo` processes run the host-side sharding logic
+(diff-volume-renderer_b200/python/sharding.py) end to end.  Each rank renders its row band with
+the CPU oracle standing in for the GPU (tests may use the oracle as the checker AND as the per-rank
+worker here: what is under test is the partition, the global ray-index base, the packed-gradient
+all-reduce and the image gather -- not the kernels, which tests/test_gpu_lean.py covers)."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import hp_abi as A
+import oracle as O
+import sharding as SH
+import synth as S
+import util as U
+
+
+# ---- pure host logic ----------------------------------------------------------------------------
+@pytest.mark.parametrize("height,world", [(48, 2), (1024, 8), (20, 8), (7, 2), (2048, 4), (100, 3)])
+def test_row_bands_partition(height, world):
+    desc = S.bench_plan(64, height, 16, stratified=True)
+    bands = SH.row_bands(desc, world)
+    assert len(bands) == world
+    assert sum(b.rows for b in bands) == height
+    y = 0
+    for b in bands:
+        assert b.y0 == y or b.empty
+        assert b.ray_index_base == (b.y0 if not b.empty else min(b.y0, height)) * 64 or b.empty
+        if not b.empty:
+            assert b.y0 % SH.TILE_ROWS == 0           # cut on CTA tile rows
+        y += b.rows
+    sizes = [b.rows for b in bands if not b.empty]
+    assert max(sizes) - min(sizes) < 2 * SH.TILE_ROWS  # one tile row of imbalance + the ragged last row
+
+
+def test_row_bands_respect_parent_roi():
+    desc = S.bench_plan(64, 64, 16, stratified=True, roi=(8, 16, 40, 24))
+    bands = SH.row_bands(desc, 2)
+    assert [(b.y0, b.rows, b.ray_index_base) for b in bands] == [(16, 16, 0), (32, 8, 16 * 40)]
+    d = SH.band_desc(desc, bands[1])
+    assert (d.roi.x, d.roi.y, d.roi.width, d.roi.height) == (8, 32, 40, 8)
+    assert d.width == 64 and d.height == 64 and d.seed == desc.seed
+
+
+def test_views_of_rank_and_u32_bands():
+    assert [SH.views_of_rank(64, 8, r) for r in (0, 7)] == [list(range(0, 8)), list(range(56, 64))]
+    got = sum((SH.views_of_rank(10, 4, r) for r in range(4)), [])
+    assert got == list(range(10))
+    c3 = S.bench_plan(2048, 2048, 1024, stratified=False)
+    assert SH.u32_safe_bands(c3, 1024) == 2            # 2^32 samples do not fit one u32 plan (SURVEY finding 9)
+    c2 = S.bench_plan(1024, 1024, 512, stratified=True)
+    assert SH.u32_safe_bands(c2, 512) == 1
+
+
+# ---- two gloo ranks -----------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        W, Hh, steps, n = 40, 24, 48, 20
+        sig, col = S.hashed_volume(n, "dense")
+        gs, gc = U.oracle_grids(sig, col, A.HP_INTERP_LINEAR, A.HP_OOB_ZERO)
+        full = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=5)
+        st, full_res = O.plan_resolve(full)
+        assert st == 0
+        dl_full = S.hashed_image_grad(W * Hh)
+        band = SH.row_bands(full, world)[rank]
+        st, bdesc = O.plan_resolve(SH.band_desc(full, band))
+        assert st == 0
+        dl = dl_full[band.ray_index_base: band.ray_index_base + band.rows * W]
+        part = O.render(bdesc, gs, gc, dl, ray_index_base=band.ray_index_base)
+        cam = O.camera_grad(bdesc, gs, gc, dl, ray_index_base=band.ray_index_base)
+        V = n ** 3
+        # packed gradient block exactly as hpx_grid_grad_buffer lays it out: [V x {dr,dg,db,dsigma} | 16 camera]
+        block = np.zeros(4 * V + 16, np.float32)
+        block[:4 * V].reshape(V, 4)[:, :3] = part["color_grad"].reshape(V, 3)
+        block[:4 * V].reshape(V, 4)[:, 3] = part["sigma_grad"]
+        block[4 * V:] = cam.astype(np.float32)
+        t = torch.from_numpy(block)
+        red = SH.GradientAllReduce(t)
+        red()
+        assert red.bytes_on_wire_per_rank == block.nbytes      # 2 (N-1)/N at N = 2
+        # image: every rank contributes its rows (disjoint pixels, no reduction needed)
+        img = torch.from_numpy(part["image"].copy())
+        dist.all_reduce(img)                                   # zeros outside the band
+        samples = torch.tensor([part["sample_count"], part["live_sample_count"]], dtype=torch.int64)
+        dist.all_reduce(samples)
+        if rank == 0:
+            ref = O.render(full_res, gs, gc, dl_full)
+            ref_cam = O.camera_grad(full_res, gs, gc, dl_full)
+            ok_img = U.bits_equal(img.numpy(), ref["image"])
+            sg = block[:4 * V].reshape(V, 4)[:, 3]
+            cg = block[:4 * V].reshape(V, 4)[:, :3].reshape(-1)
+            U.assert_close(sg, ref["sigma_grad"], U.GRAD_RTOL, "sharded sigma_grad")
+            U.assert_close(cg, ref["color_grad"], U.GRAD_RTOL, "sharded color_grad")
+            scale = np.abs(ref_cam).max()
+            assert np.all(np.abs(block[4 * V:] - ref_cam) <= 1e-4 * np.maximum(np.abs(ref_cam), 0.05 * scale))
+            q.put(("ok", ok_img, int(samples[0]) == ref["sample_count"], int(samples[1]) == ref["live_sample_count"]))
+    except Exception as e:  # surface the failure in the parent
+        if rank == 0:
+            q.put(("fail", repr(e)))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharded_step_matches_unsharded():
+    import torch.multiprocessing as mp
+    O.build_oracle()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    res = q.get(timeout=5)
+    assert res[0] == "ok", res
+    assert res[1], "sharded image differs from the unsharded one (must be bit-exact)"
+    assert res[2] and res[3], "sample counts do not add up"

@@ -34,6 +34,8 @@ def run(n_grid, W, steps, strat, kind, iters=5):
     frame.close(); grid.close(); plan.close(); ctx.close()
 
 if __name__ == "__main__":
+  if os.environ.get("DVREN_HP_LIB"):
+    D._lib = D.load(os.environ["DVREN_HP_LIB"])
   with torch.cuda.stream(torch.cuda.Stream()):
     run(64, 512, 256, False, "thin")
     run(64, 512, 256, False, "dense")
