@@ -85,6 +85,34 @@ __device__ __forceinline__ int march_step(float tn, float tf, float dts, uint64_
     return 0;
 }
 
+// Sample time of one step from the frame's step table (dv_lean.h): the table holds everything that does
+// not depend on the ray; only the stratified jitter is evaluated here.
+template <bool kStratified>
+__device__ __forceinline__ float step_time(const float4& tab, float tn, float tf, float dts, uint64_t seed,
+                                           uint64_t ray_index, uint32_t step) {
+    if (!kStratified) return tab.y;
+    float jit = jitter_unit(seed, ray_index, step);
+    jit = jit < 0.0f ? 0.0f : (jit > 1.0f ? 1.0f : jit);
+    float t = tab.x + jit * dts;
+    if (t >= tf) t = nextafterf(tf, tn);
+    return t;
+}
+
+// Conservative range of step indices [k_lo, k_hi) whose interval [base, base + dt] can overlap [t_in, t_out]:
+// loop bounds only -- the exact per-step test is still applied inside the range.
+__device__ __forceinline__ void step_range(float tn, float dts, uint32_t count, float t_in, float t_out,
+                                           uint32_t& k_lo, uint32_t& k_hi) {
+    k_lo = count;
+    k_hi = 0;
+    if (!(t_out >= t_in)) return;
+    const float qa = (t_in - tn) / dts, qb = (t_out - tn) / dts;
+    const float a = qa - (4.0f + fabsf(qa) * 1e-6f), b = qb + (4.0f + fabsf(qb) * 1e-6f);
+    const float fc = static_cast<float>(count);
+    k_lo = a <= 0.0f ? 0u : (a >= fc ? count : static_cast<uint32_t>(a));
+    k_hi = b <= 0.0f ? 0u : (b >= fc ? count : min(count, static_cast<uint32_t>(b) + 1u));
+    if (k_hi < k_lo) { k_lo = count; k_hi = 0; }
+}
+
 // ---------------------------------------------------------------------------
 // dense grid -- hotpath/src/cpu/grid_dense_cpu.cpp:56-119,143-175
 // World bounds are the unit cube (hp_runtime.cpp:289-294), so the reference's
@@ -159,6 +187,28 @@ __device__ __forceinline__ size_t voxel_index(int32_t x, int32_t y, int32_t z, i
            static_cast<size_t>(x);
 }
 
+// Packed grids are limited to 2^32 - 1 voxels (hpx_grid_create / field packing check it), so corner
+// indices are 32-bit: one IMAD.WIDE per load instead of 64-bit index chains.
+__device__ __forceinline__ uint32_t voxel_index32(int32_t x, int32_t y, int32_t z, int32_t nx, int32_t ny) {
+    return (static_cast<uint32_t>(z) * static_cast<uint32_t>(ny) + static_cast<uint32_t>(y)) * static_cast<uint32_t>(nx) +
+           static_cast<uint32_t>(x);
+}
+
+struct Corners { float4 v000, v100, v010, v110, v001, v101, v011, v111; };
+
+__device__ __forceinline__ Corners load_corners(const float4* __restrict__ g, const Cell& c, int32_t nx, int32_t ny) {
+    const uint32_t i000 = voxel_index32(c.x0, c.y0, c.z0, nx, ny);
+    const uint32_t ox = static_cast<uint32_t>(c.x1 - c.x0);                                       // 0 or 1
+    const uint32_t oy = static_cast<uint32_t>(c.y1 - c.y0) * static_cast<uint32_t>(nx);           // 0 or one row
+    const uint32_t oz = static_cast<uint32_t>(c.z1 - c.z0) * static_cast<uint32_t>(nx) * static_cast<uint32_t>(ny);
+    Corners k;
+    k.v000 = __ldg(g + i000);           k.v100 = __ldg(g + (i000 + ox));
+    k.v010 = __ldg(g + (i000 + oy));      k.v110 = __ldg(g + (i000 + oy + ox));
+    k.v001 = __ldg(g + (i000 + oz));      k.v101 = __ldg(g + (i000 + oz + ox));
+    k.v011 = __ldg(g + (i000 + oz + oy)); k.v111 = __ldg(g + (i000 + oz + oy + ox));
+    return k;
+}
+
 // Packed {r,g,b,sigma} gather: 8 x 16-byte loads through the read-only path.
 template <bool kLinear, bool kClamp, bool kExactColor = true>
 __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
@@ -169,17 +219,12 @@ __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, in
         const int32_t ix = static_cast<int32_t>(roundf(fx));
         const int32_t iy = static_cast<int32_t>(roundf(fy));
         const int32_t iz = static_cast<int32_t>(roundf(fz));
-        return __ldg(g + voxel_index(ix, iy, iz, nx, ny));
+        return __ldg(g + voxel_index32(ix, iy, iz, nx, ny));
     }
     const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
-    const size_t row00 = voxel_index(0, c.y0, c.z0, nx, ny);
-    const size_t row10 = voxel_index(0, c.y1, c.z0, nx, ny);
-    const size_t row01 = voxel_index(0, c.y0, c.z1, nx, ny);
-    const size_t row11 = voxel_index(0, c.y1, c.z1, nx, ny);
-    const float4 v000 = __ldg(g + row00 + c.x0), v100 = __ldg(g + row00 + c.x1);
-    const float4 v010 = __ldg(g + row10 + c.x0), v110 = __ldg(g + row10 + c.x1);
-    const float4 v001 = __ldg(g + row01 + c.x0), v101 = __ldg(g + row01 + c.x1);
-    const float4 v011 = __ldg(g + row11 + c.x0), v111 = __ldg(g + row11 + c.x1);
+    const Corners k = load_corners(g, c, nx, ny);
+    const float4 v000 = k.v000, v100 = k.v100, v010 = k.v010, v110 = k.v110;
+    const float4 v001 = k.v001, v101 = k.v101, v011 = k.v011, v111 = k.v111;
     float4 o;
     if (kExactColor) {
         o.x = trilerp(v000.x, v100.x, v010.x, v110.x, v001.x, v101.x, v011.x, v111.x, c.tx, c.ty, c.tz);
@@ -193,6 +238,74 @@ __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, in
     // sigma decides alpha, T and the stop test: always the reference's operation order
     o.w = trilerp(v000.w, v100.w, v010.w, v110.w, v001.w, v101.w, v011.w, v111.w, c.tx, c.ty, c.tz);
     return o;
+}
+
+// ---------------------------------------------------------------------------
+// Lean-kernel sampler.  Same gathers; the arithmetic is arranged for the Blackwell packed-fp32 pipe:
+//   (r,g) pairs: lerp = FADD2 + FFMA2          (colour may contract: it feeds no index, count or stop test)
+//   (b,sigma) pairs: FADD2 + FMUL2 on the pair, then two SCALAR adds -- sigma keeps the reference's
+//   a + (b - a) * t with every intermediate rounded.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+//   even under -fmad=false (seen in SASS), which is why the final add is scalar.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// contracted lerp of an (r,g) pair
+__device__ __forceinline__ uint64_t lerp2_fma(uint64_t a, uint64_t b, uint64_t t) { return fma2(sub2(b, a), t, a); }
+// exact lerp of a (b,sigma) pair: packed subtract and multiply, scalar adds
+__device__ __forceinline__ uint64_t lerp2_exact(uint64_t a, uint64_t b, uint64_t t) {
+    const uint64_t m = mul2(sub2(b, a), t);
+    float alo, ahi, mlo, mhi;
+    unpack2(a, alo, ahi);
+    unpack2(m, mlo, mhi);
+    return pack2(alo + mlo, ahi + mhi);
+}
+
+__device__ __forceinline__ float4 trilerp_pairs(const Corners& k, float tx, float ty, float tz) {
+    const uint64_t tx2 = pack2(tx, tx), ty2 = pack2(ty, ty), tz2 = pack2(tz, tz);
+#define DV_RG(v) pack2((v).x, (v).y)
+#define DV_BS(v) pack2((v).z, (v).w)
+    const uint64_t rg = lerp2_fma(
+        lerp2_fma(lerp2_fma(DV_RG(k.v000), DV_RG(k.v100), tx2), lerp2_fma(DV_RG(k.v010), DV_RG(k.v110), tx2), ty2),
+        lerp2_fma(lerp2_fma(DV_RG(k.v001), DV_RG(k.v101), tx2), lerp2_fma(DV_RG(k.v011), DV_RG(k.v111), tx2), ty2), tz2);
+    const uint64_t bs = lerp2_exact(
+        lerp2_exact(lerp2_exact(DV_BS(k.v000), DV_BS(k.v100), tx2), lerp2_exact(DV_BS(k.v010), DV_BS(k.v110), tx2), ty2),
+        lerp2_exact(lerp2_exact(DV_BS(k.v001), DV_BS(k.v101), tx2), lerp2_exact(DV_BS(k.v011), DV_BS(k.v111), tx2), ty2), tz2);
+#undef DV_RG
+#undef DV_BS
+    float4 o;
+    unpack2(rg, o.x, o.y);
+    unpack2(bs, o.z, o.w);
+    return o;
+}
+
+template <bool kClamp>
+__device__ __forceinline__ float4 sample_packed_lean(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+                                                     float px, float py, float pz) {
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
+    return trilerp_pairs(load_corners(g, c, nx, ny), c.tx, c.ty, c.tz);
 }
 
 // Generic single-grid query (separate sigma / colour arrays with their own
@@ -267,7 +380,20 @@ __device__ __forceinline__ void cube_interval(const Ray& r, float& t_in, float& 
 
 // ---------------------------------------------------------------------------
 // alpha -- hotpath/src/cpu/int_cpu.cpp:98-109 (+ the call-site clamp :188)
+//
+// The reference evaluates alpha = (float) clamp(-expm1(-(double)od), 0, 1) with glibc's fp64 expm1.
+// alpha_of() reproduces that FLOAT bit for bit without calling a generic fp64 expm1 (which costs ~35
+// fp64-pipe instructions per sample): od = k ln2 - r with k = rint(od log2 e), |r| <= 0.35, then
+//   1 - exp(-od) = (1 - 2^-k) - 2^-k expm1(r),   expm1(r) = r + r^2 (1/2! + r/3! + ... + r^9/11!)
+// in fp64 (12 DFMA).  The truncation error is < 2^-40 relative, far below half an fp32 ulp, and
+// tests/test_oracle_pin.py::test_alpha_bit_exact_all_floats checks the restatement in
+// oracle/dvren_oracle.c (orc_alpha_fast, same operations) against the libm form for EVERY float in
+// [1e-4, 18]; tests/test_gpu_abi.py::test_alpha_matches_oracle_bitwise checks this device code.
 // ---------------------------------------------------------------------------
+// 1/11!, 1/10!, ..., 1/2!  (operands of the DFMA chain come straight from the constant bank)
+static __constant__ double kExpm1Taylor[10] = {1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                                               1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,     1.0 / 6.0,     0.5};
+
 __device__ __forceinline__ float alpha_of(float sigma, float dt) {
     const float od = sigma * dt;
     if (od <= 0.0f) return 0.0f;
@@ -275,12 +401,22 @@ __device__ __forceinline__ float alpha_of(float sigma, float dt) {
         const float half = 0.5f * od;
         return od * (1.0f - half);
     }
-#ifdef DV_EXP_FLOAT_EXPM1   // timing experiment only: cost of the fp64 expm1
+#if defined(DV_EXP_FLOAT_EXPM1)   // timing experiment only: cost of the fp64 part
     return fminf(fmaxf(-expm1f(-od), 0.0f), 1.0f);
-#else
+#elif defined(DV_ALPHA_LIBM)       // the generic CUDA expm1 (kept for A/B timing)
     double a = -expm1(-static_cast<double>(od));
     a = a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a);
     return static_cast<float>(a);
+#else
+    if (od > 17.5f) return 1.0f;   // 1 - e^-17.5 rounds to 1.0f (e^-17.5 = 2.5e-8 < 2^-25)
+    const float kf = rintf(od * 1.44269504f);
+    const double r = __fma_rn(static_cast<double>(kf), 0.693147180559945309417, -static_cast<double>(od));
+    double q = kExpm1Taylor[0];
+#pragma unroll
+    for (int i = 1; i < 10; ++i) q = __fma_rn(q, r, kExpm1Taylor[i]);
+    const double p = __fma_rn(__dmul_rn(r, r), q, r);                       // expm1(r)
+    const double s = __hiloint2double((1023 - __float2int_rn(kf)) << 20, 0);  // 2^-k
+    return __double2float_rn(__fma_rn(-s, p, 1.0 - s));
 #endif
 }
 
@@ -366,7 +502,7 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
         const int32_t iy = static_cast<int32_t>(roundf(gy));
         const int32_t iz = static_cast<int32_t>(roundf(gz));
         if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
-        red_add4(sp.grad + voxel_index(ix, iy, iz, nx, ny), g);
+        red_add4(sp.grad + voxel_index32(ix, iy, iz, nx, ny), g);
         return;
     }
     const Cell c = make_cell(gx, gy, gz, nx, ny, nz);
@@ -382,7 +518,7 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
                 const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
                 if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
                 const float w = wx[dx] * wy[dy] * wz[dz];
-                red_add4(sp.grad + voxel_index(ix, iy, iz, nx, ny),
+                red_add4(sp.grad + voxel_index32(ix, iy, iz, nx, ny),
                          make_float4(g.x * w, g.y * w, g.z * w, g.w * w));
             }
 }

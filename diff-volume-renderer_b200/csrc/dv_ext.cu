@@ -21,6 +21,10 @@ constexpr size_t kCameraFloats = 16;
 constexpr size_t kStageVoxels = size_t(1) << 25;  // 32 Mi voxels per staging chunk (512 MiB)
 
 hp_status grid_alloc(hpx_grid* g) {
+    if (g->voxels > 0xffffffffull) {   // the kernels index voxels with 32 bits (dv_device.cuh: voxel_index32)
+        set_last_error("packed device grids are limited to 2^32 - 1 voxels");
+        return HP_STATUS_UNSUPPORTED;
+    }
     DV_CUDA(cudaMalloc(&g->d_values, std::max<size_t>(g->voxels, 1) * sizeof(float4)));
     return HP_STATUS_SUCCESS;
 }
@@ -279,6 +283,14 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
     f->buf.ckpt = static_cast<float*>(frame_take(f, segments * f->buf.ckpt_stride * 4, &st));
     f->buf.live_total = static_cast<unsigned long long*>(frame_take(f, sizeof(unsigned long long), &st));
     f->d_dL_dI = static_cast<float*>(frame_take(f, rays * 12, &st));
+    float4* d_steps = static_cast<float4*>(frame_take(f, static_cast<size_t>(plan->uniform_count) * sizeof(float4), &st));
+    f->buf.steps = d_steps;
+    if (st == HP_STATUS_SUCCESS && plan->uniform_count != 0) {
+        std::vector<float4> table(plan->uniform_count);
+        build_step_table(f->h_params.march, table.data());
+        const cudaError_t e = cudaMemcpy(d_steps, table.data(), table.size() * sizeof(float4), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMemcpy(step table)");
+    }
     f->d_cam_partials = static_cast<double*>(frame_take(f, static_cast<size_t>(lean_block_count(f->h_params.roi)) * 16 * 8, &st));
     if (st == HP_STATUS_SUCCESS) {
         const cudaError_t e = cudaMallocHost(&f->h_pinned, sizeof(FrameParams) + sizeof(unsigned long long));
@@ -340,7 +352,10 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
     if (flags & HPX_BACKWARD_ZERO)
         DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), s));
     if (flags & HPX_BACKWARD_GRID)
-        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf));
+        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf,
+                                     (flags & HPX_BACKWARD_SCATTER_MERGED)    ? kScatterMerge
+                                     : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay
+                                                                              : kScatterAuto));
     if (flags & HPX_BACKWARD_CAMERA)
         DV_CUDA(launch_camera_adjoint(s, f->d_params, f->h_params, packed_view(*g), d_dL_dI, f->buf.live,
                                       f->d_cam_partials, g->d_grad + g->voxels * 4));

@@ -45,6 +45,36 @@ __device__ __forceinline__ TilePixel tile_pixel(const RoiParams& roi) {
     return p;
 }
 
+template <bool kLinear, bool kClamp>
+__device__ __forceinline__ float4 lean_sample(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz, float px,
+                                              float py, float pz) {
+    if (kLinear) return sample_packed_lean<kClamp>(g, nx, ny, nz, px, py, pz);
+    return sample_packed<false, kClamp, false>(g, nx, ny, nz, px, py, pz);
+}
+
+// Warp-wide range of steps that can touch the unit cube (OOB-zero fields only): [lo, hi), lo aligned down to a
+// segment start.  Forward and backward kernels evaluate exactly this function, so they agree on the range.
+struct WarpRange { uint32_t lo, hi; };
+
+template <bool kSkipOutside>
+__device__ __forceinline__ WarpRange warp_step_range(const MarchParams& mp, const Ray& ray, bool inside, float& t_in,
+                                                     float& t_out) {
+    const uint32_t count = mp.uniform_count;
+    t_in = -CUDART_INF_F;
+    t_out = CUDART_INF_F;
+    uint32_t k_lo = 0, k_hi = count;
+    if (kSkipOutside) {
+        cube_interval(ray, t_in, t_out);
+        step_range(mp.t_near, mp.dt, count, t_in, t_out, k_lo, k_hi);
+    }
+    if (!inside) { k_lo = count; k_hi = 0; }
+    WarpRange r;
+    r.lo = __reduce_min_sync(0xffffffffu, k_lo) & ~static_cast<uint32_t>(kSegment - 1);
+    r.hi = __reduce_max_sync(0xffffffffu, k_hi);
+    if (r.hi < r.lo) r.hi = r.lo;
+    return r;
+}
+
 template <bool kLinear, bool kClamp, bool kStratified>
 __global__ void __launch_bounds__(kLeanThreads)
 lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
@@ -59,36 +89,42 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
     const uint64_t ray_index = mp.ray_index_base + px.ray;
 
     RayAccum acc;
-    acc.t_cursor = mp.t_near;
     bool alive = px.inside;
-    uint32_t live = 0;
     const uint32_t count = mp.uniform_count;
-    float t_in = -CUDART_INF_F, t_out = CUDART_INF_F;
-    if (!kClamp) cube_interval(ray, t_in, t_out);
+    uint32_t live = count;                       // samples integrated before the stop (all of them if the ray never stops)
+    float t_in, t_out;
+    const WarpRange wr = warp_step_range<!kClamp>(mp, ray, px.inside, t_in, t_out);
+    float* const ckpt = out.ckpt != nullptr && px.inside ? out.ckpt + px.ray : nullptr;
 
-    for (uint32_t step = 0; step < count; ++step) {
+    // segments before the range: nothing has been absorbed yet
+    if (ckpt != nullptr)
+        for (uint32_t s = 0; s < wr.lo; s += kSegment) ckpt[static_cast<size_t>(s / kSegment) * out.ckpt_stride] = 1.0f;
+
+    uint32_t step = wr.lo;
+    for (; step < wr.hi; ++step) {
         if (!__any_sync(0xffffffffu, alive)) break;
-        if ((step % kSegment) == 0 && alive && out.ckpt != nullptr) {
-            out.ckpt[static_cast<size_t>(step / kSegment) * out.ckpt_stride + px.ray] = acc.T;
-        }
+        if ((step % kSegment) == 0 && alive && ckpt != nullptr) ckpt[static_cast<size_t>(step / kSegment) * out.ckpt_stride] = acc.T;
         if (alive) {
-            ++live;
-            const float base = mp.t_near + static_cast<float>(step) * mp.dt;
-            if (!kClamp && (base > t_out || base + mp.dt < t_in)) {
-                // whole step outside the cube: sigma = 0, only the depth cursor moves (same dt arithmetic)
-                acc.t_cursor += fminf(base + mp.dt, mp.t_far) - base;
-                continue;
-            }
-            float t, dtv;
-            march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, step, t, dtv);
+            const float4 tab = __ldg(out.steps + step);
+            // whole step outside the cube: sigma = 0, nothing changes (the depth cursor comes from the table)
+            if (!kClamp && (tab.x > t_out || tab.x + mp.dt < t_in)) continue;
+            const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, step);
             const float pxw = ray.ox + ray.dx * t;
             const float pyw = ray.oy + ray.dy * t;
             const float pzw = ray.oz + ray.dz * t;
-            const float4 v = sample_packed<kLinear, kClamp, false>(grid, nx, ny, nz, pxw, pyw, pzw);
+            const float4 v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, pxw, pyw, pzw);
             float a, w, tb;
-            if (integrate_sample<false>(acc, dtv, v, a, w, tb)) alive = false;
+            acc.t_cursor = tab.w;
+            if (integrate_sample<false>(acc, tab.z, v, a, w, tb)) {
+                alive = false;
+                live = step + 1;
+            }
         }
     }
+    // segments after the range (or after the whole warp has stopped): transmittance no longer changes
+    if (ckpt != nullptr && alive)
+        for (uint32_t s = (step + kSegment - 1) & ~static_cast<uint32_t>(kSegment - 1); s < count; s += kSegment)
+            ckpt[static_cast<size_t>(s / kSegment) * out.ckpt_stride] = acc.T;
 
     if (px.inside) {
         float opacity, depth;
@@ -105,7 +141,7 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
     }
     if (out.live_total != nullptr) {
         // one 64-bit atomic per warp
-        uint32_t s = live;
+        uint32_t s = px.inside ? live : 0u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if ((threadIdx.x & 31) == 0 && s != 0) atomicAdd(out.live_total, static_cast<unsigned long long>(s));
@@ -151,14 +187,16 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) warp_nseg = max(warp_nseg, __shfl_xor_sync(0xffffffffu, warp_nseg, o));
 
-    float t_in = -CUDART_INF_F, t_out = CUDART_INF_F;
     const bool skippable = !kClamp && sp.unit_bbox != 0u;   // outside samples touch neither T nor the grid
-    if (skippable) cube_interval(ray, t_in, t_out);
+    float t_in, t_out;
+    const WarpRange wr = skippable ? warp_step_range<true>(mp, ray, px.inside, t_in, t_out)
+                                   : warp_step_range<false>(mp, ray, px.inside, t_in, t_out);
+    const uint32_t seg_lo = wr.lo / kSegment, seg_hi = min(warp_nseg, (wr.hi + kSegment - 1) / kSegment);
 
     float adj_T = 0.0f;
     // all lanes of a warp walk the same segment index in the same iteration: the warp's gathers and
     // scatters of one iteration stay inside one thin slab of the grid
-    for (uint32_t seg = warp_nseg; seg-- > 0;) {
+    for (uint32_t seg = seg_hi; seg-- > seg_lo;) {
         if (seg >= nseg) continue;
         const uint32_t first = seg * kSegment;
         const uint32_t count = min(static_cast<uint32_t>(kSegment), live - first);
@@ -166,21 +204,20 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
         // forward part: recompute the segment from its transmittance checkpoint
 #pragma unroll 1
         for (uint32_t j = 0; j < count; ++j) {
-            const float base = mp.t_near + static_cast<float>(first + j) * mp.dt;
-            if (skippable && (base > t_out || base + mp.dt < t_in)) {
+            const float4 tab = __ldg(st.steps + first + j);
+            if (skippable && (tab.x > t_out || tab.x + mp.dt < t_in)) {
                 stash.alpha[j][tid] = -1.0f;   // marker: no contribution, adj_T unchanged
                 continue;
             }
-            float t, dtv;
-            march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j, t, dtv);
-            const float4 v = sample_packed<kLinear, kClamp, false>(grid, nx, ny, nz, ray.ox + ray.dx * t,
-                                                                   ray.oy + ray.dy * t, ray.oz + ray.dz * t);
-            const float a = alpha_of(v.w, dtv);
+            const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
+            const float4 v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                          ray.oz + ray.dz * t);
+            const float a = alpha_of(v.w, tab.z);
             stash.alpha[j][tid] = a;
             stash.T_prev[j][tid] = T;
             stash.dot[j][tid] = g0 * v.x + g1 * v.y + g2 * v.z;
             stash.t[j][tid] = t;
-            stash.dt[j][tid] = dtv;
+            stash.dt[j][tid] = tab.z;
             T = T * fmaxf(1.0f - a, 0.0f);
         }
         // reverse part: the reference's adjoint recurrence, then the grid scatter
@@ -195,6 +232,185 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
             scatter_sample(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t,
                            make_float4(g0 * w, g1 * w, g2 * w, dsigma));
         }
+    }
+}
+
+// ---- backward, merged scatter ------------------------------------------------
+// The scatter primitive (red.global.add.v4.f32) costs per ACTIVE LANE: tools/mem_probe measures
+// ~300 G lane-reds/s on a B200 and ncu shows no merging of equal addresses inside a request
+// (profiles/r01_c2_lean_v1.md).  When pixels are denser than voxels (config 2: 0.3 voxel between
+// neighbouring rays, 0.75 voxel between steps) most of a warp's 256 reds per step hit the same few
+// voxels.  This kernel cuts the lane-reds by merging in REGISTERS before issuing them:
+//
+//   phase A  (lane = ray)      recompute the segment forward from its checkpoint -> stash {alpha, T_prev, g.c, t}
+//   phase A' (lane = ray)      reverse sweep with the reference's adjoint recurrence; per sample the gradient
+//                              {g w, d sigma} and the scatter cell {x0|y0|z0, tx, ty, tz} go to shared memory
+//   phase B  (lane = 2x2 pixel quad x 2 steps)   walks its 8 samples, accumulates the 8 corner contributions while
+//                              the cell stays the same and issues 8 reds only when it changes.
+//
+// Only __syncwarp() separates the phases: a quad's rays and all steps of a segment live in one warp.
+constexpr uint32_t kNoCell = 0xffffffffu;
+constexpr int kStashRow = kLeanThreads + kLeanThreads / 16;   // skewed by one float4 per 16 threads: phase B reads conflict-free
+
+struct MergeStash {
+    float4 a[kSegment][kStashRow];   // phase A: {alpha, T_prev, g.c, t};  phase A': {cell bits, tx, ty, tz}
+    float4 g[kSegment][kStashRow];   // phase A': {g0 w, g1 w, g2 w, d sigma}
+};
+
+__device__ __forceinline__ uint32_t stash_slot(uint32_t tid) { return tid + (tid >> 4); }
+
+// scatter cell of a position: src/fields/dense_grid.cpp:206-246 (linear, every axis >= 2 voxels)
+template <bool kUnitBox>
+__device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px, float py, float pz) {
+    float lx = px, ly = py, lz = pz;
+    if (!kUnitBox) {
+        const float ex = sp.bmax[0] - sp.bmin[0], ey = sp.bmax[1] - sp.bmin[1], ez = sp.bmax[2] - sp.bmin[2];
+        lx = ex != 0.0f ? (px - sp.bmin[0]) / ex : 0.0f;
+        ly = ey != 0.0f ? (py - sp.bmin[1]) / ey : 0.0f;
+        lz = ez != 0.0f ? (pz - sp.bmin[2]) / ez : 0.0f;
+    }
+    const bool outside = lx < 0.0f || lx > 1.0f || ly < 0.0f || ly > 1.0f || lz < 0.0f || lz > 1.0f;
+    if (outside) {
+        if (!sp.clamp) return make_float4(__uint_as_float(kNoCell), 0.f, 0.f, 0.f);
+        lx = fmaxf(0.0f, fminf(1.0f, lx));
+        ly = fmaxf(0.0f, fminf(1.0f, ly));
+        lz = fmaxf(0.0f, fminf(1.0f, lz));
+    }
+    const Cell c = make_cell(lx * static_cast<float>(sp.nx - 1), ly * static_cast<float>(sp.ny - 1),
+                             lz * static_cast<float>(sp.nz - 1), sp.nx, sp.ny, sp.nz);
+    const uint32_t key = static_cast<uint32_t>(c.x0) | (static_cast<uint32_t>(c.y0) << 10) | (static_cast<uint32_t>(c.z0) << 20);
+    return make_float4(__uint_as_float(key), c.tx, c.ty, c.tz);
+}
+
+__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8]) {
+    const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
+    const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
+    const uint32_t r00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), r10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
+    const uint32_t r01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), r11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
+    red_add4(sp.grad + (r00 + x0), acc[0]); red_add4(sp.grad + (r00 + x1), acc[1]);
+    red_add4(sp.grad + (r10 + x0), acc[2]); red_add4(sp.grad + (r10 + x1), acc[3]);
+    red_add4(sp.grad + (r01 + x0), acc[4]); red_add4(sp.grad + (r01 + x1), acc[5]);
+    red_add4(sp.grad + (r11 + x0), acc[6]); red_add4(sp.grad + (r11 + x1), acc[7]);
+}
+
+#ifndef DV_MERGE_MIN_BLOCKS
+#define DV_MERGE_MIN_BLOCKS 4
+#endif
+template <bool kClamp, bool kStratified, bool kUnitBox>
+__global__ void __launch_bounds__(kLeanThreads, DV_MERGE_MIN_BLOCKS)
+lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
+                           int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st) {
+    __shared__ MergeStash stash;
+    const CameraParams cam = P->cam;
+    const MarchParams mp = P->march;
+    const RoiParams roi = P->roi;
+    const TilePixel px = tile_pixel(roi);
+    const uint32_t tid = threadIdx.x, slot = stash_slot(tid);
+
+    const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
+    const uint64_t ray_index = mp.ray_index_base + px.ray;
+
+    uint32_t live = 0;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (px.inside) {
+        live = st.live[px.ray];
+        g0 = dL_dI[static_cast<size_t>(px.ray) * 3 + 0];
+        g1 = dL_dI[static_cast<size_t>(px.ray) * 3 + 1];
+        g2 = dL_dI[static_cast<size_t>(px.ray) * 3 + 2];
+    }
+    const uint32_t nseg = (live + kSegment - 1) / kSegment;
+    uint32_t warp_nseg = nseg;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_nseg = max(warp_nseg, __shfl_xor_sync(0xffffffffu, warp_nseg, o));
+
+    constexpr bool skippable = !kClamp && kUnitBox;   // outside samples touch neither T nor the grid
+    float t_in, t_out;
+    const WarpRange wr = warp_step_range<skippable>(mp, ray, px.inside, t_in, t_out);
+    const uint32_t seg_lo = wr.lo / kSegment, seg_hi = min(warp_nseg, (wr.hi + kSegment - 1) / kSegment);
+
+    // phase B role of this lane: quad q (4 x 2 quads in the warp's 8 x 4 pixel tile), step pair sb
+    const uint32_t lane = tid & 31u, warp_base = tid & ~31u;
+    const uint32_t sb = lane >> 3, qx = lane & 3u, qy = (lane >> 2) & 1u;
+    const uint32_t quad_lane = (2u * qy) * kTileW + 2u * qx;   // lane of the quad's top-left ray
+
+    float adj_T = 0.0f;
+    for (uint32_t seg = seg_hi; seg-- > seg_lo;) {
+        const uint32_t first = seg * kSegment;
+        const uint32_t count = seg < nseg ? min(static_cast<uint32_t>(kSegment), live - first) : 0u;
+        // ---- phase A: forward recompute from the checkpoint
+        if (count != 0) {
+            float T = st.ckpt[static_cast<size_t>(seg) * st.ckpt_stride + px.ray];
+#pragma unroll 1
+            for (uint32_t j = 0; j < count; ++j) {
+                const float4 tab = __ldg(st.steps + first + j);
+                if (skippable && (tab.x > t_out || tab.x + mp.dt < t_in)) {
+                    stash.a[j][slot] = make_float4(-1.0f, 0.f, 0.f, 0.f);   // marker: no contribution, adj_T unchanged
+                    continue;
+                }
+                const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
+                const float4 v = lean_sample<true, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                           ray.oz + ray.dz * t);
+                const float a = alpha_of(v.w, tab.z);
+                stash.a[j][slot] = make_float4(a, T, g0 * v.x + g1 * v.y + g2 * v.z, t);
+                T = T * fmaxf(1.0f - a, 0.0f);
+            }
+        }
+        // ---- phase A': reverse sweep (diff_cpu.cpp:170-194), gradients and scatter cells to shared memory
+#pragma unroll 1
+        for (uint32_t j = kSegment; j-- > 0;) {
+            float4 cell = make_float4(__uint_as_float(kNoCell), 0.f, 0.f, 0.f);
+            if (j < count) {
+                const float4 s = stash.a[j][slot];
+                if (s.x >= 0.0f) {
+                    const float a = s.x, Tp = s.y, t = s.w;
+                    const float dtv = __ldg(st.steps + first + j).z;
+                    const float w = Tp * a;
+                    float dsigma;
+                    adjoint_sample(s.z, a, Tp, dtv, adj_T, dsigma);
+                    cell = scatter_cell<kUnitBox>(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t);
+                    stash.g[j][slot] = make_float4(g0 * w, g1 * w, g2 * w, dsigma);
+                }
+            }
+            stash.a[j][slot] = cell;
+        }
+        __syncwarp();
+        // ---- phase B: this lane merges steps {2 sb, 2 sb + 1} of its quad's four rays
+        {
+            float4 acc[8];
+            uint32_t cur = kNoCell;
+#pragma unroll 1
+            for (uint32_t i = 0; i <= 8; ++i) {
+                uint32_t key = kNoCell;
+                float4 c = make_float4(0.f, 0.f, 0.f, 0.f), gv = c;
+                if (i < 8) {
+                    const uint32_t j = 2u * sb + (i >> 2);
+                    const uint32_t rl = quad_lane + (i & 1u) + ((i >> 1) & 1u) * kTileW;
+                    const uint32_t rs = stash_slot(warp_base + rl);
+                    c = stash.a[j][rs];
+                    key = __float_as_uint(c.x);
+                    if (key != kNoCell) gv = stash.g[j][rs];
+                }
+                if (key != cur) {
+                    if (cur != kNoCell) flush_cell(sp, cur, acc);
+                    cur = key;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (key != kNoCell) {
+                    const float ux = 1.0f - c.y, uy = 1.0f - c.z, uz = 1.0f - c.w;
+                    const float wxy[4] = {ux * uy, c.y * uy, ux * c.z, c.y * c.z};
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float w = wxy[k & 3] * ((k & 4) ? c.w : uz);
+                        acc[k].x = __fmaf_rn(gv.x, w, acc[k].x);
+                        acc[k].y = __fmaf_rn(gv.y, w, acc[k].y);
+                        acc[k].z = __fmaf_rn(gv.z, w, acc[k].z);
+                        acc[k].w = __fmaf_rn(gv.w, w, acc[k].w);
+                    }
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -367,6 +583,26 @@ uint32_t tile_blocks(const RoiParams& roi) {
 
 uint32_t lean_block_count(const RoiParams& roi) { return tile_blocks(roi); }
 
+// Host restatement of the ray-independent part of the marching loop (samp_cpu.cpp:227-241) and of the depth
+// cursor (int_cpu.cpp:170,211).  volatile forces every intermediate to be rounded to float; the host objects are
+// built with -ffp-contract=off, so the values equal what the kernels used to compute per step.
+void build_step_table(const MarchParams& mp, float4* table) {
+    const float tn = mp.t_near, tf = mp.t_far, dts = mp.dt;
+    volatile float cursor = tn;
+    for (uint32_t k = 0; k < mp.uniform_count; ++k) {
+        volatile float prod = static_cast<float>(k) * dts;
+        volatile float base = tn + prod;
+        volatile float half = 0.5f * dts;
+        volatile float mid = base + half;
+        if (mid >= tf) mid = nextafterf(tf, tn);
+        volatile float end = base + dts;
+        if (tf < end) end = tf;
+        volatile float dta = end - base;
+        table[k] = make_float4(base, mid, dta, cursor);
+        cursor = cursor + dta;
+    }
+}
+
 #define DV_DISPATCH3(FN, lin, clampo, strat, ...)                                             \
     do {                                                                                      \
         if (lin) {                                                                            \
@@ -392,12 +628,44 @@ cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params
     return cudaGetLastError();
 }
 
+// Pixel spacing, in voxels, between neighbouring rays where they cross the cube centre: below ~1 the
+// quads of the merge kernel share cells and merging pays; above it the plain per-ray scatter is used.
+static bool merge_scatter_pays(const FrameParams& h, const PackedGrid& grid, const ScatterParams& sp) {
+    if (!grid.linear || sp.nearest) return false;
+    if (sp.nx < 2 || sp.ny < 2 || sp.nz < 2 || sp.nx > 1024 || sp.ny > 1024 || sp.nz > 1024) return false;   // 10-bit cell keys
+    if (h.cam.ortho) return true;   // the reference's orthographic rays all share one origin and direction (ray_cpu.cpp:189-199)
+    const float dx = 0.5f - h.cam.ox, dy = 0.5f - h.cam.oy, dz = 0.5f - h.cam.oz;
+    const float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+    const float f = fminf(fabsf(h.cam.fx), fabsf(h.cam.fy));
+    if (!(f > 0.0f)) return false;
+    const float n = static_cast<float>(max(sp.nx, max(sp.ny, sp.nz)) - 1);
+    return dist / f * n < 1.0f;
+}
+
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
-                                 const LeanBuffers& state) {
+                                 const LeanBuffers& state, int scatter_mode) {
     const uint32_t blocks = tile_blocks(h_params.roi);
     if (blocks == 0) return cudaSuccess;
     const bool strat = h_params.march.stratified != 0;
+    const bool can_merge = grid.linear && !sp.nearest && sp.nx >= 2 && sp.ny >= 2 && sp.nz >= 2 && sp.nx <= 1024 &&
+                           sp.ny <= 1024 && sp.nz <= 1024;
+    const bool merge = scatter_mode == kScatterMerge ? can_merge
+                     : scatter_mode == kScatterPerRay ? false : merge_scatter_pays(h_params, grid, sp);
+    if (merge) {
+#define DV_MERGE(C, S, U) lean_backward_merge_kernel<C, S, U><<<blocks, kLeanThreads, 0, stream>>>( \
+        d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state)
+        const bool unit = sp.unit_bbox != 0;
+        if (grid.clamp) {
+            if (strat) { if (unit) DV_MERGE(true, true, true); else DV_MERGE(true, true, false); }
+            else       { if (unit) DV_MERGE(true, false, true); else DV_MERGE(true, false, false); }
+        } else {
+            if (strat) { if (unit) DV_MERGE(false, true, true); else DV_MERGE(false, true, false); }
+            else       { if (unit) DV_MERGE(false, false, true); else DV_MERGE(false, false, false); }
+        }
+#undef DV_MERGE
+        return cudaGetLastError();
+    }
     DV_DISPATCH3(lean_backward_kernel, grid.linear, grid.clamp, strat,
                  <<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI,
                                                       state));

@@ -26,16 +26,26 @@ struct LeanBuffers {
     float* ckpt = nullptr;         // [ceil(K / kSegment)][ckpt_stride] transmittance at segment starts
     size_t ckpt_stride = 0;
     unsigned long long* live_total = nullptr;
+    // per-step table shared by every generated ray (they all carry the plan's t_near / t_far):
+    // {base = t_near + step * dt, t of the fixed-mode sample, dt_actual, depth cursor before the step}
+    // (reference samp_cpu.cpp:227-241, int_cpu.cpp:170-211), built on the host by hpx_frame_create
+    const float4* steps = nullptr;
 };
+
+// Fills `table[uniform_count]` with the per-step values above (plain IEEE float arithmetic, no contraction).
+void build_step_table(const MarchParams& mp, float4* table);
 
 uint32_t lean_block_count(const RoiParams& roi);
 
 cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                 const PackedGrid& grid, const LeanBuffers& out, bool fill_background);
 
+// scatter_mode: how the backward issues its gradient reds
+enum : int { kScatterAuto = 0, kScatterPerRay = 1, kScatterMerge = 2 };
+
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
-                                 const LeanBuffers& state);
+                                 const LeanBuffers& state, int scatter_mode = kScatterAuto);
 
 // d_partials: [lean_block_count][16] doubles of scratch; d_cam16 is accumulated into.
 cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,

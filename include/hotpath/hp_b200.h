@@ -52,6 +52,9 @@ typedef struct hpx_frame hpx_frame;
 #define HPX_BACKWARD_GRID    0x1u /* accumulate d/d sigma, d/d rgb into the grid's gradient */
 #define HPX_BACKWARD_CAMERA  0x2u /* accumulate d/d c2w[12], d/d {fx,fy,cx,cy}               */
 #define HPX_BACKWARD_ZERO    0x4u /* zero the gradient buffers first                         */
+/* Scatter strategy of the grid backward (default: chosen from the pixel / voxel spacing ratio):  */
+#define HPX_BACKWARD_SCATTER_PER_RAY 0x10u /* one lane = one ray, 8 reds per sample                      */
+#define HPX_BACKWARD_SCATTER_MERGED  0x20u /* 2x2 pixel quads x 2 steps merged in registers before the reds */
 
 /* Per-frame counters (valid after the stream has been synchronised). */
 typedef struct hpx_counts {

@@ -281,6 +281,51 @@ float orc_alpha(float sigma, float dt) {
     return (float)(a < 0.0 ? 0.0 : (a > 1.0 ? 1.0 : a));
 }
 
+/* The polynomial form of the same alpha that the CUDA kernels use (csrc/dv_device.cuh alpha_of), operation
+ * for operation, so the claim "bit-identical to the libm form above" can be checked on the CPU for every
+ * float (orc_alpha_fast_mismatches; tests/test_oracle_pin.py). */
+float orc_alpha_fast(float sigma, float dt) {
+    const float od = sigma * dt;
+    if (od <= 0.0f) return 0.0f;
+    if (od < 1e-4f) { const float half = 0.5f * od; return od * (1.0f - half); }
+    if (od > 17.5f) return 1.0f;
+    const float kf = rintf(od * 1.44269504f);
+    const double r = fma((double)kf, 0.693147180559945309417, -(double)od);
+    double q = 1.0 / 39916800.0;
+    q = fma(q, r, 1.0 / 3628800.0);
+    q = fma(q, r, 1.0 / 362880.0);
+    q = fma(q, r, 1.0 / 40320.0);
+    q = fma(q, r, 1.0 / 5040.0);
+    q = fma(q, r, 1.0 / 720.0);
+    q = fma(q, r, 1.0 / 120.0);
+    q = fma(q, r, 1.0 / 24.0);
+    q = fma(q, r, 1.0 / 6.0);
+    q = fma(q, r, 0.5);
+    const double p = fma(r * r, q, r);
+    const uint64_t bits = (uint64_t)(1023 - (int)kf) << 52;
+    double s;
+    memcpy(&s, &bits, sizeof s);
+    return (float)fma(-s, p, 1.0 - s);
+}
+
+/* Number of floats od in [lo, hi] (every `stride`-th bit pattern) where the two forms differ. */
+uint64_t orc_alpha_fast_mismatches(float lo, float hi, uint32_t stride, uint64_t* out_checked) {
+    uint32_t a, b;
+    memcpy(&a, &lo, 4);
+    memcpy(&b, &hi, 4);
+    uint64_t bad = 0, n = 0;
+    for (uint64_t u = a; u <= b; u += (stride ? stride : 1)) {
+        const uint32_t u32 = (uint32_t)u;
+        float od;
+        memcpy(&od, &u32, 4);
+        const float x = orc_alpha(od, 1.0f), y = orc_alpha_fast(od, 1.0f);
+        ++n;
+        if (memcmp(&x, &y, 4) != 0) ++bad;
+    }
+    if (out_checked) *out_checked = n;
+    return bad;
+}
+
 typedef struct ray_state { float T, depth_w, c[3], t_cursor; } ray_state;
 
 /* One sample of the per-ray scan (:187-215).  Returns 1 when the ray stops. */

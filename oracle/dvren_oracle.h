@@ -66,6 +66,9 @@ int orc_sample(const hp_plan_desc* desc, const orc_grid* gs, const orc_grid* gc,
 
 /* Optical depth -> alpha. */
 float orc_alpha(float sigma, float dt);
+/* Same value through the fp64 polynomial the CUDA kernels use; and the exhaustive comparison. */
+float orc_alpha_fast(float sigma, float dt);
+uint64_t orc_alpha_fast_mismatches(float lo, float hi, uint32_t stride, uint64_t* out_checked);
 
 /* hp_int.  aux may be NULL. */
 int orc_integrate(const hp_plan_desc* desc, size_t n_rays, size_t n_samples, const float* dt,

@@ -63,6 +63,10 @@ def lib() -> C.CDLL:
         _lib.orc_jitter.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32]
         _lib.orc_alpha.restype = C.c_float
         _lib.orc_alpha.argtypes = [C.c_float, C.c_float]
+        _lib.orc_alpha_fast.restype = C.c_float
+        _lib.orc_alpha_fast.argtypes = [C.c_float, C.c_float]
+        _lib.orc_alpha_fast_mismatches.restype = C.c_uint64
+        _lib.orc_alpha_fast_mismatches.argtypes = [C.c_float, C.c_float, C.c_uint32, C.POINTER(C.c_uint64)]
         _lib.orc_sample.restype = C.c_int
         _lib.orc_sample.argtypes = [C.POINTER(A.hp_plan_desc), C.POINTER(orc_grid), C.POINTER(orc_grid),
                                     C.c_size_t, f32p, f32p, f32p, f32p, C.c_uint64, C.c_size_t,

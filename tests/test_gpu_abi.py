@@ -1,8 +1,9 @@
 """GPU parity of the hp.h entry points (the drop-in C ABI) against the pinned oracle and the
 reference's golden vectors, through HOST tensors (staged to the GPU by the library) and DEVICE
 tensors (used in place).  Indices, counts, positions and field lookups are bit-exact; integrals and
-gradients are held to the north_star tolerances (alpha goes through CUDA's double expm1, which may
-round differently from glibc's in rare last-bit cases; aux[:,3] uses logf)."""
+gradients are held to the north_star tolerances (alpha itself is bit-exact, see
+test_alpha_matches_oracle_bitwise; aux[:,3] uses CUDA's logf, radiance sums are contracted in the
+lean kernels)."""
 import ctypes as C
 
 import numpy as np
@@ -62,6 +63,25 @@ def staged_vs_oracle(pipe, desc, sigma, color, interp, oob, res, bmin, bmax, wha
     for k in ("radiance", "transmittance", "opacity", "depth", "aux"):
         U.assert_bits(fintl[k], intl[k], f"{what} fused intl.{k}")
     return dict(samp=samp, intl=intl, img=img, grads=grads)
+
+
+def test_alpha_matches_oracle_bitwise(pipe):
+    """alpha_of (csrc/dv_device.cuh) against the reference's libm form (int_cpu.cpp:98-109) on 2 M
+    optical depths: one single-sample ray each through hp_int, so aux = {alpha, alpha, 1, 0} and
+    transmittance = max(1 - alpha, 0), all compared bit for bit."""
+    rng = np.random.default_rng(5)
+    n = 1 << 21
+    od = np.exp(rng.uniform(np.log(2e-5), np.log(40.0), n)).astype(np.float32)
+    od[:8] = [0.0, 9.9e-5, 1e-4, 17.4999, 17.5, 17.5001, 30.0, 1e-3]
+    desc = A.make_plan_desc(n, 1, 0.0, 10.0, dt=1.0, max_steps=1, max_samples=n)
+    plan, rdesc = pipe.plan(desc)
+    st, odesc = O.plan_resolve(desc)
+    samp = {"dt": np.ones(n, np.float32), "sigma": od, "color": np.full((n, 3), 0.5, np.float32),
+            "positions": np.zeros((n, 3), np.float32), "ray_offset": np.arange(n + 1, dtype=np.uint32), "count": n}
+    got, ref = pipe.integrate(plan, samp), O.integrate(odesc, samp)
+    U.assert_bits(got["aux"][:, :3], ref["aux"][:, :3], "alpha / weight / T_prev")
+    U.assert_bits(got["transmittance"], ref["transmittance"], "transmittance")
+    U.assert_bits(got["opacity"], ref["opacity"], "opacity")
 
 
 @pytest.mark.parametrize("case", list(U.random_cases(12, seed=0)), ids=lambda c: f"case{c['case']}")

@@ -66,6 +66,43 @@ def test_lean_matches_oracle_random(ctx, case):
     U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, "color_grad")
 
 
+SCATTER_MODES = {"per_ray": D.HPX_BACKWARD_SCATTER_PER_RAY, "merged": D.HPX_BACKWARD_SCATTER_MERGED}
+
+
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+@pytest.mark.parametrize("case", list(U.random_cases(12, seed=3)), ids=lambda c: f"case{c['case']}")
+def test_lean_backward_scatter_modes_match_oracle(ctx, case, mode):
+    """Both scatter strategies of the grid backward (one lane per ray; 2x2 quads x 2 steps merged in
+    registers) against the oracle, forced through the hpx_backward flags so that the automatic choice
+    cannot hide either kernel.  The merged kernel falls back to per-ray for nearest / 1-voxel axes."""
+    desc = case["desc"]
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(case["sigma"], case["color"], case["interp"], case["oob"])
+    dl = S.hashed_image_grad(odesc.roi.width * odesc.roi.height)
+    ref = O.render(odesc, gs, gc, dl, case["res"], case["bmin"], case["bmax"])
+    got = run_lean(ctx, desc, case["sigma"], case["color"], case["interp"], case["oob"], case["bmin"], case["bmax"], dl,
+                   flags=D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+    U.assert_close(got["sigma_grad"], ref["sigma_grad"], U.GRAD_RTOL, f"{mode} sigma_grad")
+    U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{mode} color_grad")
+
+
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+@pytest.mark.parametrize("kind,strat,oob", [("thin", True, 0), ("dense", False, 0), ("dense", True, 1)])
+def test_lean_backward_scatter_modes_dense_pixels(ctx, kind, strat, oob, mode):
+    """Pixels much denser than voxels (the regime the merged scatter is built for): 128x96 rays over a 20^3 grid,
+    ragged image size so that partially filled tiles and quads are exercised."""
+    sig, col = S.hashed_volume(20, kind)
+    desc = S.bench_plan(125, 91, 120, stratified=strat, view=3, views=11)
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, oob)
+    dl = S.hashed_image_grad(125 * 91)
+    ref = O.render(odesc, gs, gc, dl)
+    got = run_lean(ctx, desc, sig, col, 1, oob, None, None, dl,
+                   flags=D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+    U.assert_close(got["sigma_grad"], ref["sigma_grad"], U.GRAD_RTOL, f"{mode} sigma_grad")
+    U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{mode} color_grad")
+
+
 @pytest.mark.parametrize("path", U.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_lean_matches_reference_golden(ctx, path):
     g = U.load_golden(path)

@@ -175,6 +175,18 @@ def test_alpha_branches():
     assert O.lib().orc_alpha(2.0, 0.5) == np.float32(-math.expm1(-1.0))
 
 
+def test_alpha_bit_exact_all_floats():
+    """The fp64-polynomial alpha the CUDA kernels use (csrc/dv_device.cuh alpha_of, restated as
+    orc_alpha_fast) equals the reference's libm form (int_cpu.cpp:98-109) for EVERY float optical
+    depth in [1e-4, 18] -- 147 M values -- and on both sides of the branch points."""
+    checked = C.c_uint64()
+    bad = O.lib().orc_alpha_fast_mismatches(np.float32(1e-4), np.float32(18.0), 1, C.byref(checked))
+    assert checked.value > 140_000_000 and bad == 0
+    for od in (0.0, -1.0, 9.9e-5, 1e-4, 17.4999, 17.5, 17.5001, 30.0, 1e30, float("inf")):
+        a, b = O.lib().orc_alpha(od, 1.0), O.lib().orc_alpha_fast(od, 1.0)
+        assert np.float32(a).tobytes() == np.float32(b).tobytes(), od
+
+
 def test_jitter_range_and_determinism():
     vals = np.array([O.lib().orc_jitter(42, r, s) for r in range(64) for s in range(16)], np.float32)
     assert vals.min() >= 0.0 and vals.max() <= 1.0
