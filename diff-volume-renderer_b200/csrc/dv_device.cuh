@@ -308,6 +308,25 @@ __device__ __forceinline__ float4 sample_packed_lean(const float4* __restrict__ 
     return trilerp_pairs(load_corners(g, c, nx, ny), c.tx, c.ty, c.tz);
 }
 
+// Same, also returning the trilinear cell {x0 | y0 << 10 | z0 << 20, tx, ty, tz}: with the unit bounding box the
+// backward scatter (src/fields/dense_grid.cpp:206-246) maps a position to exactly this cell with these
+// fractions (local = p, g = local * (n - 1), same clamp), so the recompute pass hands it over instead of
+// deriving it a second time.  Outside + OOB-zero: key = 0xffffffff.
+template <bool kClamp>
+__device__ __forceinline__ float4 sample_packed_lean_cell(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+                                                          float px, float py, float pz, float4& cell) {
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) {
+        cell = make_float4(__uint_as_float(0xffffffffu), 0.f, 0.f, 0.f);
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
+    cell = make_float4(__uint_as_float(static_cast<uint32_t>(c.x0) | (static_cast<uint32_t>(c.y0) << 10) |
+                                       (static_cast<uint32_t>(c.z0) << 20)),
+                       c.tx, c.ty, c.tz);
+    return trilerp_pairs(load_corners(g, c, nx, ny), c.tx, c.ty, c.tz);
+}
+
 // Generic single-grid query (separate sigma / colour arrays with their own
 // resolution and policies, as hp_samp allows).  `ch` selects the channel.
 __device__ __forceinline__ float sample_plain(const GridParams& g, float px, float py, float pz, int ch) {

@@ -253,22 +253,18 @@ constexpr uint32_t kNoCell = 0xffffffffu;
 constexpr int kStashRow = kLeanThreads + kLeanThreads / 16;   // skewed by one float4 per 16 threads: phase B reads conflict-free
 
 struct MergeStash {
-    float4 a[kSegment][kStashRow];   // phase A: {alpha, T_prev, g.c, t};  phase A': {cell bits, tx, ty, tz}
-    float4 g[kSegment][kStashRow];   // phase A': {g0 w, g1 w, g2 w, d sigma}
+    float4 a[kSegment][kStashRow];   // phase A: {alpha, T_prev, g.c, t};  phase A': {g0 w, g1 w, g2 w, d sigma}
+    float4 c[kSegment][kStashRow];   // scatter cell {x0 | y0 << 10 | z0 << 20, tx, ty, tz}; key 0xffffffff = nothing to scatter
 };
 
 __device__ __forceinline__ uint32_t stash_slot(uint32_t tid) { return tid + (tid >> 4); }
 
 // scatter cell of a position: src/fields/dense_grid.cpp:206-246 (linear, every axis >= 2 voxels)
-template <bool kUnitBox>
 __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px, float py, float pz) {
-    float lx = px, ly = py, lz = pz;
-    if (!kUnitBox) {
-        const float ex = sp.bmax[0] - sp.bmin[0], ey = sp.bmax[1] - sp.bmin[1], ez = sp.bmax[2] - sp.bmin[2];
-        lx = ex != 0.0f ? (px - sp.bmin[0]) / ex : 0.0f;
-        ly = ey != 0.0f ? (py - sp.bmin[1]) / ey : 0.0f;
-        lz = ez != 0.0f ? (pz - sp.bmin[2]) / ez : 0.0f;
-    }
+    const float ex = sp.bmax[0] - sp.bmin[0], ey = sp.bmax[1] - sp.bmin[1], ez = sp.bmax[2] - sp.bmin[2];
+    float lx = ex != 0.0f ? (px - sp.bmin[0]) / ex : 0.0f;
+    float ly = ey != 0.0f ? (py - sp.bmin[1]) / ey : 0.0f;
+    float lz = ez != 0.0f ? (pz - sp.bmin[2]) / ez : 0.0f;
     const bool outside = lx < 0.0f || lx > 1.0f || ly < 0.0f || ly > 1.0f || lz < 0.0f || lz > 1.0f;
     if (outside) {
         if (!sp.clamp) return make_float4(__uint_as_float(kNoCell), 0.f, 0.f, 0.f);
@@ -282,16 +278,26 @@ __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px
     return make_float4(__uint_as_float(key), c.tx, c.ty, c.tz);
 }
 
-__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8]) {
+// 8 corner accumulators as packed (x,y) / (z,w) pairs: corner k = dx + 2 dy + 4 dz
+struct CellAcc { uint64_t lo[8], hi[8]; };
+
+__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const CellAcc& acc) {
     const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
     const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
     const uint32_t r00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), r10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
     const uint32_t r01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), r11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
-    red_add4(sp.grad + (r00 + x0), acc[0]); red_add4(sp.grad + (r00 + x1), acc[1]);
-    red_add4(sp.grad + (r10 + x0), acc[2]); red_add4(sp.grad + (r10 + x1), acc[3]);
-    red_add4(sp.grad + (r01 + x0), acc[4]); red_add4(sp.grad + (r01 + x1), acc[5]);
-    red_add4(sp.grad + (r11 + x0), acc[6]); red_add4(sp.grad + (r11 + x1), acc[7]);
+    const uint32_t idx[8] = {r00 + x0, r00 + x1, r10 + x0, r10 + x1, r01 + x0, r01 + x1, r11 + x0, r11 + x1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float4 v;
+        unpack2(acc.lo[k], v.x, v.y);
+        unpack2(acc.hi[k], v.z, v.w);
+        red_add4(sp.grad + idx[k], v);
+    }
 }
+
+// compare-exchange of the 19-comparator sorting network for 8 keys
+#define DV_CE(a, b) { const uint32_t lo_ = min(k[a], k[b]), hi_ = max(k[a], k[b]); k[a] = lo_; k[b] = hi_; }
 
 #ifndef DV_MERGE_MIN_BLOCKS
 #define DV_MERGE_MIN_BLOCKS 4
@@ -319,9 +325,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
         g2 = dL_dI[static_cast<size_t>(px.ray) * 3 + 2];
     }
     const uint32_t nseg = (live + kSegment - 1) / kSegment;
-    uint32_t warp_nseg = nseg;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) warp_nseg = max(warp_nseg, __shfl_xor_sync(0xffffffffu, warp_nseg, o));
+    const uint32_t warp_nseg = __reduce_max_sync(0xffffffffu, nseg);
 
     constexpr bool skippable = !kClamp && kUnitBox;   // outside samples touch neither T nor the grid
     float t_in, t_out;
@@ -331,7 +335,8 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
     // phase B role of this lane: quad q (4 x 2 quads in the warp's 8 x 4 pixel tile), step pair sb
     const uint32_t lane = tid & 31u, warp_base = tid & ~31u;
     const uint32_t sb = lane >> 3, qx = lane & 3u, qy = (lane >> 2) & 1u;
-    const uint32_t quad_lane = (2u * qy) * kTileW + 2u * qx;   // lane of the quad's top-left ray
+    const uint32_t quad_slot = stash_slot(warp_base + (2u * qy) * kTileW + 2u * qx);   // slot of the quad's top-left ray
+    // the quad's rays sit at lanes +0, +1, +kTileW, +kTileW+1: a quad never straddles a 16-thread skew boundary
 
     float adj_T = 0.0f;
     for (uint32_t seg = seg_hi; seg-- > seg_lo;) {
@@ -348,64 +353,102 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                     continue;
                 }
                 const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
-                const float4 v = lean_sample<true, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
-                                                           ray.oz + ray.dz * t);
+                float4 cell;
+                const float4 v = sample_packed_lean_cell<kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                                 ray.oz + ray.dz * t, cell);
+                if (kUnitBox) {
+                    stash.c[j][slot] = cell;
+                    if (!kClamp && __float_as_uint(cell.x) == kNoCell) {   // outside the cube: sigma = rgb = 0, adj_T unchanged, no scatter
+                        stash.a[j][slot] = make_float4(-1.0f, 0.f, 0.f, 0.f);
+                        continue;
+                    }
+                }
                 const float a = alpha_of(v.w, tab.z);
                 stash.a[j][slot] = make_float4(a, T, g0 * v.x + g1 * v.y + g2 * v.z, t);
                 T = T * fmaxf(1.0f - a, 0.0f);
             }
         }
-        // ---- phase A': reverse sweep (diff_cpu.cpp:170-194), gradients and scatter cells to shared memory
+        // ---- phase A': reverse sweep (diff_cpu.cpp:170-194): per-sample gradients to shared memory
 #pragma unroll 1
         for (uint32_t j = kSegment; j-- > 0;) {
-            float4 cell = make_float4(__uint_as_float(kNoCell), 0.f, 0.f, 0.f);
+            bool valid = false;
             if (j < count) {
                 const float4 s = stash.a[j][slot];
                 if (s.x >= 0.0f) {
-                    const float a = s.x, Tp = s.y, t = s.w;
+                    const float a = s.x, Tp = s.y;
                     const float dtv = __ldg(st.steps + first + j).z;
                     const float w = Tp * a;
                     float dsigma;
                     adjoint_sample(s.z, a, Tp, dtv, adj_T, dsigma);
-                    cell = scatter_cell<kUnitBox>(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t);
-                    stash.g[j][slot] = make_float4(g0 * w, g1 * w, g2 * w, dsigma);
+                    stash.a[j][slot] = make_float4(g0 * w, g1 * w, g2 * w, dsigma);
+                    if (!kUnitBox) {
+                        const float t = s.w;
+                        stash.c[j][slot] = scatter_cell(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t);
+                    }
+                    valid = true;
                 }
             }
-            stash.a[j][slot] = cell;
+            if (!valid) stash.c[j][slot].x = __uint_as_float(kNoCell);
         }
         __syncwarp();
         // ---- phase B: this lane merges steps {2 sb, 2 sb + 1} of its quad's four rays
         {
-            float4 acc[8];
+            // sort the 8 samples by cell so that equal cells are adjacent.  Sort key = low 3 bits of each cell
+            // coordinate (neighbouring samples differ by far less than 8 cells; a collision would only cost a missed
+            // merge, equality below is decided on the full key) with the sample number in the low 3 bits.
+            uint32_t k[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+                const uint32_t key = __float_as_uint(stash.c[2u * sb + (i >> 2)][quad_slot + (i & 1u) + ((i >> 1) & 1u) * kTileW].x);
+                const uint32_t rel = (key & 7u) | ((key >> 7) & 0x38u) | ((key >> 14) & 0x1c0u);
+                k[i] = ((key == kNoCell ? 0xfffu : rel) << 3) | i;
+            }
+            DV_CE(0, 1) DV_CE(2, 3) DV_CE(4, 5) DV_CE(6, 7) DV_CE(0, 2) DV_CE(1, 3) DV_CE(4, 6) DV_CE(5, 7) DV_CE(1, 2) DV_CE(5, 6)
+            DV_CE(0, 4) DV_CE(3, 7) DV_CE(1, 5) DV_CE(2, 6) DV_CE(1, 4) DV_CE(3, 6) DV_CE(2, 4) DV_CE(3, 5) DV_CE(3, 4)
+            uint32_t order = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) order |= (k[i] & 7u) << (3u * i);
+
+            CellAcc acc;
             uint32_t cur = kNoCell;
+            const uint64_t one2 = pack2(1.0f, 1.0f);
 #pragma unroll 1
-            for (uint32_t i = 0; i <= 8; ++i) {
+            for (uint32_t n = 0; n <= 8; ++n) {
                 uint32_t key = kNoCell;
                 float4 c = make_float4(0.f, 0.f, 0.f, 0.f), gv = c;
-                if (i < 8) {
+                if (n < 8) {
+                    const uint32_t i = (order >> (3u * n)) & 7u;
                     const uint32_t j = 2u * sb + (i >> 2);
-                    const uint32_t rl = quad_lane + (i & 1u) + ((i >> 1) & 1u) * kTileW;
-                    const uint32_t rs = stash_slot(warp_base + rl);
-                    c = stash.a[j][rs];
+                    const uint32_t rs = quad_slot + (i & 1u) + ((i >> 1) & 1u) * kTileW;
+                    c = stash.c[j][rs];
                     key = __float_as_uint(c.x);
-                    if (key != kNoCell) gv = stash.g[j][rs];
+                    if (key != kNoCell) gv = stash.a[j][rs];
                 }
-                if (key != cur) {
+                const bool fresh = key != cur;
+                if (fresh) {
                     if (cur != kNoCell) flush_cell(sp, cur, acc);
                     cur = key;
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 if (key != kNoCell) {
-                    const float ux = 1.0f - c.y, uy = 1.0f - c.z, uz = 1.0f - c.w;
-                    const float wxy[4] = {ux * uy, c.y * uy, ux * c.z, c.y * c.z};
+                    // (1-tx)(1-ty)(1-tz) ... as duplicated pairs so that the products feed FFMA2 directly
+                    const uint64_t tx2 = pack2(c.y, c.y), ty2 = pack2(c.z, c.z), tz2 = pack2(c.w, c.w);
+                    const uint64_t ux2 = sub2(one2, tx2), uy2 = sub2(one2, ty2), uz2 = sub2(one2, tz2);
+                    const uint64_t wxy[4] = {mul2(ux2, uy2), mul2(tx2, uy2), mul2(ux2, ty2), mul2(tx2, ty2)};
+                    const uint64_t glo = pack2(gv.x, gv.y), ghi = pack2(gv.z, gv.w);
+                    if (fresh) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const float w = wxy[k & 3] * ((k & 4) ? c.w : uz);
-                        acc[k].x = __fmaf_rn(gv.x, w, acc[k].x);
-                        acc[k].y = __fmaf_rn(gv.y, w, acc[k].y);
-                        acc[k].z = __fmaf_rn(gv.z, w, acc[k].z);
-                        acc[k].w = __fmaf_rn(gv.w, w, acc[k].w);
+                        for (int q = 0; q < 8; ++q) {
+                            const uint64_t w2 = mul2(wxy[q & 3], (q & 4) ? tz2 : uz2);
+                            acc.lo[q] = mul2(glo, w2);
+                            acc.hi[q] = mul2(ghi, w2);
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint64_t w2 = mul2(wxy[q & 3], (q & 4) ? tz2 : uz2);
+                            acc.lo[q] = fma2(glo, w2, acc.lo[q]);
+                            acc.hi[q] = fma2(ghi, w2, acc.hi[q]);
+                        }
                     }
                 }
             }
@@ -413,6 +456,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
         __syncwarp();
     }
 }
+#undef DV_CE
 
 // ---- camera adjoint ---------------------------------------------------------
 // value is not needed, only d/d(position) of sigma and of h = g . rgb
