@@ -207,11 +207,15 @@ def run_ours(args):
     fwd_bytes = BYTES_FWD_PER_SAMPLE * live + 24 * n_rays
     bwd_gbs = bwd_bytes / (bwd_ms / args.steps * 1e-3) / 1e9
     fwd_gbs = fwd_bytes / (fwd_ms / args.steps * 1e-3) / 1e9
-    traffic = None
+    bwd_kernel = "lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged" else "lean_backward_kernel"
+    traffic = fwd_traffic = None
+    l1_pct = {}
     tpath = os.path.join(REPO, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.config, {}).get("lean_backward_kernel")
+            tj = json.load(f).get(args.config, {})
+        traffic, fwd_traffic = tj.get(bwd_kernel), tj.get("lean_forward_kernel")
+        l1_pct = tj.get("_l1_wavefront_pct", {})
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -228,13 +232,19 @@ def run_ours(args):
         "clocks": clocks,
         "fwd": {"ms": fwd_ms / args.steps, "msamples_s": samples / (fwd_ms / args.steps * 1e-3) / 1e6},
         "bwd": {"ms": bwd_ms / args.steps, "msamples_s": samples / (bwd_ms / args.steps * 1e-3) / 1e6},
-        "roofline": {"bound": "hbm", "kernel": "lean_backward_kernel", "achieved": bwd_gbs, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": bwd_kernel, "achieved": bwd_gbs, "peak": peak,
                      "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bwd_bytes,
-                     "note": "algorithmic bytes are gather/scatter bytes at L1/L2 level (256 B per live sample); "
-                             "compulsory HBM bytes are far smaller, see DESIGN.md",
+                     "note": "algorithmic bytes (SURVEY 8d) are gather/scatter bytes at the L1/L2 level: 256 B per live "
+                             "sample for the backward, 128 B for the forward; a pixel tile re-touches the same voxels, "
+                             "so caches absorb them and frac > 1.  Measured DRAM bytes per launch are in `traffic`; "
+                             "the binding resource is the SM's L1/LSU data pipe (l1_wavefront_pct_of_peak, from the ncu "
+                             "capture under profiles/), see DESIGN.md section 5",
+                     "l1_wavefront_pct_of_peak": l1_pct.get(bwd_kernel),
+                     "hbm_frac_of_peak": (traffic / (bwd_ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None,
                      "forward_kernel": {"kernel": "lean_forward_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
-                                        "algorithmic_bytes_per_launch": fwd_bytes}},
+                                        "algorithmic_bytes_per_launch": fwd_bytes, "traffic": fwd_traffic,
+                                        "l1_wavefront_pct_of_peak": l1_pct.get("lean_forward_kernel")}},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)

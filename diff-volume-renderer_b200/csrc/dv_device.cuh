@@ -202,6 +202,14 @@ __device__ __forceinline__ Corners load_corners(const float4* __restrict__ g, co
     const uint32_t oy = static_cast<uint32_t>(c.y1 - c.y0) * static_cast<uint32_t>(nx);           // 0 or one row
     const uint32_t oz = static_cast<uint32_t>(c.z1 - c.z0) * static_cast<uint32_t>(nx) * static_cast<uint32_t>(ny);
     Corners k;
+#ifdef DV_EXP_NOGATHER   // timing experiment only (tools/quick_time.py): everything but the gathers
+    {
+        const float f = __uint_as_float(0x3f000000u | (i000 & 0xffffu));
+        k.v000 = make_float4(f, f, f, f); k.v100 = make_float4(f + ox, f, f, f); k.v010 = make_float4(f, f + oy, f, f);
+        k.v110 = k.v000; k.v001 = make_float4(f, f, f + oz, f); k.v101 = k.v100; k.v011 = k.v010; k.v111 = k.v001;
+        return k;
+    }
+#endif
     k.v000 = __ldg(g + i000);           k.v100 = __ldg(g + (i000 + ox));
     k.v010 = __ldg(g + (i000 + oy));      k.v110 = __ldg(g + (i000 + oy + ox));
     k.v001 = __ldg(g + (i000 + oz));      k.v101 = __ldg(g + (i000 + oz + ox));

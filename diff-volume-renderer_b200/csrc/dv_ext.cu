@@ -389,6 +389,15 @@ HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_
     return enqueue_backward(f, g, d_g, flags);
 }
 
+HP_API hp_status hpx_backward_scatter(const hpx_frame* f, const hpx_grid* g, uint32_t flags, uint32_t* out_flag) {
+    if (f == nullptr || g == nullptr || out_flag == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    const int want = (flags & HPX_BACKWARD_SCATTER_MERGED) ? kScatterMerge
+                   : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay : kScatterAuto;
+    const int got = resolve_scatter_mode(f->h_params, packed_view(*g), scatter_params(*g), want);
+    *out_flag = got == kScatterMerge ? HPX_BACKWARD_SCATTER_MERGED : HPX_BACKWARD_SCATTER_PER_RAY;
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_frame_image(const hpx_frame* f, hp_img_t* out) {
     if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const hp_plan_desc& d = f->plan->desc;

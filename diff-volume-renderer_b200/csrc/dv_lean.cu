@@ -278,29 +278,25 @@ __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px
     return make_float4(__uint_as_float(key), c.tx, c.ty, c.tz);
 }
 
-// 8 corner accumulators as packed (x,y) / (z,w) pairs: corner k = dx + 2 dy + 4 dz
-struct CellAcc { uint64_t lo[8], hi[8]; };
-
-__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const CellAcc& acc) {
+// 8 corner accumulators {d r, d g, d b, d sigma}: corner k = dx + 2 dy + 4 dz.  Kept as float4 so that the register
+// allocator can place each one in an aligned quad: FFMA2 updates its (x,y) / (z,w) halves in place and
+// red.global.add.v4.f32 consumes the quad without moves.
+__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8]) {
     const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
     const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
     const uint32_t r00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), r10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
     const uint32_t r01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), r11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
-    const uint32_t idx[8] = {r00 + x0, r00 + x1, r10 + x0, r10 + x1, r01 + x0, r01 + x1, r11 + x0, r11 + x1};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        float4 v;
-        unpack2(acc.lo[k], v.x, v.y);
-        unpack2(acc.hi[k], v.z, v.w);
-        red_add4(sp.grad + idx[k], v);
-    }
+    red_add4(sp.grad + (r00 + x0), acc[0]); red_add4(sp.grad + (r00 + x1), acc[1]);
+    red_add4(sp.grad + (r10 + x0), acc[2]); red_add4(sp.grad + (r10 + x1), acc[3]);
+    red_add4(sp.grad + (r01 + x0), acc[4]); red_add4(sp.grad + (r01 + x1), acc[5]);
+    red_add4(sp.grad + (r11 + x0), acc[6]); red_add4(sp.grad + (r11 + x1), acc[7]);
 }
 
 // compare-exchange of the 19-comparator sorting network for 8 keys
 #define DV_CE(a, b) { const uint32_t lo_ = min(k[a], k[b]), hi_ = max(k[a], k[b]); k[a] = lo_; k[b] = hi_; }
 
 #ifndef DV_MERGE_MIN_BLOCKS
-#define DV_MERGE_MIN_BLOCKS 4
+#define DV_MERGE_MIN_BLOCKS 5
 #endif
 template <bool kClamp, bool kStratified, bool kUnitBox>
 __global__ void __launch_bounds__(kLeanThreads, DV_MERGE_MIN_BLOCKS)
@@ -409,7 +405,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
 #pragma unroll
             for (uint32_t i = 0; i < 8; ++i) order |= (k[i] & 7u) << (3u * i);
 
-            CellAcc acc;
+            float4 acc[8];
             uint32_t cur = kNoCell;
             const uint64_t one2 = pack2(1.0f, 1.0f);
 #pragma unroll 1
@@ -435,19 +431,19 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                     const uint64_t ux2 = sub2(one2, tx2), uy2 = sub2(one2, ty2), uz2 = sub2(one2, tz2);
                     const uint64_t wxy[4] = {mul2(ux2, uy2), mul2(tx2, uy2), mul2(ux2, ty2), mul2(tx2, ty2)};
                     const uint64_t glo = pack2(gv.x, gv.y), ghi = pack2(gv.z, gv.w);
-                    if (fresh) {
+                    if (fresh) {   // first sample of a run: plain products, no zero fill of the accumulators
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const uint64_t w2 = mul2(wxy[q & 3], (q & 4) ? tz2 : uz2);
-                            acc.lo[q] = mul2(glo, w2);
-                            acc.hi[q] = mul2(ghi, w2);
+                            unpack2(mul2(glo, w2), acc[q].x, acc[q].y);
+                            unpack2(mul2(ghi, w2), acc[q].z, acc[q].w);
                         }
                     } else {
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const uint64_t w2 = mul2(wxy[q & 3], (q & 4) ? tz2 : uz2);
-                            acc.lo[q] = fma2(glo, w2, acc.lo[q]);
-                            acc.hi[q] = fma2(ghi, w2, acc.hi[q]);
+                            unpack2(fma2(glo, w2, pack2(acc[q].x, acc[q].y)), acc[q].x, acc[q].y);
+                            unpack2(fma2(ghi, w2, pack2(acc[q].z, acc[q].w)), acc[q].z, acc[q].w);
                         }
                     }
                 }
@@ -686,16 +682,21 @@ static bool merge_scatter_pays(const FrameParams& h, const PackedGrid& grid, con
     return dist / f * n < 1.0f;
 }
 
+int resolve_scatter_mode(const FrameParams& h_params, const PackedGrid& grid, const ScatterParams& sp, int scatter_mode) {
+    const bool can_merge = grid.linear && !sp.nearest && sp.nx >= 2 && sp.ny >= 2 && sp.nz >= 2 && sp.nx <= 1024 &&
+                           sp.ny <= 1024 && sp.nz <= 1024;
+    const bool merge = scatter_mode == kScatterMerge ? can_merge
+                     : scatter_mode == kScatterPerRay ? false : merge_scatter_pays(h_params, grid, sp);
+    return merge ? kScatterMerge : kScatterPerRay;
+}
+
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
                                  const LeanBuffers& state, int scatter_mode) {
     const uint32_t blocks = tile_blocks(h_params.roi);
     if (blocks == 0) return cudaSuccess;
     const bool strat = h_params.march.stratified != 0;
-    const bool can_merge = grid.linear && !sp.nearest && sp.nx >= 2 && sp.ny >= 2 && sp.nz >= 2 && sp.nx <= 1024 &&
-                           sp.ny <= 1024 && sp.nz <= 1024;
-    const bool merge = scatter_mode == kScatterMerge ? can_merge
-                     : scatter_mode == kScatterPerRay ? false : merge_scatter_pays(h_params, grid, sp);
+    const bool merge = resolve_scatter_mode(h_params, grid, sp, scatter_mode) == kScatterMerge;
     if (merge) {
 #define DV_MERGE(C, S, U) lean_backward_merge_kernel<C, S, U><<<blocks, kLeanThreads, 0, stream>>>( \
         d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state)

@@ -43,6 +43,9 @@ cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params
 // scatter_mode: how the backward issues its gradient reds
 enum : int { kScatterAuto = 0, kScatterPerRay = 1, kScatterMerge = 2 };
 
+// kScatterPerRay or kScatterMerge: what launch_lean_backward will run for this request
+int resolve_scatter_mode(const FrameParams& h_params, const PackedGrid& grid, const ScatterParams& sp, int scatter_mode);
+
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
                                  const LeanBuffers& state, int scatter_mode = kScatterAuto);

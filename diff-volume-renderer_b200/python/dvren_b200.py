@@ -57,6 +57,7 @@ HPX_FUNCTIONS = {
     "hpx_frame_set_view": (C.c_int, [C.c_void_p, P(A.hp_camera_desc), C.c_uint64, C.c_uint64]),
     "hpx_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
+    "hpx_backward_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
     "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
     "hpx_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_counts": (C.c_int, [C.c_void_p, P(hpx_counts)]),
@@ -217,6 +218,11 @@ class Frame:
             assert self._g.size == self.plan.n_rays * 3
             ptr, ms = self._g.ctypes.data, A.HP_MEMSPACE_HOST
         check("hpx_backward", self.lib.hpx_backward(self.handle, grid.handle, ptr, ms, flags))
+
+    def scatter_mode(self, grid: Grid, flags: int = HPX_BACKWARD_GRID) -> str:
+        out = C.c_uint32()
+        check("hpx_backward_scatter", self.lib.hpx_backward_scatter(self.handle, grid.handle, flags, C.byref(out)))
+        return "merged" if out.value == HPX_BACKWARD_SCATTER_MERGED else "per_ray"
 
     def read(self):
         d = self.plan.desc

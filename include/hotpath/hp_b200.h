@@ -118,6 +118,9 @@ HP_API hp_status hpx_forward(hpx_frame* frame, const hpx_grid* grid);
 /* dL_dI: (rays,3) f32 per ray in plan order, HOST (copied on the stream) or DEVICE. */
 HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_dI,
                               hp_memspace memspace, uint32_t flags);
+/* Which scatter strategy hpx_backward(flags) runs for this frame / grid pair: writes HPX_BACKWARD_SCATTER_PER_RAY
+ * or HPX_BACKWARD_SCATTER_MERGED (kernel names lean_backward_kernel / lean_backward_merge_kernel in profiles). */
+HP_API hp_status hpx_backward_scatter(const hpx_frame* frame, const hpx_grid* grid, uint32_t flags, uint32_t* out_flag);
 /* Device views of the composed frame (shapes as hp_img_t). */
 HP_API hp_status hpx_frame_image(const hpx_frame* frame, hp_img_t* out_views);
 /* Copy the composed frame to HOST buffers (any may be NULL); synchronises. */

@@ -86,6 +86,7 @@ def main():
     lines += ["Source: `ncu --set full --clock-control none --import-source on`; figures are per launch, under the",
               "profiler (cold caches, serialised) -- bench.py times the same kernels live with CUDA events.", ""]
     traffic = {}
+    l1pct = {}
     for r in rows:
         name = r[col["Kernel Name"]]
         short = re.sub(r"^void\s+", "", name)
@@ -110,6 +111,9 @@ def main():
         wr = num(r[col["dram__bytes_write.sum"]]) * UNIT_SCALE.get(units[col["dram__bytes_write.sum"]], 1)
         base = re.sub(r"<.*$", "", short)
         traffic[base] = int(rd + wr)
+        k = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
+        if k in col:
+            l1pct[base] = num(r[col[k]])
     os.makedirs(os.path.dirname(os.path.abspath(args.out_md)), exist_ok=True)
     with open(args.out_md, "w") as f:
         f.write("\n".join(lines))
@@ -120,6 +124,7 @@ def main():
             with open(tpath) as f:
                 data = json.load(f)
         data.setdefault(args.traffic_key, {}).update(traffic)
+        data[args.traffic_key].setdefault("_l1_wavefront_pct", {}).update(l1pct)
         data[args.traffic_key]["_source"] = os.path.basename(args.out_md)
         with open(tpath, "w") as f:
             json.dump(data, f, indent=1, sort_keys=True)
