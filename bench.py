@@ -118,13 +118,28 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
 
+    import sharding as SH
+
     n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
     sigma, color = S.hashed_volume(n, "thin")       # no early termination: live samples == samples
     ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
-    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank, views=max(world, 1)))
+    rows_mode = args.sharding == "rows" and world > 1
+    if rows_mode:
+        # strong scaling: ONE frame cut into row bands, global pixel ids + global ray-index base
+        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
+        band = SH.row_bands(full, world)[rank]
+        plan = D.Plan(ctx, SH.band_desc(full, band))
+    else:
+        # weak scaling: every rank renders its own view of a `world`-view batch.  The views sit 2.5 degrees apart on an arc
+        # centred on the canonical camera, so that per-rank work is (nearly) the same: kernel time depends on the view
+        # direction relative to the grid's x-fastest layout (profiles/README.md: 2.25 ms at 0 deg, 2.83 ms at 90 deg)
+        # and a full orbit would measure that spread, not the scaling.
+        plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank - (world - 1) / 2.0, views=144))
     grid = D.Grid(ctx, sigma, color)
     del sigma, color
     frame = D.Frame(plan)
+    if rows_mode:
+        frame.set_view(None, plan.desc.seed, band.ray_index_base)
     n_rays = plan.n_rays
     g_host = torch.from_numpy(S.hashed_image_grad(n_rays)).pin_memory()
     g_dev = g_host.to(dev, non_blocking=True)
@@ -132,6 +147,7 @@ def run_ours(args):
     grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
     img = frame.image_ptrs()
     pixels = W * W
+    reducer = SH.GradientAllReduce(grad_view) if world > 1 else None
     planes = [torch.as_tensor(CudaArrayView(img.image.data, pixels * 3), device=dev),
               torch.as_tensor(CudaArrayView(img.trans.data, pixels), device=dev),
               torch.as_tensor(CudaArrayView(img.opacity.data, pixels), device=dev),
@@ -142,8 +158,8 @@ def run_ours(args):
     def step_resident():
         frame.forward(grid)
         frame.backward(grid, g_dev.data_ptr(), flags, device=True)
-        if world > 1:
-            dist.all_reduce(grad_view)
+        if reducer is not None:
+            reducer()
 
     # e2e: the same step through the C ABI with HOST buffers (pinned), i.e. what dvren::Renderer
     # Forward/Backward move per step (reference renderer.hpp:50-66): dL/dI host->device; image planes
@@ -162,10 +178,22 @@ def run_ours(args):
                                                      planes_host[2].data_ptr(), planes_host[3].data_ptr(),
                                                      mask_host.data_ptr()))
         D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
-        if world > 1:
-            dist.all_reduce(grad_view)
+        if reducer is not None:
+            reducer()
         D.check("hpx_grid_read_grad", lib.hpx_grid_read_grad(grid.handle, sg_host.data_ptr(), cg_host.data_ptr(),
                                                              cam_host.data_ptr(), A.HP_MEMSPACE_HOST))
+
+    def step_e2e_device_grads():
+        """Same, but the gradient block stays in HBM for a device-side optimiser (hpx_grid_grad_buffer): host
+        traffic is dL/dI in, the five image planes out."""
+        D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
+        D.check("hpx_frame_read", lib.hpx_frame_read(frame.handle, planes_host[0].data_ptr(), planes_host[1].data_ptr(),
+                                                     planes_host[2].data_ptr(), planes_host[3].data_ptr(),
+                                                     mask_host.data_ptr()))
+        D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
+        if reducer is not None:
+            reducer()
+        ctx.synchronize()
 
     def barrier():
         if world > 1:
@@ -195,13 +223,19 @@ def run_ours(args):
     counts = frame.counts()
     samples, live = counts["samples"], counts["live_samples"]
     e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 1))
+    e2e_dev_ms = timed(step_e2e_device_grads, args.steps, 1)
     # kernel-level timing for the roofline lines (same stream, CUDA events, after the runs above)
     fwd_ms = timed(lambda: frame.forward(grid), args.steps, 1)
     bwd_ms = timed(lambda: frame.backward(grid, g_dev.data_ptr(), D.HPX_BACKWARD_GRID, device=True), args.steps, 1)
 
     ms_per_step = total_ms / args.steps
-    value = world * samples / (ms_per_step * 1e-3) / 1e6
-    e2e_value = world * samples / (e2e_ms / args.steps * 1e-3) / 1e6
+    total_samples = samples
+    if world > 1:
+        ts = torch.tensor([samples], dtype=torch.int64, device=dev)
+        dist.all_reduce(ts)
+        total_samples = int(ts.item())
+    value = total_samples / (ms_per_step * 1e-3) / 1e6
+    e2e_value = total_samples / (e2e_ms / args.steps * 1e-3) / 1e6
     peak, peak_src = read_peaks()
     bwd_bytes = BYTES_BWD_PER_SAMPLE * live + 12 * n_rays
     fwd_bytes = BYTES_FWD_PER_SAMPLE * live + 24 * n_rays
@@ -219,15 +253,23 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
                    "rays_per_gpu": n_rays, "samples_per_gpu_step": samples, "live_samples_per_gpu_step": live,
-                   "parallelism": f"ray-tile data parallel x{world}, grid replicated, NCCL all-reduce of gradients" if world > 1 else "single GPU",
+                   "parallelism": (f"one frame in {world} row bands" if rows_mode else f"{world} views (2.5 deg apart), one per GPU") +
+                                  ", grid replicated, one NCCL all-reduce of the packed gradient block per step"
+                                  if world > 1 else "single GPU",
+                   "allreduce_bytes": int(grad_floats * 4) if world > 1 else 0,
                    "l2": "inputs larger than L2 (packed grid %d MB + gradient grid %d MB vs 126 MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(g_host.numel() * 4),
                 "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4 + grad_floats * 4),
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps,
+                "note": "full dvren::Renderer result contract: image planes AND un-interleaved sigma/colour gradient grids "
+                        "copied to host every step (PCIe-bound)",
+                "device_resident_gradients": {
+                    "value": total_samples / (e2e_dev_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_dev_ms / args.steps,
+                    "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4)}},
         "gpu_launches": 2 * args.steps,
         "clocks": clocks,
         "fwd": {"ms": fwd_ms / args.steps, "msamples_s": samples / (fwd_ms / args.steps * 1e-3) / 1e6},
@@ -341,6 +383,8 @@ def main():
     ap.add_argument("--cpu-rows-ref", type=int, default=8, help="rows per thread per step for --impl reference")
     ap.add_argument("--cpu-threads", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharding", default="views", choices=["views", "rows"],
+                    help="N > 1: one view per GPU (weak scaling, default) or one frame cut into row bands (strong)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps

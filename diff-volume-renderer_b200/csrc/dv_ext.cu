@@ -358,7 +358,7 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
                                                                               : kScatterAuto));
     if (flags & HPX_BACKWARD_CAMERA)
         DV_CUDA(launch_camera_adjoint(s, f->d_params, f->h_params, packed_view(*g), d_dL_dI, f->buf.live,
-                                      f->d_cam_partials, g->d_grad + g->voxels * 4));
+                                      f->buf.steps, f->d_cam_partials, g->d_grad + g->voxels * 4));
     return HP_STATUS_SUCCESS;
 }
 

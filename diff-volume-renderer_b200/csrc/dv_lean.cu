@@ -467,16 +467,9 @@ __device__ __forceinline__ void field_gradients(const float4* __restrict__ g, in
     float fx, fy, fz;
     if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return;
     const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
-    float4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int32_t x = (i & 1) ? c.x1 : c.x0, y = (i & 2) ? c.y1 : c.y0, z = (i & 4) ? c.z1 : c.z0;
-        v[i] = __ldg(g + voxel_index(x, y, z, nx, ny));
-    }
-    value.x = trilerp(v[0].x, v[1].x, v[2].x, v[3].x, v[4].x, v[5].x, v[6].x, v[7].x, c.tx, c.ty, c.tz);
-    value.y = trilerp(v[0].y, v[1].y, v[2].y, v[3].y, v[4].y, v[5].y, v[6].y, v[7].y, c.tx, c.ty, c.tz);
-    value.z = trilerp(v[0].z, v[1].z, v[2].z, v[3].z, v[4].z, v[5].z, v[6].z, v[7].z, c.tx, c.ty, c.tz);
-    value.w = trilerp(v[0].w, v[1].w, v[2].w, v[3].w, v[4].w, v[5].w, v[6].w, v[7].w, c.tx, c.ty, c.tz);
+    const Corners k = load_corners(g, c, nx, ny);
+    const float4 v[8] = {k.v000, k.v100, k.v010, k.v110, k.v001, k.v101, k.v011, k.v111};
+    value = trilerp_pairs(k, c.tx, c.ty, c.tz);   // sigma in the reference's operation order: alpha and T match the forward pass
     float s[8], h[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -502,7 +495,7 @@ template <bool kClamp, bool kStratified>
 __global__ void __launch_bounds__(kLeanThreads)
 camera_adjoint_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
                       int32_t nz, const float* __restrict__ dL_dI, const uint32_t* __restrict__ live_counts,
-                      double* __restrict__ partials) {
+                      const float4* __restrict__ steps, double* __restrict__ partials) {
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
     const RoiParams roi = P->roi;
@@ -525,9 +518,16 @@ camera_adjoint_kernel(const FrameParams* __restrict__ P, const float4* __restric
     float T = 1.0f;
     float acc_o[3] = {0.f, 0.f, 0.f}, acc_d[3] = {0.f, 0.f, 0.f};
     float Yo[3] = {0.f, 0.f, 0.f}, Yd[3] = {0.f, 0.f, 0.f};
-    for (uint32_t k = 0; k < live; ++k) {
-        float t, dtv;
-        march_step<kStratified>(mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, k, t, dtv);
+    // samples outside the cube (OOB zero) have sigma = 0 and zero field gradients: T, Y and the sums do not change
+    float t_in, t_out;
+    const WarpRange wr = warp_step_range<!kClamp>(mp, ray, px.inside, t_in, t_out);
+    const uint32_t k_end = min(wr.hi, __reduce_max_sync(0xffffffffu, live));
+    for (uint32_t k = wr.lo; k < k_end; ++k) {
+        if (k >= live) continue;
+        const float4 tab = __ldg(steps + k);
+        if (!kClamp && (tab.x > t_out || tab.x + mp.dt < t_in)) continue;
+        const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, k);
+        const float dtv = tab.z;
         float4 v;
         float gs[3], gh[3];
         field_gradients<kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t, g0,
@@ -719,16 +719,16 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
 
 cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                   const PackedGrid& grid, const float* d_dL_dI, const uint32_t* d_live,
-                                  double* d_partials, float* d_cam16) {
+                                  const float4* d_steps, double* d_partials, float* d_cam16) {
     const uint32_t blocks = tile_blocks(h_params.roi);
     if (blocks == 0 || !grid.linear) return cudaSuccess;  // nearest-neighbour fields have zero spatial gradient
     const bool strat = h_params.march.stratified != 0;
     if (grid.clamp) {
-        if (strat) camera_adjoint_kernel<true, true><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_partials);
-        else       camera_adjoint_kernel<true, false><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_partials);
+        if (strat) camera_adjoint_kernel<true, true><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
+        else       camera_adjoint_kernel<true, false><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
     } else {
-        if (strat) camera_adjoint_kernel<false, true><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_partials);
-        else       camera_adjoint_kernel<false, false><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_partials);
+        if (strat) camera_adjoint_kernel<false, true><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
+        else       camera_adjoint_kernel<false, false><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
     }
     camera_reduce_kernel<<<1, 512, 0, stream>>>(d_partials, blocks, d_cam16);
     return cudaGetLastError();

@@ -53,6 +53,6 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
 // d_partials: [lean_block_count][16] doubles of scratch; d_cam16 is accumulated into.
 cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                   const PackedGrid& grid, const float* d_dL_dI, const uint32_t* d_live,
-                                  double* d_partials, float* d_cam16);
+                                  const float4* d_steps, double* d_partials, float* d_cam16);
 
 }  // namespace dv
