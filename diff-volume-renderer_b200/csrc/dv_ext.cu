@@ -351,14 +351,19 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
     cudaStream_t s = f->ctx->stream;
     if (flags & HPX_BACKWARD_ZERO)
         DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), s));
+    const int want = (flags & HPX_BACKWARD_SCATTER_MERGED)    ? kScatterMerge
+                     : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay
+                                                              : kScatterAuto;
+    float* const d_cam16 = g->d_grad + g->voxels * 4;
+    // grid + camera gradients in ONE pass when the merged kernel runs (it holds the corners the camera adjoint needs)
+    const bool fuse_camera = (flags & HPX_BACKWARD_GRID) && (flags & HPX_BACKWARD_CAMERA) && g->linear &&
+                             resolve_scatter_mode(f->h_params, packed_view(*g), scatter_params(*g), want) == kScatterMerge;
     if (flags & HPX_BACKWARD_GRID)
-        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf,
-                                     (flags & HPX_BACKWARD_SCATTER_MERGED)    ? kScatterMerge
-                                     : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay
-                                                                              : kScatterAuto));
-    if (flags & HPX_BACKWARD_CAMERA)
+        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf, want,
+                                     fuse_camera ? f->d_cam_partials : nullptr, fuse_camera ? d_cam16 : nullptr));
+    if ((flags & HPX_BACKWARD_CAMERA) && !fuse_camera)
         DV_CUDA(launch_camera_adjoint(s, f->d_params, f->h_params, packed_view(*g), d_dL_dI, f->buf.live,
-                                      f->buf.steps, f->d_cam_partials, g->d_grad + g->voxels * 4));
+                                      f->buf.steps, f->d_cam_partials, d_cam16));
     return HP_STATUS_SUCCESS;
 }
 

@@ -52,6 +52,56 @@ __device__ __forceinline__ float4 lean_sample(const float4* __restrict__ g, int3
     return sample_packed<false, kClamp, false>(g, nx, ny, nz, px, py, pz);
 }
 
+// d/d(position) of sigma and of h = g . rgb inside one trilinear cell: differences of the lerped
+// faces, scaled by (n - 1) per axis; an axis on which the position was clamped (OOB clamp) has zero derivative.
+__device__ __forceinline__ void corner_gradients(const Corners& k, const Cell& c, float g0, float g1, float g2, float sx,
+                                                 float sy, float sz, float grad_sigma[3], float grad_h[3]) {
+    const float4 v[8] = {k.v000, k.v100, k.v010, k.v110, k.v001, k.v101, k.v011, k.v111};
+    float s[8], h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s[i] = v[i].w;
+        h[i] = g0 * v[i].x + g1 * v[i].y + g2 * v[i].z;
+    }
+    const float ux = 1.0f - c.tx, uy = 1.0f - c.ty, uz = 1.0f - c.tz;
+    auto partials = [&](const float* f, float* out) {
+        out[0] = ((f[1] - f[0]) * uy + (f[3] - f[2]) * c.ty) * uz + ((f[5] - f[4]) * uy + (f[7] - f[6]) * c.ty) * c.tz;
+        out[1] = ((f[2] - f[0]) * ux + (f[3] - f[1]) * c.tx) * uz + ((f[6] - f[4]) * ux + (f[7] - f[5]) * c.tx) * c.tz;
+        out[2] = ((f[4] - f[0]) * ux + (f[5] - f[1]) * c.tx) * uy + ((f[6] - f[2]) * ux + (f[7] - f[3]) * c.tx) * c.ty;
+    };
+    partials(s, grad_sigma);
+    partials(h, grad_h);
+    grad_sigma[0] *= sx; grad_sigma[1] *= sy; grad_sigma[2] *= sz;
+    grad_h[0] *= sx; grad_h[1] *= sy; grad_h[2] *= sz;
+}
+
+// Sample + scatter cell + (optionally) the field gradients the camera adjoint needs, from ONE set of corner loads.
+template <bool kClamp, bool kGradients>
+__device__ __forceinline__ float4 sample_cell_gradients(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+                                                        float px, float py, float pz, float g0, float g1, float g2,
+                                                        float4& cell, float grad_sigma[3], float grad_h[3]) {
+    if (kGradients) {
+        grad_sigma[0] = grad_sigma[1] = grad_sigma[2] = 0.f;
+        grad_h[0] = grad_h[1] = grad_h[2] = 0.f;
+    }
+    const bool ox = px < 0.0f || px > 1.0f, oy = py < 0.0f || py > 1.0f, oz = pz < 0.0f || pz > 1.0f;
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) {
+        cell = make_float4(__uint_as_float(0xffffffffu), 0.f, 0.f, 0.f);
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
+    cell = make_float4(__uint_as_float(static_cast<uint32_t>(c.x0) | (static_cast<uint32_t>(c.y0) << 10) |
+                                       (static_cast<uint32_t>(c.z0) << 20)),
+                       c.tx, c.ty, c.tz);
+    const Corners k = load_corners(g, c, nx, ny);
+    if (kGradients)
+        corner_gradients(k, c, g0, g1, g2, (kClamp && ox) ? 0.f : static_cast<float>(nx - 1),
+                         (kClamp && oy) ? 0.f : static_cast<float>(ny - 1), (kClamp && oz) ? 0.f : static_cast<float>(nz - 1),
+                         grad_sigma, grad_h);
+    return trilerp_pairs(k, c.tx, c.ty, c.tz);
+}
+
 // Warp-wide range of steps that can touch the unit cube (OOB-zero fields only): [lo, hi), lo aligned down to a
 // segment start.  Forward and backward kernels evaluate exactly this function, so they agree on the range.
 struct WarpRange { uint32_t lo, hi; };
@@ -252,9 +302,59 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
 constexpr uint32_t kNoCell = 0xffffffffu;
 constexpr int kStashRow = kLeanThreads + kLeanThreads / 16;   // skewed by one float4 per 16 threads: phase B reads conflict-free
 
+// Chain rule of one ray (d = v / |v|, v = R q) followed by a deterministic block reduction:
+// warp shuffles, then the warps summed in order; one 16-double partial per CTA.
+__device__ __forceinline__ void camera_block_reduce(const CameraParams& cam, const Ray& ray, const RayAux& ra, bool inside,
+                                                    const float acc_o[3], const float acc_d[3],
+                                                    double* __restrict__ partials) {
+    double out[16];
+    {
+        const double d[3] = {ray.dx, ray.dy, ray.dz};
+        const double dd = d[0] * acc_d[0] + d[1] * acc_d[1] + d[2] * acc_d[2];
+        double dv[3];
+        for (int i = 0; i < 3; ++i) dv[i] = (static_cast<double>(acc_d[i]) - d[i] * dd) * static_cast<double>(ra.inv_len);
+        const double q[3] = {ra.qx, ra.qy, ra.qz};
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) out[4 * i + j] = dv[i] * q[j];
+            out[4 * i + 3] = acc_o[i];
+        }
+        if (cam.ortho) {
+            out[12] = out[13] = out[14] = out[15] = 0.0;
+        } else {
+            const double dq0 = cam.r00 * dv[0] + cam.r10 * dv[1] + cam.r20 * dv[2];
+            const double dq1 = cam.r01 * dv[0] + cam.r11 * dv[1] + cam.r21 * dv[2];
+            out[12] = -q[0] / cam.fx * dq0;
+            out[13] = -q[1] / cam.fy * dq1;
+            out[14] = -dq0 / cam.fx;
+            out[15] = -dq1 / cam.fy;
+        }
+        if (!inside) {
+            for (int i = 0; i < 16; ++i) out[i] = 0.0;
+        }
+    }
+    __shared__ double smem[kLeanThreads / 32][16];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        double x = out[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0) smem[warp][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        double x = 0.0;
+        for (int w = 0; w < kLeanThreads / 32; ++w) x += smem[w][threadIdx.x];
+        partials[static_cast<size_t>(blockIdx.x) * 16 + threadIdx.x] = x;
+    }
+}
+
+template <bool kCamera>
 struct MergeStash {
     float4 a[kSegment][kStashRow];   // phase A: {alpha, T_prev, g.c, t};  phase A': {g0 w, g1 w, g2 w, d sigma}
     float4 c[kSegment][kStashRow];   // scatter cell {x0 | y0 << 10 | z0 << 20, tx, ty, tz}; key 0xffffffff = nothing to scatter
+    float s[kCamera ? 3 : 1][kCamera ? kSegment : 1][kCamera ? kStashRow : 1];   // camera adjoint only: d sigma / d position
+                                                                                  // (3 planes: 48 KB of static shared memory in all)
 };
 
 __device__ __forceinline__ uint32_t stash_slot(uint32_t tid) { return tid + (tid >> 4); }
@@ -298,11 +398,15 @@ __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key
 #ifndef DV_MERGE_MIN_BLOCKS
 #define DV_MERGE_MIN_BLOCKS 5
 #endif
-template <bool kClamp, bool kStratified, bool kUnitBox>
-__global__ void __launch_bounds__(kLeanThreads, DV_MERGE_MIN_BLOCKS)
+// kCamera: also accumulate d L / d (ray origin, ray direction) = sum_s (d sigma_s grad sigma(x_s) + w_s grad (g . rgb)(x_s)) {1, t_s}
+// from the corners phase A has in registers anyway, and reduce it to the camera parameters at the end
+// (replaces a separate camera_adjoint_kernel pass over every sample).
+template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera>
+__global__ void __launch_bounds__(kLeanThreads, kCamera ? 4 : DV_MERGE_MIN_BLOCKS)
 lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
-                           int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st) {
-    __shared__ MergeStash stash;
+                           int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
+                           double* __restrict__ cam_partials) {
+    __shared__ MergeStash<kCamera> stash;
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
     const RoiParams roi = P->roi;
@@ -311,6 +415,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
 
     const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
     const uint64_t ray_index = mp.ray_index_base + px.ray;
+    float cam_o[3] = {0.f, 0.f, 0.f}, cam_d[3] = {0.f, 0.f, 0.f};
 
     uint32_t live = 0;
     float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -350,8 +455,9 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                 }
                 const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
                 float4 cell;
-                const float4 v = sample_packed_lean_cell<kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
-                                                                 ray.oz + ray.dz * t, cell);
+                float gs[3], gh[3];
+                const float4 v = sample_cell_gradients<kClamp, kCamera>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                                        ray.oz + ray.dz * t, g0, g1, g2, cell, gs, gh);
                 if (kUnitBox) {
                     stash.c[j][slot] = cell;
                     if (!kClamp && __float_as_uint(cell.x) == kNoCell) {   // outside the cube: sigma = rgb = 0, adj_T unchanged, no scatter
@@ -361,6 +467,17 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                 }
                 const float a = alpha_of(v.w, tab.z);
                 stash.a[j][slot] = make_float4(a, T, g0 * v.x + g1 * v.y + g2 * v.z, t);
+                if (kCamera) {
+                    const float w = T * a;   // the colour part needs nothing from later samples
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        cam_o[i] += w * gh[i];
+                        cam_d[i] += t * (w * gh[i]);
+                    }
+                    stash.s[0][j][slot] = gs[0];
+                    stash.s[1][j][slot] = gs[1];
+                    stash.s[2][j][slot] = gs[2];
+                }
                 T = T * fmaxf(1.0f - a, 0.0f);
             }
         }
@@ -377,6 +494,15 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                     float dsigma;
                     adjoint_sample(s.z, a, Tp, dtv, adj_T, dsigma);
                     stash.a[j][slot] = make_float4(g0 * w, g1 * w, g2 * w, dsigma);
+                    if (kCamera) {
+                        const float t = s.w;
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+                            const float x = dsigma * stash.s[i][j][slot];
+                            cam_o[i] += x;
+                            cam_d[i] += t * x;
+                        }
+                    }
                     if (!kUnitBox) {
                         const float t = s.w;
                         stash.c[j][slot] = scatter_cell(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t);
@@ -451,6 +577,11 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
         }
         __syncwarp();
     }
+    if (kCamera) {
+        RayAux ra;
+        make_ray(cam, roi.x + px.lx, roi.y + px.ly, &ra);
+        camera_block_reduce(cam, ray, ra, px.inside, cam_o, cam_d, cam_partials);
+    }
 }
 #undef DV_CE
 
@@ -468,27 +599,10 @@ __device__ __forceinline__ void field_gradients(const float4* __restrict__ g, in
     if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return;
     const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
     const Corners k = load_corners(g, c, nx, ny);
-    const float4 v[8] = {k.v000, k.v100, k.v010, k.v110, k.v001, k.v101, k.v011, k.v111};
     value = trilerp_pairs(k, c.tx, c.ty, c.tz);   // sigma in the reference's operation order: alpha and T match the forward pass
-    float s[8], h[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        s[i] = v[i].w;
-        h[i] = g0 * v[i].x + g1 * v[i].y + g2 * v[i].z;
-    }
-    const float ux = 1.0f - c.tx, uy = 1.0f - c.ty, uz = 1.0f - c.tz;
-    auto partials = [&](const float* f, float* out) {
-        out[0] = ((f[1] - f[0]) * uy + (f[3] - f[2]) * c.ty) * uz + ((f[5] - f[4]) * uy + (f[7] - f[6]) * c.ty) * c.tz;
-        out[1] = ((f[2] - f[0]) * ux + (f[3] - f[1]) * c.tx) * uz + ((f[6] - f[4]) * ux + (f[7] - f[5]) * c.tx) * c.tz;
-        out[2] = ((f[4] - f[0]) * ux + (f[5] - f[1]) * c.tx) * uy + ((f[6] - f[2]) * ux + (f[7] - f[3]) * c.tx) * c.ty;
-    };
-    partials(s, grad_sigma);
-    partials(h, grad_h);
-    const float sx = (kClamp && ox) ? 0.f : static_cast<float>(nx - 1);
-    const float sy = (kClamp && oy) ? 0.f : static_cast<float>(ny - 1);
-    const float sz = (kClamp && oz) ? 0.f : static_cast<float>(nz - 1);
-    grad_sigma[0] *= sx; grad_sigma[1] *= sy; grad_sigma[2] *= sz;
-    grad_h[0] *= sx; grad_h[1] *= sy; grad_h[2] *= sz;
+    corner_gradients(k, c, g0, g1, g2, (kClamp && ox) ? 0.f : static_cast<float>(nx - 1),
+                     (kClamp && oy) ? 0.f : static_cast<float>(ny - 1), (kClamp && oz) ? 0.f : static_cast<float>(nz - 1),
+                     grad_sigma, grad_h);
 }
 
 template <bool kClamp, bool kStratified>
@@ -547,48 +661,7 @@ camera_adjoint_kernel(const FrameParams* __restrict__ P, const float4* __restric
         }
         T = T * fmaxf(1.0f - a, 0.0f);
     }
-    // chain rule: d = v / |v|, v = R q   
-    double out[16];
-    {
-        const double d[3] = {ray.dx, ray.dy, ray.dz};
-        const double dd = d[0] * acc_d[0] + d[1] * acc_d[1] + d[2] * acc_d[2];
-        double dv[3];
-        for (int i = 0; i < 3; ++i) dv[i] = (static_cast<double>(acc_d[i]) - d[i] * dd) * static_cast<double>(ra.inv_len);
-        const double q[3] = {ra.qx, ra.qy, ra.qz};
-        for (int i = 0; i < 3; ++i) {
-            for (int j = 0; j < 3; ++j) out[4 * i + j] = dv[i] * q[j];
-            out[4 * i + 3] = acc_o[i];
-        }
-        if (cam.ortho) {
-            out[12] = out[13] = out[14] = out[15] = 0.0;
-        } else {
-            const double dq0 = cam.r00 * dv[0] + cam.r10 * dv[1] + cam.r20 * dv[2];
-            const double dq1 = cam.r01 * dv[0] + cam.r11 * dv[1] + cam.r21 * dv[2];
-            out[12] = -q[0] / cam.fx * dq0;
-            out[13] = -q[1] / cam.fy * dq1;
-            out[14] = -dq0 / cam.fx;
-            out[15] = -dq1 / cam.fy;
-        }
-        if (!px.inside) {
-            for (int i = 0; i < 16; ++i) out[i] = 0.0;
-        }
-    }
-    // deterministic block reduction: warp shuffles, then warp 0 sums the warps in order
-    __shared__ double smem[kLeanThreads / 32][16];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        double x = out[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) smem[warp][i] = x;
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-        double x = 0.0;
-        for (int w = 0; w < kLeanThreads / 32; ++w) x += smem[w][threadIdx.x];
-        partials[static_cast<size_t>(blockIdx.x) * 16 + threadIdx.x] = x;
-    }
+    camera_block_reduce(cam, ray, ra, px.inside, acc_o, acc_d, partials);
 }
 
 __global__ void camera_reduce_kernel(const double* __restrict__ partials, uint32_t blocks, float* __restrict__ cam16) {
@@ -692,14 +765,21 @@ int resolve_scatter_mode(const FrameParams& h_params, const PackedGrid& grid, co
 
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
-                                 const LeanBuffers& state, int scatter_mode) {
+                                 const LeanBuffers& state, int scatter_mode, double* cam_partials, float* d_cam16) {
     const uint32_t blocks = tile_blocks(h_params.roi);
     if (blocks == 0) return cudaSuccess;
     const bool strat = h_params.march.stratified != 0;
     const bool merge = resolve_scatter_mode(h_params, grid, sp, scatter_mode) == kScatterMerge;
     if (merge) {
-#define DV_MERGE(C, S, U) lean_backward_merge_kernel<C, S, U><<<blocks, kLeanThreads, 0, stream>>>( \
-        d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state)
+#define DV_MERGE(C, S, U)                                                                                              \
+    do {                                                                                                               \
+        if (cam_partials != nullptr)                                                                                   \
+            lean_backward_merge_kernel<C, S, U, true><<<blocks, kLeanThreads, 0, stream>>>(                            \
+                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials);                   \
+        else                                                                                                           \
+            lean_backward_merge_kernel<C, S, U, false><<<blocks, kLeanThreads, 0, stream>>>(                           \
+                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, nullptr);                        \
+    } while (0)
         const bool unit = sp.unit_bbox != 0;
         if (grid.clamp) {
             if (strat) { if (unit) DV_MERGE(true, true, true); else DV_MERGE(true, true, false); }
@@ -709,8 +789,10 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
             else       { if (unit) DV_MERGE(false, false, true); else DV_MERGE(false, false, false); }
         }
 #undef DV_MERGE
+        if (cam_partials != nullptr) camera_reduce_kernel<<<1, 512, 0, stream>>>(cam_partials, blocks, d_cam16);
         return cudaGetLastError();
     }
+    if (cam_partials != nullptr) return cudaErrorInvalidValue;   // the fused camera adjoint exists in the merged kernel only
     DV_DISPATCH3(lean_backward_kernel, grid.linear, grid.clamp, strat,
                  <<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI,
                                                       state));

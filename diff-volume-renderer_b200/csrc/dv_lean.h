@@ -48,7 +48,10 @@ int resolve_scatter_mode(const FrameParams& h_params, const PackedGrid& grid, co
 
 cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                  const PackedGrid& grid, const ScatterParams& sp, const float* d_dL_dI,
-                                 const LeanBuffers& state, int scatter_mode = kScatterAuto);
+                                 const LeanBuffers& state, int scatter_mode = kScatterAuto,
+                                 double* cam_partials = nullptr, float* d_cam16 = nullptr);
+// cam_partials != nullptr: the MERGED kernel also evaluates the camera adjoint from the corners it has loaded anyway and
+// accumulates the 16 camera gradients into d_cam16 (only valid when resolve_scatter_mode() == kScatterMerge).
 
 // d_partials: [lean_block_count][16] doubles of scratch; d_cam16 is accumulated into.
 cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,

@@ -204,8 +204,12 @@ def test_lean_forward_is_deterministic_and_graph_replay_matches(ctx):
     frame.close(); grid.close(); plan.close()
 
 
+@pytest.mark.parametrize("scatter", [0, D.HPX_BACKWARD_SCATTER_PER_RAY, D.HPX_BACKWARD_SCATTER_MERGED],
+                         ids=["auto", "separate_kernel", "fused_in_merged_backward"])
 @pytest.mark.parametrize("strat,oob", [(False, A.HP_OOB_ZERO), (True, A.HP_OOB_ZERO), (True, A.HP_OOB_CLAMP)])
-def test_camera_gradient_matches_pinned_adjoint(ctx, strat, oob):
+def test_camera_gradient_matches_pinned_adjoint(ctx, strat, oob, scatter):
+    """Both evaluations of the camera adjoint -- the stand-alone forward-order kernel and the one fused into the
+    merged backward (reverse order, from the corners that kernel has loaded anyway) -- against the oracle."""
     sig, col = S.smooth_volume(40)
     W = Hh = 36
     desc = S.bench_plan(W, Hh, 128, stratified=strat, view=1, views=9)
@@ -214,7 +218,7 @@ def test_camera_gradient_matches_pinned_adjoint(ctx, strat, oob):
     dl = S.hashed_image_grad(W * Hh) + np.float32(0.25)
     ref = O.camera_grad(odesc, gs, gc, dl)
     got = run_lean(ctx, desc, sig, col, 1, oob, None, None, dl,
-                   flags=D.HPX_BACKWARD_CAMERA | D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO)
+                   flags=D.HPX_BACKWARD_CAMERA | D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | scatter)
     cam = got["camera_grad"].astype(np.float64)
     scale = np.abs(ref[:12]).max()
     assert np.all(np.abs(cam[:12] - ref[:12]) <= 1e-4 * np.maximum(np.abs(ref[:12]), 0.05 * scale)), (cam[:12], ref[:12])
