@@ -33,6 +33,9 @@ CONFIGS = {
                workload="BASELINE configs[1]: 256^3 dense grid, 1024x1024, stratified, 512 steps, fused fwd + sigma/color bwd"),
     "c3": dict(grid=512, width=2048, steps=1024, stratified=False,
                workload="BASELINE configs[2]: 512^3 dense grid, 2048x2048, fixed, 1024 steps, fwd+bwd"),
+    "c4": dict(grid=256, width=800, steps=512, stratified=True, views=64,
+               workload="BASELINE configs[3]: 64 views at 800x800 over a 256^3 grid, stratified, 512 steps, grid + camera "
+                        "gradients, one captured CUDA graph replayed per view"),
 }
 METRIC = "Msamples/s fwd+bwd (fused forward + backward adjoint to the dense sigma/color grid)"
 UNIT = "Msamples/s"
@@ -297,6 +300,105 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_view_batch(args):
+    """Config 4: a batch of views through ONE captured CUDA graph (forward + backward to the grid AND the camera);
+    the view changes between replays through the frame's device parameter block.  N > 1: views split across ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import dvren_b200 as D
+    import sharding as SH
+    import synth as S
+
+    cfg = CONFIGS[args.config]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    n, W, steps, views = cfg["grid"], cfg["width"], cfg["steps"], cfg["views"]
+    sigma, color = S.hashed_volume(n, "thin")
+    ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
+    my_views = SH.views_of_rank(views, world, rank)
+    descs = [S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=v, views=views) for v in my_views]
+    plan = D.Plan(ctx, descs[0])
+    grid = D.Grid(ctx, sigma, color)
+    frame = D.Frame(plan)
+    g_host = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).pin_memory()
+    g_frame = torch.as_tensor(CudaArrayView(frame.grad_input_ptr(), plan.n_rays * 3), device=dev)
+    g_frame.copy_(g_host.reshape(-1), non_blocking=True)
+    grad_ptr, grad_floats = grid.grad_buffer()
+    grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
+    reducer = SH.GradientAllReduce(grad_view) if world > 1 else None
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_CAMERA
+    frame.capture(grid, flags)
+    cams = [d.camera for d in descs]
+    cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
+
+    def step():
+        grid.zero_grad()
+        for v, cam in zip(my_views, cams):
+            frame.set_view(cam, 42 + v, 0)
+            frame.replay()
+        if reducer is not None:
+            reducer()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(args.steps):
+        step()
+    b.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    samples = views * plan.n_rays * steps
+    # e2e: per step the cameras go in (tiny) and the camera gradients + the last image come out; the grid gradient stays in HBM
+    a.record(stream)
+    for _ in range(args.steps):
+        step()
+        cam_host.copy_(grad_view[-16:], non_blocking=True)
+        frame.read()
+    b.record(stream)
+    barrier()
+    e2e_ms = a.elapsed_time(b) / args.steps
+    line = {"metric": METRIC + " + camera adjoint", "value": samples / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "views": views, "views_per_gpu": len(my_views),
+                       "volume": "hashed thin (sigma = 2u)", "samples_per_step": samples,
+                       "backward_kernel": "lean_backward_merge_kernel<..., camera>" if frame.scatter_mode(grid, flags) == "merged"
+                       else "lean_backward_kernel + camera_adjoint_kernel",
+                       "l2": "inputs larger than L2 (grid 256 MB + gradient 256 MB + checkpoints 164 MB)"},
+            "e2e": {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": len(my_views) * 128, "d2h_bytes_per_step": 64 + W * W * 28},
+            "gpu_launches": 4 * len(my_views) * args.steps, "clocks": clocks,
+            "ms_per_view": ms_per_step / len(my_views)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    frame.close(); grid.close(); plan.close(); ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def cpu_baseline(cfg, rows: int, threads: int):
     """The reference's own CPU implementation (oracle/_ref, unmodified, via dvren::Renderer) -- or the
     oracle port when that library is absent -- timed on a band of `rows` image rows per thread."""
@@ -390,6 +492,8 @@ def main():
         args.warmup = 3   # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
         run_reference(args)
+    elif "views" in CONFIGS[args.config]:
+        run_view_batch(args)
     else:
         run_ours(args)
 

@@ -696,6 +696,15 @@ uint32_t tile_blocks(const RoiParams& roi) {
 
 uint32_t lean_block_count(const RoiParams& roi) { return tile_blocks(roi); }
 
+namespace {
+__global__ void upload_params_kernel(FrameParams* dst, const FrameParams src) { *dst = src; }
+}  // namespace
+
+cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params) {
+    upload_params_kernel<<<1, 1, 0, stream>>>(d_params, h_params);
+    return cudaGetLastError();
+}
+
 // Host restatement of the ray-independent part of the marching loop (samp_cpu.cpp:227-241) and of the depth
 // cursor (int_cpu.cpp:170,211).  volatile forces every intermediate to be rounded to float; the host objects are
 // built with -ffp-contract=off, so the values equal what the kernels used to compute per step.

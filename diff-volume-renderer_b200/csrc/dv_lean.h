@@ -37,6 +37,9 @@ void build_step_table(const MarchParams& mp, float4* table);
 
 uint32_t lean_block_count(const RoiParams& roi);
 
+// Writes the frame's parameter block; the values travel as kernel arguments (no staging buffer, no host sync).
+cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params);
+
 cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                                 const PackedGrid& grid, const LeanBuffers& out, bool fill_background);
 
