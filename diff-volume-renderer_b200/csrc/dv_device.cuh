@@ -508,7 +508,24 @@ __device__ __forceinline__ void red_add4(float4* addr, float4 v) {
                  : "memory");
 }
 
-__device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px, float py, float pz, float4 g) {
+// One corner contribution: a 16-byte float red, or four 64-bit integer reds of the value in units of the quantum.
+__device__ __forceinline__ void scatter_add(const ScatterParams& sp, uint32_t voxel, float4 v, float inv_q) {
+    if (sp.fixed != nullptr) {
+        unsigned long long* p = sp.fixed + 4ull * voxel;
+        atomicAdd(p + 0, static_cast<unsigned long long>(__float2ll_rn(v.x * inv_q)));
+        atomicAdd(p + 1, static_cast<unsigned long long>(__float2ll_rn(v.y * inv_q)));
+        atomicAdd(p + 2, static_cast<unsigned long long>(__float2ll_rn(v.z * inv_q)));
+        atomicAdd(p + 3, static_cast<unsigned long long>(__float2ll_rn(v.w * inv_q)));
+    } else {
+        red_add4(sp.grad + voxel, v);
+    }
+}
+__device__ __forceinline__ float scatter_inv_quantum(const ScatterParams& sp) {
+    return sp.fixed != nullptr ? __ldg(sp.fixed_meta + 2) : 1.0f;
+}
+
+__device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px, float py, float pz, float4 g,
+                                               float inv_q = 1.0f) {
     const float ex = sp.bmax[0] - sp.bmin[0], ey = sp.bmax[1] - sp.bmin[1], ez = sp.bmax[2] - sp.bmin[2];
     float lx = ex != 0.0f ? (px - sp.bmin[0]) / ex : 0.0f;
     float ly = ey != 0.0f ? (py - sp.bmin[1]) / ey : 0.0f;
@@ -529,7 +546,7 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
         const int32_t iy = static_cast<int32_t>(roundf(gy));
         const int32_t iz = static_cast<int32_t>(roundf(gz));
         if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
-        red_add4(sp.grad + voxel_index32(ix, iy, iz, nx, ny), g);
+        scatter_add(sp, voxel_index32(ix, iy, iz, nx, ny), g, inv_q);
         return;
     }
     const Cell c = make_cell(gx, gy, gz, nx, ny, nz);
@@ -545,8 +562,7 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
                 const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
                 if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
                 const float w = wx[dx] * wy[dy] * wz[dz];
-                red_add4(sp.grad + voxel_index32(ix, iy, iz, nx, ny),
-                         make_float4(g.x * w, g.y * w, g.z * w, g.w * w));
+                scatter_add(sp, voxel_index32(ix, iy, iz, nx, ny), make_float4(g.x * w, g.y * w, g.z * w, g.w * w), inv_q);
             }
 }
 

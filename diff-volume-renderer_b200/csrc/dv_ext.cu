@@ -96,6 +96,7 @@ HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp
 }
 
 HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* color, hp_memspace memspace) {
+    if (g != nullptr) g->value_max_stale = true;
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (sigma == nullptr && color == nullptr) return HP_STATUS_SUCCESS;
     DV_TRY(ensure_device(g->ctx));
@@ -233,6 +234,8 @@ HP_API void hpx_grid_release(hpx_grid* g) {
     if (g->ctx != nullptr && g->ctx->ready) cudaSetDevice(g->ctx->device);
     cudaFree(g->d_values);
     cudaFree(g->d_grad);
+    cudaFree(g->d_fixed);
+    cudaFree(g->d_fixed_meta);
     cudaFree(g->d_unpacked);
     delete g;
 }
@@ -357,9 +360,33 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
     // grid + camera gradients in ONE pass when the merged kernel runs (it holds the corners the camera adjoint needs)
     const bool fuse_camera = (flags & HPX_BACKWARD_GRID) && (flags & HPX_BACKWARD_CAMERA) && g->linear &&
                              resolve_scatter_mode(f->h_params, packed_view(*g), scatter_params(*g), want) == kScatterMerge;
-    if (flags & HPX_BACKWARD_GRID)
-        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), scatter_params(*g), d_dL_dI, f->buf, want,
+    if (flags & HPX_BACKWARD_GRID) {
+        ScatterParams sp = scatter_params(*g);
+        const bool deterministic = (flags & HPX_BACKWARD_DETERMINISTIC) != 0;
+        if (deterministic) {
+            if (g->d_fixed == nullptr) {
+                DV_CUDA(cudaMalloc(&g->d_fixed, std::max<size_t>(g->voxels, 1) * 4 * sizeof(unsigned long long)));
+                DV_CUDA(cudaMemsetAsync(g->d_fixed, 0, g->voxels * 4 * sizeof(unsigned long long), s));
+                DV_CUDA(cudaMalloc(&g->d_fixed_meta, 4 * sizeof(float)));
+                g->value_max_stale = true;
+            }
+            uint32_t* meta_bits = reinterpret_cast<uint32_t*>(g->d_fixed_meta);
+            if (g->value_max_stale) {
+                DV_CUDA(cudaMemsetAsync(meta_bits, 0, sizeof(uint32_t), s));
+                DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits));
+                g->value_max_stale = false;
+            }
+            DV_CUDA(cudaMemsetAsync(meta_bits + 1, 0, sizeof(uint32_t), s));
+            DV_CUDA(launch_abs_max(s, d_dL_dI, f->rays * 3, meta_bits + 1));
+            DV_CUDA(launch_fixed_scale(s, g->d_fixed_meta, f->h_params.march.dt));
+            sp.fixed = g->d_fixed;
+            sp.fixed_meta = g->d_fixed_meta;
+        }
+        DV_CUDA(launch_lean_backward(s, f->d_params, f->h_params, packed_view(*g), sp, d_dL_dI, f->buf, want,
                                      fuse_camera ? f->d_cam_partials : nullptr, fuse_camera ? d_cam16 : nullptr));
+        if (deterministic)
+            DV_CUDA(launch_fixed_to_float(s, g->d_fixed, reinterpret_cast<float4*>(g->d_grad), g->voxels, g->d_fixed_meta));
+    }
     if ((flags & HPX_BACKWARD_CAMERA) && !fuse_camera)
         DV_CUDA(launch_camera_adjoint(s, f->d_params, f->h_params, packed_view(*g), d_dL_dI, f->buf.live,
                                       f->buf.steps, f->d_cam_partials, d_cam16));

@@ -20,6 +20,8 @@
 // Compiled with -fmad=false: see dv_device.cuh.
 #include "dv_lean.h"
 
+#include <algorithm>
+
 #include "dv_device.cuh"
 
 namespace dv {
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kLeanThreads)
 lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
                      int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st) {
     __shared__ SegmentStash stash;
+    const float inv_q = scatter_inv_quantum(sp);
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
     const RoiParams roi = P->roi;
@@ -280,7 +283,7 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
             adjoint_sample(stash.dot[j][tid], a, Tp, stash.dt[j][tid], adj_T, dsigma);
             const float t = stash.t[j][tid];
             scatter_sample(sp, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t,
-                           make_float4(g0 * w, g1 * w, g2 * w, dsigma));
+                           make_float4(g0 * w, g1 * w, g2 * w, dsigma), inv_q);
         }
     }
 }
@@ -381,15 +384,15 @@ __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px
 // 8 corner accumulators {d r, d g, d b, d sigma}: corner k = dx + 2 dy + 4 dz.  Kept as float4 so that the register
 // allocator can place each one in an aligned quad: FFMA2 updates its (x,y) / (z,w) halves in place and
 // red.global.add.v4.f32 consumes the quad without moves.
-__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8]) {
+__device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8], float inv_q) {
     const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
     const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
     const uint32_t r00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), r10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
     const uint32_t r01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), r11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
-    red_add4(sp.grad + (r00 + x0), acc[0]); red_add4(sp.grad + (r00 + x1), acc[1]);
-    red_add4(sp.grad + (r10 + x0), acc[2]); red_add4(sp.grad + (r10 + x1), acc[3]);
-    red_add4(sp.grad + (r01 + x0), acc[4]); red_add4(sp.grad + (r01 + x1), acc[5]);
-    red_add4(sp.grad + (r11 + x0), acc[6]); red_add4(sp.grad + (r11 + x1), acc[7]);
+    scatter_add(sp, r00 + x0, acc[0], inv_q); scatter_add(sp, r00 + x1, acc[1], inv_q);
+    scatter_add(sp, r10 + x0, acc[2], inv_q); scatter_add(sp, r10 + x1, acc[3], inv_q);
+    scatter_add(sp, r01 + x0, acc[4], inv_q); scatter_add(sp, r01 + x1, acc[5], inv_q);
+    scatter_add(sp, r11 + x0, acc[6], inv_q); scatter_add(sp, r11 + x1, acc[7], inv_q);
 }
 
 // compare-exchange of the 19-comparator sorting network for 8 keys
@@ -412,6 +415,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
     const RoiParams roi = P->roi;
     const TilePixel px = tile_pixel(roi);
     const uint32_t tid = threadIdx.x, slot = stash_slot(tid);
+    const float inv_q = scatter_inv_quantum(sp);
 
     const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
     const uint64_t ray_index = mp.ray_index_base + px.ray;
@@ -548,7 +552,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                 }
                 const bool fresh = key != cur;
                 if (fresh) {
-                    if (cur != kNoCell) flush_cell(sp, cur, acc);
+                    if (cur != kNoCell) flush_cell(sp, cur, acc, inv_q);
                     cur = key;
                 }
                 if (key != kNoCell) {
@@ -693,6 +697,70 @@ uint32_t tile_blocks(const RoiParams& roi) {
 }
 
 }  // namespace
+
+// ---- deterministic (fixed-point) gradient accumulation -----------------------------------------------------
+namespace {
+__global__ void abs_max_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float a = fabsf(v[i]);
+        if (a < CUDART_INF_F) m = fmaxf(m, a);   // ignore inf / nan: they poison the gradient either way
+    }
+    const uint32_t bits = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like their bit patterns
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
+}
+
+// quantum = 2^e with 2^40 quanta per bound B on one contribution (B = 8 max|dL/dI| max(1, max|rgb|) max(1, dt)):
+// int64 then holds 2^23 contributions of the largest possible size per voxel.
+__global__ void fixed_scale_kernel(float* __restrict__ meta, float dt) {
+    const float gmax = __uint_as_float(reinterpret_cast<const uint32_t*>(meta)[1]);
+    const float cmax = __uint_as_float(reinterpret_cast<const uint32_t*>(meta)[0]);
+    const float bound = 8.0f * gmax * fmaxf(1.0f, cmax) * fmaxf(1.0f, dt);
+    int e = 0;
+    if (bound > 0.0f && bound < CUDART_INF_F) e = ilogbf(bound) + 1 - 40;
+    e = max(-100, min(100, e));
+    meta[2] = ldexpf(1.0f, -e);
+    meta[3] = ldexpf(1.0f, e);
+}
+
+__global__ void fixed_to_float_kernel(unsigned long long* __restrict__ fixed, float4* __restrict__ grad, size_t voxels,
+                                      const float* __restrict__ meta) {
+    const float q = meta[3];
+    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < voxels;
+         v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(fixed + 4 * v);
+        const ulonglong2 a = p[0], b = p[1];
+        if ((a.x | a.y | b.x | b.y) == 0ull) continue;
+        float4 g = grad[v];
+        g.x += static_cast<float>(static_cast<long long>(a.x)) * q;
+        g.y += static_cast<float>(static_cast<long long>(a.y)) * q;
+        g.z += static_cast<float>(static_cast<long long>(b.x)) * q;
+        g.w += static_cast<float>(static_cast<long long>(b.y)) * q;
+        grad[v] = g;
+        p[0] = make_ulonglong2(0ull, 0ull);   // leave the integer grid clean for the next backward
+        p[1] = make_ulonglong2(0ull, 0ull);
+    }
+}
+}  // namespace
+
+cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits) {
+    if (n == 0) return cudaSuccess;
+    abs_max_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(d_values, n, d_out_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_scale(cudaStream_t stream, float* d_meta, float dt) {
+    fixed_scale_kernel<<<1, 1, 0, stream>>>(d_meta, dt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fixed, float4* d_grad, size_t voxels,
+                                  const float* d_meta) {
+    if (voxels == 0) return cudaSuccess;
+    fixed_to_float_kernel<<<148 * 8, 256, 0, stream>>>(d_fixed, d_grad, voxels, d_meta);
+    return cudaGetLastError();
+}
 
 uint32_t lean_block_count(const RoiParams& roi) { return tile_blocks(roi); }
 

@@ -37,6 +37,13 @@ void build_step_table(const MarchParams& mp, float4* table);
 
 uint32_t lean_block_count(const RoiParams& roi);
 
+// Deterministic (fixed-point) gradient accumulation, see ScatterParams::fixed.  meta = {bits of max|rgb|, bits of
+// max|dL/dI|, 1 / quantum, quantum}.
+cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits);
+cudaError_t launch_fixed_scale(cudaStream_t stream, float* d_meta, float dt);
+cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fixed, float4* d_grad, size_t voxels,
+                                  const float* d_meta);
+
 // Writes the frame's parameter block; the values travel as kernel arguments (no staging buffer, no host sync).
 cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params);
 

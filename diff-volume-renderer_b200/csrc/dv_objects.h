@@ -73,6 +73,10 @@ struct hpx_grid {
     float* d_unpacked = nullptr;  // [V + 3V] staging for un-interleaved read-back (lazily allocated)
     size_t unpacked_voxels = 0;
     size_t voxels = 0;
+    // deterministic backward (HPX_BACKWARD_DETERMINISTIC): 64-bit fixed-point shadow of the gradient grid, lazily allocated
+    unsigned long long* d_fixed = nullptr;   // [4V], all zero between backward passes
+    float* d_fixed_meta = nullptr;           // {bits max|grid value|, bits max|dL/dI|, 1/quantum, quantum}
+    bool value_max_stale = true;
 };
 
 struct hpx_frame {

@@ -68,6 +68,11 @@ struct ScatterParams {
     uint32_t clamp;
     uint32_t unit_bbox;      // bbox == [0,1]^3: the scatter sees the cube the forward pass sees
     float bmin[3], bmax[3];
+    // deterministic mode (HPX_BACKWARD_DETERMINISTIC): contributions are rounded to multiples of a power-of-two
+    // quantum and added with 64-bit INTEGER reds -- integer addition commutes, so the sum does not depend on the
+    // order in which warps arrive and the gradient is bitwise reproducible.  fixed == nullptr: float reds.
+    unsigned long long* fixed;   // [4 * voxels]
+    const float* fixed_meta;     // {.., .., 1 / quantum, quantum} written by fixed_scale_kernel
 };
 
 constexpr int kSegment = 8;        // samples between transmittance checkpoints

@@ -22,7 +22,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libdvren_hp.so")
 
 HPX_CTX_EXT_MAGIC = 0x42323030
 HPX_BACKWARD_GRID, HPX_BACKWARD_CAMERA, HPX_BACKWARD_ZERO = 1, 2, 4
-HPX_BACKWARD_SCATTER_PER_RAY, HPX_BACKWARD_SCATTER_MERGED = 0x10, 0x20
+HPX_BACKWARD_SCATTER_PER_RAY, HPX_BACKWARD_SCATTER_MERGED, HPX_BACKWARD_DETERMINISTIC = 0x10, 0x20, 0x40
 
 
 class hpx_ctx_ext(C.Structure):

@@ -55,6 +55,11 @@ typedef struct hpx_frame hpx_frame;
 /* Scatter strategy of the grid backward (default: chosen from the pixel / voxel spacing ratio):  */
 #define HPX_BACKWARD_SCATTER_PER_RAY 0x10u /* one lane = one ray, 8 reds per sample                      */
 #define HPX_BACKWARD_SCATTER_MERGED  0x20u /* 2x2 pixel quads x 2 steps merged in registers before the reds */
+/* Bitwise reproducible grid gradients: contributions are rounded to a power-of-two quantum (2^-40 of the largest
+ * possible contribution) and accumulated with 64-bit integer reds, whose sum is independent of arrival order; costs
+ * 32 B per voxel of extra HBM and 4 integer reds per corner instead of one 16-byte float red.  Without this flag
+ * the float reds arrive in a different order from run to run (differences at the 1e-7 relative level). */
+#define HPX_BACKWARD_DETERMINISTIC   0x40u
 
 /* Per-frame counters (valid after the stream has been synchronised). */
 typedef struct hpx_counts {

@@ -103,6 +103,26 @@ def test_lean_backward_scatter_modes_dense_pixels(ctx, kind, strat, oob, mode):
     U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{mode} color_grad")
 
 
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+def test_lean_axis_limits_of_the_merged_kernel(ctx, mode):
+    """Edge sizes: the merged kernel packs a cell into 10 bits per axis, so 1024 voxels is its largest axis and
+    1025 must fall back to the per-ray kernel; both against the oracle (thin slabs keep the grids small)."""
+    rng = np.random.default_rng(9)
+    for shape in [(2, 3, 1024), (2, 1024, 3), (1024, 2, 3), (3, 2, 1025)]:      # (nz, ny, nx)
+        sig = (rng.random(shape, dtype=np.float32) * 4).astype(np.float32)
+        col = rng.random(shape + (3,), dtype=np.float32)
+        desc = S.bench_plan(33, 21, 48, stratified=True, view=1, views=5)
+        st, odesc = O.plan_resolve(desc)
+        gs, gc = U.oracle_grids(sig, col, 1, 0)
+        dl = S.hashed_image_grad(33 * 21)
+        ref = O.render(odesc, gs, gc, dl)
+        got = run_lean(ctx, desc, sig, col, 1, 0, None, None, dl,
+                       flags=D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+        check_forward(got, ref, str(shape))
+        U.assert_close(got["sigma_grad"], ref["sigma_grad"], U.GRAD_RTOL, f"{shape} sigma_grad")
+        U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{shape} color_grad")
+
+
 @pytest.mark.parametrize("path", U.golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
 def test_lean_matches_reference_golden(ctx, path):
     g = U.load_golden(path)
@@ -151,6 +171,32 @@ def test_lean_backward_accumulates_and_is_linear(ctx):
     frame.backward(grid, dl, D.HPX_BACKWARD_GRID)
     sg, cg, _ = grid.read_grad()
     U.assert_close(sg, 2.0 * a["sigma_grad"], U.GRAD_RTOL, "accumulate sigma")
+    frame.close(); grid.close(); plan.close()
+
+
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+def test_deterministic_backward_is_bitwise_reproducible(ctx, mode):
+    """HPX_BACKWARD_DETERMINISTIC: fixed-point integer accumulation -> the same bits on every run, within the gradient
+    tolerance of the oracle, and accumulation across calls (no ZERO flag) still works."""
+    sig, col = S.hashed_volume(24, "dense")
+    desc = S.bench_plan(101, 67, 96, stratified=True, view=2, views=9)
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, 0)
+    dl = S.hashed_image_grad(101 * 67) * np.float32(3.7)
+    ref = O.render(odesc, gs, gc, dl)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_DETERMINISTIC | SCATTER_MODES[mode]
+    runs = [run_lean(ctx, desc, sig, col, 1, 0, None, None, dl, flags=flags) for _ in range(3)]
+    for r in runs[1:]:
+        U.assert_bits(r["sigma_grad"], runs[0]["sigma_grad"], "deterministic sigma_grad")
+        U.assert_bits(r["color_grad"], runs[0]["color_grad"], "deterministic color_grad")
+    U.assert_close(runs[0]["sigma_grad"], ref["sigma_grad"], U.GRAD_RTOL, "sigma_grad")
+    U.assert_close(runs[0]["color_grad"], ref["color_grad"], U.GRAD_RTOL, "color_grad")
+    plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+    frame.forward(grid)
+    frame.backward(grid, dl, flags)
+    frame.backward(grid, dl, flags & ~D.HPX_BACKWARD_ZERO)
+    sg, cg, _ = grid.read_grad()
+    U.assert_close(sg, 2.0 * ref["sigma_grad"], U.GRAD_RTOL, "accumulated sigma_grad")
     frame.close(); grid.close(); plan.close()
 
 

@@ -29,9 +29,10 @@ def run(n_grid, W, steps, strat, kind, iters=5):
     z = timeit(lambda: frame.backward(grid, dl.data_ptr(), D.HPX_BACKWARD_ZERO, device=True))
     cam = timeit(lambda: frame.backward(grid, dl.data_ptr(), D.HPX_BACKWARD_CAMERA, device=True))
     fused = timeit(lambda: frame.backward(grid, dl.data_ptr(), D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_CAMERA | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_SCATTER_MERGED, device=True))
+    det = timeit(lambda: frame.backward(grid, dl.data_ptr(), D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_DETERMINISTIC, device=True))
     M = c["samples"]
     print(json.dumps(dict(grid=n_grid, W=W, steps=steps, strat=strat, kind=kind, samples=M, live=c["live_samples"],
-          fwd_ms=f, bwd_ms=b, bwd_merged_ms=bm, zero_ms=z, cam_ms=cam, bwd_cam_fused_ms=fused, fwd_gsamp=M / f / 1e6, fwdbwd_gsamp=M / (f + b) / 1e6,
+          fwd_ms=f, bwd_ms=b, bwd_merged_ms=bm, zero_ms=z, cam_ms=cam, bwd_cam_fused_ms=fused, bwd_deterministic_ms=det, fwd_gsamp=M / f / 1e6, fwdbwd_gsamp=M / (f + b) / 1e6,
           live_fwd_gsamp=c["live_samples"] / f / 1e6)), flush=True)
     frame.close(); grid.close(); plan.close(); ctx.close()
 
