@@ -508,6 +508,17 @@ __device__ __forceinline__ void red_add4(float4* addr, float4 v) {
                  : "memory");
 }
 
+// Index of voxel (x,y,z) in the scatter target (whole grid or box); false when a boxed target does not contain it.
+__device__ __forceinline__ bool scatter_index(const ScatterParams& sp, int32_t x, int32_t y, int32_t z, uint32_t& idx) {
+    const int32_t lx = x - sp.box_ox, ly = y - sp.box_oy, lz = z - sp.box_oz;
+    if (sp.boxed && (lx < 0 || lx >= sp.box_nx || ly < 0 || ly >= sp.box_ny || lz < 0 || lz >= sp.box_nz)) {
+        atomicAdd(sp.box_miss, 1u);
+        return false;
+    }
+    idx = static_cast<uint32_t>(lz) * sp.box_sz + static_cast<uint32_t>(ly) * sp.box_sy + static_cast<uint32_t>(lx);
+    return true;
+}
+
 // One corner contribution: a 16-byte float red, or four 64-bit integer reds of the value in units of the quantum.
 __device__ __forceinline__ void scatter_add(const ScatterParams& sp, uint32_t voxel, float4 v, float inv_q) {
     if (sp.fixed != nullptr) {
@@ -546,7 +557,8 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
         const int32_t iy = static_cast<int32_t>(roundf(gy));
         const int32_t iz = static_cast<int32_t>(roundf(gz));
         if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
-        scatter_add(sp, voxel_index32(ix, iy, iz, nx, ny), g, inv_q);
+        uint32_t idx;
+        if (scatter_index(sp, ix, iy, iz, idx)) scatter_add(sp, idx, g, inv_q);
         return;
     }
     const Cell c = make_cell(gx, gy, gz, nx, ny, nz);
@@ -562,7 +574,9 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
                 const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
                 if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
                 const float w = wx[dx] * wy[dy] * wz[dz];
-                scatter_add(sp, voxel_index32(ix, iy, iz, nx, ny), make_float4(g.x * w, g.y * w, g.z * w, g.w * w), inv_q);
+                uint32_t idx;
+                if (scatter_index(sp, ix, iy, iz, idx))
+                    scatter_add(sp, idx, make_float4(g.x * w, g.y * w, g.z * w, g.w * w), inv_q);
             }
 }
 

@@ -2,6 +2,7 @@
 // lean forward / backward entry points and CUDA-graph capture; plus the
 // hp_graph_* entry points of hp.h built on the same machinery.
 #include <algorithm>
+#include <climits>
 #include <cstring>
 #include <new>
 
@@ -286,6 +287,11 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
     f->buf.ckpt = static_cast<float*>(frame_take(f, segments * f->buf.ckpt_stride * 4, &st));
     f->buf.live_total = static_cast<unsigned long long*>(frame_take(f, sizeof(unsigned long long), &st));
     f->d_dL_dI = static_cast<float*>(frame_take(f, rays * 12, &st));
+    f->d_box_miss = static_cast<unsigned int*>(frame_take(f, sizeof(unsigned int), &st));
+    if (st == HP_STATUS_SUCCESS) {
+        const cudaError_t e = cudaMemset(f->d_box_miss, 0, sizeof(unsigned int));
+        if (e != cudaSuccess) st = cuda_fail(e, "cudaMemset(frame)");
+    }
     float4* d_steps = static_cast<float4*>(frame_take(f, static_cast<size_t>(plan->uniform_count) * sizeof(float4), &st));
     f->buf.steps = d_steps;
     if (st == HP_STATUS_SUCCESS && plan->uniform_count != 0) {
@@ -344,15 +350,27 @@ static hp_status enqueue_forward(hpx_frame* f, const hpx_grid* g) {
     cudaStream_t s = f->ctx->stream;
     DV_CUDA(cudaMemsetAsync(f->buf.live_total, 0, sizeof(unsigned long long), s));
     const RoiParams& roi = f->h_params.roi;
-    const bool partial = roi.w != roi.img_w || roi.h != roi.img_h;
+    const bool partial = roi.w != roi.img_w || roi.h != roi.img_h || roi.tile_row_stride > 1;
     DV_CUDA(launch_lean_forward(s, f->d_params, f->h_params, packed_view(*g), f->buf, partial));
     return HP_STATUS_SUCCESS;
 }
 
-static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_dI, uint32_t flags) {
+struct GradBox {
+    float* data = nullptr;   // [bz][by][bx][4], DEVICE
+    int32_t o[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+};
+
+static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_dI, uint32_t flags,
+                                  const GradBox* box = nullptr) {
     cudaStream_t s = f->ctx->stream;
-    if (flags & HPX_BACKWARD_ZERO)
-        DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), s));
+    if (flags & HPX_BACKWARD_ZERO) {
+        if (box != nullptr) {   // the caller's box is the grid-gradient target; the grid keeps the camera slots
+            DV_CUDA(cudaMemsetAsync(box->data, 0, static_cast<size_t>(box->n[0]) * box->n[1] * box->n[2] * 16, s));
+            DV_CUDA(cudaMemsetAsync(g->d_grad + g->voxels * 4, 0, kCameraFloats * sizeof(float), s));
+        } else {
+            DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), s));
+        }
+    }
     const int want = (flags & HPX_BACKWARD_SCATTER_MERGED)    ? kScatterMerge
                      : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay
                                                               : kScatterAuto;
@@ -362,7 +380,16 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
                              resolve_scatter_mode(f->h_params, packed_view(*g), scatter_params(*g), want) == kScatterMerge;
     if (flags & HPX_BACKWARD_GRID) {
         ScatterParams sp = scatter_params(*g);
-        const bool deterministic = (flags & HPX_BACKWARD_DETERMINISTIC) != 0;
+        if (box != nullptr) {
+            sp.grad = reinterpret_cast<float4*>(box->data);
+            sp.box_ox = box->o[0]; sp.box_oy = box->o[1]; sp.box_oz = box->o[2];
+            sp.box_nx = box->n[0]; sp.box_ny = box->n[1]; sp.box_nz = box->n[2];
+            sp.box_sy = static_cast<uint32_t>(box->n[0]);
+            sp.box_sz = static_cast<uint32_t>(box->n[0]) * static_cast<uint32_t>(box->n[1]);
+            sp.boxed = 1u;
+            sp.box_miss = f->d_box_miss;
+        }
+        const bool deterministic = (flags & HPX_BACKWARD_DETERMINISTIC) != 0 && box == nullptr;
         if (deterministic) {
             if (g->d_fixed == nullptr) {
                 DV_CUDA(cudaMalloc(&g->d_fixed, std::max<size_t>(g->voxels, 1) * 4 * sizeof(unsigned long long)));
@@ -377,7 +404,7 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
                 g->value_max_stale = false;
             }
             DV_CUDA(cudaMemsetAsync(meta_bits + 1, 0, sizeof(uint32_t), s));
-            DV_CUDA(launch_abs_max(s, d_dL_dI, f->rays * 3, meta_bits + 1));
+            DV_CUDA(launch_abs_max(s, d_dL_dI, static_cast<size_t>(f->h_params.roi.w) * f->h_params.roi.h * 3, meta_bits + 1));
             DV_CUDA(launch_fixed_scale(s, g->d_fixed_meta, f->h_params.march.dt));
             sp.fixed = g->d_fixed;
             sp.fixed_meta = g->d_fixed_meta;
@@ -414,10 +441,96 @@ HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_
     DV_TRY(frame_push_params(f));
     const float* d_g = dL_dI;
     if (memspace == HP_MEMSPACE_HOST) {
-        DV_CUDA(cudaMemcpyAsync(f->d_dL_dI, dL_dI, f->rays * 12, cudaMemcpyHostToDevice, f->ctx->stream));
+        DV_CUDA(cudaMemcpyAsync(f->d_dL_dI, dL_dI, static_cast<size_t>(f->h_params.roi.w) * f->h_params.roi.h * 12,
+                                cudaMemcpyHostToDevice, f->ctx->stream));
         d_g = f->d_dL_dI;
     }
     return enqueue_backward(f, g, d_g, flags);
+}
+
+HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_t phase) {
+    if (f == nullptr || stride == 0 || phase >= stride) return HP_STATUS_INVALID_ARGUMENT;
+    RoiParams& roi = f->h_params.roi;
+    roi.tile_row_stride = stride;
+    roi.tile_row_phase = phase;
+    // rays / samples this frame now marches (hpx_frame_counts)
+    const uint32_t tile_h = kTileH * kWarpsY;
+    uint64_t rows = 0;
+    for (uint32_t t = phase, tiles = (roi.h + tile_h - 1) / tile_h; t < tiles; t += stride)
+        rows += std::min<uint32_t>(tile_h, roi.h - t * tile_h);
+    f->rays = rows * roi.w;
+    f->samples = f->rays * f->plan->uniform_count;
+    f->params_dirty = true;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_box[6]) {
+    DV_TRY(frame_check_grid(f, g));
+    if (out_box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(frame_push_params(f));
+    cudaStream_t s = f->ctx->stream;
+    DeviceScratch scratch;
+    int* d_bounds = static_cast<int*>(scratch.take(6 * sizeof(int)));
+    if (d_bounds == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    const int init[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    DV_CUDA(cudaMemcpyAsync(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    DV_CUDA(launch_ray_bounds(s, f->d_params, f->h_params, g->nx, g->ny, g->nz, d_bounds));
+    int got[6];
+    DV_CUDA(cudaMemcpyAsync(got, d_bounds, sizeof(got), cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    const int32_t dims[3] = {g->nx, g->ny, g->nz};
+    for (int i = 0; i < 3; ++i) {
+        if (got[i] == INT_MAX) {   // no ray of this frame enters the cube: empty box at the origin
+            out_box[i] = 0;
+            out_box[3 + i] = 0;
+            continue;
+        }
+        const int32_t lo = std::max(0, got[i] - 1), hi = std::min(dims[i] - 1, got[3 + i] + 2);   // +1 upper corner, +-1 slack
+        out_box[i] = lo;
+        out_box[3 + i] = hi - lo + 1;
+    }
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags,
+                                  float* box_grad, const int32_t box[6]) {
+    DV_TRY(frame_check_grid(f, g));
+    if (dL_dI == nullptr || box_grad == nullptr || box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    for (int i = 0; i < 3; ++i)
+        if (box[i] < 0 || box[3 + i] < 0) return HP_STATUS_INVALID_ARGUMENT;
+    if (box[0] + box[3] > g->nx || box[1] + box[4] > g->ny || box[2] + box[5] > g->nz) return HP_STATUS_INVALID_ARGUMENT;
+    if (!f->forward_done) return HP_STATUS_INVALID_ARGUMENT;
+    const ScatterParams probe = scatter_params(*g);
+    if (!probe.unit_bbox || probe.nearest) {
+        set_last_error("hpx_backward_box needs a linear field whose scatter box is the unit cube");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    DV_TRY(frame_push_params(f));
+    const float* d_g = dL_dI;
+    if (memspace == HP_MEMSPACE_HOST) {
+        DV_CUDA(cudaMemcpyAsync(f->d_dL_dI, dL_dI, static_cast<size_t>(f->h_params.roi.w) * f->h_params.roi.h * 12,
+                                cudaMemcpyHostToDevice, f->ctx->stream));
+        d_g = f->d_dL_dI;
+    }
+    GradBox gb;
+    gb.data = box_grad;
+    for (int i = 0; i < 3; ++i) { gb.o[i] = box[i]; gb.n[i] = box[3 + i]; }
+    if (static_cast<size_t>(gb.n[0]) * gb.n[1] * gb.n[2] == 0) return HP_STATUS_SUCCESS;   // nothing of this frame enters the cube
+    return enqueue_backward(f, g, d_g, flags, &gb);
+}
+
+HP_API hp_status hpx_frame_box_misses(hpx_frame* f, uint32_t* out_count) {
+    if (f == nullptr || out_count == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    unsigned int host = 0;
+    DV_CUDA(cudaMemcpyAsync(&host, f->d_box_miss, sizeof(host), cudaMemcpyDeviceToHost, f->ctx->stream));
+    DV_CUDA(cudaMemsetAsync(f->d_box_miss, 0, sizeof(host), f->ctx->stream));
+    DV_CUDA(cudaStreamSynchronize(f->ctx->stream));
+    *out_count = host;
+    return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_backward_scatter(const hpx_frame* f, const hpx_grid* g, uint32_t flags, uint32_t* out_flag) {

@@ -21,6 +21,7 @@
 #include "dv_lean.h"
 
 #include <algorithm>
+#include <climits>
 
 #include "dv_device.cuh"
 
@@ -37,7 +38,7 @@ struct TilePixel {
 __device__ __forceinline__ TilePixel tile_pixel(const RoiParams& roi) {
     const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
     const uint32_t tile_x = blockIdx.x % tiles_x;
-    const uint32_t tile_y = blockIdx.x / tiles_x;
+    const uint32_t tile_y = (blockIdx.x / tiles_x) * roi.tile_row_stride + roi.tile_row_phase;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TilePixel p;
     p.lx = tile_x * (kTileW * kWarpsX) + (warp % kWarpsX) * kTileW + (lane % kTileW);
@@ -387,12 +388,22 @@ __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px
 __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8], float inv_q) {
     const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
     const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
-    const uint32_t r00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), r10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
-    const uint32_t r01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), r11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
-    scatter_add(sp, r00 + x0, acc[0], inv_q); scatter_add(sp, r00 + x1, acc[1], inv_q);
-    scatter_add(sp, r10 + x0, acc[2], inv_q); scatter_add(sp, r10 + x1, acc[3], inv_q);
-    scatter_add(sp, r01 + x0, acc[4], inv_q); scatter_add(sp, r01 + x1, acc[5], inv_q);
-    scatter_add(sp, r11 + x0, acc[6], inv_q); scatter_add(sp, r11 + x1, acc[7], inv_q);
+    if (sp.boxed) {
+        const int32_t lx0 = x0 - sp.box_ox, ly0 = y0 - sp.box_oy, lz0 = z0 - sp.box_oz;
+        const int32_t lx1 = x1 - sp.box_ox, ly1 = y1 - sp.box_oy, lz1 = z1 - sp.box_oz;
+        if (lx0 < 0 || lx1 >= sp.box_nx || ly0 < 0 || ly1 >= sp.box_ny || lz0 < 0 || lz1 >= sp.box_nz) {
+            atomicAdd(sp.box_miss, 1u);   // cannot happen with the bounds of hpx_frame_bounds; never write outside the box
+            return;
+        }
+    }
+    const uint32_t bx0 = static_cast<uint32_t>(x0 - sp.box_ox), bx1 = static_cast<uint32_t>(x1 - sp.box_ox);
+    const uint32_t ry0 = static_cast<uint32_t>(y0 - sp.box_oy) * sp.box_sy, ry1 = static_cast<uint32_t>(y1 - sp.box_oy) * sp.box_sy;
+    const uint32_t rz0 = static_cast<uint32_t>(z0 - sp.box_oz) * sp.box_sz, rz1 = static_cast<uint32_t>(z1 - sp.box_oz) * sp.box_sz;
+    const uint32_t r00 = rz0 + ry0, r10 = rz0 + ry1, r01 = rz1 + ry0, r11 = rz1 + ry1;
+    scatter_add(sp, r00 + bx0, acc[0], inv_q); scatter_add(sp, r00 + bx1, acc[1], inv_q);
+    scatter_add(sp, r10 + bx0, acc[2], inv_q); scatter_add(sp, r10 + bx1, acc[3], inv_q);
+    scatter_add(sp, r01 + bx0, acc[4], inv_q); scatter_add(sp, r01 + bx1, acc[5], inv_q);
+    scatter_add(sp, r11 + bx0, acc[6], inv_q); scatter_add(sp, r11 + bx1, acc[7], inv_q);
 }
 
 // compare-exchange of the 19-comparator sorting network for 8 keys
@@ -693,7 +704,9 @@ __global__ void background_kernel(LeanBuffers out, RoiParams roi, float t_far) {
 uint32_t tile_blocks(const RoiParams& roi) {
     const uint32_t tx = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
     const uint32_t ty = (roi.h + kTileH * kWarpsY - 1) / (kTileH * kWarpsY);
-    return tx * ty;
+    const uint32_t stride = roi.tile_row_stride ? roi.tile_row_stride : 1u;
+    const uint32_t owned = ty > roi.tile_row_phase ? (ty - roi.tile_row_phase + stride - 1) / stride : 0u;
+    return tx * owned;
 }
 
 }  // namespace
@@ -759,6 +772,56 @@ cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fix
                                   const float* d_meta) {
     if (voxels == 0) return cudaSuccess;
     fixed_to_float_kernel<<<148 * 8, 256, 0, stream>>>(d_fixed, d_grad, voxels, d_meta);
+    return cudaGetLastError();
+}
+
+// ---- voxel bounds of a frame's rays ------------------------------------------------------------------------------
+namespace {
+// Box of grid voxels the backward of this launch can touch: along a ray the position is linear in t, so the cells of
+// all in-cube samples lie between the cells of the two ends of the (padded) in-cube interval.  bounds = {min x,y,z,
+// max x,y,z} as ints, pre-set to {INT_MAX.., INT_MIN..}; the upper corner of a cell (+1) and one voxel of slack for
+// rounding are added on the host.
+__global__ void __launch_bounds__(kLeanThreads)
+ray_bounds_kernel(const FrameParams* __restrict__ P, int32_t nx, int32_t ny, int32_t nz, int* __restrict__ bounds) {
+    const CameraParams cam = P->cam;
+    const MarchParams mp = P->march;
+    const RoiParams roi = P->roi;
+    const TilePixel px = tile_pixel(roi);
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    if (px.inside && mp.uniform_count != 0) {
+        const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
+        float t_in, t_out;
+        cube_interval(ray, t_in, t_out);
+        const float t_last = mp.t_near + static_cast<float>(mp.uniform_count) * mp.dt;
+        const float ta = fmaxf(t_in, mp.t_near), tb = fminf(t_out, fminf(t_last, mp.t_far));
+        if (ta <= tb) {
+            const float n[3] = {static_cast<float>(nx - 1), static_cast<float>(ny - 1), static_cast<float>(nz - 1)};
+            const float o[3] = {ray.ox, ray.oy, ray.oz}, d[3] = {ray.dx, ray.dy, ray.dz};
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float pa = fminf(fmaxf(o[i] + d[i] * ta, 0.0f), 1.0f) * n[i];
+                const float pb = fminf(fmaxf(o[i] + d[i] * tb, 0.0f), 1.0f) * n[i];
+                lo[i] = static_cast<int>(floorf(fminf(pa, pb)));
+                hi[i] = static_cast<int>(floorf(fmaxf(pa, pb)));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int l = __reduce_min_sync(0xffffffffu, lo[i]), h = __reduce_max_sync(0xffffffffu, hi[i]);
+        if ((threadIdx.x & 31) == 0) {
+            if (l != INT_MAX) atomicMin(bounds + i, l);
+            if (h != INT_MIN) atomicMax(bounds + 3 + i, h);
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params, int32_t nx,
+                              int32_t ny, int32_t nz, int* d_bounds) {
+    const uint32_t blocks = tile_blocks(h_params.roi);
+    if (blocks == 0) return cudaSuccess;
+    ray_bounds_kernel<<<blocks, kLeanThreads, 0, stream>>>(d_params, nx, ny, nz, d_bounds);
     return cudaGetLastError();
 }
 

@@ -37,6 +37,10 @@ void build_step_table(const MarchParams& mp, float4* table);
 
 uint32_t lean_block_count(const RoiParams& roi);
 
+// d_bounds: 6 ints pre-set to {INT_MAX x3, INT_MIN x3}; receives min / max cell coordinates of the in-cube samples.
+cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params, int32_t nx,
+                              int32_t ny, int32_t nz, int* d_bounds);
+
 // Deterministic (fixed-point) gradient accumulation, see ScatterParams::fixed.  meta = {bits of max|rgb|, bits of
 // max|dL/dI|, 1 / quantum, quantum}.
 cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits);

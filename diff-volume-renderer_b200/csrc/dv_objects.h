@@ -89,6 +89,7 @@ struct hpx_frame {
     dv::LeanBuffers buf{};
     float* d_dL_dI = nullptr;     // [rays][3]
     double* d_cam_partials = nullptr;
+    unsigned int* d_box_miss = nullptr;   // contributions hpx_backward_box had to drop (must stay 0)
     size_t device_bytes = 0;
     uint64_t rays = 0, samples = 0;
     bool forward_done = false;

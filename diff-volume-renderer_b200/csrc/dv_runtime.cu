@@ -166,7 +166,7 @@ FrameParams frame_params_from_plan(const hp_plan& plan) {
     p.march.uniform_count = plan.uniform_count;
     p.march.seed = d.seed;
     p.march.ray_index_base = 0;
-    p.roi = RoiParams{d.roi.x, d.roi.y, d.roi.width, d.roi.height, d.width, d.height};
+    p.roi = RoiParams{d.roi.x, d.roi.y, d.roi.width, d.roi.height, d.width, d.height, 1u, 0u};
     return p;
 }
 
@@ -242,6 +242,9 @@ ScatterParams scatter_params(const hpx_grid& g) {
         sp.bmax[i] = g.bmax[i];
         if (g.bmin[i] != 0.0f || g.bmax[i] != 1.0f) sp.unit_bbox = 0u;
     }
+    sp.box_nx = g.nx; sp.box_ny = g.ny; sp.box_nz = g.nz;
+    sp.box_sy = static_cast<uint32_t>(g.nx);
+    sp.box_sz = static_cast<uint32_t>(g.nx) * static_cast<uint32_t>(g.ny);
     return sp;
 }
 

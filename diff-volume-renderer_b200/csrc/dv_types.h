@@ -33,6 +33,10 @@ struct MarchParams {
 struct RoiParams {
     uint32_t x, y, w, h;     // region marched
     uint32_t img_w, img_h;   // full frame
+    // CTA tile rows (kTileH * kWarpsY pixel rows each) this launch owns: rows t with t % stride == phase.  stride 1 = all.
+    // Interleaving the tile rows of one frame over the GPUs of a box gives every rank the same mix of short and long
+    // rays (strong scaling, diff-volume-renderer_b200/python/sharding.py).
+    uint32_t tile_row_stride, tile_row_phase;
 };
 
 struct FrameParams {
@@ -73,6 +77,13 @@ struct ScatterParams {
     // order in which warps arrive and the gradient is bitwise reproducible.  fixed == nullptr: float reds.
     unsigned long long* fixed;   // [4 * voxels]
     const float* fixed_meta;     // {.., .., 1 / quantum, quantum} written by fixed_scale_kernel
+    // Scatter target: the whole grid (origin 0, strides nx and nx * ny) or a dense box [bz][by][bx] of it
+    // (hpx_backward_box): voxel (x,y,z) lives at (z - box_oz) * box_sz + (y - box_oy) * box_sy + (x - box_ox).
+    int32_t box_ox, box_oy, box_oz;
+    int32_t box_nx, box_ny, box_nz;
+    uint32_t box_sy, box_sz;
+    uint32_t boxed;              // 1: contributions outside the box are dropped and counted in *box_miss
+    unsigned int* box_miss;
 };
 
 constexpr int kSegment = 8;        // samples between transmittance checkpoints

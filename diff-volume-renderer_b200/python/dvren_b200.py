@@ -58,6 +58,10 @@ HPX_FUNCTIONS = {
     "hpx_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "hpx_backward_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
+    "hpx_frame_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
+    "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
+    "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
     "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
     "hpx_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_counts": (C.c_int, [C.c_void_p, P(hpx_counts)]),
@@ -218,6 +222,26 @@ class Frame:
             assert self._g.size == self.plan.n_rays * 3
             ptr, ms = self._g.ctypes.data, A.HP_MEMSPACE_HOST
         check("hpx_backward", self.lib.hpx_backward(self.handle, grid.handle, ptr, ms, flags))
+
+    def set_interleave(self, stride: int, phase: int):
+        check("hpx_frame_set_interleave", self.lib.hpx_frame_set_interleave(self.handle, stride, phase))
+
+    def bounds(self, grid: Grid):
+        """(x0, y0, z0, nx, ny, nz): box of voxels this frame's backward can touch."""
+        box = (C.c_int32 * 6)()
+        check("hpx_frame_bounds", self.lib.hpx_frame_bounds(self.handle, grid.handle, C.byref(box)))
+        return tuple(int(v) for v in box)
+
+    def backward_box(self, grid: Grid, dL_dI_device_ptr: int, box, box_device_ptr: int,
+                     flags=HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO):
+        b = (C.c_int32 * 6)(*box)
+        check("hpx_backward_box", self.lib.hpx_backward_box(self.handle, grid.handle, int(dL_dI_device_ptr),
+                                                           A.HP_MEMSPACE_DEVICE, flags, int(box_device_ptr), C.byref(b)))
+
+    def box_misses(self) -> int:
+        n = C.c_uint32()
+        check("hpx_frame_box_misses", self.lib.hpx_frame_box_misses(self.handle, C.byref(n)))
+        return n.value
 
     def scatter_mode(self, grid: Grid, flags: int = HPX_BACKWARD_GRID) -> str:
         out = C.c_uint32()

@@ -123,6 +123,21 @@ HP_API hp_status hpx_forward(hpx_frame* frame, const hpx_grid* grid);
 /* dL_dI: (rays,3) f32 per ray in plan order, HOST (copied on the stream) or DEVICE. */
 HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_dI,
                               hp_memspace memspace, uint32_t flags);
+/* ---- strong scaling of ONE frame over several GPUs (diff-volume-renderer_b200/python/sharding.py) ----------------
+ * hpx_frame_set_interleave: this frame marches only the CTA tile rows (8 pixel rows each) t of its ROI with
+ *   t % stride == phase; ray indices, pixel ids and buffers stay those of the whole ROI.  stride 1 = everything.
+ * hpx_frame_bounds: box {x0, y0, z0, nx, ny, nz} of grid voxels the frame's backward can touch (blocks until done).
+ * hpx_backward_box: like hpx_backward, but the grid gradient goes to the caller's dense DEVICE box
+ *   box_grad[nz][ny][nx][4] ({dr,dg,db,dsigma}) instead of the grid's own gradient block, so that a group of image
+ *   rows can be all-reduced (contiguously) while the next group is still being rendered.  HPX_BACKWARD_ZERO clears the
+ *   box.  Unit scatter bbox + linear fields only; HPX_BACKWARD_DETERMINISTIC is ignored. */
+HP_API hp_status hpx_frame_set_interleave(hpx_frame* frame, uint32_t stride, uint32_t phase);
+HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_t out_box[6]);
+HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
+                                  uint32_t flags, float* box_grad, const int32_t box[6]);
+/* Contributions hpx_backward_box found outside its box and dropped since the last call (0 with the boxes of
+ * hpx_frame_bounds; reading clears the counter and synchronises). */
+HP_API hp_status hpx_frame_box_misses(hpx_frame* frame, uint32_t* out_count);
 /* Which scatter strategy hpx_backward(flags) runs for this frame / grid pair: writes HPX_BACKWARD_SCATTER_PER_RAY
  * or HPX_BACKWARD_SCATTER_MERGED (kernel names lean_backward_kernel / lean_backward_merge_kernel in profiles). */
 HP_API hp_status hpx_backward_scatter(const hpx_frame* frame, const hpx_grid* grid, uint32_t flags, uint32_t* out_flag);

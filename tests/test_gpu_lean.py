@@ -224,6 +224,58 @@ def test_lean_roi_tiles_reproduce_full_frame(ctx):
     U.assert_close(cg, full["color_grad"], U.GRAD_RTOL, "tiled color_grad")
 
 
+def test_interleaved_rows_and_box_backward_reproduce_full_frame(ctx):
+    """Strong-scaling building blocks (hp_b200.h): 2 row groups x 2 'ranks' that own interleaved CTA tile rows, each
+    scattering into the dense voxel box hpx_frame_bounds reports.  Run one after the other on one GPU, the pieces must
+    tile the plain full-frame result: images bit for bit, gradients within the tolerance, no contribution dropped."""
+    import sharding as SH
+    sig, col = S.hashed_volume(28, "dense")
+    W, Hh, steps, world, groups = 72, 61, 96, 2, 2
+    full_desc = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=7)
+    dl_full = S.hashed_image_grad(W * Hh)
+    full = run_lean(ctx, full_desc, sig, col, 1, 0, None, None, dl_full)
+    lib = ctx.lib
+    grid = D.Grid(ctx, sig, col)
+    nx = ny = nz = 28
+    G = np.zeros((nz, ny, nx, 4), np.float64)
+    image = np.zeros_like(full["image"]); hit = np.zeros_like(full["hitmask"])
+    total_samples = total_live = 0
+    for band in SH.row_bands(full_desc, groups, align=16):
+        n_rays = band.rows * W
+        dl = np.ascontiguousarray(dl_full[band.ray_index_base: band.ray_index_base + n_rays])
+        d_dl = C.c_void_p()
+        D.check("alloc", lib.hpx_device_alloc(ctx.handle, dl.nbytes, C.byref(d_dl)))
+        D.check("h2d", lib.hpx_copy_to_device(ctx.handle, d_dl, dl.ctypes.data, dl.nbytes))
+        for rank in range(world):
+            plan = D.Plan(ctx, SH.band_desc(full_desc, band)); frame = D.Frame(plan)
+            frame.set_view(None, plan.desc.seed, band.ray_index_base)
+            frame.set_interleave(world, rank)
+            frame.forward(grid)
+            part = frame.read(); cnt = frame.counts()
+            total_samples += cnt["samples"]; total_live += cnt["live_samples"]
+            own = part["hitmask"] == 1
+            assert not (hit.astype(bool) & own).any()          # ranks own disjoint pixels
+            image[own] = part["image"][own]; hit[own] = 1
+            box = frame.bounds(grid)
+            x0, y0, z0, bx, by, bz = box
+            assert bx > 0 and by > 0 and bz > 0 and x0 + bx <= nx and y0 + by <= ny and z0 + bz <= nz
+            d_box = C.c_void_p()
+            D.check("alloc", lib.hpx_device_alloc(ctx.handle, bx * by * bz * 16, C.byref(d_box)))
+            frame.backward_box(grid, d_dl.value, box, d_box.value)
+            assert frame.box_misses() == 0
+            host = np.zeros((bz, by, bx, 4), np.float32)
+            D.check("d2h", lib.hpx_copy_to_host(ctx.handle, host.ctypes.data, d_box, host.nbytes))
+            G[z0:z0 + bz, y0:y0 + by, x0:x0 + bx] += host
+            lib.hpx_device_free(ctx.handle, d_box)
+            frame.close(); plan.close()
+        lib.hpx_device_free(ctx.handle, d_dl)
+    grid.close()
+    assert hit.all() and total_samples == full["samples"] and total_live == full["live_samples"]
+    U.assert_bits(image, full["image"], "interleaved image")
+    U.assert_close(G[..., 3].reshape(-1), full["sigma_grad"], U.GRAD_RTOL, "boxed sigma_grad")
+    U.assert_close(G[..., :3].reshape(-1), full["color_grad"], U.GRAD_RTOL, "boxed color_grad")
+
+
 def test_lean_forward_is_deterministic_and_graph_replay_matches(ctx):
     sig, col = S.hashed_volume(32, "dense")
     desc = S.bench_plan(72, 40, 128, stratified=True)
