@@ -515,7 +515,7 @@ __device__ __forceinline__ bool scatter_index(const ScatterParams& sp, int32_t x
         atomicAdd(sp.box_miss, 1u);
         return false;
     }
-    idx = static_cast<uint32_t>(lz) * sp.box_sz + static_cast<uint32_t>(ly) * sp.box_sy + static_cast<uint32_t>(lx);
+    idx = static_cast<uint32_t>(lz) * sp.box_sz + static_cast<uint32_t>(ly) * sp.box_sy + static_cast<uint32_t>(lx) * sp.box_sx;
     return true;
 }
 

@@ -173,8 +173,10 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
     DV_TRY(grid_ensure_grad(g));
     cudaStream_t s = g->ctx->stream;
     const float4* packed = reinterpret_cast<const float4*>(g->d_grad);
+    const ScatterParams lay = scatter_params(*g);   // strides of the gradient block
+    const uint32_t unx = static_cast<uint32_t>(g->nx), uny = static_cast<uint32_t>(g->ny);
     if (memspace == HP_MEMSPACE_DEVICE) {
-        DV_CUDA(launch_unpack_grad(s, packed, sigma_grad, color_grad, g->voxels));
+        DV_CUDA(launch_unpack_grad(s, packed, sigma_grad, color_grad, 0, g->voxels, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
         if (camera16) DV_CUDA(cudaMemcpyAsync(camera16, g->d_grad + g->voxels * 4, kCameraFloats * sizeof(float),
                                               cudaMemcpyDeviceToDevice, s));
         return HP_STATUS_SUCCESS;
@@ -191,7 +193,7 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
     float* d_col = color_grad ? g->d_unpacked + chunk : nullptr;
     for (size_t off = 0; off < g->voxels && (sigma_grad || color_grad); off += chunk) {
         const size_t n = std::min(chunk, g->voxels - off);
-        DV_CUDA(launch_unpack_grad(s, packed + off, d_sig, d_col, n));
+        DV_CUDA(launch_unpack_grad(s, packed, d_sig, d_col, off, n, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
         if (sigma_grad) DV_CUDA(cudaMemcpyAsync(sigma_grad + off, d_sig, n * 4, cudaMemcpyDeviceToHost, s));
         if (color_grad) DV_CUDA(cudaMemcpyAsync(color_grad + 3 * off, d_col, n * 12, cudaMemcpyDeviceToHost, s));
     }
@@ -520,6 +522,40 @@ HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI,
     for (int i = 0; i < 3; ++i) { gb.o[i] = box[i]; gb.n[i] = box[3 + i]; }
     if (static_cast<size_t>(gb.n[0]) * gb.n[1] * gb.n[2] == 0) return HP_STATUS_SUCCESS;   // nothing of this frame enters the cube
     return enqueue_backward(f, g, d_g, flags, &gb);
+}
+
+HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* g, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs) {
+    if (g == nullptr || slow_axis < 0 || slow_axis > 2) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(g->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    const uint32_t nx = static_cast<uint32_t>(g->nx), ny = static_cast<uint32_t>(g->ny), nz = static_cast<uint32_t>(g->nz);
+    int32_t slabs = g->nz;
+    if (slow_axis == 2) { g->gsx = 1; g->gsy = nx; g->gsz = nx * ny; slabs = g->nz; }        // [z][y][x]
+    else if (slow_axis == 1) { g->gsx = 1; g->gsz = nx; g->gsy = nx * nz; slabs = g->ny; }   // [y][z][x]
+    else { g->gsy = 1; g->gsz = ny; g->gsx = ny * nz; slabs = g->nx; }                        // [x][z][y]
+    g->grad_slow_axis = slow_axis;
+    // whatever was accumulated in the old order is meaningless in the new one
+    DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), g->ctx->stream));
+    if (out_slab_floats) *out_slab_floats = slabs > 0 ? g->voxels / static_cast<size_t>(slabs) * 4 : 0;
+    if (out_slabs) *out_slabs = slabs;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* g, float* box_grad, const int32_t box[6]) {
+    if (stream_ctx == nullptr || g == nullptr || box_grad == nullptr || box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    for (int i = 0; i < 3; ++i)
+        if (box[i] < 0 || box[3 + i] < 0) return HP_STATUS_INVALID_ARGUMENT;
+    if (box[0] + box[3] > g->nx || box[1] + box[4] > g->ny || box[2] + box[5] > g->nz) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(stream_ctx));
+    if (stream_ctx->device != g->ctx->device) return HP_STATUS_INVALID_ARGUMENT;
+    if (g->grad_slow_axis != 2) {
+        set_last_error("hpx_grid_add_box needs the default gradient layout (z slowest)");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_TRY(grid_ensure_grad(g));
+    DV_CUDA(launch_add_box(stream_ctx->stream, reinterpret_cast<float4*>(g->d_grad), reinterpret_cast<float4*>(box_grad),
+                           g->nx, g->ny, box));
+    return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_frame_box_misses(hpx_frame* f, uint32_t* out_count) {

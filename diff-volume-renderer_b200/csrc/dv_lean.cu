@@ -396,7 +396,7 @@ __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key
             return;
         }
     }
-    const uint32_t bx0 = static_cast<uint32_t>(x0 - sp.box_ox), bx1 = static_cast<uint32_t>(x1 - sp.box_ox);
+    const uint32_t bx0 = static_cast<uint32_t>(x0 - sp.box_ox) * sp.box_sx, bx1 = static_cast<uint32_t>(x1 - sp.box_ox) * sp.box_sx;
     const uint32_t ry0 = static_cast<uint32_t>(y0 - sp.box_oy) * sp.box_sy, ry1 = static_cast<uint32_t>(y1 - sp.box_oy) * sp.box_sy;
     const uint32_t rz0 = static_cast<uint32_t>(z0 - sp.box_oz) * sp.box_sz, rz1 = static_cast<uint32_t>(z1 - sp.box_oz) * sp.box_sz;
     const uint32_t r00 = rz0 + ry0, r10 = rz0 + ry1, r01 = rz1 + ry0, r11 = rz1 + ry1;

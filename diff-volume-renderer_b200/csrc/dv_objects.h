@@ -77,6 +77,9 @@ struct hpx_grid {
     unsigned long long* d_fixed = nullptr;   // [4V], all zero between backward passes
     float* d_fixed_meta = nullptr;           // {bits max|grid value|, bits max|dL/dI|, 1/quantum, quantum}
     bool value_max_stale = true;
+    // element strides of the gradient block (hpx_grid_set_grad_layout); default: x fastest, z slowest like the values
+    int grad_slow_axis = 2;
+    uint32_t gsx = 0, gsy = 0, gsz = 0;
 };
 
 struct hpx_frame {

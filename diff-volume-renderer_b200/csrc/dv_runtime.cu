@@ -243,8 +243,13 @@ ScatterParams scatter_params(const hpx_grid& g) {
         if (g.bmin[i] != 0.0f || g.bmax[i] != 1.0f) sp.unit_bbox = 0u;
     }
     sp.box_nx = g.nx; sp.box_ny = g.ny; sp.box_nz = g.nz;
-    sp.box_sy = static_cast<uint32_t>(g.nx);
-    sp.box_sz = static_cast<uint32_t>(g.nx) * static_cast<uint32_t>(g.ny);
+    if (g.gsx != 0) {
+        sp.box_sx = g.gsx; sp.box_sy = g.gsy; sp.box_sz = g.gsz;
+    } else {
+        sp.box_sx = 1u;
+        sp.box_sy = static_cast<uint32_t>(g.nx);
+        sp.box_sz = static_cast<uint32_t>(g.nx) * static_cast<uint32_t>(g.ny);
+    }
     return sp;
 }
 

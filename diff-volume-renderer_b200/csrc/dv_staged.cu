@@ -352,6 +352,26 @@ __global__ void scatter_kernel(ScatterParams sp, const float* __restrict__ posit
 }
 
 // ---- K8: pack / unpack -------------------------------------------------------
+// grid[z0+z][y0+y][x0+x] += box[z][y][x] (float4 per voxel), then box = 0: the hand-over of one all-reduced gradient box
+// (hpx_backward_box) to the grid's gradient block; clearing in the same pass leaves the box ready for the next step.
+__global__ void add_box_kernel(float4* __restrict__ grid, float4* __restrict__ box, int32_t nx, int32_t ny, int32_t x0,
+                               int32_t y0, int32_t z0, int32_t bx, int32_t by, int32_t bz) {
+    const size_t n = static_cast<size_t>(bx) * by * bz;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int32_t x = static_cast<int32_t>(i % bx);
+        const size_t r = i / bx;
+        const int32_t y = static_cast<int32_t>(r % by), z = static_cast<int32_t>(r / by);
+        const float4 v = box[i];
+        box[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f) continue;
+        float4* g = grid + (static_cast<size_t>(z0 + z) * ny + (y0 + y)) * nx + (x0 + x);
+        float4 a = *g;
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        *g = a;
+    }
+}
+
 __global__ void pack_grid_kernel(const float* __restrict__ sigma, const float* __restrict__ color,
                                  float4* __restrict__ packed, size_t voxels, bool keep_missing) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels;
@@ -364,11 +384,17 @@ __global__ void pack_grid_kernel(const float* __restrict__ sigma, const float* _
     }
 }
 
+// first..first+voxels of the REFERENCE order (z slowest, x fastest); the packed block may use any axis order (strides)
 __global__ void unpack_grad_kernel(const float4* __restrict__ packed, float* __restrict__ sigma_grad,
-                                   float* __restrict__ color_grad, size_t voxels) {
+                                   float* __restrict__ color_grad, size_t first, size_t voxels, uint32_t nx, uint32_t ny,
+                                   uint32_t sx, uint32_t sy, uint32_t sz) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const float4 v = packed[i];
+        const size_t v_ref = first + i;
+        const uint32_t x = static_cast<uint32_t>(v_ref % nx);
+        const size_t r = v_ref / nx;
+        const uint32_t y = static_cast<uint32_t>(r % ny), z = static_cast<uint32_t>(r / ny);
+        const float4 v = packed[static_cast<size_t>(x) * sx + static_cast<size_t>(y) * sy + static_cast<size_t>(z) * sz];
         if (sigma_grad != nullptr) sigma_grad[i] = v.w;
         if (color_grad != nullptr) { color_grad[3 * i] = v.x; color_grad[3 * i + 1] = v.y; color_grad[3 * i + 2] = v.z; }
     }
@@ -463,6 +489,13 @@ cudaError_t launch_compose_sequential(cudaStream_t s, const ImagePlanes& img, si
     return cudaGetLastError();
 }
 
+cudaError_t launch_add_box(cudaStream_t s, float4* grid, float4* box, int32_t nx, int32_t ny, const int32_t b[6]) {
+    const size_t n = static_cast<size_t>(b[3]) * b[4] * b[5];
+    if (n == 0) return cudaSuccess;
+    add_box_kernel<<<148 * 8, 256, 0, s>>>(grid, box, nx, ny, b[0], b[1], b[2], b[3], b[4], b[5]);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scatter(cudaStream_t s, const ScatterParams& sp, const float* positions, const float* grad_sigma,
                            const float* grad_color, size_t n_samples) {
     if (n_samples == 0) return cudaSuccess;
@@ -478,11 +511,11 @@ cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* co
     return cudaGetLastError();
 }
 
-cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad,
-                               size_t voxels) {
+cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, size_t first,
+                               size_t voxels, uint32_t nx, uint32_t ny, uint32_t sx, uint32_t sy, uint32_t sz) {
     if (voxels == 0) return cudaSuccess;
     const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (voxels + 255) / 256));
-    unpack_grad_kernel<<<blocks, 256, 0, s>>>(packed, sigma_grad, color_grad, voxels);
+    unpack_grad_kernel<<<blocks, 256, 0, s>>>(packed, sigma_grad, color_grad, first, voxels, nx, ny, sx, sy, sz);
     return cudaGetLastError();
 }
 

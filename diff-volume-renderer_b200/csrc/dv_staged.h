@@ -78,6 +78,9 @@ cudaError_t launch_compose_sequential(cudaStream_t s, const ImagePlanes& img, si
                                       const uint32_t* pixel_ids, const IntegralArrays& intl, uint32_t n_rays);
 
 // DenseGridField::AccumulateSampleGradients on materialised samples
+// grid gradient += box, box = 0 (see add_box_kernel)
+cudaError_t launch_add_box(cudaStream_t s, float4* grid, float4* box, int32_t nx, int32_t ny, const int32_t box6[6]);
+
 cudaError_t launch_scatter(cudaStream_t s, const ScatterParams& sp, const float* positions, const float* grad_sigma,
                            const float* grad_color, size_t n_samples);
 
@@ -85,7 +88,7 @@ cudaError_t launch_scatter(cudaStream_t s, const ScatterParams& sp, const float*
 // missing (null) component: zero, or left as it is when keep_missing
 cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* color, float4* packed, size_t voxels,
                              bool keep_missing);
-cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad,
-                               size_t voxels);
+cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, size_t first,
+                               size_t voxels, uint32_t nx, uint32_t ny, uint32_t sx, uint32_t sy, uint32_t sz);
 
 }  // namespace dv

@@ -77,11 +77,12 @@ struct ScatterParams {
     // order in which warps arrive and the gradient is bitwise reproducible.  fixed == nullptr: float reds.
     unsigned long long* fixed;   // [4 * voxels]
     const float* fixed_meta;     // {.., .., 1 / quantum, quantum} written by fixed_scale_kernel
-    // Scatter target: the whole grid (origin 0, strides nx and nx * ny) or a dense box [bz][by][bx] of it
-    // (hpx_backward_box): voxel (x,y,z) lives at (z - box_oz) * box_sz + (y - box_oy) * box_sy + (x - box_ox).
+    // Scatter target: the grid's gradient block (origin 0; strides of its layout -- z slowest by default, any axis
+    // slowest after hpx_grid_set_grad_layout) or a dense box [bz][by][bx] of the grid (hpx_backward_box):
+    // voxel (x,y,z) lives at (x - box_ox) * box_sx + (y - box_oy) * box_sy + (z - box_oz) * box_sz.
     int32_t box_ox, box_oy, box_oz;
     int32_t box_nx, box_ny, box_nz;
-    uint32_t box_sy, box_sz;
+    uint32_t box_sx, box_sy, box_sz;
     uint32_t boxed;              // 1: contributions outside the box are dropped and counted in *box_miss
     unsigned int* box_miss;
 };

@@ -62,6 +62,8 @@ HPX_FUNCTIONS = {
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
+    "hpx_grid_add_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
+    "hpx_grid_set_grad_layout": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_size_t), P(C.c_int32)]),
     "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
     "hpx_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_counts": (C.c_int, [C.c_void_p, P(hpx_counts)]),
@@ -172,6 +174,17 @@ class Grid:
 
     def zero_grad(self):
         check("hpx_grid_zero_grad", self.lib.hpx_grid_zero_grad(self.handle))
+
+    def set_grad_layout(self, slow_axis: int):
+        """Make axis 0 = x / 1 = y / 2 = z the slowest one of the gradient block; returns (floats per slab, slabs)."""
+        f, n = C.c_size_t(), C.c_int32()
+        check("hpx_grid_set_grad_layout", self.lib.hpx_grid_set_grad_layout(self.handle, slow_axis, C.byref(f), C.byref(n)))
+        return f.value, n.value
+
+    def add_box(self, stream_ctx: "Context", box_device_ptr: int, box):
+        """gradient[box] += box buffer, box buffer = 0, on stream_ctx's stream."""
+        b = (C.c_int32 * 6)(*box)
+        check("hpx_grid_add_box", self.lib.hpx_grid_add_box(stream_ctx.handle, self.handle, int(box_device_ptr), C.byref(b)))
 
     def grad_buffer(self):
         ptr, n = C.c_void_p(), C.c_size_t()

@@ -119,3 +119,129 @@ class GradientAllReduce:
         """Ring all-reduce volume: 2 (N-1)/N of the buffer leaves and enters every rank."""
         n = self.world
         return 0 if n == 1 else int(2 * (n - 1) / n * self.tensor.numel() * self.tensor.element_size())
+
+
+def final_slab_runs(ranges: Sequence[Optional[Tuple[int, int]]]) -> List[List[Tuple[int, int]]]:
+    """ranges[g] = [lo, hi) of gradient slabs group g can touch (None: touches nothing), groups processed in order.
+    Returns, per group, the contiguous runs of slabs that are FINAL once that group is done: touched by it or an earlier
+    group and by no later one.  Every touched slab appears in exactly one run, so reducing the runs reduces the whole
+    gradient once."""
+    out: List[List[Tuple[int, int]]] = []
+    n = len(ranges)
+    done: set = set()
+    for g in range(n):
+        touched = set()
+        for r in ranges[: g + 1]:
+            if r is not None:
+                touched.update(range(r[0], r[1]))
+        later = set()
+        for r in ranges[g + 1:]:
+            if r is not None:
+                later.update(range(r[0], r[1]))
+        final = sorted(touched - later - done)
+        done.update(final)
+        runs: List[Tuple[int, int]] = []
+        for s_ in final:
+            if runs and runs[-1][1] == s_:
+                runs[-1] = (runs[-1][0], s_ + 1)
+            else:
+                runs.append((s_, s_ + 1))
+        out.append(runs)
+    return out
+
+
+class PipelinedFrame:
+    """Strong scaling of ONE frame over the ranks of a box with the gradient all-reduce hidden behind the rendering.
+
+    The frame is cut into `groups` row groups, rendered one after the other.  Inside a group every rank owns the CTA
+    tile rows t with t % world == rank (hpx_frame_set_interleave): all ranks carry the same mix of short and long rays
+    and all of them touch the same region of the grid.  The gradient block is laid out with the world axis the image
+    rows run along as its SLOWEST axis (hpx_grid_set_grad_layout), so the region a group touches is a contiguous range
+    of slabs (hpx_frame_bounds, unioned over ranks).  When a group is done, the slabs no later group will touch are
+    final on every rank: a side stream all-reduces exactly those, IN PLACE, while the compute stream is already
+    rendering the next group.  Every slab is reduced once (no extra copies, buffers or passes); only the last group's
+    share is exposed.
+
+    Everything here is host orchestration (torch streams / events / torch.distributed); kernels are the library's.
+    """
+
+    def __init__(self, D, ctx, grid, full_desc, groups: int, world: int, rank: int, device, compute_stream):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.D = torch, dist, D
+        self.ctx, self.grid, self.world, self.rank = ctx, grid, world, rank
+        self.compute = compute_stream
+        self.side = torch.cuda.Stream(device=device)
+        self.reduce = True   # False: skip the collectives (timing experiments)
+        # world axis the image rows advance along = the camera's "down" vector (second column of c2w's rotation)
+        st_desc = full_desc
+        c2w = [st_desc.camera.c2w[i] for i in range(12)]
+        down = [abs(c2w[1]), abs(c2w[5]), abs(c2w[9])]
+        if not any(down):
+            down = [0.0, 1.0, 0.0]           # all-zero pose = identity (hp_plan_create default)
+        self.slow_axis = max(range(3), key=lambda i: down[i])
+        self.slab_floats, self.n_slabs = grid.set_grad_layout(self.slow_axis)
+        ptr, floats = grid.grad_buffer()
+        self.block = torch.as_tensor(_CudaView(ptr, floats), device=device)
+        self.parts = []
+        ranges: List[Optional[Tuple[int, int]]] = []
+        for band in row_bands(full_desc, groups, align=TILE_ROWS * world):
+            if band.empty:
+                continue
+            plan = D.Plan(ctx, band_desc(full_desc, band))
+            frame = D.Frame(plan)
+            frame.set_view(None, plan.desc.seed, band.ray_index_base)
+            frame.set_interleave(world, rank)
+            box = frame.bounds(grid)
+            lo = box[self.slow_axis] if box[3 + self.slow_axis] > 0 else 1 << 40
+            hi = box[self.slow_axis] + box[3 + self.slow_axis] if box[3 + self.slow_axis] > 0 else -1
+            if world > 1:   # every rank must reduce the same slabs: union of the ranks' ranges
+                t_lo = torch.tensor([lo], dtype=torch.int64, device=device)
+                t_hi = torch.tensor([hi], dtype=torch.int64, device=device)
+                dist.all_reduce(t_lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(t_hi, op=dist.ReduceOp.MAX)
+                lo, hi = int(t_lo.item()), int(t_hi.item())
+            ranges.append((lo, hi) if hi > lo else None)
+            self.parts.append(dict(band=band, plan=plan, frame=frame, done=torch.cuda.Event()))
+        for p, runs in zip(self.parts, final_slab_runs(ranges)):
+            p["runs"] = runs
+        self.ranges = ranges
+
+    @property
+    def samples(self) -> int:
+        return sum(p["frame"].counts()["samples"] for p in self.parts)
+
+    def step(self, dL_dI_ptr: int, flags: int):
+        """dL_dI_ptr: DEVICE pointer of the WHOLE frame's (rays, 3) gradient.  Leaves the summed gradient of all
+        ranks in the grid's gradient block (hpx_grid_grad_buffer, slab order of hpx_grid_set_grad_layout)."""
+        torch = self.torch
+        self.grid.zero_grad()
+        last = len(self.parts) - 1
+        for i, p in enumerate(self.parts):
+            band, frame = p["band"], p["frame"]
+            frame.forward(self.grid)
+            frame.backward(self.grid, dL_dI_ptr + band.ray_index_base * 12, flags & ~self.D.HPX_BACKWARD_ZERO, device=True)
+            if self.world == 1 or not self.reduce:
+                continue
+            p["done"].record(self.compute)
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(p["done"])
+                for a, b in p["runs"]:
+                    self.dist.all_reduce(self.block[a * self.slab_floats: b * self.slab_floats], op=self.dist.ReduceOp.SUM)
+                if i == last:   # camera gradients ride with the last group
+                    self.dist.all_reduce(self.block[-16:], op=self.dist.ReduceOp.SUM)
+        self.compute.wait_stream(self.side)
+
+    def close(self):
+        for p in self.parts:
+            p["frame"].close()
+            p["plan"].close()
+        self.parts = []
+        self.grid.set_grad_layout(2)
+
+
+class _CudaView:
+    """Raw device pointer as a torch-importable array (zero copy)."""
+
+    def __init__(self, ptr: int, n_floats: int):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}

@@ -135,6 +135,17 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* frame, uint32_t stride, uin
 HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_t out_box[6]);
 HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
                                   uint32_t flags, float* box_grad, const int32_t box[6]);
+/* Axis order of the gradient block: slow_axis 0 = x, 1 = y, 2 = z (default) becomes the slowest-varying one, so that a
+ * range of voxel planes perpendicular to that axis ("slabs") is one CONTIGUOUS piece of hpx_grid_grad_buffer:
+ *   slow z: [z][y][x]   slow y: [y][z][x]   slow x: [x][z][y]   (x {r,g,b,sigma} floats).
+ * A caller that renders one frame in groups of image rows picks the world axis the rows run along; the slabs a
+ * finished group will never touch again can then be all-reduced IN PLACE while the next group is rendered
+ * (sharding.PipelinedFrame).  Clears the gradient block.  hpx_grid_read_grad always returns the reference order.
+ * out_slab_floats: floats per slab; out_slabs: number of slabs. */
+HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* grid, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs);
+/* grid gradient[box] += box_grad, then box_grad = 0, enqueued on the stream of `stream_ctx` (any context of the grid's
+ * device: the caller's side stream, so that the hand-over overlaps the rendering of the next group). */
+HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* grid, float* box_grad, const int32_t box[6]);
 /* Contributions hpx_backward_box found outside its box and dropped since the last call (0 with the boxes of
  * hpx_frame_bounds; reading clears the counter and synchronises). */
 HP_API hp_status hpx_frame_box_misses(hpx_frame* frame, uint32_t* out_count);

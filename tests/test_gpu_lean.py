@@ -224,6 +224,28 @@ def test_lean_roi_tiles_reproduce_full_frame(ctx):
     U.assert_close(cg, full["color_grad"], U.GRAD_RTOL, "tiled color_grad")
 
 
+@pytest.mark.parametrize("slow_axis", [0, 1, 2])
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+def test_gradient_block_axis_orders(ctx, slow_axis, mode):
+    """hpx_grid_set_grad_layout: any axis may be the slowest one of the gradient block (contiguous slabs for the in-place
+    pipelined all-reduce); hpx_grid_read_grad always returns the reference order."""
+    sig, col = S.hashed_volume((9, 14, 11), "dense")
+    desc = S.bench_plan(70, 45, 64, stratified=True, view=2, views=11)
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, 0)
+    dl = S.hashed_image_grad(70 * 45)
+    ref = O.render(odesc, gs, gc, dl)
+    plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+    slab_floats, slabs = grid.set_grad_layout(slow_axis)
+    assert slabs == (9, 14, 11)[slow_axis] and slab_floats * slabs == 9 * 14 * 11 * 4
+    frame.forward(grid)
+    frame.backward(grid, dl, D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+    sg, cg, _ = grid.read_grad()
+    U.assert_close(sg, ref["sigma_grad"], U.GRAD_RTOL, "sigma_grad")
+    U.assert_close(cg, ref["color_grad"], U.GRAD_RTOL, "color_grad")
+    frame.close(); grid.close(); plan.close()
+
+
 def test_interleaved_rows_and_box_backward_reproduce_full_frame(ctx):
     """Strong-scaling building blocks (hp_b200.h): 2 row groups x 2 'ranks' that own interleaved CTA tile rows, each
     scattering into the dense voxel box hpx_frame_bounds reports.  Run one after the other on one GPU, the pieces must

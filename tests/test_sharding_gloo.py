@@ -54,6 +54,30 @@ def test_views_of_rank_and_u32_bands():
     assert SH.u32_safe_bands(c2, 512) == 1
 
 
+def test_final_slab_runs_cover_every_touched_slab_once():
+    # monotone ranges with overlap (the usual case), a group that touches nothing, and a reversed order
+    for ranges in ([(0, 10), (7, 18), (15, 30), (27, 40)], [(0, 10), None, (8, 20)], [(30, 40), (18, 33), (5, 20), (0, 8)],
+                   [(3, 9), (3, 9)], [None, None]):
+        runs = SH.final_slab_runs(ranges)
+        assert len(runs) == len(ranges)
+        seen = []
+        for g, rs in enumerate(runs):
+            later = set()
+            for r in ranges[g + 1:]:
+                if r:
+                    later.update(range(*r))
+            for a, b in rs:
+                assert a < b
+                assert not (set(range(a, b)) & later), "a slab was declared final while a later group still writes it"
+                seen += list(range(a, b))
+        touched = set()
+        for r in ranges:
+            if r:
+                touched.update(range(*r))
+        assert sorted(seen) == sorted(touched)          # each touched slab exactly once
+    assert SH.final_slab_runs([(0, 10), (7, 18)]) == [[(0, 7)], [(7, 18)]]
+
+
 # ---- two gloo ranks -----------------------------------------------------------------------------
 def _free_port():
     with socket.socket() as s:
