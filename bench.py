@@ -319,7 +319,8 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
     del sigma, color
     g_host = torch.from_numpy(S.hashed_image_grad(W * W)).pin_memory()
     g_dev = g_host.to(dev, non_blocking=True)
-    pf = SH.PipelinedFrame(D, ctx, grid, full, args.groups, world, rank, dev, stream)
+    groups = [float(v) for v in args.group_split.split(",")] if args.group_split else args.groups
+    pf = SH.PipelinedFrame(D, ctx, grid, full, groups, world, rank, dev, stream)
     flags = D.HPX_BACKWARD_GRID
     cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
 
@@ -390,7 +391,7 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
                        "parallelism": f"one frame, {len(pf.parts)} row groups, tile rows interleaved over {world} GPUs; gradient "
                                       f"block laid out with axis {'xyz'[pf.slow_axis]} slowest, the slabs a finished group leaves "
                                       "behind all-reduced in place on a side stream while the next group renders",
-                       "slab_ranges": pf.ranges, "allreduce_bytes": grid.voxels * 16,
+                       "slab_ranges": pf.ranges, "group_rows": [p["band"].rows for p in pf.parts], "allreduce_bytes": grid.voxels * 16,
                        "verify_max_rel_err_vs_single_gpu": verify,
                        "ms_per_step_without_collectives": no_reduce_ms / args.steps,
                        "l2": "inputs larger than L2"},
@@ -593,7 +594,8 @@ def main():
     ap.add_argument("--sharding", default="views", choices=["views", "rows", "pipeline"],
                     help="N > 1: one view per GPU (weak scaling, default); one frame cut into row bands (strong); or one "
                          "frame in row groups with interleaved tile rows and the all-reduce overlapped (strong, pipelined)")
-    ap.add_argument("--groups", type=int, default=4, help="row groups of --sharding pipeline")
+    ap.add_argument("--groups", type=int, default=2, help="equal row groups of --sharding pipeline")
+    ap.add_argument("--group-split", default="", help="relative heights of the row groups instead, e.g. 0.75,0.25")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3   # timing rule: at least 3 warm-up steps

@@ -70,6 +70,25 @@ def row_bands(desc: A.hp_plan_desc, world: int, align: int = TILE_ROWS) -> List[
     return bands
 
 
+def weighted_row_bands(desc: A.hp_plan_desc, weights: Sequence[float], align: int = TILE_ROWS) -> List[Band]:
+    """Contiguous row bands whose heights follow `weights` (cut on multiples of `align` rows).  Used by the pipelined
+    strong scaling to make the LAST group small: only its share of the all-reduce is exposed."""
+    x, y, w, h = resolved_roi(desc)
+    units = (h + align - 1) // align
+    total = float(sum(weights))
+    cuts, acc = [0], 0.0
+    for wgt in weights[:-1]:
+        acc += wgt
+        cuts.append(min(units, max(cuts[-1], int(round(units * acc / total)))))
+    cuts.append(units)
+    bands = []
+    for i in range(len(weights)):
+        r0, r1 = min(cuts[i] * align, h), min(cuts[i + 1] * align, h)
+        bands.append(Band(i, y + r0, r1 - r0, r0 * w))
+    assert sum(b.rows for b in bands) == h
+    return bands
+
+
 def band_desc(desc: A.hp_plan_desc, band: Band) -> A.hp_plan_desc:
     """Sub-plan of `desc` restricted to `band` (same frame size, camera, sampling and seed)."""
     if band.empty:
@@ -165,7 +184,8 @@ class PipelinedFrame:
     Everything here is host orchestration (torch streams / events / torch.distributed); kernels are the library's.
     """
 
-    def __init__(self, D, ctx, grid, full_desc, groups: int, world: int, rank: int, device, compute_stream):
+    def __init__(self, D, ctx, grid, full_desc, groups, world: int, rank: int, device, compute_stream):
+        """groups: number of equal row groups, or a sequence of relative heights (e.g. (0.75, 0.25))."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.D = torch, dist, D
@@ -173,6 +193,7 @@ class PipelinedFrame:
         self.compute = compute_stream
         self.side = torch.cuda.Stream(device=device)
         self.reduce = True   # False: skip the collectives (timing experiments)
+        weights = [1.0] * groups if isinstance(groups, int) else [float(v) for v in groups]
         # world axis the image rows advance along = the camera's "down" vector (second column of c2w's rotation)
         st_desc = full_desc
         c2w = [st_desc.camera.c2w[i] for i in range(12)]
@@ -185,7 +206,7 @@ class PipelinedFrame:
         self.block = torch.as_tensor(_CudaView(ptr, floats), device=device)
         self.parts = []
         ranges: List[Optional[Tuple[int, int]]] = []
-        for band in row_bands(full_desc, groups, align=TILE_ROWS * world):
+        for band in weighted_row_bands(full_desc, weights, align=TILE_ROWS * world):
             if band.empty:
                 continue
             plan = D.Plan(ctx, band_desc(full_desc, band))

@@ -54,6 +54,17 @@ def test_views_of_rank_and_u32_bands():
     assert SH.u32_safe_bands(c2, 512) == 1
 
 
+def test_weighted_row_bands():
+    desc = S.bench_plan(64, 2048, 16, stratified=False)
+    bands = SH.weighted_row_bands(desc, (0.75, 0.25), align=64)
+    assert [(b.y0, b.rows) for b in bands] == [(0, 1536), (1536, 512)]
+    assert bands[1].ray_index_base == 1536 * 64
+    bands = SH.weighted_row_bands(desc, (1, 1, 1), align=8)
+    assert sum(b.rows for b in bands) == 2048 and all(b.y0 % 8 == 0 for b in bands)
+    ragged = SH.weighted_row_bands(S.bench_plan(64, 100, 16, stratified=False), (0.9, 0.1), align=16)
+    assert sum(b.rows for b in ragged) == 100 and ragged[0].rows % 16 == 0
+
+
 def test_final_slab_runs_cover_every_touched_slab_once():
     # monotone ranges with overlap (the usual case), a group that touches nothing, and a reversed order
     for ranges in ([(0, 10), (7, 18), (15, 30), (27, 40)], [(0, 10), None, (8, 20)], [(30, 40), (18, 33), (5, 20), (0, 8)],
