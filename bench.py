@@ -168,7 +168,9 @@ def run_ours(args):
 
     # e2e: the same step through the C ABI with HOST buffers (pinned), i.e. what dvren::Renderer
     # Forward/Backward move per step (reference renderer.hpp:50-66): dL/dI host->device; image planes
-    # and the un-interleaved sigma / colour gradient grids device->host.  Both read calls block.
+    # and the un-interleaved sigma / colour gradient grids device->host.  The image planes are read from
+    # the frame's device views (hpx_frame_image) on a side stream while the backward runs; the gradient
+    # read blocks.
     import ctypes as C
     import hp_abi as A
     lib = ctx.lib
@@ -177,27 +179,38 @@ def run_ours(args):
     cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
     mask_host = torch.empty(pixels, dtype=torch.int32).pin_memory()
 
+    side = torch.cuda.Stream(device=dev)
+    fwd_done = torch.cuda.Event()
+    mask_dev = torch.as_tensor(CudaArrayView(img.hitmask.data, pixels), device=dev).view(torch.int32)
+
+    def read_planes_async():
+        """Image planes device -> pinned host on a side stream, so that the copy runs under the backward kernel."""
+        fwd_done.record(stream)
+        with torch.cuda.stream(side):
+            side.wait_event(fwd_done)
+            for h, d in zip(planes_host, planes):
+                h.copy_(d, non_blocking=True)
+            mask_host.copy_(mask_dev, non_blocking=True)
+
     def step_e2e():
         D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
-        D.check("hpx_frame_read", lib.hpx_frame_read(frame.handle, planes_host[0].data_ptr(), planes_host[1].data_ptr(),
-                                                     planes_host[2].data_ptr(), planes_host[3].data_ptr(),
-                                                     mask_host.data_ptr()))
+        read_planes_async()
         D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
         if reducer is not None:
             reducer()
         D.check("hpx_grid_read_grad", lib.hpx_grid_read_grad(grid.handle, sg_host.data_ptr(), cg_host.data_ptr(),
                                                              cam_host.data_ptr(), A.HP_MEMSPACE_HOST))
+        stream.wait_stream(side)
 
     def step_e2e_device_grads():
         """Same, but the gradient block stays in HBM for a device-side optimiser (hpx_grid_grad_buffer): host
         traffic is dL/dI in, the five image planes out."""
         D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
-        D.check("hpx_frame_read", lib.hpx_frame_read(frame.handle, planes_host[0].data_ptr(), planes_host[1].data_ptr(),
-                                                     planes_host[2].data_ptr(), planes_host[3].data_ptr(),
-                                                     mask_host.data_ptr()))
+        read_planes_async()
         D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
         if reducer is not None:
             reducer()
+        stream.wait_stream(side)
         ctx.synchronize()
 
     def barrier():

@@ -510,26 +510,31 @@ __device__ __forceinline__ void red_add4(float4* addr, float4 v) {
 
 // Index of voxel (x,y,z) in the scatter target (whole grid or box); false when a boxed target does not contain it.
 __device__ __forceinline__ bool scatter_index(const ScatterParams& sp, int32_t x, int32_t y, int32_t z, uint32_t& idx) {
-    const int32_t lx = x - sp.box_ox, ly = y - sp.box_oy, lz = z - sp.box_oz;
-    if (sp.boxed && (lx < 0 || lx >= sp.box_nx || ly < 0 || ly >= sp.box_ny || lz < 0 || lz >= sp.box_nz)) {
-        atomicAdd(sp.box_miss, 1u);
-        return false;
+    if (sp.boxed) {
+        const int32_t lx = x - sp.box_ox, ly = y - sp.box_oy, lz = z - sp.box_oz;
+        if (lx < 0 || lx >= sp.box_nx || ly < 0 || ly >= sp.box_ny || lz < 0 || lz >= sp.box_nz) {
+            atomicAdd(sp.box_miss, 1u);
+            return false;
+        }
     }
-    idx = static_cast<uint32_t>(lz) * sp.box_sz + static_cast<uint32_t>(ly) * sp.box_sy + static_cast<uint32_t>(lx) * sp.box_sx;
+    // sp.grad / sp.fixed are biased by the box origin on the host, so grid coordinates index them directly
+    idx = static_cast<uint32_t>(z) * sp.box_sz + static_cast<uint32_t>(y) * sp.box_sy + static_cast<uint32_t>(x) * sp.box_sx;
     return true;
 }
 
 // One corner contribution: a 16-byte float red, or four 64-bit integer reds of the value in units of the quantum.
+__device__ __forceinline__ void scatter_add_fixed(unsigned long long* p, float4 v, float inv_q) {
+    atomicAdd(p + 0, static_cast<unsigned long long>(__float2ll_rn(v.x * inv_q)));
+    atomicAdd(p + 1, static_cast<unsigned long long>(__float2ll_rn(v.y * inv_q)));
+    atomicAdd(p + 2, static_cast<unsigned long long>(__float2ll_rn(v.z * inv_q)));
+    atomicAdd(p + 3, static_cast<unsigned long long>(__float2ll_rn(v.w * inv_q)));
+}
 __device__ __forceinline__ void scatter_add(const ScatterParams& sp, uint32_t voxel, float4 v, float inv_q) {
-    if (sp.fixed != nullptr) {
-        unsigned long long* p = sp.fixed + 4ull * voxel;
-        atomicAdd(p + 0, static_cast<unsigned long long>(__float2ll_rn(v.x * inv_q)));
-        atomicAdd(p + 1, static_cast<unsigned long long>(__float2ll_rn(v.y * inv_q)));
-        atomicAdd(p + 2, static_cast<unsigned long long>(__float2ll_rn(v.z * inv_q)));
-        atomicAdd(p + 3, static_cast<unsigned long long>(__float2ll_rn(v.w * inv_q)));
-    } else {
+#ifndef DV_EXP_NO_FIXED
+    if (sp.fixed != nullptr) scatter_add_fixed(sp.fixed + 4ull * voxel, v, inv_q);
+    else
+#endif
         red_add4(sp.grad + voxel, v);
-    }
 }
 __device__ __forceinline__ float scatter_inv_quantum(const ScatterParams& sp) {
     return sp.fixed != nullptr ? __ldg(sp.fixed_meta + 2) : 1.0f;
@@ -563,21 +568,18 @@ __device__ __forceinline__ void scatter_sample(const ScatterParams& sp, float px
     }
     const Cell c = make_cell(gx, gy, gz, nx, ny, nz);
     const float ux = 1.0f - c.tx, uy = 1.0f - c.ty, uz = 1.0f - c.tz;
-    const int32_t xs[2] = {c.x0, c.x1}, ys[2] = {c.y0, c.y1}, zs[2] = {c.z0, c.z1};
-    const float wx[2] = {ux, c.tx}, wy[2] = {uy, c.ty}, wz[2] = {uz, c.tz};
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx)
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dz = 0; dz < 2; ++dz) {
-                const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
-                if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
-                const float w = wx[dx] * wy[dy] * wz[dz];
-                uint32_t idx;
-                if (scatter_index(sp, ix, iy, iz, idx))
-                    scatter_add(sp, idx, make_float4(g.x * w, g.y * w, g.z * w, g.w * w), inv_q);
-            }
+    // Rolled on purpose (corner order dx, dy, dz as in the reference): eight unrolled copies of the index / bounds /
+    // red sequence push the per-ray backward over an instruction-cache cliff (+75 % on early-terminating volumes).
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const bool hx = (k & 4) != 0, hy = (k & 2) != 0, hz = (k & 1) != 0;
+        const int32_t ix = hx ? c.x1 : c.x0, iy = hy ? c.y1 : c.y0, iz = hz ? c.z1 : c.z0;
+        if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
+        const float w = (hx ? c.tx : ux) * (hy ? c.ty : uy) * (hz ? c.tz : uz);
+        uint32_t idx;
+        if (scatter_index(sp, ix, iy, iz, idx))
+            scatter_add(sp, idx, make_float4(g.x * w, g.y * w, g.z * w, g.w * w), inv_q);
+    }
 }
 
 }  // namespace dv

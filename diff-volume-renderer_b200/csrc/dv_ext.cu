@@ -383,11 +383,15 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
     if (flags & HPX_BACKWARD_GRID) {
         ScatterParams sp = scatter_params(*g);
         if (box != nullptr) {
-            sp.grad = reinterpret_cast<float4*>(box->data);
             sp.box_ox = box->o[0]; sp.box_oy = box->o[1]; sp.box_oz = box->o[2];
             sp.box_nx = box->n[0]; sp.box_ny = box->n[1]; sp.box_nz = box->n[2];
+            sp.box_sx = 1u;
             sp.box_sy = static_cast<uint32_t>(box->n[0]);
             sp.box_sz = static_cast<uint32_t>(box->n[0]) * static_cast<uint32_t>(box->n[1]);
+            // biased base: voxel (x,y,z) of the GRID lives at grad[x + y * sy + z * sz] (never dereferenced outside the box)
+            sp.grad = reinterpret_cast<float4*>(box->data) -
+                      (static_cast<ptrdiff_t>(box->o[0]) + static_cast<ptrdiff_t>(box->o[1]) * sp.box_sy +
+                       static_cast<ptrdiff_t>(box->o[2]) * sp.box_sz);
             sp.boxed = 1u;
             sp.box_miss = f->d_box_miss;
         }
