@@ -390,9 +390,21 @@ __device__ __forceinline__ float4 scatter_cell(const ScatterParams& sp, float px
 // 8 corner accumulators {d r, d g, d b, d sigma}: corner k = dx + 2 dy + 4 dz.  Kept as float4 so that the register
 // allocator can place each one in an aligned quad: FFMA2 updates its (x,y) / (z,w) halves in place and
 // red.global.add.v4.f32 consumes the quad without moves.
+// kPlain: float reds into the grid's own gradient block in its default order (the common case) -- no box test, no
+// stride multiplies, no fixed-point branch.
+template <bool kPlain>
 __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key, const float4 (&acc)[8], float inv_q) {
     const int32_t x0 = key & 1023u, y0 = (key >> 10) & 1023u, z0 = key >> 20;
     const int32_t x1 = min(x0 + 1, sp.nx - 1), y1 = min(y0 + 1, sp.ny - 1), z1 = min(z0 + 1, sp.nz - 1);
+    if (kPlain) {
+        const uint32_t p00 = voxel_index32(0, y0, z0, sp.nx, sp.ny), p10 = voxel_index32(0, y1, z0, sp.nx, sp.ny);
+        const uint32_t p01 = voxel_index32(0, y0, z1, sp.nx, sp.ny), p11 = voxel_index32(0, y1, z1, sp.nx, sp.ny);
+        red_add4(sp.grad + (p00 + x0), acc[0]); red_add4(sp.grad + (p00 + x1), acc[1]);
+        red_add4(sp.grad + (p10 + x0), acc[2]); red_add4(sp.grad + (p10 + x1), acc[3]);
+        red_add4(sp.grad + (p01 + x0), acc[4]); red_add4(sp.grad + (p01 + x1), acc[5]);
+        red_add4(sp.grad + (p11 + x0), acc[6]); red_add4(sp.grad + (p11 + x1), acc[7]);
+        return;
+    }
     if (sp.boxed) {
         const int32_t lx0 = x0 - sp.box_ox, ly0 = y0 - sp.box_oy, lz0 = z0 - sp.box_oz;
         const int32_t lx1 = x1 - sp.box_ox, ly1 = y1 - sp.box_oy, lz1 = z1 - sp.box_oz;
@@ -423,7 +435,7 @@ __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key
 // kCamera: also accumulate d L / d (ray origin, ray direction) = sum_s (d sigma_s grad sigma(x_s) + w_s grad (g . rgb)(x_s)) {1, t_s}
 // from the corners phase A has in registers anyway, and reduce it to the camera parameters at the end
 // (replaces a separate camera_adjoint_kernel pass over every sample).
-template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera>
+template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera, bool kPlain>
 __global__ void __launch_bounds__(kLeanThreads, kCamera ? 4 : DV_MERGE_MIN_BLOCKS)
 lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
                            int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
@@ -571,7 +583,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                 }
                 const bool fresh = key != cur;
                 if (fresh) {
-                    if (cur != kNoCell) flush_cell(sp, cur, acc, inv_q);
+                    if (cur != kNoCell) flush_cell<kPlain>(sp, cur, acc, inv_q);
                     cur = key;
                 }
                 if (key != kNoCell) {
@@ -920,14 +932,22 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
     const bool strat = h_params.march.stratified != 0;
     const bool merge = resolve_scatter_mode(h_params, grid, sp, scatter_mode) == kScatterMerge;
     if (merge) {
-#define DV_MERGE(C, S, U)                                                                                              \
+        // plain = float reds into the grid's own block in default order: the specialised flush
+        const bool plain = sp.fixed == nullptr && sp.boxed == 0u && sp.box_sx == 1u && sp.box_sy == static_cast<uint32_t>(sp.nx) &&
+                           sp.box_sz == static_cast<uint32_t>(sp.nx) * static_cast<uint32_t>(sp.ny);
+#define DV_MERGE2(C, S, U, K)                                                                                          \
     do {                                                                                                               \
-        if (cam_partials != nullptr)                                                                                   \
-            lean_backward_merge_kernel<C, S, U, true><<<blocks, kLeanThreads, 0, stream>>>(                            \
+        if (plain)                                                                                                     \
+            lean_backward_merge_kernel<C, S, U, K, true><<<blocks, kLeanThreads, 0, stream>>>(                         \
                 d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials);                   \
         else                                                                                                           \
-            lean_backward_merge_kernel<C, S, U, false><<<blocks, kLeanThreads, 0, stream>>>(                           \
-                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, nullptr);                        \
+            lean_backward_merge_kernel<C, S, U, K, false><<<blocks, kLeanThreads, 0, stream>>>(                        \
+                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials);                   \
+    } while (0)
+#define DV_MERGE(C, S, U)                                                                                              \
+    do {                                                                                                               \
+        if (cam_partials != nullptr) DV_MERGE2(C, S, U, true);                                                         \
+        else DV_MERGE2(C, S, U, false);                                                                                \
     } while (0)
         const bool unit = sp.unit_bbox != 0;
         if (grid.clamp) {
@@ -938,6 +958,7 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
             else       { if (unit) DV_MERGE(false, false, true); else DV_MERGE(false, false, false); }
         }
 #undef DV_MERGE
+#undef DV_MERGE2
         if (cam_partials != nullptr) camera_reduce_kernel<<<1, 512, 0, stream>>>(cam_partials, blocks, d_cam16);
         return cudaGetLastError();
     }
