@@ -381,3 +381,68 @@ def test_full_size_config2_properties(ctx):
     expect = full["opacity"].astype(np.float64).sum()
     np.testing.assert_allclose(mass, [expect] * 3, rtol=2e-4)
     frame.close(); grid.close(); plan.close()
+
+
+@pytest.mark.parametrize("mode", sorted(SCATTER_MODES))
+@pytest.mark.parametrize("strat", [False, True])
+def test_scatter_modes_sparse_pixels(ctx, mode, strat):
+    """Pixels much SPARSER than voxels (3 voxels between neighbouring rays, 0.5 voxel between steps): the regime
+    where the merged kernel merges only along a ray; both kernels must still be exact."""
+    sig, col = S.hashed_volume(64, "thin")
+    desc = S.bench_plan(27, 22, 128, stratified=strat, view=1, views=9)
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, 0)
+    dl = np.ones((27 * 22, 3), np.float32)
+    ref = O.render(odesc, gs, gc, dl)
+    got = run_lean(ctx, desc, sig, col, 1, 0, None, None, dl,
+                   flags=D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+    check_forward(got, ref, "sparse")
+    np.testing.assert_allclose(got["color_grad"].reshape(-1, 3).astype(np.float64).sum(axis=0),
+                               [ref["opacity"].astype(np.float64).sum()] * 3, rtol=1e-4)
+    U.assert_close(got["sigma_grad"], ref["sigma_grad"], U.GRAD_RTOL, f"{mode} sigma_grad")
+    U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{mode} color_grad")
+
+
+def test_grid_1024_cubed_maximum_size_properties(ctx):
+    """BASELINE config 5's grid: 1024^3 voxels (17.2 GB packed + 17.2 GB gradient), the largest axis the merged kernel's
+    10-bit cell keys allow and 2^30 voxels for the 32-bit voxel indices.  Far beyond the CPU oracle, so the check is by
+    size-independent properties; the volume is generated on the device and handed over as DEVICE arrays."""
+    torch = pytest.importorskip("torch")
+    free, _total = torch.cuda.mem_get_info()
+    if free < 80 * (1 << 30):
+        pytest.skip("needs ~80 GB of free HBM")
+    n, W, steps = 1024, 256, 1024
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sigma = torch.rand((n, n, n), generator=gen, device="cuda", dtype=torch.float32) * 3.0
+    color = torch.rand((n, n, n, 3), generator=gen, device="cuda", dtype=torch.float32)
+    torch.cuda.synchronize()
+    grid = D.Grid(ctx, sigma.data_ptr(), color.data_ptr(), device_shape=(n, n, n))
+    ctx.synchronize()
+    corner = (float(sigma[-1, -1, -1]), [float(v) for v in color[-1, -1, -1]])
+    del sigma, color
+    torch.cuda.empty_cache()
+    desc = S.bench_plan(W, W, steps, stratified=False)
+    plan = D.Plan(ctx, desc); frame = D.Frame(plan)
+    assert frame.scatter_mode(grid) == "per_ray"          # 4 voxels between neighbouring rays: nothing to merge
+    frame.forward(grid)
+    out = frame.read(); counts = frame.counts()
+    assert counts["samples"] == W * W * steps and counts["live_samples"] == counts["samples"]
+    assert np.isfinite(out["image"]).all() and (out["trans"] > 0).all() and (out["trans"] < 1).all()
+    np.testing.assert_allclose(out["opacity"], 1.0 - out["trans"], atol=1e-6)
+    dl = np.ones((W * W, 3), np.float32)
+    for mode in ("per_ray", "merged"):
+        frame.backward(grid, dl, D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | SCATTER_MODES[mode])
+        ctx.synchronize()   # the library has its own stream: torch must not read the block before the kernel is done
+        # colour-gradient mass = sum of the weights = sum of opacity (trilinear weights sum to 1), through a device reduction
+        ptr, floats = grid.grad_buffer()
+        class _V:  # zero-copy view of the packed gradient block
+            __cuda_array_interface__ = {"shape": (floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        block = torch.as_tensor(_V(), device="cuda")
+        g4 = block[: n * n * n * 4].view(-1, 4)
+        mass = g4[:, :3].sum(dim=0, dtype=torch.float64).cpu().numpy()
+        assert torch.isfinite(g4).all()
+        np.testing.assert_allclose(mass, [out["opacity"].astype(np.float64).sum()] * 3, rtol=2e-4)
+        # the far corner voxel (index 2^30 - 1) is reachable: its gradient slot exists and is finite
+        assert np.isfinite(g4[-1].cpu().numpy()).all()
+    assert np.isfinite(corner[0]) and len(corner[1]) == 3
+    frame.close(); grid.close(); plan.close()
