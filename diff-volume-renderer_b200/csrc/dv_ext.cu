@@ -290,6 +290,7 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
     f->buf.live_total = static_cast<unsigned long long*>(frame_take(f, sizeof(unsigned long long), &st));
     f->d_dL_dI = static_cast<float*>(frame_take(f, rays * 12, &st));
     f->d_box_miss = static_cast<unsigned int*>(frame_take(f, sizeof(unsigned int), &st));
+    f->d_group_done = static_cast<unsigned int*>(frame_take(f, 8 * sizeof(unsigned int), &st));
     if (st == HP_STATUS_SUCCESS) {
         const cudaError_t e = cudaMemset(f->d_box_miss, 0, sizeof(unsigned int));
         if (e != cudaSuccess) st = cuda_fail(e, "cudaMemset(frame)");
@@ -526,6 +527,72 @@ HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI,
     for (int i = 0; i < 3; ++i) { gb.o[i] = box[i]; gb.n[i] = box[3 + i]; }
     if (static_cast<size_t>(gb.n[0]) * gb.n[1] * gb.n[2] == 0) return HP_STATUS_SUCCESS;   // nothing of this frame enters the cube
     return enqueue_backward(f, g, d_g, flags, &gb);
+}
+
+HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags,
+                                        const uint32_t* group_end_rows, uint32_t n_groups, uint32_t** out_device_counters,
+                                        uint32_t* out_expected) {
+    DV_TRY(frame_check_grid(f, g));
+    if (dL_dI == nullptr || group_end_rows == nullptr || n_groups == 0 || n_groups > 8 || out_expected == nullptr)
+        return HP_STATUS_INVALID_ARGUMENT;
+    if (!f->forward_done) return HP_STATUS_INVALID_ARGUMENT;
+    const RoiParams& roi = f->h_params.roi;
+    const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
+    const uint32_t owned_rows = lean_block_count(roi) / std::max(1u, tiles_x);
+    uint32_t prev = 0;
+    for (uint32_t i = 0; i < n_groups; ++i) {
+        if (group_end_rows[i] < prev) return HP_STATUS_INVALID_ARGUMENT;
+        const uint32_t end = i + 1 == n_groups ? owned_rows : std::min(group_end_rows[i], owned_rows);
+        out_expected[i] = (end - std::min(prev, end)) * tiles_x;
+        prev = end;
+    }
+    DV_TRY(ensure_device(f->ctx));
+    DV_TRY(grid_ensure_grad(g));
+    DV_TRY(frame_push_params(f));
+    const float* d_g = dL_dI;
+    if (memspace == HP_MEMSPACE_HOST) {
+        DV_CUDA(cudaMemcpyAsync(f->d_dL_dI, dL_dI, static_cast<size_t>(roi.w) * roi.h * 12, cudaMemcpyHostToDevice, f->ctx->stream));
+        d_g = f->d_dL_dI;
+    }
+    const LeanBuffers saved = f->buf;
+    f->buf.group_done = f->d_group_done;
+    f->buf.group_count = n_groups;
+    for (uint32_t i = 0; i < n_groups; ++i) f->buf.group_end[i] = i + 1 == n_groups ? owned_rows : group_end_rows[i];
+    const hp_status st = enqueue_backward(f, g, d_g, flags);
+    f->buf = saved;
+    if (out_device_counters) *out_device_counters = f->d_group_done;
+    return st;
+}
+
+HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_device_counters) {
+    if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(f->ctx));
+    DV_CUDA(cudaMemsetAsync(f->d_group_done, 0, 8 * sizeof(unsigned int), f->ctx->stream));
+    if (out_device_counters) *out_device_counters = f->d_group_done;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_t* device_counter, uint32_t value) {
+    if (stream_ctx == nullptr || device_counter == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_TRY(ensure_device(stream_ctx));
+    typedef int (*wait_fn)(CUstream_st*, unsigned long long, uint32_t, unsigned int);   // cuStreamWaitValue32
+    static wait_fn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DV_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q));
+        if (p == nullptr || q != cudaDriverEntryPointSuccess) {
+            set_last_error("cuStreamWaitValue32 is not available from this driver");
+            return HP_STATUS_UNSUPPORTED;
+        }
+        fn = reinterpret_cast<wait_fn>(p);
+    }
+    const int rc = fn(stream_ctx->stream, reinterpret_cast<unsigned long long>(device_counter), value, 0u /* GEQ */);
+    if (rc != 0) {
+        set_last_error("cuStreamWaitValue32 failed with driver error " + std::to_string(rc));
+        return HP_STATUS_INTERNAL_ERROR;
+    }
+    return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* g, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs) {

@@ -201,6 +201,20 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
     }
 }
 
+// End-of-CTA completion signal, see LeanBuffers::group_done.
+__device__ __forceinline__ void signal_group_done(const LeanBuffers& st, const RoiParams& roi) {
+    if (st.group_done == nullptr) return;
+    __syncthreads();                       // every warp of the CTA has issued its reds
+    if (threadIdx.x == 0) {
+        __threadfence();                   // ... and they are visible device-wide before the counter moves
+        const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
+        const uint32_t row = blockIdx.x / tiles_x;
+        uint32_t g = 0;
+        while (g + 1 < st.group_count && row >= st.group_end[g]) ++g;
+        atomicAdd(st.group_done + g, 1u);
+    }
+}
+
 // Per-sample state of one segment, stashed in shared memory between the forward recompute and the
 // reverse sweep: [sample][field][thread] so that a warp touches 32 consecutive banks.  Keeping the
 // two loops rolled (dynamic index into shared memory instead of unrolled register arrays) keeps the
@@ -292,6 +306,7 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
                            make_float4(g0 * w, g1 * w, g2 * w, dsigma), inv_q);
         }
     }
+    signal_group_done(st, roi);
 }
 
 // ---- backward, merged scatter ------------------------------------------------
@@ -617,6 +632,7 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
         make_ray(cam, roi.x + px.lx, roi.y + px.ly, &ra);
         camera_block_reduce(cam, ray, ra, px.inside, cam_o, cam_d, cam_partials);
     }
+    signal_group_done(st, roi);
 }
 #undef DV_CE
 

@@ -30,6 +30,13 @@ struct LeanBuffers {
     // {base = t_near + step * dt, t of the fixed-mode sample, dt_actual, depth cursor before the step}
     // (reference samp_cpu.cpp:227-241, int_cpu.cpp:170-211), built on the host by hpx_frame_create
     const float4* steps = nullptr;
+    // Device-side completion signal of the backward kernels (hpx_backward_signalled): CTAs are dispatched in tile-row
+    // order; a CTA whose (owned) tile row lies in group g adds 1 to group_done[g] when all its reds are issued and
+    // fenced.  A stream can then wait for a whole group of image rows (cuStreamWaitValue32) and all-reduce the gradient
+    // slabs that group finished while later rows are still running -- one launch, no per-group launch tails.
+    unsigned int* group_done = nullptr;
+    uint32_t group_count = 0;
+    uint32_t group_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // exclusive end (owned tile rows) of each group
 };
 
 // Fills `table[uniform_count]` with the per-step values above (plain IEEE float arithmetic, no contraction).

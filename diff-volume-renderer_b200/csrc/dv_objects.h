@@ -93,6 +93,7 @@ struct hpx_frame {
     float* d_dL_dI = nullptr;     // [rays][3]
     double* d_cam_partials = nullptr;
     unsigned int* d_box_miss = nullptr;   // contributions hpx_backward_box had to drop (must stay 0)
+    unsigned int* d_group_done = nullptr; // [8] completion counters of hpx_backward_signalled
     size_t device_bytes = 0;
     uint64_t rays = 0, samples = 0;
     bool forward_done = false;

@@ -62,6 +62,10 @@ HPX_FUNCTIONS = {
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
+    "hpx_backward_signalled": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, P(C.c_uint32), C.c_uint32,
+                                         P(C.c_void_p), P(C.c_uint32)]),
+    "hpx_stream_wait_counter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "hpx_frame_reset_group_counters": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
     "hpx_grid_add_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_grid_set_grad_layout": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_size_t), P(C.c_int32)]),
     "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
@@ -121,6 +125,10 @@ class Context:
 
     def synchronize(self):
         check("hpx_ctx_synchronize", self.lib.hpx_ctx_synchronize(self.handle))
+
+    def wait_counter(self, device_counter_ptr: int, value: int):
+        """This context's stream waits (without occupying an SM) until *device_counter_ptr >= value."""
+        check("hpx_stream_wait_counter", self.lib.hpx_stream_wait_counter(self.handle, int(device_counter_ptr), int(value)))
 
     def close(self):
         if self.handle:
@@ -250,6 +258,22 @@ class Frame:
         b = (C.c_int32 * 6)(*box)
         check("hpx_backward_box", self.lib.hpx_backward_box(self.handle, grid.handle, int(dL_dI_device_ptr),
                                                            A.HP_MEMSPACE_DEVICE, flags, int(box_device_ptr), C.byref(b)))
+
+    def reset_group_counters(self) -> int:
+        p = C.c_void_p()
+        check("hpx_frame_reset_group_counters", self.lib.hpx_frame_reset_group_counters(self.handle, C.byref(p)))
+        return p.value
+
+    def backward_signalled(self, grid: Grid, dL_dI_device_ptr: int, group_end_rows, flags=HPX_BACKWARD_GRID):
+        """One backward launch with a completion counter per row group; returns (device pointer of the counters,
+        expected counts)."""
+        n = len(group_end_rows)
+        ends = (C.c_uint32 * n)(*[int(v) for v in group_end_rows])
+        expected = (C.c_uint32 * n)()
+        counters = C.c_void_p()
+        check("hpx_backward_signalled", self.lib.hpx_backward_signalled(
+            self.handle, grid.handle, int(dL_dI_device_ptr), A.HP_MEMSPACE_DEVICE, flags, ends, n, C.byref(counters), expected))
+        return counters.value, [int(v) for v in expected]
 
     def box_misses(self) -> int:
         n = C.c_uint32()

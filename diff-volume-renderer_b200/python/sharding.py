@@ -261,6 +261,89 @@ class PipelinedFrame:
         self.grid.set_grad_layout(2)
 
 
+class SignalledFrame:
+    """PipelinedFrame without per-group launches: ONE forward and ONE backward launch over the rank's interleaved tile
+    rows.  The backward's CTAs run in tile-row order and count themselves into a per-group device counter
+    (hpx_backward_signalled); the side stream waits on those counters (hpx_stream_wait_counter -> cuStreamWaitValue32) and
+    all-reduces, in place, the gradient slabs each finished group leaves behind while later rows are still running.
+    The GPU stays full the whole time (no launch tails); only the last group's slabs are reduced after the kernel."""
+
+    def __init__(self, D, ctx, grid, full_desc, groups, world: int, rank: int, device, compute_stream):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.D = torch, dist, D
+        self.ctx, self.grid, self.world, self.rank = ctx, grid, world, rank
+        self.compute = compute_stream
+        self.side = torch.cuda.Stream(device=device, priority=-1)   # waits + collectives go ahead of queued rendering CTAs
+        self.side_ctx = D.Context(device=device.index, stream=self.side.cuda_stream)
+        self.reduce = True
+        weights = [1.0] * groups if isinstance(groups, int) else [float(v) for v in groups]
+        c2w = [full_desc.camera.c2w[i] for i in range(12)]
+        down = [abs(c2w[1]), abs(c2w[5]), abs(c2w[9])]
+        if not any(down):
+            down = [0.0, 1.0, 0.0]
+        self.slow_axis = max(range(3), key=lambda i: down[i])
+        self.slab_floats, self.n_slabs = grid.set_grad_layout(self.slow_axis)
+        ptr, floats = grid.grad_buffer()
+        self.block = torch.as_tensor(_CudaView(ptr, floats), device=device)
+        self.plan = D.Plan(ctx, full_desc)
+        self.frame = D.Frame(self.plan)
+        self.frame.set_interleave(world, rank)
+        # groups: row bands cut on multiples of (tile rows x world) so that every rank owns the same number of tile rows
+        ranges: List[Optional[Tuple[int, int]]] = []
+        ends, owned = [], 0
+        bands = [b for b in weighted_row_bands(full_desc, weights, align=TILE_ROWS * world) if not b.empty]
+        for band in bands:
+            plan = D.Plan(ctx, band_desc(full_desc, band))
+            probe = D.Frame(plan)
+            probe.set_interleave(world, rank)
+            box = probe.bounds(grid)
+            probe.close(); plan.close()
+            lo = box[self.slow_axis] if box[3 + self.slow_axis] > 0 else 1 << 40
+            hi = box[self.slow_axis] + box[3 + self.slow_axis] if box[3 + self.slow_axis] > 0 else -1
+            if world > 1:
+                t_lo = torch.tensor([lo], dtype=torch.int64, device=device)
+                t_hi = torch.tensor([hi], dtype=torch.int64, device=device)
+                dist.all_reduce(t_lo, op=dist.ReduceOp.MIN)
+                dist.all_reduce(t_hi, op=dist.ReduceOp.MAX)
+                lo, hi = int(t_lo.item()), int(t_hi.item())
+            ranges.append((lo, hi) if hi > lo else None)
+            tile_rows = (band.rows + TILE_ROWS - 1) // TILE_ROWS
+            owned += (tile_rows - rank + world - 1) // world if tile_rows > rank else 0
+            ends.append(owned)
+        self.group_end_rows, self.ranges, self.bands = ends, ranges, bands
+        self.runs = final_slab_runs(ranges)
+        self.start = torch.cuda.Event()
+
+    @property
+    def samples(self) -> int:
+        return self.frame.counts()["samples"]
+
+    def step(self, dL_dI_ptr: int, flags: int):
+        torch = self.torch
+        self.grid.zero_grad()
+        self.frame.forward(self.grid)
+        counters = self.frame.reset_group_counters()
+        self.start.record(self.compute)
+        _, expected = self.frame.backward_signalled(self.grid, dL_dI_ptr, self.group_end_rows,
+                                                    flags & ~self.D.HPX_BACKWARD_ZERO)
+        if self.world > 1 and self.reduce:
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.start)     # counters cleared: the previous step's counts cannot satisfy the waits
+                for g, runs in enumerate(self.runs):
+                    self.side_ctx.wait_counter(counters + 4 * g, expected[g])
+                    for a, b in runs:
+                        self.dist.all_reduce(self.block[a * self.slab_floats: b * self.slab_floats], op=self.dist.ReduceOp.SUM)
+                self.dist.all_reduce(self.block[-16:], op=self.dist.ReduceOp.SUM)
+            self.compute.wait_stream(self.side)
+
+    def close(self):
+        self.frame.close()
+        self.plan.close()
+        self.side_ctx.close()
+        self.grid.set_grad_layout(2)
+
+
 class _CudaView:
     """Raw device pointer as a torch-importable array (zero copy)."""
 

@@ -149,6 +149,20 @@ HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* grid, floa
 /* Contributions hpx_backward_box found outside its box and dropped since the last call (0 with the boxes of
  * hpx_frame_bounds; reading clears the counter and synchronises). */
 HP_API hp_status hpx_frame_box_misses(hpx_frame* frame, uint32_t* out_count);
+/* hpx_backward with a DEVICE-SIDE completion signal per group of image rows: ONE launch whose CTAs run in tile-row order;
+ * group i covers the frame's owned tile rows [group_end_rows[i-1], group_end_rows[i]) (the last group runs to the end).
+ * Every CTA adds 1 to counter i when its reds are issued and fenced; out_expected[i] is the count that means "group i is
+ * done".  hpx_stream_wait_counter makes ANOTHER stream (stream_ctx's) wait until a counter has reached a value
+ * (cuStreamWaitValue32, no SM is occupied by the wait): that stream can all-reduce the gradient slabs a group finished
+ * while the later rows are still running -- no per-group launches, hence no launch tails.
+ * Protocol per step: hpx_frame_reset_group_counters (clears them on the frame's stream) -> record an event there and make
+ * the waiting stream wait for it (so that it cannot see the previous step's counts) -> hpx_backward_signalled ->
+ * hpx_stream_wait_counter + collective per group on the waiting stream. */
+HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* frame, uint32_t** out_device_counters);
+HP_API hp_status hpx_backward_signalled(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
+                                        uint32_t flags, const uint32_t* group_end_rows, uint32_t n_groups,
+                                        uint32_t** out_device_counters, uint32_t* out_expected);
+HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_t* device_counter, uint32_t value);
 /* Which scatter strategy hpx_backward(flags) runs for this frame / grid pair: writes HPX_BACKWARD_SCATTER_PER_RAY
  * or HPX_BACKWARD_SCATTER_MERGED (kernel names lean_backward_kernel / lean_backward_merge_kernel in profiles). */
 HP_API hp_status hpx_backward_scatter(const hpx_frame* frame, const hpx_grid* grid, uint32_t flags, uint32_t* out_flag);

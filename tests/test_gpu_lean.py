@@ -403,6 +403,46 @@ def test_scatter_modes_sparse_pixels(ctx, mode, strat):
     U.assert_close(got["color_grad"], ref["color_grad"], U.GRAD_RTOL, f"{mode} color_grad")
 
 
+def test_signalled_backward_counts_every_cta_and_matches_plain(ctx):
+    """hpx_backward_signalled: one launch, a device counter per group of tile rows.  After the stream drains every counter
+    equals the expected CTA count, a second context's stream can wait on them (cuStreamWaitValue32), and the gradient
+    equals the plain backward's."""
+    sig, col = S.hashed_volume(24, "dense")
+    W, Hh, steps = 150, 131, 64
+    desc = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=6)
+    dl = S.hashed_image_grad(W * Hh)
+    plain = run_lean(ctx, desc, sig, col, 1, 0, None, None, dl)
+    lib = ctx.lib
+    for world, rank in ((1, 0), (3, 1)):
+        plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+        frame.set_interleave(world, rank)
+        frame.forward(grid)
+        d_dl = C.c_void_p()
+        D.check("alloc", lib.hpx_device_alloc(ctx.handle, dl.nbytes, C.byref(d_dl)))
+        D.check("h2d", lib.hpx_copy_to_device(ctx.handle, d_dl, np.ascontiguousarray(dl).ctypes.data, dl.nbytes))
+        grid.zero_grad()
+        counters = frame.reset_group_counters()
+        tile_rows = (Hh + 7) // 8
+        owned = (tile_rows - rank + world - 1) // world
+        ends = [owned // 3, 2 * owned // 3, owned]
+        ptr, expected = frame.backward_signalled(grid, d_dl.value, ends, D.HPX_BACKWARD_GRID)
+        assert ptr == counters and sum(expected) == owned * ((W + 15) // 16)
+        other = D.Context(device=0)                       # a second stream waits for the last group, then we read
+        other.wait_counter(counters + 8, expected[2])
+        other.synchronize()
+        ctx.synchronize()
+        got = np.zeros(8, np.uint32)
+        D.check("d2h", lib.hpx_copy_to_host(ctx.handle, got.ctypes.data, C.c_void_p(counters), 32))
+        assert list(got[:3]) == expected and not got[3:].any()
+        if world == 1:
+            sg, cg, _ = grid.read_grad()
+            U.assert_close(sg, plain["sigma_grad"], U.GRAD_RTOL, "signalled sigma_grad")
+            U.assert_close(cg, plain["color_grad"], U.GRAD_RTOL, "signalled color_grad")
+        other.close()
+        lib.hpx_device_free(ctx.handle, d_dl)
+        frame.close(); grid.close(); plan.close()
+
+
 def test_grid_1024_cubed_maximum_size_properties(ctx):
     """BASELINE config 5's grid: 1024^3 voxels (17.2 GB packed + 17.2 GB gradient), the largest axis the merged kernel's
     10-bit cell keys allow and 2^30 voxels for the 32-bit voxel indices.  Far beyond the CPU oracle, so the check is by
