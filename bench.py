@@ -53,12 +53,15 @@ def read_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled through NVML DURING the timed region."""
+    """SM clock and throttle reasons sampled through NVML DURING the timed region.  The thread starts (NVML init
+    included) before the warm-up and samples every 5 ms; only samples between mark_begin() and mark_end() count."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.err = index, False, [], set(), None, None
+        self.index, self.stop_flag, self.samples, self.max_mhz, self.err = index, False, [], None, None
+        self.t0 = self.t1 = None
         self.thread = None
+        self.ready = threading.Event()
 
     def _run(self):
         try:
@@ -66,27 +69,42 @@ class ClockSampler:
             N.nvmlInit()
             h = N.nvmlDeviceGetHandleByIndex(self.index)
             self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            self.ready.set()
             while not self.stop_flag:
-                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
-                mask = int(N.nvmlDeviceGetCurrentClocksEventReasons(h))
-                for bit, name in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                time.sleep(0.02)
+                self.samples.append((time.perf_counter(), float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)),
+                                     int(N.nvmlDeviceGetCurrentClocksEventReasons(h))))
+                time.sleep(0.005)
         except Exception as e:  # NVML missing: report it, never fake a clock
             self.err = repr(e)
+            self.ready.set()
 
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+        self.ready.wait(timeout=10.0)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
+        if self.t1 is None:
+            self.mark_end()
         self.stop_flag = True
         if self.thread is not None:
             self.thread.join(timeout=2.0)
-        sm = sorted(self.sm)
-        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
-               "reasons": sorted(self.reasons), "samples": len(sm)}
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [s for s in self.samples if t0 <= s[0] <= self.t1]
+        sm = sorted(s[1] for s in inside)
+        reasons = set()
+        for s in inside:
+            for bit, name in self.REASONS.items():
+                if s[2] & bit:
+                    reasons.add(name)
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+               "samples": len(sm)}
         if self.err:
             out["error"] = self.err
         return out
@@ -222,16 +240,20 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, k, warm):
+    def timed(fn, k, warm, sampler=None):
         for _ in range(warm):
             fn()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark_begin()
         a.record(stream)
         for _ in range(k):
             fn()
         b.record(stream)
         barrier()
+        if sampler is not None:
+            sampler.mark_end()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -240,7 +262,7 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step_resident, args.steps, args.warmup)
+    total_ms = timed(step_resident, args.steps, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     counts = frame.counts()
     samples, live = counts["samples"], counts["live_samples"]
@@ -602,7 +624,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
