@@ -22,6 +22,9 @@ import sys
 import threading
 import time
 
+# stdout carries exactly ONE JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(REPO, "diff-volume-renderer_b200", "python")]
 
