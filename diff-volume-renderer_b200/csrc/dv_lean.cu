@@ -918,8 +918,9 @@ cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params
     return cudaGetLastError();
 }
 
-// Pixel spacing, in voxels, between neighbouring rays where they cross the cube centre: below ~1 the
-// quads of the merge kernel share cells and merging pays; above it the plain per-ray scatter is used.
+// Pixel spacing, in voxels, between neighbouring rays where they cross the cube centre.  Measured crossover
+// (tools/heuristic_time.py, profiles/README.md): merged wins by 25-35 % at 0.3-0.5 voxel, 7-19 % at 0.6-0.83,
+// loses 3-8 % at 0.93 and 12-27 % at 1.25.
 static bool merge_scatter_pays(const FrameParams& h, const PackedGrid& grid, const ScatterParams& sp) {
     if (!grid.linear || sp.nearest) return false;
     if (sp.nx < 2 || sp.ny < 2 || sp.nz < 2 || sp.nx > 1024 || sp.ny > 1024 || sp.nz > 1024) return false;   // 10-bit cell keys
@@ -929,7 +930,7 @@ static bool merge_scatter_pays(const FrameParams& h, const PackedGrid& grid, con
     const float f = fminf(fabsf(h.cam.fx), fabsf(h.cam.fy));
     if (!(f > 0.0f)) return false;
     const float n = static_cast<float>(max(sp.nx, max(sp.ny, sp.nz)) - 1);
-    return dist / f * n < 1.0f;
+    return dist / f * n < 0.9f;
 }
 
 int resolve_scatter_mode(const FrameParams& h_params, const PackedGrid& grid, const ScatterParams& sp, int scatter_mode) {
