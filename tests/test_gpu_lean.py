@@ -258,6 +258,7 @@ def test_interleaved_rows_and_box_backward_reproduce_full_frame(ctx):
     full = run_lean(ctx, full_desc, sig, col, 1, 0, None, None, dl_full)
     lib = ctx.lib
     grid = D.Grid(ctx, sig, col)
+    grid.zero_grad()
     nx = ny = nz = 28
     G = np.zeros((nz, ny, nx, 4), np.float64)
     image = np.zeros_like(full["image"]); hit = np.zeros_like(full["hitmask"])
@@ -288,9 +289,15 @@ def test_interleaved_rows_and_box_backward_reproduce_full_frame(ctx):
             host = np.zeros((bz, by, bx, 4), np.float32)
             D.check("d2h", lib.hpx_copy_to_host(ctx.handle, host.ctypes.data, d_box, host.nbytes))
             G[z0:z0 + bz, y0:y0 + by, x0:x0 + bx] += host
+            grid.add_box(ctx, d_box.value, box)            # device hand-over: gradient block += box, box = 0
+            D.check("d2h", lib.hpx_copy_to_host(ctx.handle, host.ctypes.data, d_box, host.nbytes))
+            assert not host.any()
             lib.hpx_device_free(ctx.handle, d_box)
             frame.close(); plan.close()
         lib.hpx_device_free(ctx.handle, d_dl)
+    sg_dev, cg_dev, _ = grid.read_grad()                   # what hpx_grid_add_box accumulated on the device
+    U.assert_close(sg_dev, full["sigma_grad"], U.GRAD_RTOL, "add_box sigma_grad")
+    U.assert_close(cg_dev, full["color_grad"], U.GRAD_RTOL, "add_box color_grad")
     grid.close()
     assert hit.all() and total_samples == full["samples"] and total_live == full["live_samples"]
     U.assert_bits(image, full["image"], "interleaved image")
