@@ -23,6 +23,11 @@
  *                   reference src/render/renderer.cpp:415-427,
  *                   src/fields/dense_grid.cpp:171-309)
  *   hpx_frame_capture / hpx_frame_replay   real CUDA-graph capture of the above
+ *   hpx_frame_set_interleave / hpx_frame_bounds / hpx_grid_set_grad_layout / hpx_backward_signalled /
+ *   hpx_stream_wait_counter / hpx_backward_box / hpx_grid_add_box
+ *                   building blocks for strong scaling of ONE frame over several GPUs (interleaved tile
+ *                   rows, contiguous gradient slabs, device-signalled or per-group overlapped all-reduce;
+ *                   orchestrated by diff-volume-renderer_b200/python/sharding.py)
  *
  * All functions return hp_status; none blocks the host unless documented.
  * Work is enqueued on the context's stream.
