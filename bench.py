@@ -22,8 +22,15 @@ import sys
 import threading
 import time
 
-# stdout carries exactly ONE JSON line: NCCL's version banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there), so descriptor 1 is pointed at stderr for the whole run and the JSON line goes to the saved one.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [os.path.join(REPO, "diff-volume-renderer_b200", "python")]
@@ -39,6 +46,9 @@ CONFIGS = {
     "c4": dict(grid=256, width=800, steps=512, stratified=True, views=64,
                workload="BASELINE configs[3]: 64 views at 800x800 over a 256^3 grid, stratified, 512 steps, grid + camera "
                         "gradients, one captured CUDA graph replayed per view"),
+    "c5": dict(grid=1024, width=1024, steps=1024, stratified=True, views=128, camera=False, device_volume=True,
+               workload="BASELINE configs[4]: 1024^3 dense grid (17.2 GB packed, replicated per GPU), 128 views at 1024x1024, "
+                        "stratified, 1024 steps, fwd+bwd, views sharded across the GPUs, one captured CUDA graph replayed per view"),
 }
 METRIC = "Msamples/s fwd+bwd (fused forward + backward adjoint to the dense sigma/color grid)"
 UNIT = "Msamples/s"
@@ -338,7 +348,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     frame.close(); grid.close(); plan.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -444,7 +454,7 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
                     "note": "gradient block stays in HBM (device-side optimiser)"},
             "gpu_launches": (2 if hasattr(pf, "frame") else 2 * len(pf.parts)) * args.steps, "clocks": clocks}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     pf.close(); grid.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -472,12 +482,24 @@ def run_view_batch(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     n, W, steps, views = cfg["grid"], cfg["width"], cfg["steps"], cfg["views"]
-    sigma, color = S.hashed_volume(n, "thin")
     ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
     my_views = SH.views_of_rank(views, world, rank)
     descs = [S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=v, views=views) for v in my_views]
     plan = D.Plan(ctx, descs[0])
-    grid = D.Grid(ctx, sigma, color)
+    if cfg.get("device_volume"):
+        # too large to hash on the host in reasonable time: a seeded device generator (same seed on every rank = replicas)
+        gen = torch.Generator(device=dev).manual_seed(1234)
+        sigma = torch.rand((n, n, n), generator=gen, device=dev, dtype=torch.float32) * 2.0
+        color = torch.rand((n, n, n, 3), generator=gen, device=dev, dtype=torch.float32)
+        torch.cuda.synchronize()
+        grid = D.Grid(ctx, sigma.data_ptr(), color.data_ptr(), device_shape=(n, n, n))
+        ctx.synchronize()
+        del sigma, color
+        torch.cuda.empty_cache()
+    else:
+        sigma, color = S.hashed_volume(n, "thin")
+        grid = D.Grid(ctx, sigma, color)
+        del sigma, color
     frame = D.Frame(plan)
     g_host = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).pin_memory()
     g_frame = torch.as_tensor(CudaArrayView(frame.grad_input_ptr(), plan.n_rays * 3), device=dev)
@@ -485,7 +507,7 @@ def run_view_batch(args):
     grad_ptr, grad_floats = grid.grad_buffer()
     grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
     reducer = SH.GradientAllReduce(grad_view) if world > 1 else None
-    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_CAMERA
+    flags = D.HPX_BACKWARD_GRID | (D.HPX_BACKWARD_CAMERA if cfg.get("camera", True) else 0)
     frame.capture(grid, flags)
     cams = [d.camera for d in descs]
     cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
@@ -530,20 +552,21 @@ def run_view_batch(args):
     b.record(stream)
     barrier()
     e2e_ms = a.elapsed_time(b) / args.steps
-    line = {"metric": METRIC + " + camera adjoint", "value": samples / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
+    line = {"metric": METRIC + (" + camera adjoint" if cfg.get("camera", True) else ""), "value": samples / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "views": views, "views_per_gpu": len(my_views),
-                       "volume": "hashed thin (sigma = 2u)", "samples_per_step": samples,
-                       "backward_kernel": "lean_backward_merge_kernel<..., camera>" if frame.scatter_mode(grid, flags) == "merged"
-                       else "lean_backward_kernel + camera_adjoint_kernel",
-                       "l2": "inputs larger than L2 (grid 256 MB + gradient 256 MB + checkpoints 164 MB)"},
+                       "volume": "device-generated uniform (sigma = 2u)" if cfg.get("device_volume") else "hashed thin (sigma = 2u)",
+                       "samples_per_step": samples, "allreduce_bytes": int(grad_floats * 4) if world > 1 else 0,
+                       "backward_kernel": ("lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged"
+                                           else "lean_backward_kernel") + (" (+ camera adjoint)" if cfg.get("camera", True) else ""),
+                       "l2": "inputs larger than L2 (grid %d MB + gradient %d MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
             "e2e": {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": len(my_views) * 128, "d2h_bytes_per_step": 64 + W * W * 28},
             "gpu_launches": 4 * len(my_views) * args.steps, "clocks": clocks,
             "ms_per_view": ms_per_step / len(my_views)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     frame.close(); grid.close(); plan.close(); ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -621,7 +644,7 @@ def run_reference(args):
             "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
