@@ -434,13 +434,14 @@ def test_signalled_backward_counts_every_cta_and_matches_plain(ctx):
         ends = [owned // 3, 2 * owned // 3, owned]
         ptr, expected = frame.backward_signalled(grid, d_dl.value, ends, D.HPX_BACKWARD_GRID)
         assert ptr == counters and sum(expected) == owned * ((W + 15) // 16)
-        other = D.Context(device=0)                       # a second stream waits for the last group, then we read
-        other.wait_counter(counters + 8, expected[2])
-        other.synchronize()
         ctx.synchronize()
         got = np.zeros(8, np.uint32)
         D.check("d2h", lib.hpx_copy_to_host(ctx.handle, got.ctypes.data, C.c_void_p(counters), 32))
         assert list(got[:3]) == expected and not got[3:].any()
+        # only now (the counts are known to be there, so this cannot hang): a second context's stream waits on a counter
+        other = D.Context(device=0)
+        other.wait_counter(counters + 8, expected[2])
+        other.synchronize()
         if world == 1:
             sg, cg, _ = grid.read_grad()
             U.assert_close(sg, plain["sigma_grad"], U.GRAD_RTOL, "signalled sigma_grad")
