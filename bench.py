@@ -162,7 +162,7 @@ def run_ours(args):
     sigma, color = S.hashed_volume(n, "thin")       # no early termination: live samples == samples
     ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
     rows_mode = args.sharding == "rows" and world > 1
-    if args.sharding in ("pipeline", "signalled"):
+    if args.sharding in ("pipeline", "signalled", "views-overlap"):
         return run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank)
     if rows_mode:
         # strong scaling: ONE frame cut into row bands, global pixel ids + global ray-index base
@@ -366,14 +366,21 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
     import synth as S
 
     n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
-    full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
+    weak = args.sharding == "views-overlap"
+    if weak:   # every rank its own view (2.5 degrees apart, like the default weak-scaling run), all-reduce hidden behind the backward
+        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank - (world - 1) / 2.0, views=144)
+    else:
+        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
     grid = D.Grid(ctx, sigma, color)
     del sigma, color
     g_host = torch.from_numpy(S.hashed_image_grad(W * W)).pin_memory()
     g_dev = g_host.to(dev, non_blocking=True)
     groups = [float(v) for v in args.group_split.split(",")] if args.group_split else args.groups
-    cls = SH.SignalledFrame if args.sharding == "signalled" else SH.PipelinedFrame
-    pf = cls(D, ctx, grid, full, groups, world, rank, dev, stream)
+    if weak:
+        pf = SH.SignalledFrame(D, ctx, grid, full, groups, world, rank, dev, stream, interleave=False)
+    else:
+        cls = SH.SignalledFrame if args.sharding == "signalled" else SH.PipelinedFrame
+        pf = cls(D, ctx, grid, full, groups, world, rank, dev, stream)
     flags = D.HPX_BACKWARD_GRID
     cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
 
@@ -410,7 +417,7 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
     step()
     barrier()
     verify = None
-    if rank == 0:
+    if rank == 0 and not weak:   # (weak mode sums DIFFERENT views: no single-GPU frame to compare with)
         got = pf.block.clone()
         plan = D.Plan(ctx, full)
         frame = D.Frame(plan)
@@ -438,7 +445,7 @@ def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
     total = int(samples.item())
     ms_per_step = total_ms / args.steps
     line = {"metric": METRIC, "value": total / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
                        "parallelism": f"one frame, {len(pf.ranges)} row groups ({args.sharding}), tile rows interleaved over {world} GPUs; gradient "
@@ -658,7 +665,7 @@ def main():
     ap.add_argument("--cpu-rows-ref", type=int, default=8, help="rows per thread per step for --impl reference")
     ap.add_argument("--cpu-threads", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", default="views", choices=["views", "rows", "pipeline", "signalled"],
+    ap.add_argument("--sharding", default="views", choices=["views", "rows", "pipeline", "signalled", "views-overlap"],
                     help="N > 1: one view per GPU (weak scaling, default); one frame cut into row bands (strong); or one "
                          "frame in row groups with interleaved tile rows and the all-reduce overlapped (strong, pipelined)")
     ap.add_argument("--groups", type=int, default=2, help="equal row groups of --sharding pipeline")

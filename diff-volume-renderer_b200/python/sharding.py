@@ -268,13 +268,18 @@ class SignalledFrame:
     all-reduces, in place, the gradient slabs each finished group leaves behind while later rows are still running.
     The GPU stays full the whole time (no launch tails); only the last group's slabs are reduced after the kernel."""
 
-    def __init__(self, D, ctx, grid, full_desc, groups, world: int, rank: int, device, compute_stream):
+    def __init__(self, D, ctx, grid, full_desc, groups, world: int, rank: int, device, compute_stream, interleave: bool = True):
+        """interleave=True: ONE frame shared by the ranks (strong scaling, tile rows t % world == rank).
+        interleave=False: every rank renders its OWN full frame `full_desc` (weak scaling over views); the slab ranges are
+        still unioned over the ranks, so the overlap works whenever the views' image rows advance along the same world
+        axis in the same order (views of one orbit about that axis, neighbouring views of a batch)."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.D = torch, dist, D
         self.ctx, self.grid, self.world, self.rank = ctx, grid, world, rank
         self.compute = compute_stream
         self.side = torch.cuda.Stream(device=device, priority=-1)   # waits + collectives go ahead of queued rendering CTAs
+        stride, phase = (world, rank) if interleave else (1, 0)
         self.side_ctx = D.Context(device=device.index, stream=self.side.cuda_stream)
         self.reduce = True
         weights = [1.0] * groups if isinstance(groups, int) else [float(v) for v in groups]
@@ -288,15 +293,15 @@ class SignalledFrame:
         self.block = torch.as_tensor(_CudaView(ptr, floats), device=device)
         self.plan = D.Plan(ctx, full_desc)
         self.frame = D.Frame(self.plan)
-        self.frame.set_interleave(world, rank)
-        # groups: row bands cut on multiples of (tile rows x world) so that every rank owns the same number of tile rows
+        self.frame.set_interleave(stride, phase)
+        # groups: row bands cut on multiples of (tile rows x stride) so that every rank owns the same number of tile rows
         ranges: List[Optional[Tuple[int, int]]] = []
         ends, owned = [], 0
-        bands = [b for b in weighted_row_bands(full_desc, weights, align=TILE_ROWS * world) if not b.empty]
+        bands = [b for b in weighted_row_bands(full_desc, weights, align=TILE_ROWS * stride) if not b.empty]
         for band in bands:
             plan = D.Plan(ctx, band_desc(full_desc, band))
             probe = D.Frame(plan)
-            probe.set_interleave(world, rank)
+            probe.set_interleave(stride, phase)
             box = probe.bounds(grid)
             probe.close(); plan.close()
             lo = box[self.slow_axis] if box[3 + self.slow_axis] > 0 else 1 << 40
@@ -309,7 +314,7 @@ class SignalledFrame:
                 lo, hi = int(t_lo.item()), int(t_hi.item())
             ranges.append((lo, hi) if hi > lo else None)
             tile_rows = (band.rows + TILE_ROWS - 1) // TILE_ROWS
-            owned += (tile_rows - rank + world - 1) // world if tile_rows > rank else 0
+            owned += (tile_rows - phase + stride - 1) // stride if tile_rows > phase else 0
             ends.append(owned)
         self.group_end_rows, self.ranges, self.bands = ends, ranges, bands
         self.runs = final_slab_runs(ranges)
