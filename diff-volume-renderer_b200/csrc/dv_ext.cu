@@ -319,6 +319,19 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
 
 HP_API size_t hpx_frame_bytes(const hpx_frame* f) { return f ? f->device_bytes : 0; }
 
+// Host-only: the per-step table a frame of this plan uploads (no device needed) -- lets the CPU test suite pin the
+// ray-independent part of the marching loop against the oracle.
+HP_API hp_status hpx_plan_step_table(const hp_plan* plan, float* out_steps4, size_t capacity_steps, uint32_t* out_count) {
+    if (plan == nullptr || out_count == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    *out_count = plan->uniform_count;
+    if (!plan->gap_free) return HP_STATUS_UNSUPPORTED;
+    if (out_steps4 == nullptr) return HP_STATUS_SUCCESS;
+    if (capacity_steps < plan->uniform_count) return HP_STATUS_OUT_OF_MEMORY;
+    const FrameParams p = frame_params_from_plan(*plan);
+    build_step_table(p.march, reinterpret_cast<float4*>(out_steps4));
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_frame_set_view(hpx_frame* f, const hp_camera_desc* camera, uint64_t seed,
                                     uint64_t ray_index_base) {
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;

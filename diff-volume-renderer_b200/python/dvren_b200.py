@@ -54,6 +54,7 @@ HPX_FUNCTIONS = {
     "hpx_grid_release": (None, [C.c_void_p]),
     "hpx_frame_create": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
     "hpx_frame_bytes": (C.c_size_t, [C.c_void_p]),
+    "hpx_plan_step_table": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, P(C.c_uint32)]),
     "hpx_frame_set_view": (C.c_int, [C.c_void_p, P(A.hp_camera_desc), C.c_uint64, C.c_uint64]),
     "hpx_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),

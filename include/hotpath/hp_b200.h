@@ -118,6 +118,10 @@ HP_API void      hpx_grid_release(hpx_grid* grid);
 
 /* ---- per-plan frame workspace ------------------------------------------- */
 HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame);
+/* Host-only (works without a GPU): the per-step table {base = t_near + k dt, fixed-mode sample time, dt_actual,
+ * depth cursor before the step} that frames of this plan upload; out_steps4 may be NULL to query the count.
+ * All rays generated from a plan share it (reference samp_cpu.cpp:227-241, int_cpu.cpp:170-211). */
+HP_API hp_status hpx_plan_step_table(const hp_plan* plan, float* out_steps4, size_t capacity_steps, uint32_t* out_count);
 /* Bytes of device memory the frame owns (workspace accounting). */
 HP_API size_t    hpx_frame_bytes(const hpx_frame* frame);
 /* Change camera / seed / global ray-index base without re-planning (graph friendly:

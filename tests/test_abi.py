@@ -218,3 +218,42 @@ def test_no_gpu_means_unsupported_not_fallback():
         D.Grid(D.Context(), grid, np.ones((2, 2, 2, 3), np.float32))
     lib.hp_plan_release(plan)
     lib.hp_ctx_release(ctx)
+
+
+@pytest.mark.parametrize("t_near,t_far,dt,steps", [(0.9, 4.0, 1.5 / 512, 512), (0.1, 2.0, 0.1, 64), (0.0, 1.0, 0.1, 16),
+                                                   (0.5, 1.6, 0.04, 40), (0.3, 0.95, 0.0371, 100), (2.0, 2.5, 0.3, 7)])
+def test_step_table_matches_the_oracle_march(t_near, t_far, dt, steps):
+    """The host-built per-step table of the lean kernels (hpx_plan_step_table; no GPU needed) against the oracle's march of
+    one ray: sample count, dt_actual of every step and the fixed-mode sample position bit for bit; base and depth cursor
+    against their float32 definitions (reference samp_cpu.cpp:227-241, int_cpu.cpp:170,211)."""
+    import ctypes as C
+    import dvren_b200 as D
+    import oracle as O
+    lib = D.load()
+    desc = A.make_plan_desc(1, 1, t_near, t_far, dt=dt, max_steps=steps)
+    ctx, plan = C.c_void_p(), C.c_void_p()
+    assert lib.hp_ctx_create(None, C.byref(ctx)) == 0
+    assert lib.hp_plan_create(ctx, C.byref(desc), C.byref(plan)) == 0
+    count = C.c_uint32()
+    assert lib.hpx_plan_step_table(plan, None, 0, C.byref(count)) == 0
+    table = np.zeros((count.value, 4), np.float32)
+    assert lib.hpx_plan_step_table(plan, table.ctypes.data, count.value, C.byref(count)) == 0
+    st, odesc = O.plan_resolve(desc)
+    rays = O.rays(odesc)
+    sig = np.ones((2, 2, 2), np.float32)
+    gs, gc = O.make_grid(sig, 1), O.make_grid(np.ones((2, 2, 2, 3), np.float32), 3)
+    st, samp = O.sample(odesc, gs, gc, rays, odesc.max_samples)
+    assert st == 0 and samp["count"] == count.value
+    assert table[:, 2].tobytes() == samp["dt"].tobytes()                       # dt_actual
+    o, d = rays["origins"][0], rays["directions"][0]
+    pos = np.stack([o + d * np.float32(t) for t in table[:, 1]]).astype(np.float32)
+    assert pos.tobytes() == samp["positions"].tobytes()                         # fixed-mode sample time -> position
+    k = np.arange(count.value, dtype=np.float32)
+    base = (np.float32(odesc.t_near) + k * np.float32(odesc.sampling.dt)).astype(np.float32)
+    assert table[:, 0].tobytes() == base.tobytes()
+    cursor = np.float32(odesc.t_near)
+    for i in range(count.value):
+        assert table[i, 3] == cursor
+        cursor = np.float32(cursor + table[i, 2])
+    lib.hp_plan_release(plan)
+    lib.hp_ctx_release(ctx)
