@@ -257,3 +257,25 @@ def test_step_table_matches_the_oracle_march(t_near, t_far, dt, steps):
         cursor = np.float32(cursor + table[i, 2])
     lib.hp_plan_release(plan)
     lib.hp_ctx_release(ctx)
+
+
+def test_extension_entry_points_validate_arguments_without_a_gpu():
+    """hp_b200.h: null / out-of-range arguments are rejected before any device call (so this runs on a CPU-only box)."""
+    import ctypes as C
+    import dvren_b200 as D
+    lib = D.load()
+    INV = A.HP_STATUS_INVALID_ARGUMENT
+    box = (C.c_int32 * 6)()
+    n = C.c_uint32()
+    ptr = C.c_void_p()
+    assert lib.hpx_frame_set_interleave(None, 2, 0) == INV
+    assert lib.hpx_frame_bounds(None, None, C.byref(box)) == INV
+    assert lib.hpx_backward_box(None, None, None, A.HP_MEMSPACE_DEVICE, 1, None, C.byref(box)) == INV
+    assert lib.hpx_frame_box_misses(None, C.byref(n)) == INV
+    assert lib.hpx_grid_add_box(None, None, None, C.byref(box)) == INV
+    assert lib.hpx_grid_set_grad_layout(None, 1, None, None) == INV
+    assert lib.hpx_backward_signalled(None, None, None, A.HP_MEMSPACE_DEVICE, 1, None, 0, C.byref(ptr), C.byref(n)) == INV
+    assert lib.hpx_frame_reset_group_counters(None, C.byref(ptr)) == INV
+    assert lib.hpx_stream_wait_counter(None, None, 1) == INV
+    assert lib.hpx_backward_scatter(None, None, 0, C.byref(n)) == INV
+    assert lib.hpx_plan_step_table(None, None, 0, C.byref(n)) == INV
