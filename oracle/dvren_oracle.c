@@ -410,9 +410,27 @@ int orc_diff(size_t n_rays, size_t n_samples, const float* dL_dI, int64_t stride
 /* ------------------------------------------------------------------------ */
 /* sample -> grid scatter: src/fields/dense_grid.cpp:198-306                 */
 /* ------------------------------------------------------------------------ */
+/* Optional float64 shadow of the scatter (test adjudication only, no reference counterpart): the SAME float32
+ * per-corner terms the reference adds, accumulated in double, plus the sum of their magnitudes, over a box of
+ * voxels [o, o + n).  It separates "the float32 sum depends on the order of its terms" from real defects. */
+static void shadow_add(orc_render_shadow* sh, int32_t ix, int32_t iy, int32_t iz, float ts, const float tc[3]) {
+    const int32_t bx = ix - sh->box_o[0], by = iy - sh->box_o[1], bz = iz - sh->box_o[2];
+    if (bx < 0 || bx >= sh->box_n[0] || by < 0 || by >= sh->box_n[1] || bz < 0 || bz >= sh->box_n[2]) {
+        ++sh->misses;
+        return;
+    }
+    const size_t v = ((size_t)bz * (size_t)sh->box_n[1] + (size_t)by) * (size_t)sh->box_n[0] + (size_t)bx;
+    if (sh->sigma_sum) sh->sigma_sum[v] += (double)ts;
+    if (sh->sigma_abs) sh->sigma_abs[v] += fabs((double)ts);
+    for (int c = 0; c < 3; ++c) {
+        if (sh->color_sum) sh->color_sum[3 * v + c] += (double)tc[c];
+        if (sh->color_abs) sh->color_abs[3 * v + c] += fabs((double)tc[c]);
+    }
+}
+
 static void scatter_one(const int32_t res[3], const float bmin[3], const float bmax[3],
                         uint32_t interp, uint32_t oob, const float pos[3], float gsig,
-                        const float gcol[3], float* sg, float* cg) {
+                        const float gcol[3], float* sg, float* cg, orc_render_shadow* sh) {
     const int32_t nx = res[0], ny = res[1], nz = res[2];
     float l[3];
     int outside = 0;
@@ -434,9 +452,10 @@ static void scatter_one(const int32_t res[3], const float bmin[3], const float b
     if (interp == HP_INTERP_NEAREST || nx == 1 || ny == 1 || nz == 1) {        /* :232-246 */
         const int32_t ix = (int32_t)roundf(gx), iy = (int32_t)roundf(gy), iz = (int32_t)roundf(gz);
         if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) return;
-        const size_t v = (size_t)((iz * ny + iy) * nx + ix);
+        const size_t v = ((size_t)iz * (size_t)ny + (size_t)iy) * (size_t)nx + (size_t)ix;
         sg[v] += gsig;
         cg[3 * v] += gcol[0]; cg[3 * v + 1] += gcol[1]; cg[3 * v + 2] += gcol[2];
+        if (sh) shadow_add(sh, ix, iy, iz, gsig, gcol);
         return;
     }
     const int32_t x0 = (int32_t)floorf(gx), y0 = (int32_t)floorf(gy), z0 = (int32_t)floorf(gz);
@@ -451,9 +470,12 @@ static void scatter_one(const int32_t res[3], const float bmin[3], const float b
                 const int32_t ix = xs[dx], iy = ys[dy], iz = zs[dz];
                 if (ix < 0 || ix >= nx || iy < 0 || iy >= ny || iz < 0 || iz >= nz) continue;
                 const float w = wx[dx] * wy[dy] * wz[dz];                      /* :259-266 */
-                const size_t v = (size_t)((iz * ny + iy) * nx + ix);
-                sg[v] += gsig * w;
-                cg[3 * v] += gcol[0] * w; cg[3 * v + 1] += gcol[1] * w; cg[3 * v + 2] += gcol[2] * w;
+                const size_t v = ((size_t)iz * (size_t)ny + (size_t)iy) * (size_t)nx + (size_t)ix;
+                const float ts = gsig * w;
+                const float tc[3] = {gcol[0] * w, gcol[1] * w, gcol[2] * w};
+                sg[v] += ts;
+                cg[3 * v] += tc[0]; cg[3 * v + 1] += tc[1]; cg[3 * v + 2] += tc[2];
+                if (sh) shadow_add(sh, ix, iy, iz, ts, tc);
             }
 }
 
@@ -464,7 +486,7 @@ int orc_scatter(const int32_t res[3], const float bbox_min[3], const float bbox_
     if (res[0] <= 0 || res[1] <= 0 || res[2] <= 0) return HP_STATUS_INVALID_ARGUMENT;
     for (size_t i = 0; i < n_samples; ++i)
         scatter_one(res, bbox_min, bbox_max, interp, oob, positions + 3 * i, grad_sigma[i],
-                    grad_color + 3 * i, sigma_grad, color_grad);
+                    grad_color + 3 * i, sigma_grad, color_grad, NULL);
     return HP_STATUS_SUCCESS;
 }
 
@@ -514,6 +536,13 @@ int orc_image(const hp_plan_desc* p, size_t n_rays, const uint32_t* pixel_ids,
 int orc_render(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* gc,
                uint64_t ray_index_base, const float* dL_dI, const int32_t res[3],
                const float bbox_min[3], const float bbox_max[3], orc_render_out* out) {
+    return orc_render_shadowed(p, gs, gc, ray_index_base, dL_dI, res, bbox_min, bbox_max, out, NULL);
+}
+
+int orc_render_shadowed(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* gc,
+                        uint64_t ray_index_base, const float* dL_dI, const int32_t res[3],
+                        const float bbox_min[3], const float bbox_max[3], orc_render_out* out,
+                        orc_render_shadow* shadow) {
     if (!p || !out || (!gs && !gc)) return HP_STATUS_INVALID_ARGUMENT;
     const hp_roi_desc roi = p->roi;
     const uint32_t K = p->sampling.max_steps;
@@ -579,7 +608,7 @@ int orc_render(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* gc,
                 for (uint32_t i = 0; i < n; ++i)
                     scatter_one(res, bbox_min, bbox_max, gs ? gs->interp : gc->interp,
                                 gs ? gs->oob : gc->oob, pos + 3 * i, gsg[i], gcl + 3 * i,
-                                out->sigma_grad, out->color_grad);
+                                out->sigma_grad, out->color_grad, shadow);
             }
         }
     }
@@ -637,8 +666,16 @@ static double channel_grad(const orc_grid* g, const float pos[3], int ch, int st
 
 int orc_camera_grad(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* gc,
                     uint64_t ray_index_base, const float* dL_dI, double out16[16]) {
+    return orc_camera_grad_mag(p, gs, gc, ray_index_base, dL_dI, out16, NULL);
+}
+
+/* mag16 (may be NULL): the same chain rule applied to the per-sample MAGNITUDES |g_x|, |g_x t|: an upper bound of the
+ * sum of |terms| behind each of the 16 outputs -- the scale float32 rounding of a different summation order refers to. */
+int orc_camera_grad_mag(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* gc,
+                        uint64_t ray_index_base, const float* dL_dI, double out16[16], double mag16[16]) {
     if (!p || !gs || !gc || !dL_dI || !out16) return HP_STATUS_INVALID_ARGUMENT;
     for (int i = 0; i < 16; ++i) out16[i] = 0.0;
+    if (mag16) for (int i = 0; i < 16; ++i) mag16[i] = 0.0;
     const hp_roi_desc roi = p->roi;
     const hp_camera_desc* cam = &p->camera;
     const uint32_t K = p->sampling.max_steps;
@@ -674,7 +711,7 @@ int orc_camera_grad(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* g
             if (T <= 1e-4f) break;
         }
         const float* g = dL_dI + 3 * ray;
-        double adj_T = 0.0, dLdo[3] = {0, 0, 0}, dLdd[3] = {0, 0, 0};
+        double adj_T = 0.0, dLdo[3] = {0, 0, 0}, dLdd[3] = {0, 0, 0}, Ao[3] = {0, 0, 0}, Ad[3] = {0, 0, 0};
         for (uint32_t i = n; i-- > 0;) {
             const double dot = g[0] * cval[3 * i] + g[1] * cval[3 * i + 1] + g[2] * cval[3 * i + 2];
             const double w = Tprev[i] * alpha[i];
@@ -683,9 +720,15 @@ int orc_camera_grad(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* g
             adj_T = dot * alpha[i] + adj_T * (1.0 - alpha[i]);
             for (int ax = 0; ax < 3; ++ax) {
                 double gx = gsig * gsv[3 * i + ax];
-                for (int ch = 0; ch < 3; ++ch) gx += g[ch] * w * gcv[9 * i + 3 * ch + ax];
+                double ga = fabs(gx);
+                for (int ch = 0; ch < 3; ++ch) {
+                    gx += g[ch] * w * gcv[9 * i + 3 * ch + ax];
+                    ga += fabs(g[ch] * w * gcv[9 * i + 3 * ch + ax]);
+                }
                 dLdo[ax] += gx;
                 dLdd[ax] += gx * tval[i];
+                Ao[ax] += ga;
+                Ad[ax] += ga * fabs(tval[i]);
             }
         }
         /* d = v / |v|, v = R q */
@@ -711,6 +754,23 @@ int orc_camera_grad(const hp_plan_desc* p, const orc_grid* gs, const orc_grid* g
             out16[13] += -q[1] / fy * dLdq[1];
             out16[14] += -dLdq[0] / fx;
             out16[15] += -dLdq[1] / fy;
+        }
+        if (mag16) {
+            const double ad = fabs(dn[0]) * Ad[0] + fabs(dn[1]) * Ad[1] + fabs(dn[2]) * Ad[2];
+            double Av[3];
+            for (int i = 0; i < 3; ++i) Av[i] = (Ad[i] + fabs(dn[i]) * ad) / len;
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) mag16[4 * i + j] += Av[i] * fabs(q[j]);
+                mag16[4 * i + 3] += Ao[i];
+            }
+            if (!ortho) {
+                double Aq[2] = {0, 0};
+                for (int i = 0; i < 3; ++i) { Aq[0] += fabs(cam->c2w[4 * i]) * Av[i]; Aq[1] += fabs(cam->c2w[4 * i + 1]) * Av[i]; }
+                mag16[12] += fabs(q[0] / fx) * Aq[0];
+                mag16[13] += fabs(q[1] / fy) * Aq[1];
+                mag16[14] += Aq[0] / fabs(fx);
+                mag16[15] += Aq[1] / fabs(fy);
+            }
         }
     }
     free(alpha); free(Tprev); free(tval); free(dtv); free(cval); free(gsv); free(gcv);

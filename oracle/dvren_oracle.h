@@ -111,10 +111,31 @@ int orc_render(const hp_plan_desc* desc, const orc_grid* gs, const orc_grid* gc,
                uint64_t ray_index_base, const float* dL_dI, const int32_t res[3],
                const float bbox_min[3], const float bbox_max[3], orc_render_out* out);
 
+/* orc_render with a float64 SHADOW of the gradient scatter over a box of voxels (test adjudication; no reference
+ * counterpart).  The float32 outputs are untouched -- same arithmetic, same order.  The shadow receives, per voxel of
+ * the box [box_o, box_o + box_n) (x fastest), the sum in double of the very float32 terms the reference adds
+ * (`*_sum`) and the sum of their magnitudes (`*_abs`); any pointer may be NULL.  `misses` counts contributions that
+ * fell outside the box.  Lets a test tell "two float32 summation orders of the same terms" from a defect. */
+typedef struct orc_render_shadow {
+    int32_t box_o[3], box_n[3];
+    double* sigma_sum; double* sigma_abs;   /* [box voxels]     */
+    double* color_sum; double* color_abs;   /* [3 * box voxels] */
+    uint64_t misses;
+} orc_render_shadow;
+
+int orc_render_shadowed(const hp_plan_desc* desc, const orc_grid* gs, const orc_grid* gc,
+                        uint64_t ray_index_base, const float* dL_dI, const int32_t res[3],
+                        const float bbox_min[3], const float bbox_max[3], orc_render_out* out,
+                        orc_render_shadow* shadow);
+
 /* Analytic camera adjoint (double accumulation), SURVEY Appendix A.11.  No
  * reference counterpart.  out16 = d/d c2w[12] followed by d/d {fx,fy,cx,cy}. */
 int orc_camera_grad(const hp_plan_desc* desc, const orc_grid* gs, const orc_grid* gc,
                     uint64_t ray_index_base, const float* dL_dI, double out16[16]);
+
+/* Same, also returning per output an upper bound of the sum of the magnitudes of its terms (mag16, may be NULL). */
+int orc_camera_grad_mag(const hp_plan_desc* desc, const orc_grid* gs, const orc_grid* gc,
+                        uint64_t ray_index_base, const float* dL_dI, double out16[16], double mag16[16]);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,12 @@ class orc_render_out(C.Structure):
                                                             ("live_sample_count", C.c_uint64)]
 
 
+class orc_render_shadow(C.Structure):
+    _fields_ = [("box_o", C.c_int32 * 3), ("box_n", C.c_int32 * 3), ("sigma_sum", C.c_void_p),
+                ("sigma_abs", C.c_void_p), ("color_sum", C.c_void_p), ("color_abs", C.c_void_p),
+                ("misses", C.c_uint64)]
+
+
 def build_oracle(force: bool = False) -> str:
     """Compile liboracle.so if missing (gcc, seconds)."""
     if force or not os.path.exists(ORACLE_SO) or \
@@ -88,10 +94,14 @@ def lib() -> C.CDLL:
         _lib.orc_render.argtypes = [C.POINTER(A.hp_plan_desc), C.POINTER(orc_grid), C.POINTER(orc_grid),
                                     C.c_uint64, f32p, C.POINTER(C.c_int32 * 3), C.POINTER(C.c_float * 3),
                                     C.POINTER(C.c_float * 3), C.POINTER(orc_render_out)]
+        _lib.orc_render_shadowed.restype = C.c_int
+        _lib.orc_render_shadowed.argtypes = _lib.orc_render.argtypes + [C.POINTER(orc_render_shadow)]
         _lib.orc_camera_grad.restype = C.c_int
         _lib.orc_camera_grad.argtypes = [C.POINTER(A.hp_plan_desc), C.POINTER(orc_grid),
                                          C.POINTER(orc_grid), C.c_uint64, f32p,
                                          C.POINTER(C.c_double * 16)]
+        _lib.orc_camera_grad_mag.restype = C.c_int
+        _lib.orc_camera_grad_mag.argtypes = _lib.orc_camera_grad.argtypes + [C.POINTER(C.c_double * 16)]
     return _lib
 
 
@@ -199,8 +209,13 @@ def image(desc, r, intl):
 
 
 def render(desc, gs, gc, dL_dI=None, res=None, bmin=(0, 0, 0), bmax=(1, 1, 1), ray_index_base=0,
-           per_ray=True, frames=True):
-    """Whole path; returns dict with per-ray, per-pixel and (if dL_dI) grid-gradient arrays."""
+           per_ray=True, frames=True, shadow=False, shadow_box=None):
+    """Whole path; returns dict with per-ray, per-pixel and (if dL_dI) grid-gradient arrays.
+
+    shadow=True (needs dL_dI) adds the float64 shadow of the scatter (orc_render_shadowed): `sigma_sum`,
+    `color_sum` = the reference's own float32 terms accumulated in double, `sigma_abs`, `color_abs` = the
+    sums of their magnitudes, over `shadow_box` = (x0, y0, z0, nx, ny, nz) (default: the whole grid),
+    flattened x-fastest like the gradient arrays; `shadow_misses` counts contributions outside the box."""
     n = desc.roi.width * desc.roi.height
     h, w = desc.height, desc.width
     out = orc_render_out()
@@ -231,19 +246,40 @@ def render(desc, gs, gc, dL_dI=None, res=None, bmin=(0, 0, 0), bmax=(1, 1, 1), r
     r3 = (C.c_int32 * 3)(*[int(x) for x in res])
     lo = (C.c_float * 3)(*[float(x) for x in bmin])
     hi = (C.c_float * 3)(*[float(x) for x in bmax])
-    st = lib().orc_render(C.byref(desc), C.byref(gs) if gs else None, C.byref(gc) if gc else None,
-                          ray_index_base, _p(dl), C.byref(r3), C.byref(lo), C.byref(hi), C.byref(out))
+    sh = None
+    if shadow and dl is not None:
+        box = tuple(int(v) for v in (shadow_box if shadow_box is not None else (0, 0, 0) + tuple(res)))
+        bv = box[3] * box[4] * box[5]
+        sh = orc_render_shadow()
+        for i in range(3):
+            sh.box_o[i], sh.box_n[i] = box[i], box[3 + i]
+        o.update(sigma_sum=np.zeros(bv, np.float64), sigma_abs=np.zeros(bv, np.float64),
+                 color_sum=np.zeros(bv * 3, np.float64), color_abs=np.zeros(bv * 3, np.float64))
+        sh.sigma_sum, sh.sigma_abs = _p(o["sigma_sum"]), _p(o["sigma_abs"])
+        sh.color_sum, sh.color_abs = _p(o["color_sum"]), _p(o["color_abs"])
+        o["shadow_box"] = box
+    st = lib().orc_render_shadowed(C.byref(desc), C.byref(gs) if gs else None, C.byref(gc) if gc else None,
+                                   ray_index_base, _p(dl), C.byref(r3), C.byref(lo), C.byref(hi), C.byref(out),
+                                   C.byref(sh) if sh is not None else None)
+    if sh is not None:
+        o["shadow_misses"] = int(sh.misses)
     o["status"] = st
     o["sample_count"] = int(out.sample_count)
     o["live_sample_count"] = int(out.live_sample_count)
     return o
 
 
-def camera_grad(desc, gs, gc, dL_dI, ray_index_base=0) -> np.ndarray:
+def camera_grad(desc, gs, gc, dL_dI, ray_index_base=0, with_mag=False):
+    """Analytic camera adjoint d/d c2w[12], d/d {fx,fy,cx,cy}; with_mag=True also returns the per-output upper
+    bound of the sum of |terms| (orc_camera_grad_mag)."""
     dl = np.ascontiguousarray(dL_dI, np.float32)
     out = (C.c_double * 16)()
-    st = lib().orc_camera_grad(C.byref(desc), C.byref(gs), C.byref(gc), ray_index_base, _p(dl), C.byref(out))
+    mag = (C.c_double * 16)()
+    st = lib().orc_camera_grad_mag(C.byref(desc), C.byref(gs), C.byref(gc), ray_index_base, _p(dl), C.byref(out),
+                                   C.byref(mag) if with_mag else None)
     assert st == 0, st
+    if with_mag:
+        return np.array(list(out), dtype=np.float64), np.array(list(mag), dtype=np.float64)
     return np.array(list(out), dtype=np.float64)
 
 

@@ -57,6 +57,67 @@ def test_oracle_matches_golden(path):
     U.assert_bits(r["depth"], g["img_depth"], "render.depth")
     U.assert_bits(r["sigma_grad"], g["sigma_grad"], "render.sigma_grad")
     U.assert_bits(r["color_grad"], g["color_grad"], "render.color_grad")
+    # the float64 shadow (test adjudication) must not disturb the pinned float32 result, and it is the sum of the same terms
+    sh = O.render(desc, gs, gc, g["dL_dI"], (nx, ny, nz), g["bmin"], g["bmax"], shadow=True)
+    U.assert_bits(sh["sigma_grad"], g["sigma_grad"], "shadowed render.sigma_grad")
+    U.assert_bits(sh["color_grad"], g["color_grad"], "shadowed render.color_grad")
+    assert sh["shadow_misses"] == 0
+    for key in ("sigma", "color"):
+        err = np.abs(sh[f"{key}_sum"] - sh[f"{key}_grad"].astype(np.float64))
+        assert (err <= U.SUM_ORDER_ALLOWANCE * sh[f"{key}_abs"]).all(), key      # the reference's own float32 sum sits inside the allowance
+        assert (np.abs(sh[f"{key}_sum"]) <= sh[f"{key}_abs"] * (1 + 1e-12)).all()
+        assert U.assert_grad_close(sh[f"{key}_grad"], sh, "self " + key, key) == 0
+
+
+def test_gradient_gate_contract_floor_and_adjudication():
+    """The gradient gate of the GPU tests (tests/util.py): contract floor 1e-3 of the largest entry; an entry outside it
+    passes only through the float64 adjudication; a real defect (one corner weight off by 1e-3) fails both."""
+    sig, col = S.hashed_volume(12, "dense")
+    desc = S.bench_plan(48, 40, 64, stratified=True, view=1, views=7)
+    st, od = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, 0)
+    dl = S.hashed_image_grad(48 * 40)
+    ref = O.render(od, gs, gc, dl, shadow=True)
+    assert U.GRAD_FLOOR_FRAC == 1e-3 and U.GRAD_RTOL == 1e-4
+    # (1) the exact float64 sum rounded to float32 -- another valid summation order -- passes
+    n_adj = U.assert_grads(ref["sigma_sum"].astype(np.float32), ref["color_sum"].astype(np.float32), ref, "f64-rounded")
+    assert n_adj <= U.ADJUDICATED_MAX_FRAC * ref["sigma_sum"].size * 4 + 16
+    # (2) a boxed shadow addresses the same voxels
+    box = (2, 3, 1, 9, 8, 10)
+    part = O.render(od, gs, gc, dl, shadow=True, shadow_box=box)
+    full = ref["sigma_sum"].reshape(12, 12, 12)[1:11, 3:11, 2:11]
+    assert np.array_equal(full.reshape(-1), part["sigma_sum"]) and part["shadow_misses"] > 0
+    # (3) a defect is not adjudicated away: 0.1 % error on the largest entries
+    bad = ref["sigma_grad"].copy()
+    top = np.argsort(-np.abs(bad))[:5]
+    bad[top] *= np.float32(1.001)
+    with pytest.raises(AssertionError):
+        U.assert_grad_close(bad, ref, "defect", "sigma")
+    # (4) nor is a small absolute error on an entry whose terms do not cancel
+    bad = ref["color_grad"].copy()
+    i = np.argmax(ref["color_abs"])
+    bad[i] += np.float32(3e-4 * abs(ref["color_grad"][i]) + 3e-7 * np.abs(ref["color_grad"]).max())
+    with pytest.raises(AssertionError):
+        U.assert_grad_close(bad, ref, "defect", "color")
+    # (5) without a shadow there is nothing to adjudicate against: outside the contract gate = failure
+    plain = O.render(od, gs, gc, dl)
+    noisy = plain["sigma_grad"] + np.float32(1e-5) * np.abs(plain["sigma_grad"]).max()
+    with pytest.raises(AssertionError):
+        U.assert_grad_close(noisy, plain, "no shadow", "sigma")
+
+
+def test_camera_gradient_magnitudes_bound_the_adjoint():
+    sig, col = S.smooth_volume(24)
+    desc = S.bench_plan(30, 26, 64, stratified=True, view=1, views=9)
+    st, od = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig, col, 1, 0)
+    dl = S.hashed_image_grad(30 * 26) + np.float32(0.25)
+    a = O.camera_grad(od, gs, gc, dl)
+    b, mag = O.camera_grad(od, gs, gc, dl, with_mag=True)
+    assert np.array_equal(a, b) and (np.abs(b) <= mag * (1 + 1e-12)).all() and (mag > 0).all()
+    U.assert_camera_close(b.astype(np.float32), b, mag, "float32-rounded adjoint")
+    with pytest.raises(AssertionError):
+        U.assert_camera_close(b * 1.001, b, mag, "defect")
 
 
 def test_cli_example_counts():

@@ -131,15 +131,13 @@ def _worker(rank, world, port, q):
         samples = torch.tensor([part["sample_count"], part["live_sample_count"]], dtype=torch.int64)
         dist.all_reduce(samples)
         if rank == 0:
-            ref = O.render(full_res, gs, gc, dl_full)
-            ref_cam = O.camera_grad(full_res, gs, gc, dl_full)
+            ref = O.render(full_res, gs, gc, dl_full, shadow=True)
+            ref_cam, cam_mag = O.camera_grad(full_res, gs, gc, dl_full, with_mag=True)
             ok_img = U.bits_equal(img.numpy(), ref["image"])
             sg = block[:4 * V].reshape(V, 4)[:, 3]
             cg = block[:4 * V].reshape(V, 4)[:, :3].reshape(-1)
-            U.assert_close(sg, ref["sigma_grad"], U.GRAD_RTOL, "sharded sigma_grad")
-            U.assert_close(cg, ref["color_grad"], U.GRAD_RTOL, "sharded color_grad")
-            scale = np.abs(ref_cam).max()
-            assert np.all(np.abs(block[4 * V:] - ref_cam) <= 1e-4 * np.maximum(np.abs(ref_cam), 0.05 * scale))
+            U.assert_grads(sg, cg, ref, "sharded")
+            U.assert_camera_close(block[4 * V:], ref_cam, cam_mag, "sharded camera gradient")
             q.put(("ok", ok_img, int(samples[0]) == ref["sample_count"], int(samples[1]) == ref["live_sample_count"]))
     except Exception as e:  # surface the failure in the parent
         if rank == 0:
