@@ -263,7 +263,7 @@ extern "C" HP_API hp_status hp_ray(const hp_plan* plan, const hp_rays_t* overrid
             std::memcpy(rays->pixel_ids.data, o.pixel_ids.data, n * 4);
             return HP_STATUS_SUCCESS;
         }
-        DV_TRY(ensure_device(plan->ctx));
+        DV_ENTER(plan->ctx);
         cudaStream_t s = plan->ctx->stream;
         DV_CUDA(cudaMemcpyAsync(rays->origins.data, o.origins.data, n * 12, cudaMemcpyDefault, s));
         DV_CUDA(cudaMemcpyAsync(rays->directions.data, o.directions.data, n * 12, cudaMemcpyDefault, s));
@@ -273,7 +273,7 @@ extern "C" HP_API hp_status hp_ray(const hp_plan* plan, const hp_rays_t* overrid
         return sync_stream(plan->ctx);
     }
 
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     const hp_ctx* ctx = plan->ctx;
     const FrameParams fp = frame_params_from_plan(*plan);
     if (ms == kDev) {
@@ -335,7 +335,7 @@ hp_status sampler_entry(const hp_plan* plan, const hp_field* fs, const hp_field*
     if (!rays->origins.data || !rays->directions.data || !rays->t_near.data || !rays->t_far.data)
         return HP_STATUS_INVALID_ARGUMENT;
 
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     const hp_ctx* ctx = plan->ctx;
     DeviceScratch scratch;
     const MarchParams mp = march_params(plan);
@@ -482,7 +482,7 @@ extern "C" HP_API hp_status hp_int(const hp_plan* plan, const hp_samp_t* samp, h
     DV_TRY(alloc_intl(intl, n_rays, m, bump));
     if (n_rays == 0) return HP_STATUS_SUCCESS;
 
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     const hp_ctx* ctx = plan->ctx;
     DeviceScratch scratch;
     SampleArrays ds = sample_arrays(*samp);
@@ -545,7 +545,7 @@ extern "C" HP_API hp_status hp_img(const hp_plan* plan, const hp_intl_t* intl, c
     if (n_rays > 0 && (!intl->radiance.data || !intl->transmittance.data || !intl->opacity.data || !intl->depth.data))
         return HP_STATUS_INVALID_ARGUMENT;
 
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     const hp_ctx* ctx = plan->ctx;
     DeviceScratch scratch;
     ImagePlanes dimg = image_planes(*img);
@@ -623,7 +623,8 @@ extern "C" HP_API hp_status hp_diff(const hp_plan* plan, const hp_tensor* dL_dI,
     if (m > plan->desc.max_samples || n_rays > plan->desc.max_rays) return HP_STATUS_INVALID_ARGUMENT;
     if (ms == kDev && (m == 0 || n_rays == 0)) return HP_STATUS_SUCCESS;   // diff_cuda.cu:112-114
 
-    if (ms == kDev || m > 0) DV_TRY(ensure_device(plan->ctx));
+    dv::DeviceScope dv_scope__;
+    if (ms == kDev || m > 0) DV_TRY(dv_scope__.enter(plan->ctx));
     const hp_ctx* ctx = plan->ctx;
 
     float *g_sigma = nullptr, *g_color = nullptr, *g_camera = nullptr;

@@ -73,10 +73,10 @@ HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp
             fs->oob != fc->oob || fc->channels != 3)
             return HP_STATUS_UNSUPPORTED;
     }
-    DV_TRY(ensure_device(ctx));
+    DV_ENTER(ctx);
     hpx_grid* g = new (std::nothrow) hpx_grid();
     if (g == nullptr) return HP_STATUS_OUT_OF_MEMORY;
-    g->ctx = ctx;
+    g->ctx = ctx_retain(ctx);
     g->nx = ref->nx; g->ny = ref->ny; g->nz = ref->nz;
     g->linear = ref->interp == HP_INTERP_LINEAR;
     g->clamp = ref->oob == HP_OOB_CLAMP;
@@ -84,8 +84,9 @@ HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp
     set_bbox(g, bbox_min, bbox_max);
     hp_status st = grid_alloc(g);
     if (st == HP_STATUS_SUCCESS) {
-        const cudaError_t e = launch_pack_grid(ctx->stream, fs ? fs->d_data : nullptr, fc ? fc->d_data : nullptr,
-                                               g->d_values, g->voxels, false);
+        // (fields that already view another packed grid have stride 4: unpack through the generic strided pack)
+        const cudaError_t e = launch_pack_grid_strided(ctx->stream, fs ? fs->d_data : nullptr, fs ? fs->stride : 1,
+                                                       fc ? fc->d_data : nullptr, fc ? fc->stride : 3, g->d_values, g->voxels, false);
         if (e != cudaSuccess) st = cuda_fail(e, "pack_grid");
     }
     if (st != HP_STATUS_SUCCESS) {
@@ -100,7 +101,7 @@ HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* c
     if (g != nullptr) g->value_max_stale = true;
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (sigma == nullptr && color == nullptr) return HP_STATUS_SUCCESS;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     cudaStream_t s = g->ctx->stream;
     if (memspace == HP_MEMSPACE_DEVICE) {
         DV_CUDA(launch_pack_grid(s, sigma, color, g->d_values, g->voxels, true));
@@ -126,10 +127,10 @@ HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, 
                                      const float* color, hp_memspace memspace, uint32_t interp, uint32_t oob,
                                      const float bbox_min[3], const float bbox_max[3], hpx_grid** out_grid) {
     if (ctx == nullptr || out_grid == nullptr || nx <= 0 || ny <= 0 || nz <= 0) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(ctx));
+    DV_ENTER(ctx);
     hpx_grid* g = new (std::nothrow) hpx_grid();
     if (g == nullptr) return HP_STATUS_OUT_OF_MEMORY;
-    g->ctx = ctx;
+    g->ctx = ctx_retain(ctx);
     g->nx = nx; g->ny = ny; g->nz = nz;
     g->linear = interp != static_cast<uint32_t>(HP_INTERP_NEAREST);
     g->clamp = oob == static_cast<uint32_t>(HP_OOB_CLAMP);
@@ -151,7 +152,7 @@ HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, 
 
 HP_API hp_status hpx_grid_zero_grad(hpx_grid* g) {
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     if (g->d_grad == nullptr) return grid_ensure_grad(g);
     DV_CUDA(cudaMemsetAsync(g->d_grad, 0, (g->voxels * 4 + kCameraFloats) * sizeof(float), g->ctx->stream));
     return HP_STATUS_SUCCESS;
@@ -159,7 +160,7 @@ HP_API hp_status hpx_grid_zero_grad(hpx_grid* g) {
 
 HP_API hp_status hpx_grid_grad_buffer(hpx_grid* g, float** out_device_ptr, size_t* out_floats) {
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
     if (out_device_ptr) *out_device_ptr = g->d_grad;
     if (out_floats) *out_floats = g->voxels * 4 + kCameraFloats;
@@ -169,7 +170,7 @@ HP_API hp_status hpx_grid_grad_buffer(hpx_grid* g, float** out_device_ptr, size_
 HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color_grad, float* camera16,
                                     hp_memspace memspace) {
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
     cudaStream_t s = g->ctx->stream;
     const float4* packed = reinterpret_cast<const float4*>(g->d_grad);
@@ -208,7 +209,7 @@ HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* g, const float* positions
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (count == 0) return HP_STATUS_SUCCESS;
     if (positions == nullptr || grad_sigma == nullptr || grad_color == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
     cudaStream_t s = g->ctx->stream;
     if (memspace == HP_MEMSPACE_DEVICE) {
@@ -234,13 +235,48 @@ HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* g, const float* positions
 
 HP_API void hpx_grid_release(hpx_grid* g) {
     if (g == nullptr) return;
-    if (g->ctx != nullptr && g->ctx->ready) cudaSetDevice(g->ctx->device);
-    cudaFree(g->d_values);
-    cudaFree(g->d_grad);
-    cudaFree(g->d_fixed);
-    cudaFree(g->d_fixed_meta);
-    cudaFree(g->d_unpacked);
+    for (hp_field* v : g->views) {   // adopted fields lose their values with the grid: later queries fail cleanly
+        v->d_data = nullptr;
+        v->alias_of = nullptr;
+    }
+    if (g->ctx != nullptr && g->ctx->ready) {
+        DeviceScope scope;
+        scope.enter(g->ctx);
+        cudaStreamSynchronize(g->ctx->stream);
+        cudaFree(g->d_values);
+        cudaFree(g->d_grad);
+        cudaFree(g->d_fixed);
+        cudaFree(g->d_fixed_meta);
+        cudaFree(g->d_unpacked);
+    }
+    ctx_unref(g->ctx);
     delete g;
+}
+
+// One copy of the values in HBM: the two fields the grid was built from drop their own snapshots and become strided
+// views of the packed {r,g,b,sigma} voxels, so hpx_grid_update is what the staged hp_samp / hp_graph paths see too.
+HP_API hp_status hpx_grid_adopt_fields(hpx_grid* g, hp_field* fs, hp_field* fc) {
+    if (g == nullptr || (fs == nullptr && fc == nullptr)) return HP_STATUS_INVALID_ARGUMENT;
+    if ((fs && fs->kind != FieldKind::kDenseSigma) || (fc && fc->kind != FieldKind::kDenseColor)) return HP_STATUS_INVALID_ARGUMENT;
+    for (hp_field* f : {fs, fc}) {
+        if (f == nullptr) continue;
+        if (f->ctx != g->ctx || f->nx != g->nx || f->ny != g->ny || f->nz != g->nz ||
+            (f->interp == HP_INTERP_LINEAR) != g->linear || (f->oob == HP_OOB_CLAMP) != g->clamp ||
+            (f->alias_of != nullptr && f->alias_of != g))
+            return HP_STATUS_INVALID_ARGUMENT;
+    }
+    DV_ENTER(g->ctx);
+    DV_CUDA(cudaStreamSynchronize(g->ctx->stream));   // the pack that read the snapshots has finished
+    for (hp_field* f : {fs, fc}) {
+        if (f == nullptr || f->alias_of == g) continue;
+        if (f->owns_data) cudaFree(f->d_data);
+        f->owns_data = false;
+        f->alias_of = g;
+        f->stride = 4;
+        f->d_data = reinterpret_cast<float*>(g->d_values) + (f->kind == FieldKind::kDenseSigma ? 3 : 0);
+        g->views.push_back(f);
+    }
+    return HP_STATUS_SUCCESS;
 }
 
 // =============================================================================
@@ -265,11 +301,11 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
         set_last_error("plan skips marching steps (dt below float resolution); use the materialising hp_* path");
         return HP_STATUS_UNSUPPORTED;
     }
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     hpx_frame* f = new (std::nothrow) hpx_frame();
     if (f == nullptr) return HP_STATUS_OUT_OF_MEMORY;
-    f->plan = plan;
-    f->ctx = plan->ctx;
+    f->plan = plan_retain(plan);
+    f->ctx = ctx_retain(plan->ctx);
     f->h_params = frame_params_from_plan(*plan);
     const hp_plan_desc& d = plan->desc;
     const size_t pixels = static_cast<size_t>(d.width) * d.height;
@@ -358,7 +394,12 @@ static hp_status frame_push_params(hpx_frame* f) {
 
 static hp_status frame_check_grid(const hpx_frame* f, const hpx_grid* g) {
     if (f == nullptr || g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    if (f->ctx != g->ctx && (f->ctx->device != g->ctx->device)) return HP_STATUS_INVALID_ARGUMENT;
+    // ONE context = one stream: the grid's own memsets / packing (hpx_grid_zero_grad, hpx_grid_update, the lazy gradient
+    // block) and the frame's kernels are ordered only because they share it
+    if (f->ctx != g->ctx) {
+        set_last_error("frame and grid belong to different contexts (streams): create both from the same hp_ctx");
+        return HP_STATUS_INVALID_ARGUMENT;
+    }
     return HP_STATUS_SUCCESS;
 }
 
@@ -376,8 +417,22 @@ struct GradBox {
     int32_t o[3] = {0, 0, 0}, n[3] = {0, 0, 0};
 };
 
+// Fixed-point shadow of the gradient grid (HPX_BACKWARD_DETERMINISTIC).  Allocation and the first clear happen HERE,
+// outside any stream capture: cudaMalloc inside a capture invalidates it.
+static hp_status grid_ensure_fixed(hpx_grid* g) {
+    if (g->d_fixed != nullptr) return HP_STATUS_SUCCESS;
+    DV_CUDA(cudaMalloc(&g->d_fixed, std::max<size_t>(g->voxels, 1) * 4 * sizeof(unsigned long long)));
+    DV_CUDA(cudaMalloc(&g->d_fixed_meta, 4 * sizeof(float)));
+    DV_CUDA(cudaMemsetAsync(g->d_fixed, 0, std::max<size_t>(g->voxels, 1) * 4 * sizeof(unsigned long long), g->ctx->stream));
+    DV_CUDA(cudaMemsetAsync(g->d_fixed_meta, 0, 4 * sizeof(float), g->ctx->stream));
+    g->value_max_stale = true;
+    return HP_STATUS_SUCCESS;
+}
+
+// capturing: the launches are being recorded into a CUDA graph that will be replayed after hpx_grid_update calls this
+// function never sees -- so the |value| maximum is ALWAYS part of the graph and the host-side staleness flag is left alone.
 static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_dI, uint32_t flags,
-                                  const GradBox* box = nullptr) {
+                                  const GradBox* box = nullptr, bool capturing = false) {
     cudaStream_t s = f->ctx->stream;
     if (flags & HPX_BACKWARD_ZERO) {
         if (box != nullptr) {   // the caller's box is the grid-gradient target; the grid keeps the camera slots
@@ -412,16 +467,17 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
         const bool deterministic = (flags & HPX_BACKWARD_DETERMINISTIC) != 0 && box == nullptr;
         if (deterministic) {
             if (g->d_fixed == nullptr) {
-                DV_CUDA(cudaMalloc(&g->d_fixed, std::max<size_t>(g->voxels, 1) * 4 * sizeof(unsigned long long)));
-                DV_CUDA(cudaMemsetAsync(g->d_fixed, 0, g->voxels * 4 * sizeof(unsigned long long), s));
-                DV_CUDA(cudaMalloc(&g->d_fixed_meta, 4 * sizeof(float)));
-                g->value_max_stale = true;
+                if (capturing) {
+                    set_last_error("deterministic backward: the fixed-point grid must exist before the capture begins");
+                    return HP_STATUS_INTERNAL_ERROR;
+                }
+                DV_TRY(grid_ensure_fixed(g));
             }
             uint32_t* meta_bits = reinterpret_cast<uint32_t*>(g->d_fixed_meta);
-            if (g->value_max_stale) {
+            if (g->value_max_stale || capturing) {
                 DV_CUDA(cudaMemsetAsync(meta_bits, 0, sizeof(uint32_t), s));
                 DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits));
-                g->value_max_stale = false;
+                if (!capturing) g->value_max_stale = false;
             }
             DV_CUDA(cudaMemsetAsync(meta_bits + 1, 0, sizeof(uint32_t), s));
             DV_CUDA(launch_abs_max(s, d_dL_dI, static_cast<size_t>(f->h_params.roi.w) * f->h_params.roi.h * 3, meta_bits + 1));
@@ -442,7 +498,7 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
 
 HP_API hp_status hpx_forward(hpx_frame* f, const hpx_grid* g) {
     DV_TRY(frame_check_grid(f, g));
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(frame_push_params(f));
     DV_TRY(enqueue_forward(f, g));
     f->forward_done = true;
@@ -456,7 +512,7 @@ HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_
         set_last_error("hpx_backward needs the checkpoints of a preceding hpx_forward on the same frame");
         return HP_STATUS_INVALID_ARGUMENT;
     }
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(grid_ensure_grad(g));
     DV_TRY(frame_push_params(f));
     const float* d_g = dL_dI;
@@ -481,13 +537,22 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_
     f->rays = rows * roi.w;
     f->samples = f->rays * f->plan->uniform_count;
     f->params_dirty = true;
+    // a captured graph has the old CTA count / background decision baked in: replay must fail until it is recaptured
+    if (f->graph_exec != nullptr || f->graph != nullptr) {
+        DV_ENTER(f->ctx);
+        DV_CUDA(cudaStreamSynchronize(f->ctx->stream));
+        if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+        if (f->graph) cudaGraphDestroy(f->graph);
+        f->graph_exec = nullptr;
+        f->graph = nullptr;
+    }
     return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_box[6]) {
     DV_TRY(frame_check_grid(f, g));
     if (out_box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(frame_push_params(f));
     cudaStream_t s = f->ctx->stream;
     DeviceScratch scratch;
@@ -526,7 +591,7 @@ HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI,
         set_last_error("hpx_backward_box needs a linear field whose scatter box is the unit cube");
         return HP_STATUS_UNSUPPORTED;
     }
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(grid_ensure_grad(g));
     DV_TRY(frame_push_params(f));
     const float* d_g = dL_dI;
@@ -559,7 +624,7 @@ HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* 
         out_expected[i] = (end - std::min(prev, end)) * tiles_x;
         prev = end;
     }
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(grid_ensure_grad(g));
     DV_TRY(frame_push_params(f));
     const float* d_g = dL_dI;
@@ -579,7 +644,7 @@ HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* 
 
 HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_device_counters) {
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_CUDA(cudaMemsetAsync(f->d_group_done, 0, 8 * sizeof(unsigned int), f->ctx->stream));
     if (out_device_counters) *out_device_counters = f->d_group_done;
     return HP_STATUS_SUCCESS;
@@ -587,7 +652,7 @@ HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_dev
 
 HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_t* device_counter, uint32_t value) {
     if (stream_ctx == nullptr || device_counter == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(stream_ctx));
+    DV_ENTER(stream_ctx);
     typedef int (*wait_fn)(CUstream_st*, unsigned long long, uint32_t, unsigned int);   // cuStreamWaitValue32
     static wait_fn fn = nullptr;
     if (fn == nullptr) {
@@ -610,7 +675,7 @@ HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_
 
 HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* g, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs) {
     if (g == nullptr || slow_axis < 0 || slow_axis > 2) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
     const uint32_t nx = static_cast<uint32_t>(g->nx), ny = static_cast<uint32_t>(g->ny), nz = static_cast<uint32_t>(g->nz);
     int32_t slabs = g->nz;
@@ -630,7 +695,7 @@ HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* g, float* 
     for (int i = 0; i < 3; ++i)
         if (box[i] < 0 || box[3 + i] < 0) return HP_STATUS_INVALID_ARGUMENT;
     if (box[0] + box[3] > g->nx || box[1] + box[4] > g->ny || box[2] + box[5] > g->nz) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(stream_ctx));
+    DV_ENTER(stream_ctx);
     if (stream_ctx->device != g->ctx->device) return HP_STATUS_INVALID_ARGUMENT;
     if (g->grad_slow_axis != 2) {
         set_last_error("hpx_grid_add_box needs the default gradient layout (z slowest)");
@@ -644,7 +709,7 @@ HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* g, float* 
 
 HP_API hp_status hpx_frame_box_misses(hpx_frame* f, uint32_t* out_count) {
     if (f == nullptr || out_count == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     unsigned int host = 0;
     DV_CUDA(cudaMemcpyAsync(&host, f->d_box_miss, sizeof(host), cudaMemcpyDeviceToHost, f->ctx->stream));
     DV_CUDA(cudaMemsetAsync(f->d_box_miss, 0, sizeof(host), f->ctx->stream));
@@ -682,7 +747,7 @@ HP_API hp_status hpx_frame_image(const hpx_frame* f, hp_img_t* out) {
 HP_API hp_status hpx_frame_read(hpx_frame* f, float* image, float* trans, float* opacity, float* depth,
                                 uint32_t* hitmask) {
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     cudaStream_t s = f->ctx->stream;
     const size_t pixels = static_cast<size_t>(f->plan->desc.width) * f->plan->desc.height;
     if (image) DV_CUDA(cudaMemcpyAsync(image, f->buf.image, pixels * 12, cudaMemcpyDeviceToHost, s));
@@ -696,7 +761,7 @@ HP_API hp_status hpx_frame_read(hpx_frame* f, float* image, float* trans, float*
 
 HP_API hp_status hpx_frame_counts(hpx_frame* f, hpx_counts* out) {
     if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     auto* h_live = reinterpret_cast<unsigned long long*>(f->h_pinned + 1);
     DV_CUDA(cudaMemcpyAsync(h_live, f->buf.live_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             f->ctx->stream));
@@ -704,6 +769,47 @@ HP_API hp_status hpx_frame_counts(hpx_frame* f, hpx_counts* out) {
     out->rays = f->rays;
     out->samples = f->samples;
     out->live_samples = *h_live;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_frame_cube_samples(hpx_frame* f, const hpx_grid* g, uint64_t* out_samples) {
+    DV_TRY(frame_check_grid(f, g));
+    if (out_samples == nullptr || !f->forward_done) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(f->ctx);
+    cudaStream_t s = f->ctx->stream;
+    auto* h = reinterpret_cast<unsigned long long*>(f->h_pinned + 1);
+    if (g->clamp) {   // clamped fields gather at every live sample
+        DV_CUDA(cudaMemcpyAsync(h, f->buf.live_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        DV_CUDA(cudaStreamSynchronize(s));
+        *out_samples = *h;
+        return HP_STATUS_SUCCESS;
+    }
+    DV_TRY(frame_push_params(f));
+    DeviceScratch scratch;
+    auto* d_total = static_cast<unsigned long long*>(scratch.take(sizeof(unsigned long long)));
+    if (d_total == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    DV_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+    DV_CUDA(launch_cube_count(s, f->d_params, f->h_params, f->buf, d_total));
+    DV_CUDA(cudaMemcpyAsync(h, d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    *out_samples = *h;
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_grid_touched_voxels(hpx_grid* g, uint64_t* out_voxels) {
+    if (g == nullptr || out_voxels == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(g->ctx);
+    DV_TRY(grid_ensure_grad(g));
+    cudaStream_t s = g->ctx->stream;
+    DeviceScratch scratch;
+    auto* d_total = static_cast<unsigned long long*>(scratch.take(sizeof(unsigned long long)));
+    if (d_total == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    DV_CUDA(cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), s));
+    DV_CUDA(launch_touched_voxels(s, reinterpret_cast<const float4*>(g->d_grad), g->voxels, d_total));
+    unsigned long long host = 0;
+    DV_CUDA(cudaMemcpyAsync(&host, d_total, sizeof(host), cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    *out_voxels = host;
     return HP_STATUS_SUCCESS;
 }
 
@@ -717,8 +823,9 @@ HP_API hp_status hpx_frame_grad_input(hpx_frame* f, float** out) {
 // allocation, no synchronisation and no host read inside the captured region.
 HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_flags) {
     DV_TRY(frame_check_grid(f, g));
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     if (backward_flags != 0) DV_TRY(grid_ensure_grad(g));
+    if ((backward_flags & HPX_BACKWARD_GRID) && (backward_flags & HPX_BACKWARD_DETERMINISTIC)) DV_TRY(grid_ensure_fixed(g));
     DV_TRY(frame_push_params(f));
     cudaStream_t s = f->ctx->stream;
     DV_CUDA(cudaStreamSynchronize(s));
@@ -726,7 +833,7 @@ HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_
     if (f->graph) { cudaGraphDestroy(f->graph); f->graph = nullptr; }
     DV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
     hp_status st = enqueue_forward(f, g);
-    if (st == HP_STATUS_SUCCESS && backward_flags != 0) st = enqueue_backward(f, g, f->d_dL_dI, backward_flags);
+    if (st == HP_STATUS_SUCCESS && backward_flags != 0) st = enqueue_backward(f, g, f->d_dL_dI, backward_flags, nullptr, true);
     const cudaError_t e = cudaStreamEndCapture(s, &f->graph);
     if (st != HP_STATUS_SUCCESS) return st;
     if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
@@ -736,7 +843,7 @@ HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_
 
 HP_API hp_status hpx_frame_replay(hpx_frame* f) {
     if (f == nullptr || f->graph_exec == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(f->ctx));
+    DV_ENTER(f->ctx);
     DV_TRY(frame_push_params(f));
     DV_CUDA(cudaGraphLaunch(f->graph_exec, f->ctx->stream));
     f->forward_done = true;
@@ -746,13 +853,16 @@ HP_API hp_status hpx_frame_replay(hpx_frame* f) {
 HP_API void hpx_frame_release(hpx_frame* f) {
     if (f == nullptr) return;
     if (f->ctx != nullptr && f->ctx->ready) {
-        cudaSetDevice(f->ctx->device);
+        DeviceScope scope;
+        scope.enter(f->ctx);
         cudaStreamSynchronize(f->ctx->stream);
+        if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
+        if (f->graph) cudaGraphDestroy(f->graph);
+        for (void* p : f->allocations) cudaFree(p);
+        if (f->h_pinned) cudaFreeHost(f->h_pinned);
     }
-    if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
-    if (f->graph) cudaGraphDestroy(f->graph);
-    for (void* p : f->allocations) cudaFree(p);
-    if (f->h_pinned) cudaFreeHost(f->h_pinned);
+    plan_unref(f->plan);
+    ctx_unref(f->ctx);
     delete f;
 }
 

@@ -66,10 +66,10 @@ HP_API hp_status hp_graph_create(const hp_plan* plan, const hp_field* fs, const 
                                  size_t, void** out_graph_handle) {
     if (plan == nullptr || fs == nullptr || fc == nullptr || out_graph_handle == nullptr)
         return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(plan->ctx));
+    DV_ENTER(plan->ctx);
     GraphExec* g = new (std::nothrow) GraphExec();
     if (g == nullptr) return HP_STATUS_OUT_OF_MEMORY;
-    g->ctx = plan->ctx;
+    g->ctx = ctx_retain(plan->ctx);
     *out_graph_handle = g;
     return HP_STATUS_SUCCESS;
 }
@@ -80,7 +80,7 @@ HP_API hp_status hp_graph_capture(void* handle, const hp_plan* plan, const hp_fi
     if (fs->kind != FieldKind::kDenseSigma || fc->kind != FieldKind::kDenseColor) return HP_STATUS_INVALID_ARGUMENT;
     GraphExec* g = static_cast<GraphExec*>(handle);
     if (plan->ctx != g->ctx) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     cudaStream_t s = g->ctx->stream;
     DV_CUDA(cudaStreamSynchronize(s));
     drop_graph(g);
@@ -206,7 +206,7 @@ HP_API hp_status hp_graph_execute(void* handle, hp_rays_t* out_rays, hp_samp_t* 
     if (handle == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     GraphExec* g = static_cast<GraphExec*>(handle);
     if (!g->captured || g->exec == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    DV_TRY(ensure_device(g->ctx));
+    DV_ENTER(g->ctx);
     DV_CUDA(cudaGraphLaunch(g->exec, g->ctx->stream));
     DV_CUDA(cudaStreamSynchronize(g->ctx->stream));
     if (out_rays) *out_rays = g->rays;
@@ -221,11 +221,13 @@ HP_API void hp_graph_release(void* handle) {
     if (handle == nullptr) return;
     GraphExec* g = static_cast<GraphExec*>(handle);
     if (g->ctx != nullptr && g->ctx->ready) {
-        cudaSetDevice(g->ctx->device);
+        DeviceScope scope;
+        scope.enter(g->ctx);
         cudaStreamSynchronize(g->ctx->stream);
+        drop_graph(g);
+        for (void* p : g->owned) cudaFree(p);
     }
-    drop_graph(g);
-    for (void* p : g->owned) cudaFree(p);
+    ctx_unref(g->ctx);
     delete g;
 }
 

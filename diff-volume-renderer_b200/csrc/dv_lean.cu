@@ -864,6 +864,64 @@ cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, 
 
 uint32_t lean_block_count(const RoiParams& roi) { return tile_blocks(roi); }
 
+// ---- measurement helpers (bench.py roofline) ----------------------------------------------------------------------
+namespace {
+// Live samples inside the unit cube: the samples that actually gather 8 corners (forward) and issue 8 reds (backward).
+// Re-marches the rays with the forward kernel's own step logic, without touching the grid.
+template <bool kStratified>
+__global__ void __launch_bounds__(kLeanThreads)
+cube_count_kernel(const FrameParams* __restrict__ P, const uint32_t* __restrict__ live_counts, const float4* __restrict__ steps,
+                  unsigned long long* __restrict__ total) {
+    const CameraParams cam = P->cam;
+    const MarchParams mp = P->march;
+    const RoiParams roi = P->roi;
+    const TilePixel px = tile_pixel(roi);
+    const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
+    const uint64_t ray_index = mp.ray_index_base + px.ray;
+    const uint32_t live = px.inside ? live_counts[px.ray] : 0u;
+    float t_in, t_out;
+    const WarpRange wr = warp_step_range<true>(mp, ray, px.inside, t_in, t_out);
+    uint32_t n = 0;
+    for (uint32_t k = wr.lo; k < min(wr.hi, live); ++k) {
+        const float4 tab = __ldg(steps + k);
+        if (tab.x > t_out || tab.x + mp.dt < t_in) continue;
+        const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, k);
+        const float x = ray.ox + ray.dx * t, y = ray.oy + ray.dy * t, z = ray.oz + ray.dz * t;
+        n += (x < 0.0f || x > 1.0f || y < 0.0f || y > 1.0f || z < 0.0f || z > 1.0f) ? 0u : 1u;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n != 0) atomicAdd(total, static_cast<unsigned long long>(n));
+}
+
+__global__ void touched_voxels_kernel(const float4* __restrict__ grad, size_t voxels, unsigned long long* __restrict__ total) {
+    uint32_t n = 0;
+    for (size_t v = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; v < voxels;
+         v += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 g = grad[v];
+        n += (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f || g.w != 0.0f) ? 1u : 0u;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if ((threadIdx.x & 31) == 0 && n != 0) atomicAdd(total, static_cast<unsigned long long>(n));
+}
+}  // namespace
+
+cudaError_t launch_cube_count(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
+                              const LeanBuffers& buf, unsigned long long* d_total) {
+    const uint32_t blocks = tile_blocks(h_params.roi);
+    if (blocks == 0) return cudaSuccess;
+    if (h_params.march.stratified != 0)
+        cube_count_kernel<true><<<blocks, kLeanThreads, 0, stream>>>(d_params, buf.live, buf.steps, d_total);
+    else
+        cube_count_kernel<false><<<blocks, kLeanThreads, 0, stream>>>(d_params, buf.live, buf.steps, d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, size_t voxels, unsigned long long* d_total) {
+    if (voxels == 0) return cudaSuccess;
+    touched_voxels_kernel<<<148 * 8, 256, 0, stream>>>(d_grad, voxels, d_total);
+    return cudaGetLastError();
+}
+
 namespace {
 __global__ void upload_params_kernel(FrameParams* dst, const FrameParams src) { *dst = src; }
 }  // namespace

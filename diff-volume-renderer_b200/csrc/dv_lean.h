@@ -55,6 +55,12 @@ cudaError_t launch_fixed_scale(cudaStream_t stream, float* d_meta, float dt);
 cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fixed, float4* d_grad, size_t voxels,
                                   const float* d_meta);
 
+// Measurement helpers: live in-cube samples of the last forward (OOB-zero fields; *d_total is accumulated into), and the
+// number of voxels with a non-zero gradient.
+cudaError_t launch_cube_count(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
+                              const LeanBuffers& buf, unsigned long long* d_total);
+cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, size_t voxels, unsigned long long* d_total);
+
 // Writes the frame's parameter block; the values travel as kernel arguments (no staging buffer, no host sync).
 cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params);
 

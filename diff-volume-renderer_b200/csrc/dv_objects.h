@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <string>
@@ -20,6 +21,10 @@
 // hp_runtime.cpp:15-146) work on machines without a GPU; every compute entry
 // point fails with HP_STATUS_UNSUPPORTED there.
 struct hp_ctx {
+    // Plans, fields, grids and frames keep their context alive: hp_ctx_release only drops the caller's reference, the
+    // stream and the device buffers go away with the last object (the reference's fields never touch their context, so
+    // releasing it first is legal there: hp_runtime.cpp:33-36).
+    mutable std::atomic<int> refs{1};
     hp_ctx_desc desc{};
     std::string device_name;      // owned copy of desc.preferred_device
     hp_version version{HP_VERSION_MAJOR, HP_VERSION_MINOR, HP_VERSION_PATCH};
@@ -39,6 +44,7 @@ struct hp_ctx {
 };
 
 struct hp_plan {
+    mutable std::atomic<int> refs{1};   // frames and graphs keep their plan alive
     hp_plan_desc desc{};
     const hp_ctx* ctx = nullptr;
     uint32_t uniform_count = 0;   // samples a generated ray emits
@@ -56,11 +62,12 @@ struct hp_field {
     hp_interp_mode interp = HP_INTERP_LINEAR;
     hp_oob_policy oob = HP_OOB_ZERO;
     int32_t nx = 0, ny = 0, nz = 0, channels = 1;
-    float* d_data = nullptr;      // [nz][ny][nx][channels]
+    int32_t stride = 1;           // floats between consecutive voxels of d_data (= channels for an own snapshot)
+    float* d_data = nullptr;      // [nz][ny][nx] x stride floats; channel c of voxel v at d_data[v * stride + c]
     bool owns_data = true;
-    // lazily built packed partner cache (sigma field only): packed grid for (this, partner)
-    mutable const hp_field* packed_partner = nullptr;
-    mutable float4* d_packed = nullptr;
+    // hpx_grid_adopt_fields: the field no longer owns a snapshot but views the packed {r,g,b,sigma} grid (stride 4),
+    // so that hpx_grid_update is seen by the staged hp_samp path as well -- one copy of the values in HBM.
+    struct hpx_grid* alias_of = nullptr;
 };
 
 struct hpx_grid {
@@ -73,6 +80,7 @@ struct hpx_grid {
     float* d_unpacked = nullptr;  // [V + 3V] staging for un-interleaved read-back (lazily allocated)
     size_t unpacked_voxels = 0;
     size_t voxels = 0;
+    std::vector<hp_field*> views;   // fields adopted by hpx_grid_adopt_fields (detached again when the grid goes away)
     // deterministic backward (HPX_BACKWARD_DETERMINISTIC): 64-bit fixed-point shadow of the gradient grid, lazily allocated
     unsigned long long* d_fixed = nullptr;   // [4V], all zero between backward passes
     float* d_fixed_meta = nullptr;           // {bits max|grid value|, bits max|dL/dI|, 1/quantum, quantum}
@@ -118,6 +126,26 @@ hp_status cuda_fail(cudaError_t err, const char* what);  // records text, maps t
 
 // Makes ctx's device current and creates its stream on first use.
 hp_status ensure_device(const hp_ctx* ctx);
+
+// Entry-point scope: ensure_device + the caller's current device restored on exit (a library call must not change it).
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false;
+    hp_status enter(const hp_ctx* ctx);
+    ~DeviceScope();
+};
+#define DV_ENTER(ctx)                                                        \
+    dv::DeviceScope dv_scope__;                                              \
+    do {                                                                     \
+        const hp_status dv_enter_st__ = dv_scope__.enter(ctx);               \
+        if (dv_enter_st__ != HP_STATUS_SUCCESS) return dv_enter_st__;        \
+    } while (0)
+
+// Reference counting of contexts and plans (see hp_ctx::refs).
+const hp_ctx* ctx_retain(const hp_ctx* ctx);
+void ctx_unref(const hp_ctx* ctx);
+const hp_plan* plan_retain(const hp_plan* plan);
+void plan_unref(const hp_plan* plan);
 
 // ---- plan helpers -----------------------------------------------------------
 hp_status resolve_plan_desc(hp_plan_desc* desc);   // reference hp_runtime.cpp:54-142

@@ -35,6 +35,17 @@ hp_status cuda_fail(cudaError_t err, const char* what) {
     }
 }
 
+static void destroy_device_state(const hp_ctx* ctx) {
+    if (ctx->owns_stream && ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->d_status);
+    cudaFree(ctx->d_total);
+    if (ctx->h_status != nullptr) cudaFreeHost(ctx->h_status);
+    if (ctx->h_total != nullptr) cudaFreeHost(ctx->h_total);
+    ctx->stream = nullptr;
+    ctx->owns_stream = false;
+    ctx->d_status = nullptr; ctx->d_total = nullptr; ctx->h_status = nullptr; ctx->h_total = nullptr;
+}
+
 hp_status ensure_device(const hp_ctx* ctx) {
     if (ctx == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (ctx->failed) return HP_STATUS_UNSUPPORTED;
@@ -58,22 +69,74 @@ hp_status ensure_device(const hp_ctx* ctx) {
         }
         ctx->device = dev;
         DV_CUDA(cudaSetDevice(dev));
+        // all or nothing: a failure half way rolls back what was created, so that a retry starts clean (no leak)
+        cudaError_t err = cudaSuccess;
         if (ctx->has_user_stream) {
             ctx->stream = ctx->user_stream;
             ctx->owns_stream = false;
         } else {
-            DV_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-            ctx->owns_stream = true;
+            err = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+            ctx->owns_stream = err == cudaSuccess;
         }
-        DV_CUDA(cudaMalloc(&ctx->d_status, sizeof(uint32_t)));
-        DV_CUDA(cudaMalloc(&ctx->d_total, sizeof(unsigned long long)));
-        DV_CUDA(cudaMallocHost(&ctx->h_status, sizeof(uint32_t)));
-        DV_CUDA(cudaMallocHost(&ctx->h_total, sizeof(unsigned long long)));
+        if (err == cudaSuccess) err = cudaMalloc(&ctx->d_status, sizeof(uint32_t));
+        if (err == cudaSuccess) err = cudaMalloc(&ctx->d_total, sizeof(unsigned long long));
+        if (err == cudaSuccess) err = cudaMallocHost(&ctx->h_status, sizeof(uint32_t));
+        if (err == cudaSuccess) err = cudaMallocHost(&ctx->h_total, sizeof(unsigned long long));
+        if (err != cudaSuccess) {
+            destroy_device_state(ctx);
+            return cuda_fail(err, "context device state");
+        }
         ctx->ready = true;
         return HP_STATUS_SUCCESS;
     }
-    DV_CUDA(cudaSetDevice(ctx->device));
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) DV_CUDA(cudaSetDevice(ctx->device));
     return HP_STATUS_SUCCESS;
+}
+
+hp_status DeviceScope::enter(const hp_ctx* ctx) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+        cudaGetLastError();
+        cur = -1;
+    }
+    const hp_status st = ensure_device(ctx);
+    if (st == HP_STATUS_SUCCESS && cur >= 0 && cur != ctx->device) {
+        prev = cur;
+        switched = true;
+    }
+    return st;
+}
+
+DeviceScope::~DeviceScope() {
+    if (switched) cudaSetDevice(prev);
+}
+
+const hp_ctx* ctx_retain(const hp_ctx* ctx) {
+    if (ctx != nullptr) ctx->refs.fetch_add(1, std::memory_order_relaxed);
+    return ctx;
+}
+
+void ctx_unref(const hp_ctx* ctx) {
+    if (ctx == nullptr || ctx->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    if (ctx->ready) {
+        DeviceScope scope;
+        scope.enter(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        destroy_device_state(ctx);
+    }
+    delete ctx;
+}
+
+const hp_plan* plan_retain(const hp_plan* plan) {
+    if (plan != nullptr) plan->refs.fetch_add(1, std::memory_order_relaxed);
+    return plan;
+}
+
+void plan_unref(const hp_plan* plan) {
+    if (plan == nullptr || plan->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) return;
+    ctx_unref(plan->ctx);
+    delete plan;
 }
 
 // ---- plan ---------------------------------------------------------------------
@@ -215,7 +278,7 @@ static GridParams grid_params(const hp_field* f) {
     GridParams g{};
     if (f == nullptr) return g;
     g.data = f->d_data;
-    g.nx = f->nx; g.ny = f->ny; g.nz = f->nz; g.channels = f->channels;
+    g.nx = f->nx; g.ny = f->ny; g.nz = f->nz; g.channels = f->stride;   // GridParams::channels is the voxel stride
     g.linear = f->interp == HP_INTERP_LINEAR ? 1u : 0u;
     g.clamp = f->oob == HP_OOB_CLAMP ? 1u : 0u;
     g.present = 1u;
@@ -298,19 +361,7 @@ HP_API hp_status hp_ctx_create(const hp_ctx_desc* desc, hp_ctx** out_ctx) {
     return HP_STATUS_SUCCESS;
 }
 
-HP_API void hp_ctx_release(hp_ctx* ctx) {
-    if (ctx == nullptr) return;
-    if (ctx->ready) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
-        if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
-        cudaFree(ctx->d_status);
-        cudaFree(ctx->d_total);
-        cudaFreeHost(ctx->h_status);
-        cudaFreeHost(ctx->h_total);
-    }
-    delete ctx;
-}
+HP_API void hp_ctx_release(hp_ctx* ctx) { ctx_unref(ctx); }   // objects created from it keep it alive (hp_ctx::refs)
 
 HP_API hp_status hp_ctx_get_desc(const hp_ctx* ctx, hp_ctx_desc* out_desc) {
     if (ctx == nullptr || out_desc == nullptr) return HP_STATUS_INVALID_ARGUMENT;
@@ -319,16 +370,14 @@ HP_API hp_status hp_ctx_get_desc(const hp_ctx* ctx, hp_ctx_desc* out_desc) {
 }
 
 HP_API hp_status hpx_ctx_synchronize(const hp_ctx* ctx) {
-    const hp_status st = ensure_device(ctx);
-    if (st != HP_STATUS_SUCCESS) return st;
+    DV_ENTER(ctx);
     DV_CUDA(cudaStreamSynchronize(ctx->stream));
     return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void* device_src, size_t bytes) {
     if (host_dst == nullptr || device_src == nullptr) return bytes == 0 ? HP_STATUS_SUCCESS : HP_STATUS_INVALID_ARGUMENT;
-    const hp_status st = ensure_device(ctx);
-    if (st != HP_STATUS_SUCCESS) return st;
+    DV_ENTER(ctx);
     DV_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     DV_CUDA(cudaStreamSynchronize(ctx->stream));
     return HP_STATUS_SUCCESS;
@@ -336,31 +385,29 @@ HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void*
 
 HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_device_ptr) {
     if (out_device_ptr == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    const hp_status st = ensure_device(ctx);
-    if (st != HP_STATUS_SUCCESS) return st;
+    DV_ENTER(ctx);
     DV_CUDA(cudaMalloc(out_device_ptr, bytes ? bytes : 16));
     return HP_STATUS_SUCCESS;
 }
 
 HP_API void hpx_device_free(const hp_ctx* ctx, void* device_ptr) {
     if (device_ptr == nullptr || ctx == nullptr || !ctx->ready) return;
-    cudaSetDevice(ctx->device);
+    DeviceScope scope;
+    if (scope.enter(ctx) != HP_STATUS_SUCCESS) return;
     cudaStreamSynchronize(ctx->stream);
     cudaFree(device_ptr);
 }
 
 HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const void* host_src, size_t bytes) {
     if (device_dst == nullptr || host_src == nullptr) return bytes == 0 ? HP_STATUS_SUCCESS : HP_STATUS_INVALID_ARGUMENT;
-    const hp_status st = ensure_device(ctx);
-    if (st != HP_STATUS_SUCCESS) return st;
+    DV_ENTER(ctx);
     DV_CUDA(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     DV_CUDA(cudaStreamSynchronize(ctx->stream));
     return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream) {
-    const hp_status st = ensure_device(ctx);
-    if (st != HP_STATUS_SUCCESS) return st;
+    DV_ENTER(ctx);
     if (out_ordinal != nullptr) *out_ordinal = ctx->device;
     if (out_stream != nullptr) *out_stream = ctx->stream;
     return HP_STATUS_SUCCESS;
@@ -371,19 +418,19 @@ HP_API hp_status hp_plan_create(const hp_ctx* ctx, const hp_plan_desc* desc, hp_
     if (ctx == nullptr || desc == nullptr || out_plan == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     hp_plan* plan = new (std::nothrow) hp_plan();
     if (plan == nullptr) return HP_STATUS_OUT_OF_MEMORY;
-    plan->ctx = ctx;
     plan->desc = *desc;
     const hp_status st = resolve_plan_desc(&plan->desc);
     if (st != HP_STATUS_SUCCESS) {
         delete plan;
         return st;
     }
+    plan->ctx = ctx_retain(ctx);
     emitted_samples(plan->desc, &plan->uniform_count, &plan->gap_free);
     *out_plan = plan;
     return HP_STATUS_SUCCESS;
 }
 
-HP_API void hp_plan_release(hp_plan* plan) { delete plan; }
+HP_API void hp_plan_release(hp_plan* plan) { plan_unref(plan); }
 
 HP_API hp_status hp_plan_get_desc(const hp_plan* plan, hp_plan_desc* out_desc) {
     if (plan == nullptr || out_desc == nullptr) return HP_STATUS_INVALID_ARGUMENT;
@@ -418,6 +465,7 @@ static hp_status create_dense_field(const hp_ctx* ctx, const hp_tensor* grid, ui
     f->ny = static_cast<int32_t>(grid->shape[1]);
     f->nx = static_cast<int32_t>(grid->shape[2]);
     f->channels = color ? static_cast<int32_t>(grid->shape[3]) : 1;
+    f->stride = f->channels;
     if (color && f->channels < 3) {
         delete f;
         return HP_STATUS_INVALID_ARGUMENT;
@@ -427,7 +475,8 @@ static hp_status create_dense_field(const hp_ctx* ctx, const hp_tensor* grid, ui
         delete f;
         return HP_STATUS_INVALID_ARGUMENT;
     }
-    hp_status st = ensure_device(ctx);
+    DeviceScope scope;
+    hp_status st = scope.enter(ctx);
     if (st != HP_STATUS_SUCCESS) {
         delete f;
         return st;
@@ -446,6 +495,7 @@ static hp_status create_dense_field(const hp_ctx* ctx, const hp_tensor* grid, ui
         delete f;
         return st;
     }
+    ctx_retain(ctx);
     *out_field = f;
     return HP_STATUS_SUCCESS;
 }
@@ -470,9 +520,16 @@ HP_API hp_status hp_field_create_hash_mlp(const hp_ctx* ctx, const hp_tensor* pa
 
 HP_API void hp_field_release(hp_field* field) {
     if (field == nullptr) return;
-    if (field->ctx != nullptr && field->ctx->ready) cudaSetDevice(field->ctx->device);
-    if (field->owns_data) cudaFree(field->d_data);
-    cudaFree(field->d_packed);
+    if (field->ctx != nullptr && field->ctx->ready) {
+        DeviceScope scope;
+        scope.enter(field->ctx);
+        if (field->alias_of != nullptr) {   // a view of a packed grid: tell the grid it is gone
+            auto& v = field->alias_of->views;
+            v.erase(std::remove(v.begin(), v.end(), field), v.end());
+        }
+        if (field->owns_data) cudaFree(field->d_data);
+    }
+    ctx_unref(field->ctx);
     delete field;
 }
 

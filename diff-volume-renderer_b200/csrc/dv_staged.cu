@@ -372,14 +372,16 @@ __global__ void add_box_kernel(float4* __restrict__ grid, float4* __restrict__ b
     }
 }
 
-__global__ void pack_grid_kernel(const float* __restrict__ sigma, const float* __restrict__ color,
-                                 float4* __restrict__ packed, size_t voxels, bool keep_missing) {
+// sigma_stride / color_stride: floats between consecutive voxels of the sources (1 / 3 for the ABI layouts, 4 for fields
+// that view another packed grid)
+__global__ void pack_grid_kernel(const float* __restrict__ sigma, size_t sigma_stride, const float* __restrict__ color,
+                                 size_t color_stride, float4* __restrict__ packed, size_t voxels, bool keep_missing) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (keep_missing && (sigma == nullptr || color == nullptr)) v = packed[i];
-        if (color != nullptr) { v.x = color[3 * i]; v.y = color[3 * i + 1]; v.z = color[3 * i + 2]; }
-        if (sigma != nullptr) v.w = sigma[i];
+        if (color != nullptr) { v.x = color[color_stride * i]; v.y = color[color_stride * i + 1]; v.z = color[color_stride * i + 2]; }
+        if (sigma != nullptr) v.w = sigma[sigma_stride * i];
         packed[i] = v;
     }
 }
@@ -507,7 +509,16 @@ cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* co
                              bool keep_missing) {
     if (voxels == 0) return cudaSuccess;
     const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (voxels + 255) / 256));
-    pack_grid_kernel<<<blocks, 256, 0, s>>>(sigma, color, packed, voxels, keep_missing);
+    pack_grid_kernel<<<blocks, 256, 0, s>>>(sigma, 1, color, 3, packed, voxels, keep_missing);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_grid_strided(cudaStream_t s, const float* sigma, int32_t sigma_stride, const float* color,
+                                     int32_t color_stride, float4* packed, size_t voxels, bool keep_missing) {
+    if (voxels == 0) return cudaSuccess;
+    const uint32_t blocks = static_cast<uint32_t>(min(static_cast<size_t>(148 * 8), (voxels + 255) / 256));
+    pack_grid_kernel<<<blocks, 256, 0, s>>>(sigma, static_cast<size_t>(sigma_stride), color, static_cast<size_t>(color_stride),
+                                            packed, voxels, keep_missing);
     return cudaGetLastError();
 }
 

@@ -88,6 +88,8 @@ cudaError_t launch_scatter(cudaStream_t s, const ScatterParams& sp, const float*
 // missing (null) component: zero, or left as it is when keep_missing
 cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* color, float4* packed, size_t voxels,
                              bool keep_missing);
+cudaError_t launch_pack_grid_strided(cudaStream_t s, const float* sigma, int32_t sigma_stride, const float* color,
+                                     int32_t color_stride, float4* packed, size_t voxels, bool keep_missing);
 cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, size_t first,
                                size_t voxels, uint32_t nx, uint32_t ny, uint32_t sx, uint32_t sy, uint32_t sz);
 

@@ -32,9 +32,9 @@ DenseGridField& DenseGridField::operator=(DenseGridField&& o) noexcept {
 }
 
 void DenseGridField::Release() {
-    if (grid_ != nullptr) hpx_grid_release(grid_);
-    if (sigma_field_ != nullptr) hp_field_release(sigma_field_);
+    if (sigma_field_ != nullptr) hp_field_release(sigma_field_);   // the views first, then the grid they look into
     if (color_field_ != nullptr) hp_field_release(color_field_);
+    if (grid_ != nullptr) hpx_grid_release(grid_);
     grid_ = nullptr;
     sigma_field_ = color_field_ = nullptr;
     sigma_grad_.clear();
@@ -67,6 +67,10 @@ Status DenseGridField::Create(const Context& ctx, const DenseGridConfig& config,
     hs = hpx_grid_create(ctx.handle(), f.sigma_field_, f.color_field_, config.bbox_min.data(), config.bbox_max.data(),
                          &f.grid_);
     if (hs != HP_STATUS_SUCCESS) return Status::FromHotpath(hs, std::string("hpx_grid_create failed: ") + hpx_last_error());
+    // one copy of the values in HBM: the two fields become views of the packed grid, so UpdateValues reaches the staged
+    // hp_samp / hp_graph paths (sigma_field() / color_field()) as well as the fused one
+    hs = hpx_grid_adopt_fields(f.grid_, f.sigma_field_, f.color_field_);
+    if (hs != HP_STATUS_SUCCESS) return Status::FromHotpath(hs, std::string("hpx_grid_adopt_fields failed: ") + hpx_last_error());
     f.resolution_ = config.resolution;
     f.bbox_min_ = config.bbox_min;
     f.bbox_max_ = config.bbox_max;

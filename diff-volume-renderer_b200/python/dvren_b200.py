@@ -47,6 +47,7 @@ HPX_FUNCTIONS = {
     "hpx_grid_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(f3), P(f3), P(C.c_void_p)]),
     "hpx_grid_create_raw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_uint32, C.c_uint32, P(f3), P(f3), P(C.c_void_p)]),
+    "hpx_grid_adopt_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_grid_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hpx_grid_zero_grad": (C.c_int, [C.c_void_p]),
     "hpx_grid_grad_buffer": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]),
@@ -72,6 +73,8 @@ HPX_FUNCTIONS = {
     "hpx_frame_image": (C.c_int, [C.c_void_p, P(A.hp_img_t)]),
     "hpx_frame_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_counts": (C.c_int, [C.c_void_p, P(hpx_counts)]),
+    "hpx_frame_cube_samples": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_uint64)]),
+    "hpx_grid_touched_voxels": (C.c_int, [C.c_void_p, P(C.c_uint64)]),
     "hpx_frame_capture": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "hpx_frame_replay": (C.c_int, [C.c_void_p]),
     "hpx_frame_grad_input": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
@@ -208,6 +211,12 @@ class Grid:
                                                                 cam.ctypes.data, A.HP_MEMSPACE_HOST))
         return sg, cg, cam
 
+    def touched_voxels(self) -> int:
+        """Voxels whose gradient is non-zero (what the backward passes since the last zero have written)."""
+        n = C.c_uint64()
+        check("hpx_grid_touched_voxels", self.lib.hpx_grid_touched_voxels(self.handle, C.byref(n)))
+        return n.value
+
     def update(self, sigma=None, color=None):
         s = np.ascontiguousarray(sigma, np.float32) if sigma is not None else None
         c = np.ascontiguousarray(color, np.float32) if color is not None else None
@@ -301,6 +310,12 @@ class Frame:
         c = hpx_counts()
         check("hpx_frame_counts", self.lib.hpx_frame_counts(self.handle, C.byref(c)))
         return {"rays": c.rays, "samples": c.samples, "live_samples": c.live_samples}
+
+    def cube_samples(self, grid: Grid) -> int:
+        """Live samples of the last forward that lie inside the unit cube (gather 8 corners / scatter 8 reds)."""
+        n = C.c_uint64()
+        check("hpx_frame_cube_samples", self.lib.hpx_frame_cube_samples(self.handle, grid.handle, C.byref(n)))
+        return n.value
 
     def capture(self, grid: Grid, backward_flags: int = 0):
         check("hpx_frame_capture", self.lib.hpx_frame_capture(self.handle, grid.handle, backward_flags))

@@ -98,6 +98,11 @@ HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, 
                                      const float* sigma, const float* color, hp_memspace memspace,
                                      uint32_t interp, uint32_t oob, const float bbox_min[3],
                                      const float bbox_max[3], hpx_grid** out_grid);
+/* One copy of the values in HBM: the fields the grid was built from (either may be NULL) give up their own snapshots and
+ * become strided views of the packed voxels, so that hpx_grid_update is also what the staged hp_samp / hp_graph_* calls
+ * on those fields read.  The fields must come from the grid's context and match its shape and policies; they must be
+ * released before, or stop being used after, the grid is released. */
+HP_API hp_status hpx_grid_adopt_fields(hpx_grid* grid, hp_field* fs, hp_field* fc);
 /* Replace the values (parameter update); either pointer may be NULL to keep it. */
 HP_API hp_status hpx_grid_update(hpx_grid* grid, const float* sigma, const float* color,
                                  hp_memspace memspace);
@@ -140,6 +145,8 @@ HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_
  *   box_grad[nz][ny][nx][4] ({dr,dg,db,dsigma}) instead of the grid's own gradient block, so that a group of image
  *   rows can be all-reduced (contiguously) while the next group is still being rendered.  HPX_BACKWARD_ZERO clears the
  *   box.  Unit scatter bbox + linear fields only; HPX_BACKWARD_DETERMINISTIC is ignored. */
+/* (A captured graph of the frame is dropped: hpx_frame_replay fails until hpx_frame_capture is called again.  The
+ * scatter strategy and the fused-camera choice of a captured graph are those of the view it was captured with.) */
 HP_API hp_status hpx_frame_set_interleave(hpx_frame* frame, uint32_t stride, uint32_t phase);
 HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_t out_box[6]);
 HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
@@ -181,6 +188,12 @@ HP_API hp_status hpx_frame_image(const hpx_frame* frame, hp_img_t* out_views);
 HP_API hp_status hpx_frame_read(hpx_frame* frame, float* image, float* trans, float* opacity,
                                 float* depth, uint32_t* hitmask);
 HP_API hp_status hpx_frame_counts(hpx_frame* frame, hpx_counts* out_counts);
+/* Measurement helpers (bench.py roofline): live samples of the last hpx_forward that lie INSIDE the unit cube, i.e. the
+ * samples that gather 8 corners and scatter 8 reds (a separate counting kernel that re-marches the rays without touching
+ * the grid; blocks until done), and the number of voxels whose gradient the backward has written since the last zero
+ * (V_touched of the compulsory-HBM-bytes formula; blocks until done). */
+HP_API hp_status hpx_frame_cube_samples(hpx_frame* frame, const hpx_grid* grid, uint64_t* out_samples);
+HP_API hp_status hpx_grid_touched_voxels(hpx_grid* grid, uint64_t* out_voxels);
 /* Capture forward (+ backward when flags != 0, reading dL/dI from the frame's own
  * device buffer, see hpx_frame_grad_input) into a CUDA graph; replay launches it. */
 HP_API hp_status hpx_frame_capture(hpx_frame* frame, hpx_grid* grid, uint32_t backward_flags);

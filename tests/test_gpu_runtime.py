@@ -1,0 +1,248 @@
+"""GPU tests of the device-resident training surface and of object lifetimes (hp_b200.h):
+parameter updates (hpx_grid_update, hpx_grid_adopt_fields), graph capture with the deterministic
+backward, context / stream rules, release order, and the measurement counters bench.py relies on."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import dvren_b200 as D
+import hp_abi as A
+import hp_host as H
+import oracle as O
+import synth as S
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = D.Context()
+    yield c
+    c.close()
+
+
+def _render(ctx, grid, desc, dl=None, flags=D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO):
+    plan = D.Plan(ctx, desc)
+    frame = D.Frame(plan)
+    frame.forward(grid)
+    out = frame.read()
+    out.update(frame.counts())
+    if dl is not None:
+        frame.backward(grid, dl, flags)
+        out["sigma_grad"], out["color_grad"], out["camera_grad"] = grid.read_grad()
+    frame.close(); plan.close()
+    return out
+
+
+def test_grid_update_equals_a_fresh_grid_bit_for_bit(ctx):
+    """hpx_grid_update (the optimiser hand-off): after replacing the values -- both arrays, sigma only, colour only --
+    forward AND backward equal those of a grid created from the new values, bit for bit on the images and on the
+    deterministic gradients."""
+    desc = S.bench_plan(70, 52, 96, stratified=True, view=2, views=9)
+    dl = S.hashed_image_grad(70 * 52)
+    sig0, col0 = S.hashed_volume(24, "dense", seed=11)
+    sig1, col1 = S.hashed_volume(24, "thin", seed=99)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_DETERMINISTIC
+    for new_sig, new_col in ((sig1, col1), (sig1, None), (None, col1)):
+        grid = D.Grid(ctx, sig0, col0)
+        before = _render(ctx, grid, desc, dl, flags)                     # also primes the deterministic |value| maximum
+        grid.update(new_sig, new_col)
+        got = _render(ctx, grid, desc, dl, flags)
+        grid.close()
+        fresh_grid = D.Grid(ctx, new_sig if new_sig is not None else sig0, new_col if new_col is not None else col0)
+        fresh = _render(ctx, fresh_grid, desc, dl, flags)
+        fresh_grid.close()
+        for k in ("image", "trans", "opacity", "depth", "hitmask"):
+            U.assert_bits(got[k], fresh[k], f"updated grid {k}")
+        assert got["live_samples"] == fresh["live_samples"]
+        U.assert_bits(got["sigma_grad"], fresh["sigma_grad"], "updated grid sigma_grad (deterministic)")
+        U.assert_bits(got["color_grad"], fresh["color_grad"], "updated grid color_grad (deterministic)")
+        assert not U.bits_equal(before["image"], got["image"])           # the update really changed the result
+
+
+def test_adopted_fields_follow_grid_updates_in_the_staged_path():
+    """DenseGridField::UpdateValues refreshed only the packed grid; the staged path (hp_samp on the two
+    hp_fields) kept rendering the old values.  With hpx_grid_adopt_fields the fields are views of the packed voxels:
+    after an update, staged hp_samp output equals the oracle on the NEW values bit for bit, and equals the fused path."""
+    lib = D.load()
+    pipe = H.HpHostPipeline(lib)
+    sig0, col0 = S.hashed_volume((7, 9, 11), "dense", seed=5)
+    sig1, col1 = S.hashed_volume((7, 9, 11), "thin", seed=6)
+    desc = S.bench_plan(21, 17, 40, stratified=True, view=1, views=7)
+    plan, rdesc = pipe.plan(desc)
+    n = rdesc.roi.width * rdesc.roi.height
+    rays = pipe.ray(plan, n)
+    fs, fc = pipe.sigma_field(sig0), pipe.color_field(col0)
+    grid = C.c_void_p()
+    D.check("hpx_grid_create", lib.hpx_grid_create(pipe.ctx, fs, fc, None, None, C.byref(grid)))
+    D.check("hpx_grid_adopt_fields", lib.hpx_grid_adopt_fields(grid, fs, fc))
+    st, odesc = O.plan_resolve(desc)
+    orays = O.rays(odesc)
+    for sig, col, what in ((sig0, col0, "adopted"), (sig1, col1, "updated")):
+        if what == "updated":
+            D.check("hpx_grid_update", lib.hpx_grid_update(grid, sig.ctypes.data, col.ctypes.data, A.HP_MEMSPACE_HOST))
+        samp = pipe.samp(plan, fs, fc, rays, rdesc.max_samples)
+        gs, gc = U.oracle_grids(sig, col, 1, 0)
+        st, osamp = O.sample(odesc, gs, gc, orays, odesc.max_samples)
+        assert st == 0 and samp["count"] == osamp["count"]
+        for k in ("positions", "dt", "ray_offset", "sigma", "color"):
+            U.assert_bits(samp[k], osamp[k], f"{what} fields samp.{k}")
+        fsamp, fintl = pipe.fused(plan, fs, fc, rays, rdesc.max_samples)
+        U.assert_bits(fsamp["sigma"], osamp["sigma"], f"{what} fused sigma")
+        # a second grid packed FROM the views (stride-4 sources) holds the same voxels
+        grid2 = C.c_void_p()
+        D.check("hpx_grid_create", lib.hpx_grid_create(pipe.ctx, fs, fc, None, None, C.byref(grid2)))
+        frame = C.c_void_p()
+        D.check("hpx_frame_create", lib.hpx_frame_create(plan, C.byref(frame)))
+        imgs = []
+        for g in (grid, grid2):
+            D.check("hpx_forward", lib.hpx_forward(frame, g))
+            img = np.zeros((rdesc.height, rdesc.width, 3), np.float32)
+            D.check("hpx_frame_read", lib.hpx_frame_read(frame, img.ctypes.data, None, None, None, None))
+            imgs.append(img)
+        U.assert_bits(imgs[0], imgs[1], f"{what}: grid packed from the views")
+        ref = O.render(odesc, gs, gc)
+        U.assert_close(imgs[0], ref["image"], U.IMAGE_RTOL, f"{what} lean image")
+        lib.hpx_frame_release(frame)
+        lib.hpx_grid_release(grid2)
+    # releasing the grid first leaves the views empty, not dangling: the next query fails cleanly
+    lib.hpx_grid_release(grid)
+    with pytest.raises(H.HpError):
+        pipe.samp(plan, fs, fc, rays, rdesc.max_samples)
+    pipe.close()
+
+
+def test_capture_with_deterministic_backward_survives_value_updates(ctx):
+    """capturing HPX_BACKWARD_DETERMINISTIC used to cudaMalloc inside the capture (first use) and to freeze the
+    fixed-point quantum of the values at capture time.  Capture FIRST (no eager deterministic backward before), replay,
+    grow the values 1000x with hpx_grid_update, replay again: each replay must equal an eager deterministic backward on
+    the same values bit for bit."""
+    desc = S.bench_plan(64, 40, 64, stratified=True, view=1, views=5)
+    n = 64 * 40
+    dl = S.hashed_image_grad(n)
+    sig, col = S.hashed_volume(16, "thin", seed=3)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_DETERMINISTIC
+    plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+    d_dl = frame.grad_input_ptr()
+    D.check("h2d", ctx.lib.hpx_copy_to_device(ctx.handle, C.c_void_p(d_dl), np.ascontiguousarray(dl).ctypes.data, dl.nbytes))
+    frame.capture(grid, flags)                       # nothing deterministic has run eagerly on this grid yet
+    for scale in (1.0, 1000.0, 0.001):
+        grid.update(None, col * np.float32(scale))   # colour magnitudes set the quantum (fixed_scale_kernel)
+        frame.replay()
+        sg_r, cg_r, _ = grid.read_grad()
+        fresh = D.Grid(ctx, sig, col * np.float32(scale))
+        eager = _render(ctx, fresh, desc, dl, flags)
+        fresh.close()
+        U.assert_bits(sg_r, eager["sigma_grad"], f"replayed deterministic sigma_grad, colours x{scale}")
+        U.assert_bits(cg_r, eager["color_grad"], f"replayed deterministic color_grad, colours x{scale}")
+        assert np.isfinite(cg_r).all() and np.abs(cg_r).max() > 0
+    # an eager deterministic backward after the capture still works (meta block initialised, staleness honoured)
+    frame.backward(grid, dl, flags)
+    sg_e, cg_e, _ = grid.read_grad()
+    U.assert_bits(sg_e, sg_r, "eager after capture")
+    frame.close(); grid.close(); plan.close()
+
+
+def test_frame_and_grid_must_share_a_context(ctx):
+    """a frame and a grid from different contexts (= different streams) are rejected instead of racing."""
+    other = D.Context(device=0)
+    sig, col = S.hashed_volume(8, "thin")
+    desc = S.bench_plan(16, 16, 16, stratified=False)
+    plan = D.Plan(ctx, desc); frame = D.Frame(plan)
+    foreign = D.Grid(other, sig, col)
+    with pytest.raises(D.DvrenError) as e:
+        frame.forward(foreign)
+    assert e.value.status == A.HP_STATUS_INVALID_ARGUMENT
+    own = D.Grid(ctx, sig, col)
+    frame.forward(own)
+    with pytest.raises(D.DvrenError):
+        frame.backward(foreign, np.zeros((256, 3), np.float32))
+    frame.close(); plan.close(); own.close(); foreign.close(); other.close()
+
+
+def test_set_interleave_drops_a_captured_graph(ctx):
+    """a captured graph has the CTA count of the old interleave baked in; replay must fail until recapture."""
+    sig, col = S.hashed_volume(12, "thin")
+    desc = S.bench_plan(48, 40, 32, stratified=True)
+    plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+    frame.capture(grid, 0)
+    frame.replay()
+    full = frame.read()
+    frame.set_interleave(2, 1)
+    with pytest.raises(D.DvrenError):
+        frame.replay()
+    frame.capture(grid, 0)
+    frame.replay()
+    half = frame.read()
+    own = half["hitmask"] == 1
+    assert own.sum() == frame.counts()["rays"] and 0 < own.sum() < full["hitmask"].sum()
+    U.assert_bits(half["image"][own], full["image"][own], "interleaved replay")
+    frame.close(); grid.close(); plan.close()
+
+
+def test_context_may_be_released_before_its_objects():
+    """the reference's fields never touch their context, so releasing the context first is legal there
+    (hp_runtime.cpp:33-36).  Here every object keeps its context alive: use after hp_ctx_release still works and the
+    releases in any order neither crash nor leak the stream."""
+    lib = D.load()
+    c = D.Context(device=0)
+    sig, col = S.hashed_volume(10, "thin")
+    plan = D.Plan(c, S.bench_plan(24, 20, 24, stratified=False))
+    grid = D.Grid(c, sig, col)
+    frame = D.Frame(plan)
+    pipe_field = C.c_void_p()
+    t = A.host_tensor(np.ascontiguousarray(sig))
+    D.check("field", lib.hp_field_create_grid_sigma(c.handle, C.byref(t), 1, 0, C.byref(pipe_field)))
+    c.close()                                   # the caller's reference goes first
+    plan_handle = plan.handle
+    frame.forward(grid)                         # still usable: the objects hold the context
+    assert frame.read()["hitmask"].all()
+    plan.close()                                # the frame keeps its plan alive too
+    frame.forward(grid)
+    frame.close()
+    lib.hp_field_release(pipe_field)
+    grid.close()                                # last object: the context goes away here
+    assert plan_handle
+
+
+def test_entry_points_restore_the_callers_device():
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    c = D.Context(device=1)
+    sig, col = S.hashed_volume(8, "thin")
+    grid = D.Grid(c, sig, col)
+    assert torch.cuda.current_device() == 0
+    grid.close(); c.close()
+
+
+def test_cube_sample_and_touched_voxel_counters_match_the_oracle(ctx):
+    """The counters behind bench.py's roofline line: in-cube live samples (the samples that gather and scatter) and touched
+    voxels, against counts derived from the oracle's materialised samples."""
+    for kind, strat in (("thin", True), ("dense", False)):
+        sig, col = S.hashed_volume(20, kind)
+        desc = S.bench_plan(57, 43, 80, stratified=strat, view=2, views=9)
+        st, odesc = O.plan_resolve(desc)
+        gs, gc = U.oracle_grids(sig, col, 1, 0)
+        orays = O.rays(odesc)
+        st, osamp = O.sample(odesc, gs, gc, orays, odesc.max_samples)
+        ointl = O.integrate(odesc, osamp)
+        live = ointl["aux"][:, 2] != 0                      # T_before > 0 on every integrated sample, rows after the stop stay 0
+        pos = osamp["positions"]
+        inside = np.all((pos >= 0) & (pos <= 1), axis=1)
+        plan = D.Plan(ctx, desc); grid = D.Grid(ctx, sig, col); frame = D.Frame(plan)
+        frame.forward(grid)
+        assert frame.counts()["live_samples"] == int(live.sum())
+        assert frame.cube_samples(grid) == int((live & inside).sum())
+        dl = np.ones((57 * 43, 3), np.float32)
+        frame.backward(grid, dl)
+        sg, cg, _ = grid.read_grad()
+        touched = (sg != 0) | (cg.reshape(-1, 3) != 0).any(axis=1)
+        assert grid.touched_voxels() == int(touched.sum()) > 0
+        ref = O.render(odesc, gs, gc, dl)
+        ref_touched = (ref["sigma_grad"] != 0) | (ref["color_grad"].reshape(-1, 3) != 0).any(axis=1)
+        assert abs(int(touched.sum()) - int(ref_touched.sum())) <= 0.001 * ref_touched.sum() + 2   # exact zeros may differ by rounding
+        frame.close(); grid.close(); plan.close()
