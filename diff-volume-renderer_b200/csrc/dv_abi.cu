@@ -231,6 +231,7 @@ hp_status sampler_offsets(const hp_plan* plan, const RayArrays& rays, size_t n_r
 // =============================================================================
 extern "C" HP_API hp_status hp_ray(const hp_plan* plan, const hp_rays_t* override_or_null, hp_rays_t* rays, void* ws,
                                    size_t ws_bytes) {
+    DV_RANGE("hp_ray");
     if (rays == nullptr || plan == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const hp_memspace ms = rays->origins.memspace == kDev ? kDev : kHost;
     const hp_plan_desc& d = plan->desc;
@@ -446,6 +447,7 @@ hp_status sampler_entry(const hp_plan* plan, const hp_field* fs, const hp_field*
 
 extern "C" HP_API hp_status hp_samp(const hp_plan* plan, const hp_field* fs, const hp_field* fc, const hp_rays_t* rays,
                                     hp_samp_t* samp, void* ws, size_t ws_bytes) {
+    DV_RANGE("hp_samp");
     if (plan == nullptr || rays == nullptr || samp == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     return sampler_entry(plan, fs, fc, rays, samp, nullptr, ws, ws_bytes);
 }
@@ -453,6 +455,7 @@ extern "C" HP_API hp_status hp_samp(const hp_plan* plan, const hp_field* fs, con
 extern "C" HP_API hp_status hp_samp_int_fused(const hp_plan* plan, const hp_field* fs, const hp_field* fc,
                                               const hp_rays_t* rays, hp_samp_t* samp, hp_intl_t* intl, void* ws,
                                               size_t ws_bytes) {
+    DV_RANGE("hp_samp_int_fused");
     if (plan == nullptr || rays == nullptr || samp == nullptr || intl == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     return sampler_entry(plan, fs, fc, rays, samp, intl, ws, ws_bytes);
 }
@@ -462,6 +465,7 @@ extern "C" HP_API hp_status hp_samp_int_fused(const hp_plan* plan, const hp_fiel
 // =============================================================================
 extern "C" HP_API hp_status hp_int(const hp_plan* plan, const hp_samp_t* samp, hp_intl_t* intl, void* ws,
                                    size_t ws_bytes) {
+    DV_RANGE("hp_int");
     if (plan == nullptr || samp == nullptr || intl == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const hp_memspace ms = samp->sigma.memspace == kDev ? kDev : kHost;
     if (samp->dt.memspace != ms || samp->sigma.memspace != ms || samp->ray_offset.memspace != ms ||
@@ -528,6 +532,7 @@ extern "C" HP_API hp_status hp_int(const hp_plan* plan, const hp_samp_t* samp, h
 // =============================================================================
 extern "C" HP_API hp_status hp_img(const hp_plan* plan, const hp_intl_t* intl, const hp_rays_t* rays, hp_img_t* img,
                                    void* ws, size_t ws_bytes) {
+    DV_RANGE("hp_img");
     if (plan == nullptr || intl == nullptr || rays == nullptr || img == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const hp_memspace ms = rays->pixel_ids.memspace == kDev ? kDev : kHost;
     if (intl->radiance.memspace != ms || intl->transmittance.memspace != ms || intl->opacity.memspace != ms ||
@@ -601,6 +606,7 @@ extern "C" HP_API hp_status hp_img(const hp_plan* plan, const hp_intl_t* intl, c
 // =============================================================================
 extern "C" HP_API hp_status hp_diff(const hp_plan* plan, const hp_tensor* dL_dI, const hp_samp_t* samp,
                                     const hp_intl_t* intl, hp_grads_t* grads, void* ws, size_t ws_bytes) {
+    DV_RANGE("hp_diff");
     if (plan == nullptr || dL_dI == nullptr || samp == nullptr || intl == nullptr || grads == nullptr)
         return HP_STATUS_INVALID_ARGUMENT;
     const hp_memspace ms = dL_dI->memspace == kDev ? kDev : kHost;

@@ -63,6 +63,7 @@ extern "C" {
 // =============================================================================
 HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp_field* fc, const float bbox_min[3],
                                  const float bbox_max[3], hpx_grid** out_grid) {
+    DV_RANGE("hpx_grid_create");
     if (ctx == nullptr || out_grid == nullptr || (fs == nullptr && fc == nullptr)) return HP_STATUS_INVALID_ARGUMENT;
     if ((fs && fs->kind != FieldKind::kDenseSigma) || (fc && fc->kind != FieldKind::kDenseColor))
         return HP_STATUS_INVALID_ARGUMENT;
@@ -98,6 +99,7 @@ HP_API hp_status hpx_grid_create(const hp_ctx* ctx, const hp_field* fs, const hp
 }
 
 HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* color, hp_memspace memspace) {
+    DV_RANGE("hpx_grid_update");
     if (g != nullptr) g->value_max_stale = true;
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (sigma == nullptr && color == nullptr) return HP_STATUS_SUCCESS;
@@ -126,6 +128,7 @@ HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* c
 HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, int32_t nz, const float* sigma,
                                      const float* color, hp_memspace memspace, uint32_t interp, uint32_t oob,
                                      const float bbox_min[3], const float bbox_max[3], hpx_grid** out_grid) {
+    DV_RANGE("hpx_grid_create_raw");
     if (ctx == nullptr || out_grid == nullptr || nx <= 0 || ny <= 0 || nz <= 0) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(ctx);
     hpx_grid* g = new (std::nothrow) hpx_grid();
@@ -151,6 +154,7 @@ HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, 
 }
 
 HP_API hp_status hpx_grid_zero_grad(hpx_grid* g) {
+    DV_RANGE("hpx_grid_zero_grad");
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     if (g->d_grad == nullptr) return grid_ensure_grad(g);
@@ -159,6 +163,7 @@ HP_API hp_status hpx_grid_zero_grad(hpx_grid* g) {
 }
 
 HP_API hp_status hpx_grid_grad_buffer(hpx_grid* g, float** out_device_ptr, size_t* out_floats) {
+    DV_RANGE("hpx_grid_grad_buffer");
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
@@ -169,6 +174,7 @@ HP_API hp_status hpx_grid_grad_buffer(hpx_grid* g, float** out_device_ptr, size_
 
 HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color_grad, float* camera16,
                                     hp_memspace memspace) {
+    DV_RANGE("hpx_grid_read_grad");
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
@@ -206,6 +212,7 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
 
 HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* g, const float* positions, const float* grad_sigma,
                                              const float* grad_color, size_t count, hp_memspace memspace) {
+    DV_RANGE("hpx_grid_accumulate_samples");
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (count == 0) return HP_STATUS_SUCCESS;
     if (positions == nullptr || grad_sigma == nullptr || grad_color == nullptr) return HP_STATUS_INVALID_ARGUMENT;
@@ -234,6 +241,7 @@ HP_API hp_status hpx_grid_accumulate_samples(hpx_grid* g, const float* positions
 }
 
 HP_API void hpx_grid_release(hpx_grid* g) {
+    DV_RANGE("hpx_grid_release");
     if (g == nullptr) return;
     for (hp_field* v : g->views) {   // adopted fields lose their values with the grid: later queries fail cleanly
         v->d_data = nullptr;
@@ -256,6 +264,7 @@ HP_API void hpx_grid_release(hpx_grid* g) {
 // One copy of the values in HBM: the two fields the grid was built from drop their own snapshots and become strided
 // views of the packed {r,g,b,sigma} voxels, so hpx_grid_update is what the staged hp_samp / hp_graph paths see too.
 HP_API hp_status hpx_grid_adopt_fields(hpx_grid* g, hp_field* fs, hp_field* fc) {
+    DV_RANGE("hpx_grid_adopt_fields");
     if (g == nullptr || (fs == nullptr && fc == nullptr)) return HP_STATUS_INVALID_ARGUMENT;
     if ((fs && fs->kind != FieldKind::kDenseSigma) || (fc && fc->kind != FieldKind::kDenseColor)) return HP_STATUS_INVALID_ARGUMENT;
     for (hp_field* f : {fs, fc}) {
@@ -296,6 +305,7 @@ static void* frame_take(hpx_frame* f, size_t bytes, hp_status* st) {
 }
 
 HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
+    DV_RANGE("hpx_frame_create");
     if (plan == nullptr || out_frame == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (!plan->gap_free) {
         set_last_error("plan skips marching steps (dt below float resolution); use the materialising hp_* path");
@@ -353,11 +363,12 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
     return HP_STATUS_SUCCESS;
 }
 
-HP_API size_t hpx_frame_bytes(const hpx_frame* f) { return f ? f->device_bytes : 0; }
+HP_API size_t hpx_frame_bytes(const hpx_frame* f) { DV_RANGE("hpx_frame_bytes"); return f ? f->device_bytes : 0; }
 
 // Host-only: the per-step table a frame of this plan uploads (no device needed) -- lets the CPU test suite pin the
 // ray-independent part of the marching loop against the oracle.
 HP_API hp_status hpx_plan_step_table(const hp_plan* plan, float* out_steps4, size_t capacity_steps, uint32_t* out_count) {
+    DV_RANGE("hpx_plan_step_table");
     if (plan == nullptr || out_count == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     *out_count = plan->uniform_count;
     if (!plan->gap_free) return HP_STATUS_UNSUPPORTED;
@@ -370,6 +381,7 @@ HP_API hp_status hpx_plan_step_table(const hp_plan* plan, float* out_steps4, siz
 
 HP_API hp_status hpx_frame_set_view(hpx_frame* f, const hp_camera_desc* camera, uint64_t seed,
                                     uint64_t ray_index_base) {
+    DV_RANGE("hpx_frame_set_view");
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (camera != nullptr) {
         hp_plan_desc tmp = f->plan->desc;   // apply the plan-time camera defaults to the new camera too
@@ -476,7 +488,7 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
             uint32_t* meta_bits = reinterpret_cast<uint32_t*>(g->d_fixed_meta);
             if (g->value_max_stale || capturing) {
                 DV_CUDA(cudaMemsetAsync(meta_bits, 0, sizeof(uint32_t), s));
-                DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits));
+                DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits, true));
                 if (!capturing) g->value_max_stale = false;
             }
             DV_CUDA(cudaMemsetAsync(meta_bits + 1, 0, sizeof(uint32_t), s));
@@ -497,6 +509,7 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
 }
 
 HP_API hp_status hpx_forward(hpx_frame* f, const hpx_grid* g) {
+    DV_RANGE("hpx_forward");
     DV_TRY(frame_check_grid(f, g));
     DV_ENTER(f->ctx);
     DV_TRY(frame_push_params(f));
@@ -506,6 +519,7 @@ HP_API hp_status hpx_forward(hpx_frame* f, const hpx_grid* g) {
 }
 
 HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags) {
+    DV_RANGE("hpx_backward");
     DV_TRY(frame_check_grid(f, g));
     if (dL_dI == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (!f->forward_done) {
@@ -525,6 +539,7 @@ HP_API hp_status hpx_backward(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_
 }
 
 HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_t phase) {
+    DV_RANGE("hpx_frame_set_interleave");
     if (f == nullptr || stride == 0 || phase >= stride) return HP_STATUS_INVALID_ARGUMENT;
     RoiParams& roi = f->h_params.roi;
     roi.tile_row_stride = stride;
@@ -550,6 +565,7 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_
 }
 
 HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_box[6]) {
+    DV_RANGE("hpx_frame_bounds");
     DV_TRY(frame_check_grid(f, g));
     if (out_box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
@@ -580,6 +596,7 @@ HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_b
 
 HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags,
                                   float* box_grad, const int32_t box[6]) {
+    DV_RANGE("hpx_backward_box");
     DV_TRY(frame_check_grid(f, g));
     if (dL_dI == nullptr || box_grad == nullptr || box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     for (int i = 0; i < 3; ++i)
@@ -610,6 +627,7 @@ HP_API hp_status hpx_backward_box(hpx_frame* f, hpx_grid* g, const float* dL_dI,
 HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags,
                                         const uint32_t* group_end_rows, uint32_t n_groups, uint32_t** out_device_counters,
                                         uint32_t* out_expected) {
+    DV_RANGE("hpx_backward_signalled");
     DV_TRY(frame_check_grid(f, g));
     if (dL_dI == nullptr || group_end_rows == nullptr || n_groups == 0 || n_groups > 8 || out_expected == nullptr)
         return HP_STATUS_INVALID_ARGUMENT;
@@ -643,6 +661,7 @@ HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* 
 }
 
 HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_device_counters) {
+    DV_RANGE("hpx_frame_reset_group_counters");
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
     DV_CUDA(cudaMemsetAsync(f->d_group_done, 0, 8 * sizeof(unsigned int), f->ctx->stream));
@@ -651,6 +670,7 @@ HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_dev
 }
 
 HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_t* device_counter, uint32_t value) {
+    DV_RANGE("hpx_stream_wait_counter");
     if (stream_ctx == nullptr || device_counter == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(stream_ctx);
     typedef int (*wait_fn)(CUstream_st*, unsigned long long, uint32_t, unsigned int);   // cuStreamWaitValue32
@@ -674,6 +694,7 @@ HP_API hp_status hpx_stream_wait_counter(const hp_ctx* stream_ctx, const uint32_
 }
 
 HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* g, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs) {
+    DV_RANGE("hpx_grid_set_grad_layout");
     if (g == nullptr || slow_axis < 0 || slow_axis > 2) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
@@ -691,6 +712,7 @@ HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* g, int32_t slow_axis, size_t
 }
 
 HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* g, float* box_grad, const int32_t box[6]) {
+    DV_RANGE("hpx_grid_add_box");
     if (stream_ctx == nullptr || g == nullptr || box_grad == nullptr || box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     for (int i = 0; i < 3; ++i)
         if (box[i] < 0 || box[3 + i] < 0) return HP_STATUS_INVALID_ARGUMENT;
@@ -708,6 +730,7 @@ HP_API hp_status hpx_grid_add_box(const hp_ctx* stream_ctx, hpx_grid* g, float* 
 }
 
 HP_API hp_status hpx_frame_box_misses(hpx_frame* f, uint32_t* out_count) {
+    DV_RANGE("hpx_frame_box_misses");
     if (f == nullptr || out_count == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
     unsigned int host = 0;
@@ -719,6 +742,7 @@ HP_API hp_status hpx_frame_box_misses(hpx_frame* f, uint32_t* out_count) {
 }
 
 HP_API hp_status hpx_backward_scatter(const hpx_frame* f, const hpx_grid* g, uint32_t flags, uint32_t* out_flag) {
+    DV_RANGE("hpx_backward_scatter");
     if (f == nullptr || g == nullptr || out_flag == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const int want = (flags & HPX_BACKWARD_SCATTER_MERGED) ? kScatterMerge
                    : (flags & HPX_BACKWARD_SCATTER_PER_RAY) ? kScatterPerRay : kScatterAuto;
@@ -728,6 +752,7 @@ HP_API hp_status hpx_backward_scatter(const hpx_frame* f, const hpx_grid* g, uin
 }
 
 HP_API hp_status hpx_frame_image(const hpx_frame* f, hp_img_t* out) {
+    DV_RANGE("hpx_frame_image");
     if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const hp_plan_desc& d = f->plan->desc;
     const int64_t w = d.width, h = d.height;
@@ -746,6 +771,7 @@ HP_API hp_status hpx_frame_image(const hpx_frame* f, hp_img_t* out) {
 
 HP_API hp_status hpx_frame_read(hpx_frame* f, float* image, float* trans, float* opacity, float* depth,
                                 uint32_t* hitmask) {
+    DV_RANGE("hpx_frame_read");
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
     cudaStream_t s = f->ctx->stream;
@@ -760,6 +786,7 @@ HP_API hp_status hpx_frame_read(hpx_frame* f, float* image, float* trans, float*
 }
 
 HP_API hp_status hpx_frame_counts(hpx_frame* f, hpx_counts* out) {
+    DV_RANGE("hpx_frame_counts");
     if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
     auto* h_live = reinterpret_cast<unsigned long long*>(f->h_pinned + 1);
@@ -773,6 +800,7 @@ HP_API hp_status hpx_frame_counts(hpx_frame* f, hpx_counts* out) {
 }
 
 HP_API hp_status hpx_frame_cube_samples(hpx_frame* f, const hpx_grid* g, uint64_t* out_samples) {
+    DV_RANGE("hpx_frame_cube_samples");
     DV_TRY(frame_check_grid(f, g));
     if (out_samples == nullptr || !f->forward_done) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
@@ -797,6 +825,7 @@ HP_API hp_status hpx_frame_cube_samples(hpx_frame* f, const hpx_grid* g, uint64_
 }
 
 HP_API hp_status hpx_grid_touched_voxels(hpx_grid* g, uint64_t* out_voxels) {
+    DV_RANGE("hpx_grid_touched_voxels");
     if (g == nullptr || out_voxels == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
@@ -814,6 +843,7 @@ HP_API hp_status hpx_grid_touched_voxels(hpx_grid* g, uint64_t* out_voxels) {
 }
 
 HP_API hp_status hpx_frame_grad_input(hpx_frame* f, float** out) {
+    DV_RANGE("hpx_frame_grad_input");
     if (f == nullptr || out == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     *out = f->d_dL_dI;
     return HP_STATUS_SUCCESS;
@@ -822,6 +852,7 @@ HP_API hp_status hpx_frame_grad_input(hpx_frame* f, float** out) {
 // Real capture: every node is a kernel or memset on the context's stream; no
 // allocation, no synchronisation and no host read inside the captured region.
 HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_flags) {
+    DV_RANGE("hpx_frame_capture");
     DV_TRY(frame_check_grid(f, g));
     DV_ENTER(f->ctx);
     if (backward_flags != 0) DV_TRY(grid_ensure_grad(g));
@@ -842,6 +873,7 @@ HP_API hp_status hpx_frame_capture(hpx_frame* f, hpx_grid* g, uint32_t backward_
 }
 
 HP_API hp_status hpx_frame_replay(hpx_frame* f) {
+    DV_RANGE("hpx_frame_replay");
     if (f == nullptr || f->graph_exec == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
     DV_TRY(frame_push_params(f));
@@ -851,6 +883,7 @@ HP_API hp_status hpx_frame_replay(hpx_frame* f) {
 }
 
 HP_API void hpx_frame_release(hpx_frame* f) {
+    DV_RANGE("hpx_frame_release");
     if (f == nullptr) return;
     if (f->ctx != nullptr && f->ctx->ready) {
         DeviceScope scope;

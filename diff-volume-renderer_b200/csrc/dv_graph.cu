@@ -64,6 +64,7 @@ extern "C" {
 
 HP_API hp_status hp_graph_create(const hp_plan* plan, const hp_field* fs, const hp_field* fc, size_t, size_t, size_t,
                                  size_t, void** out_graph_handle) {
+    DV_RANGE("hp_graph_create");
     if (plan == nullptr || fs == nullptr || fc == nullptr || out_graph_handle == nullptr)
         return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(plan->ctx);
@@ -76,6 +77,7 @@ HP_API hp_status hp_graph_create(const hp_plan* plan, const hp_field* fs, const 
 
 HP_API hp_status hp_graph_capture(void* handle, const hp_plan* plan, const hp_field* fs, const hp_field* fc,
                                   const hp_tensor* dL_dI) {
+    DV_RANGE("hp_graph_capture");
     if (handle == nullptr || plan == nullptr || fs == nullptr || fc == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     if (fs->kind != FieldKind::kDenseSigma || fc->kind != FieldKind::kDenseColor) return HP_STATUS_INVALID_ARGUMENT;
     GraphExec* g = static_cast<GraphExec*>(handle);
@@ -203,6 +205,7 @@ HP_API hp_status hp_graph_capture(void* handle, const hp_plan* plan, const hp_fi
 
 HP_API hp_status hp_graph_execute(void* handle, hp_rays_t* out_rays, hp_samp_t* out_samp, hp_intl_t* out_intl,
                                   hp_img_t* out_img, hp_grads_t* out_grads) {
+    DV_RANGE("hp_graph_execute");
     if (handle == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     GraphExec* g = static_cast<GraphExec*>(handle);
     if (!g->captured || g->exec == nullptr) return HP_STATUS_INVALID_ARGUMENT;
@@ -218,6 +221,7 @@ HP_API hp_status hp_graph_execute(void* handle, hp_rays_t* out_rays, hp_samp_t* 
 }
 
 HP_API void hp_graph_release(void* handle) {
+    DV_RANGE("hp_graph_release");
     if (handle == nullptr) return;
     GraphExec* g = static_cast<GraphExec*>(handle);
     if (g->ctx != nullptr && g->ctx->ready) {

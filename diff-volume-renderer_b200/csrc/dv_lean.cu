@@ -750,10 +750,12 @@ uint32_t tile_blocks(const RoiParams& roi) {
 
 // ---- deterministic (fixed-point) gradient accumulation -----------------------------------------------------
 namespace {
-__global__ void abs_max_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ out_bits) {
+// skip_w: v is a packed {r,g,b,sigma} array and only the colours count (sigma never scales a gradient contribution)
+__global__ void abs_max_kernel(const float* __restrict__ v, size_t n, uint32_t* __restrict__ out_bits, bool skip_w) {
     float m = 0.0f;
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        if (skip_w && (i & 3u) == 3u) continue;
         const float a = fabsf(v[i]);
         if (a < CUDART_INF_F) m = fmaxf(m, a);   // ignore inf / nan: they poison the gradient either way
     }
@@ -761,14 +763,16 @@ __global__ void abs_max_kernel(const float* __restrict__ v, size_t n, uint32_t* 
     if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
 }
 
-// quantum = 2^e with 2^40 quanta per bound B on one contribution (B = 8 max|dL/dI| max(1, max|rgb|) max(1, dt)):
-// int64 then holds 2^23 contributions of the largest possible size per voxel.
+// quantum = 2^e with 2^44 quanta per bound B on one contribution: |d colour| <= max|dL/dI|, |d sigma| = |adj_alpha| dt (1 - alpha)
+// <= 6 max|dL/dI| max|rgb| dt (adj_alpha = (g.c - adj_T) T_prev with |g.c|, |adj_T| <= 3 max|dL/dI| max|rgb|), so
+// B = 8 max|dL/dI| max(1, max|rgb|) max(1, dt); int64 then holds 2^19 contributions of the largest possible size per voxel.
+// Rounding error per contribution <= quantum / 2 ~ 3e-14 B: far inside the float32 rounding of the plain path.
 __global__ void fixed_scale_kernel(float* __restrict__ meta, float dt) {
     const float gmax = __uint_as_float(reinterpret_cast<const uint32_t*>(meta)[1]);
     const float cmax = __uint_as_float(reinterpret_cast<const uint32_t*>(meta)[0]);
     const float bound = 8.0f * gmax * fmaxf(1.0f, cmax) * fmaxf(1.0f, dt);
     int e = 0;
-    if (bound > 0.0f && bound < CUDART_INF_F) e = ilogbf(bound) + 1 - 40;
+    if (bound > 0.0f && bound < CUDART_INF_F) e = ilogbf(bound) + 1 - 44;
     e = max(-100, min(100, e));
     meta[2] = ldexpf(1.0f, -e);
     meta[3] = ldexpf(1.0f, e);
@@ -794,9 +798,10 @@ __global__ void fixed_to_float_kernel(unsigned long long* __restrict__ fixed, fl
 }
 }  // namespace
 
-cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits) {
+cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits, bool packed_rgb_only) {
     if (n == 0) return cudaSuccess;
-    abs_max_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(d_values, n, d_out_bits);
+    abs_max_kernel<<<static_cast<unsigned>(std::min<size_t>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(d_values, n, d_out_bits,
+                                                                                                      packed_rgb_only);
     return cudaGetLastError();
 }
 

@@ -50,7 +50,7 @@ cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, 
 
 // Deterministic (fixed-point) gradient accumulation, see ScatterParams::fixed.  meta = {bits of max|rgb|, bits of
 // max|dL/dI|, 1 / quantum, quantum}.
-cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits);
+cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits, bool packed_rgb_only = false);
 cudaError_t launch_fixed_scale(cudaStream_t stream, float* d_meta, float dt);
 cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fixed, float4* d_grad, size_t voxels,
                                   const float* d_meta);

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <atomic>
 #include <cstddef>
@@ -41,6 +42,7 @@ struct hp_ctx {
     mutable unsigned long long* d_total = nullptr;   // device sample total
     mutable uint32_t* h_status = nullptr;            // pinned mirrors
     mutable unsigned long long* h_total = nullptr;
+    mutable cudaEvent_t marks[16] = {};              // hpx_ctx_mark / hpx_ctx_elapsed_ms: device-side stage timing
 };
 
 struct hp_plan {
@@ -112,6 +114,16 @@ struct hpx_frame {
 };
 
 namespace dv {
+
+// NVTX range around every exported entry point (a timeline tool shows the hp.h / hp_b200.h calls by
+// name; header-only NVTX v3: a no-op unless a profiler is attached).
+struct ApiRange {
+    explicit ApiRange(const char* name) { nvtxRangePushA(name); }
+    ~ApiRange() { nvtxRangePop(); }
+    ApiRange(const ApiRange&) = delete;
+    ApiRange& operator=(const ApiRange&) = delete;
+};
+#define DV_RANGE(name) dv::ApiRange dv_api_range__(name)
 
 // ---- errors ----------------------------------------------------------------
 void set_last_error(const std::string& what);

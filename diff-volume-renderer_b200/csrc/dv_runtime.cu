@@ -41,6 +41,10 @@ static void destroy_device_state(const hp_ctx* ctx) {
     cudaFree(ctx->d_total);
     if (ctx->h_status != nullptr) cudaFreeHost(ctx->h_status);
     if (ctx->h_total != nullptr) cudaFreeHost(ctx->h_total);
+    for (cudaEvent_t& e : ctx->marks) {
+        if (e != nullptr) cudaEventDestroy(e);
+        e = nullptr;
+    }
     ctx->stream = nullptr;
     ctx->owns_stream = false;
     ctx->d_status = nullptr; ctx->d_total = nullptr; ctx->h_status = nullptr; ctx->h_total = nullptr;
@@ -325,12 +329,13 @@ using namespace dv;
 // =============================================================================
 extern "C" {
 
-HP_API hp_version hp_get_version(void) { return hp_version{HP_VERSION_MAJOR, HP_VERSION_MINOR, HP_VERSION_PATCH}; }
+HP_API hp_version hp_get_version(void) { DV_RANGE("hp_get_version"); return hp_version{HP_VERSION_MAJOR, HP_VERSION_MINOR, HP_VERSION_PATCH}; }
 
-HP_API const char* hpx_last_error(void) { return dv::last_error_text(); }
+HP_API const char* hpx_last_error(void) { DV_RANGE("hpx_last_error"); return dv::last_error_text(); }
 
 // reference hp_runtime.cpp:15-31
 HP_API hp_status hp_ctx_create(const hp_ctx_desc* desc, hp_ctx** out_ctx) {
+    DV_RANGE("hp_ctx_create");
     if (out_ctx == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     hp_ctx* ctx = new (std::nothrow) hp_ctx();
     if (ctx == nullptr) return HP_STATUS_OUT_OF_MEMORY;
@@ -361,21 +366,45 @@ HP_API hp_status hp_ctx_create(const hp_ctx_desc* desc, hp_ctx** out_ctx) {
     return HP_STATUS_SUCCESS;
 }
 
-HP_API void hp_ctx_release(hp_ctx* ctx) { ctx_unref(ctx); }   // objects created from it keep it alive (hp_ctx::refs)
+HP_API void hp_ctx_release(hp_ctx* ctx) { DV_RANGE("hp_ctx_release"); ctx_unref(ctx); }   // objects created from it keep it alive (hp_ctx::refs)
 
 HP_API hp_status hp_ctx_get_desc(const hp_ctx* ctx, hp_ctx_desc* out_desc) {
+    DV_RANGE("hp_ctx_get_desc");
     if (ctx == nullptr || out_desc == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     *out_desc = ctx->desc;
     return HP_STATUS_SUCCESS;
 }
 
 HP_API hp_status hpx_ctx_synchronize(const hp_ctx* ctx) {
+    DV_RANGE("hpx_ctx_synchronize");
     DV_ENTER(ctx);
     DV_CUDA(cudaStreamSynchronize(ctx->stream));
     return HP_STATUS_SUCCESS;
 }
 
+// Device-side stage timing for callers without a CUDA runtime of their own (dvren::Renderer's RenderStats): record an
+// event on the context's stream under a small integer name, read the elapsed time between two of them later.
+HP_API hp_status hpx_ctx_mark(const hp_ctx* ctx, uint32_t slot) {
+    DV_RANGE("hpx_ctx_mark");
+    if (slot >= 16) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(ctx);
+    if (ctx->marks[slot] == nullptr) DV_CUDA(cudaEventCreate(&ctx->marks[slot]));
+    DV_CUDA(cudaEventRecord(ctx->marks[slot], ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_ctx_elapsed_ms(const hp_ctx* ctx, uint32_t slot_begin, uint32_t slot_end, float* out_ms) {
+    DV_RANGE("hpx_ctx_elapsed_ms");
+    if (slot_begin >= 16 || slot_end >= 16 || out_ms == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(ctx);
+    if (ctx->marks[slot_begin] == nullptr || ctx->marks[slot_end] == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_CUDA(cudaEventSynchronize(ctx->marks[slot_end]));
+    DV_CUDA(cudaEventElapsedTime(out_ms, ctx->marks[slot_begin], ctx->marks[slot_end]));
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void* device_src, size_t bytes) {
+    DV_RANGE("hpx_copy_to_host");
     if (host_dst == nullptr || device_src == nullptr) return bytes == 0 ? HP_STATUS_SUCCESS : HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(ctx);
     DV_CUDA(cudaMemcpyAsync(host_dst, device_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -383,7 +412,31 @@ HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void*
     return HP_STATUS_SUCCESS;
 }
 
+// Page-lock a caller-owned host range so that copies to / from it are direct DMA (dvren::Renderer registers result
+// vectors it sees repeatedly).  Returns UNSUPPORTED when the range cannot be registered; the caller just keeps going.
+HP_API hp_status hpx_host_register(const hp_ctx* ctx, void* host_ptr, size_t bytes) {
+    DV_RANGE("hpx_host_register");
+    if (host_ptr == nullptr || bytes == 0) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(ctx);
+    const cudaError_t e = cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaHostRegister");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API void hpx_host_unregister(const hp_ctx* ctx, void* host_ptr) {
+    DV_RANGE("hpx_host_unregister");
+    if (host_ptr == nullptr || ctx == nullptr || !ctx->ready) return;
+    DeviceScope scope;
+    if (scope.enter(ctx) != HP_STATUS_SUCCESS) return;
+    cudaStreamSynchronize(ctx->stream);
+    if (cudaHostUnregister(host_ptr) != cudaSuccess) cudaGetLastError();
+}
+
 HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_device_ptr) {
+    DV_RANGE("hpx_device_alloc");
     if (out_device_ptr == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(ctx);
     DV_CUDA(cudaMalloc(out_device_ptr, bytes ? bytes : 16));
@@ -391,6 +444,7 @@ HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_de
 }
 
 HP_API void hpx_device_free(const hp_ctx* ctx, void* device_ptr) {
+    DV_RANGE("hpx_device_free");
     if (device_ptr == nullptr || ctx == nullptr || !ctx->ready) return;
     DeviceScope scope;
     if (scope.enter(ctx) != HP_STATUS_SUCCESS) return;
@@ -399,6 +453,7 @@ HP_API void hpx_device_free(const hp_ctx* ctx, void* device_ptr) {
 }
 
 HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const void* host_src, size_t bytes) {
+    DV_RANGE("hpx_copy_to_device");
     if (device_dst == nullptr || host_src == nullptr) return bytes == 0 ? HP_STATUS_SUCCESS : HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(ctx);
     DV_CUDA(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -407,6 +462,7 @@ HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const v
 }
 
 HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream) {
+    DV_RANGE("hpx_ctx_device");
     DV_ENTER(ctx);
     if (out_ordinal != nullptr) *out_ordinal = ctx->device;
     if (out_stream != nullptr) *out_stream = ctx->stream;
@@ -415,6 +471,7 @@ HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** 
 
 // reference hp_runtime.cpp:45-146
 HP_API hp_status hp_plan_create(const hp_ctx* ctx, const hp_plan_desc* desc, hp_plan** out_plan) {
+    DV_RANGE("hp_plan_create");
     if (ctx == nullptr || desc == nullptr || out_plan == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     hp_plan* plan = new (std::nothrow) hp_plan();
     if (plan == nullptr) return HP_STATUS_OUT_OF_MEMORY;
@@ -430,9 +487,10 @@ HP_API hp_status hp_plan_create(const hp_ctx* ctx, const hp_plan_desc* desc, hp_
     return HP_STATUS_SUCCESS;
 }
 
-HP_API void hp_plan_release(hp_plan* plan) { plan_unref(plan); }
+HP_API void hp_plan_release(hp_plan* plan) { DV_RANGE("hp_plan_release"); plan_unref(plan); }
 
 HP_API hp_status hp_plan_get_desc(const hp_plan* plan, hp_plan_desc* out_desc) {
+    DV_RANGE("hp_plan_get_desc");
     if (plan == nullptr || out_desc == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     *out_desc = plan->desc;
     return HP_STATUS_SUCCESS;
@@ -502,23 +560,27 @@ static hp_status create_dense_field(const hp_ctx* ctx, const hp_tensor* grid, ui
 
 HP_API hp_status hp_field_create_grid_sigma(const hp_ctx* ctx, const hp_tensor* grid, uint32_t interp, uint32_t oob,
                                             hp_field** out_field) {
+    DV_RANGE("hp_field_create_grid_sigma");
     return create_dense_field(ctx, grid, interp, oob, false, out_field);
 }
 
 HP_API hp_status hp_field_create_grid_color(const hp_ctx* ctx, const hp_tensor* grid, uint32_t interp, uint32_t oob,
                                             hp_field** out_field) {
+    DV_RANGE("hp_field_create_grid_color");
     return create_dense_field(ctx, grid, interp, oob, true, out_field);
 }
 
 // The reference's hash-MLP field is a fixed-size toy outside the dense-grid hot
 // path; this library does not implement it.
 HP_API hp_status hp_field_create_hash_mlp(const hp_ctx* ctx, const hp_tensor* params, hp_field** out_field) {
+    DV_RANGE("hp_field_create_hash_mlp");
     if (ctx == nullptr || params == nullptr || out_field == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     *out_field = nullptr;
     return HP_STATUS_UNSUPPORTED;
 }
 
 HP_API void hp_field_release(hp_field* field) {
+    DV_RANGE("hp_field_release");
     if (field == nullptr) return;
     if (field->ctx != nullptr && field->ctx->ready) {
         DeviceScope scope;

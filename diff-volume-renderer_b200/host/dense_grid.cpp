@@ -76,17 +76,22 @@ Status DenseGridField::Create(const Context& ctx, const DenseGridConfig& config,
     f.bbox_max_ = config.bbox_max;
     f.interp_ = config.interp == HP_INTERP_NEAREST ? HP_INTERP_NEAREST : HP_INTERP_LINEAR;
     f.oob_ = config.oob == HP_OOB_CLAMP ? HP_OOB_CLAMP : HP_OOB_ZERO;
-    f.sigma_grad_.assign(static_cast<size_t>(voxels), 0.0f);
-    f.color_grad_.assign(static_cast<size_t>(voxels) * 3, 0.0f);
+    // host mirrors of the gradients are created on first use (sigma_gradients() / color_gradients()): a 512^3 field
+    // would otherwise pin down 2.1 GB of host memory nobody may ever read
+    f.mirrors_stale_ = true;
     out = std::move(f);
     return Status::Ok();
 }
 
 void DenseGridField::ZeroGradients() {
     if (grid_ != nullptr) hpx_grid_zero_grad(grid_);
+    camera_grad_.fill(0.0f);
+    if (sigma_grad_.empty() && color_grad_.empty()) {   // mirrors not materialised yet: the device grid is the truth
+        mirrors_stale_ = true;
+        return;
+    }
     std::fill(sigma_grad_.begin(), sigma_grad_.end(), 0.0f);
     std::fill(color_grad_.begin(), color_grad_.end(), 0.0f);
-    camera_grad_.fill(0.0f);
     mirrors_stale_ = false;
 }
 
@@ -110,6 +115,8 @@ Status DenseGridField::AccumulateSampleGradients(const hp_samp_t& samples, std::
 
 void DenseGridField::RefreshMirrors() const {
     if (!mirrors_stale_ || grid_ == nullptr) return;
+    sigma_grad_.resize(voxel_count());
+    color_grad_.resize(voxel_count() * 3);
     hpx_grid_read_grad(grid_, sigma_grad_.data(), color_grad_.data(), camera_grad_.data(), HP_MEMSPACE_HOST);
     mirrors_stale_ = false;
 }

@@ -11,6 +11,8 @@
 #include <chrono>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 namespace dvren {
 
@@ -32,6 +34,15 @@ Status Fail(hp_status st, const char* what) {
     return Status::FromHotpath(st, std::string(what) + " failed: " + hpx_last_error());
 }
 
+// event slots of hpx_ctx_mark (GPU-side stage times for RenderStats)
+enum : uint32_t { kMarkBegin = 0, kMarkRays = 1, kMarkSample = 2, kMarkIntegrate = 3, kMarkCompose = 4,
+                  kMarkBwdBegin = 5, kMarkBwdKernels = 6, kMarkBwdRead = 7 };
+
+double GpuMs(const hp_ctx* ctx, uint32_t a, uint32_t b) {
+    float ms = 0.0f;
+    return hpx_ctx_elapsed_ms(ctx, a, b, &ms) == HP_STATUS_SUCCESS ? static_cast<double>(ms) : 0.0;
+}
+
 }  // namespace
 
 struct Renderer::Impl {
@@ -50,9 +61,34 @@ struct Renderer::Impl {
     hp_samp_t samp{};
     hp_intl_t intl{};
 
+    // Result vectors the caller hands in again and again (a training loop reuses its ForwardResult / BackwardResult)
+    // are page-locked the second time they are seen: from then on the read-back is direct DMA into the vector.
+    std::vector<std::pair<void*, size_t>> seen, pinned;
+
     ~Impl() {
+        for (auto& r : pinned) hpx_host_unregister(ctx, r.first);
         if (frame) hpx_frame_release(frame);
         for (void* p : {d_rays, d_ws, d_img, d_grads, d_dl}) hpx_device_free(ctx, p);
+    }
+
+    void PinIfRepeated(void* ptr, size_t bytes) {
+        if (ptr == nullptr || bytes < (size_t(1) << 20)) return;   // small results are not worth a registration
+        for (auto it = pinned.begin(); it != pinned.end(); ++it) {
+            if (it->first == ptr && it->second >= bytes) return;
+            if (it->first == ptr) {   // same address, grown: register afresh
+                hpx_host_unregister(ctx, ptr);
+                pinned.erase(it);
+                break;
+            }
+        }
+        for (auto& r : seen) {
+            if (r.first == ptr && r.second == bytes) {
+                if (hpx_host_register(ctx, ptr, bytes) == HP_STATUS_SUCCESS) pinned.emplace_back(ptr, bytes);
+                return;
+            }
+        }
+        if (seen.size() >= 16) seen.erase(seen.begin());
+        seen.emplace_back(ptr, bytes);
     }
 
     Status Ensure(void*& ptr, size_t& have, size_t want) {
@@ -83,8 +119,8 @@ Status Renderer::EnsureFrame() {
 Status Renderer::ForwardFused(const DenseGridField& field, RenderStats& stats) {
     Status st = EnsureFrame();
     if (!st.ok()) return st;
-    const auto t0 = Clock::now();
-    hp_status hs;
+    hp_status hs = hpx_ctx_mark(impl_->ctx, kMarkBegin);
+    if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_ctx_mark");
     if (options_.enable_graph) {
         if (!impl_->graph_captured || impl_->graph_grid != field.device_grid()) {
             hs = hpx_frame_capture(impl_->frame, field.device_grid(), 0);
@@ -98,10 +134,14 @@ Status Renderer::ForwardFused(const DenseGridField& field, RenderStats& stats) {
         hs = hpx_forward(impl_->frame, field.device_grid());
     }
     if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_forward");
+    hpx_ctx_mark(impl_->ctx, kMarkSample);
     hpx_counts counts{};
     hs = hpx_frame_counts(impl_->frame, &counts);   // synchronises the stream
     if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_frame_counts");
-    stats.sample_ms = MsSince(t0);                  // ray generation, marching and integration are one kernel
+    // ray generation, marching, integration and image composition are ONE kernel: its GPU time (CUDA events) is
+    // reported as sample_ms; ray_ms / integrate_ms stay 0 on the fused path
+    stats.sample_ms = GpuMs(impl_->ctx, kMarkBegin, kMarkSample);
+    stats.notes.emplace_back("timing=cuda_events");
     last_ray_count_ = static_cast<size_t>(counts.rays);
     last_sample_count_ = static_cast<size_t>(counts.samples);
     live_samples_ = static_cast<size_t>(counts.live_samples);
@@ -128,25 +168,27 @@ Status Renderer::ForwardStaged(const DenseGridField& field, RenderStats& stats) 
     impl_->rays.t_near = DeviceTensor(rb + n * 24);
     impl_->rays.t_far = DeviceTensor(rb + n * 28);
     impl_->rays.pixel_ids = DeviceTensor(rb + n * 32);
-    auto t0 = Clock::now();
+    hpx_ctx_mark(impl_->ctx, kMarkBegin);
     hp_status hs = hp_ray(plan_->handle(), nullptr, &impl_->rays, nullptr, 0);
     if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_ray");
-    stats.ray_ms = MsSince(t0);
+    hpx_ctx_mark(impl_->ctx, kMarkRays);
     last_ray_count_ = impl_->rays.t_near.rank >= 1 ? static_cast<size_t>(impl_->rays.t_near.shape[0]) : 0;
 
     const size_t samp_bytes = cap * 32 + (n + 1) * 4;
     impl_->samp = hp_samp_t{};
     impl_->intl = hp_intl_t{};
-    t0 = Clock::now();
     hs = hp_samp(plan_->handle(), field.sigma_field(), field.color_field(), &impl_->rays, &impl_->samp, impl_->d_ws,
                  samp_bytes);
     if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_samp");
-    stats.sample_ms = MsSince(t0);
-    t0 = Clock::now();
+    hpx_ctx_mark(impl_->ctx, kMarkSample);
     hs = hp_int(plan_->handle(), &impl_->samp, &impl_->intl, static_cast<char*>(impl_->d_ws) + samp_bytes,
                 impl_->ws_bytes - samp_bytes);
     if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hp_int");
-    stats.integrate_ms = MsSince(t0);
+    hpx_ctx_mark(impl_->ctx, kMarkIntegrate);
+    stats.ray_ms = GpuMs(impl_->ctx, kMarkBegin, kMarkRays);
+    stats.sample_ms = GpuMs(impl_->ctx, kMarkRays, kMarkSample);
+    stats.integrate_ms = GpuMs(impl_->ctx, kMarkSample, kMarkIntegrate);
+    stats.notes.emplace_back("timing=cuda_events");
     last_sample_count_ = impl_->samp.dt.rank >= 1 ? static_cast<size_t>(impl_->samp.dt.shape[0]) : 0;
     live_samples_ = 0;   // not tracked by the staged entry points
     return Status::Ok();
@@ -179,12 +221,17 @@ Status Renderer::Forward(const DenseGridField& field, ForwardResult& out) {
         return Status::Ok();
     }
 
-    const auto img0 = Clock::now();
     out.image.resize(pixels * 3);
     out.transmittance.resize(pixels);
     out.opacity.resize(pixels);
     out.depth.resize(pixels);
     out.hitmask.resize(pixels);
+    impl_->PinIfRepeated(out.image.data(), pixels * 12);
+    impl_->PinIfRepeated(out.transmittance.data(), pixels * 4);
+    impl_->PinIfRepeated(out.opacity.data(), pixels * 4);
+    impl_->PinIfRepeated(out.depth.data(), pixels * 4);
+    impl_->PinIfRepeated(out.hitmask.data(), pixels * 4);
+    hpx_ctx_mark(impl_->ctx, kMarkIntegrate);   // start of the compose stage (re-recorded: the forward stages were read above)
     if (fused) {
         const hp_status hs = hpx_frame_read(impl_->frame, out.image.data(), out.transmittance.data(),
                                             out.opacity.data(), out.depth.data(), out.hitmask.data());
@@ -207,7 +254,8 @@ Status Renderer::Forward(const DenseGridField& field, ForwardResult& out) {
         if (hs == HP_STATUS_SUCCESS) hs = hpx_copy_to_host(c, out.hitmask.data(), img.hitmask.data, pixels * 4);
         if (hs != HP_STATUS_SUCCESS) return Fail(hs, "image read-back");
     }
-    stats.compose_ms = MsSince(img0);
+    hpx_ctx_mark(impl_->ctx, kMarkCompose);
+    stats.compose_ms = GpuMs(impl_->ctx, kMarkIntegrate, kMarkCompose);   // staged: hp_img + read-back; fused: the read-back
     out.ray_count = last_ray_count_;
     out.sample_count = last_sample_count_;
     stats.total_ms = MsSince(total0);
@@ -251,6 +299,9 @@ Status Renderer::Backward(DenseGridField& field, std::span<const float> dL_dI, B
         return Status(StatusCode::kInvalidArgument, "forward pass not executed or produced zero samples");
     if (dL_dI.size() != last_ray_count_ * 3) return Status(StatusCode::kInvalidArgument, "dL/dI size mismatch");
 
+    const auto total0 = Clock::now();
+    backward_stats_ = RenderStats{};
+    hpx_ctx_mark(impl_->ctx, kMarkBwdBegin);
     if (last_forward_staged_) {
         const Status st = BackwardStaged(field, dL_dI);
         if (!st.ok()) return st;
@@ -260,16 +311,31 @@ Status Renderer::Backward(DenseGridField& field, std::span<const float> dL_dI, B
         const hp_status hs = hpx_backward(impl_->frame, field.device_grid(), dL_dI.data(), HP_MEMSPACE_HOST, flags);
         if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_backward");
     }
-    field.MarkGradientsStale();
-    out.sigma = field.sigma_gradients();   // full-grid copies: what the reference's API returns (renderer.cpp:441-442)
-    out.color = field.color_gradients();
+    hpx_ctx_mark(impl_->ctx, kMarkBwdKernels);
+    field.MarkGradientsStale();   // the field's own host mirrors are refreshed only if somebody asks for them
+    // full-grid copies are what the reference's API returns (renderer.cpp:441-442): un-interleaved on the device and
+    // read STRAIGHT into the caller's vectors (no intermediate host copy; page-locked once the vectors repeat)
+    const size_t voxels = field.voxel_count();
+    out.sigma.resize(voxels);
+    out.color.resize(voxels * 3);
+    impl_->PinIfRepeated(out.sigma.data(), voxels * 4);
+    impl_->PinIfRepeated(out.color.data(), voxels * 12);
+    std::array<float, 16> cam16{};
+    const hp_status rs = hpx_grid_read_grad(field.device_grid(), out.sigma.data(), out.color.data(), cam16.data(), HP_MEMSPACE_HOST);
+    if (rs != HP_STATUS_SUCCESS) return Fail(rs, "hpx_grid_read_grad");
+    hpx_ctx_mark(impl_->ctx, kMarkBwdRead);
     out.camera.fill(0.0f);
     intrinsics_grad_.fill(0.0f);
     if (options_.camera_gradients && !last_forward_staged_) {
-        for (int i = 0; i < 12; ++i) out.camera[static_cast<size_t>(i)] = field.camera_grad_[static_cast<size_t>(i)];
-        for (int i = 0; i < 4; ++i) intrinsics_grad_[static_cast<size_t>(i)] = field.camera_grad_[static_cast<size_t>(12 + i)];
+        for (int i = 0; i < 12; ++i) out.camera[static_cast<size_t>(i)] = cam16[static_cast<size_t>(i)];
+        for (int i = 0; i < 4; ++i) intrinsics_grad_[static_cast<size_t>(i)] = cam16[static_cast<size_t>(12 + i)];
     }
     out.sample_count = last_sample_count_;
+    backward_stats_.sample_ms = GpuMs(impl_->ctx, kMarkBwdBegin, kMarkBwdKernels);
+    backward_stats_.compose_ms = GpuMs(impl_->ctx, kMarkBwdKernels, kMarkBwdRead);
+    backward_stats_.total_ms = MsSince(total0);
+    backward_stats_.notes.emplace_back(last_forward_staged_ ? "backward_mode=staged" : "backward_mode=fused");
+    backward_stats_.notes.emplace_back("timing=cuda_events");
     return Status::Ok();
 }
 

@@ -39,10 +39,14 @@ HPX_FUNCTIONS = {
     "hpx_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "hpx_ctx_device": (C.c_int, [C.c_void_p, P(C.c_int32), P(C.c_void_p)]),
     "hpx_last_error": (C.c_char_p, []),
+    "hpx_ctx_mark": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "hpx_ctx_elapsed_ms": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, P(C.c_float)]),
     "hpx_copy_to_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "hpx_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, P(C.c_void_p)]),
     "hpx_device_free": (None, [C.c_void_p, C.c_void_p]),
     "hpx_copy_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hpx_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hpx_host_unregister": (None, [C.c_void_p, C.c_void_p]),
     "hpx_grid_accumulate_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "hpx_grid_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(f3), P(f3), P(C.c_void_p)]),
     "hpx_grid_create_raw": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,

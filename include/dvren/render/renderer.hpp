@@ -87,6 +87,9 @@ public:
     // ---- additive -------------------------------------------------------------------------
     [[nodiscard]] std::array<float, 4> intrinsics_gradient() const { return intrinsics_grad_; }
     [[nodiscard]] size_t live_sample_count() const { return live_samples_; }
+    // Stage times of the last Backward (the reference's BackwardResult carries no stats): sample_ms = adjoint + grid
+    // scatter kernels (GPU time, CUDA events), compose_ms = gradient read-back, total_ms = host wall clock.
+    [[nodiscard]] const RenderStats& backward_stats() const { return backward_stats_; }
 
 private:
     struct Impl;
@@ -104,6 +107,7 @@ private:
     size_t live_samples_{0};
     bool last_forward_staged_{false};
     std::array<float, 4> intrinsics_grad_{};
+    RenderStats backward_stats_{};
 };
 
 }  // namespace dvren

@@ -60,7 +60,7 @@ typedef struct hpx_frame hpx_frame;
 /* Scatter strategy of the grid backward (default: chosen from the pixel / voxel spacing ratio):  */
 #define HPX_BACKWARD_SCATTER_PER_RAY 0x10u /* one lane = one ray, 8 reds per sample                      */
 #define HPX_BACKWARD_SCATTER_MERGED  0x20u /* 2x2 pixel quads x 2 steps merged in registers before the reds */
-/* Bitwise reproducible grid gradients: contributions are rounded to a power-of-two quantum (2^-40 of the largest
+/* Bitwise reproducible grid gradients: contributions are rounded to a power-of-two quantum (2^-44 of the largest
  * possible contribution) and accumulated with 64-bit integer reds, whose sum is independent of arrival order; costs
  * 32 B per voxel of extra HBM and 4 integer reds per corner instead of one 16-byte float red.  Without this flag
  * the float reds arrive in a different order from run to run (differences at the 1e-7 relative level). */
@@ -76,6 +76,11 @@ typedef struct hpx_counts {
 /* ---- context helpers ---------------------------------------------------- */
 HP_API hp_status hpx_ctx_synchronize(const hp_ctx* ctx);
 HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream);
+/* Device-side stage timing (CUDA events on the context's stream) for callers that do not link a CUDA runtime:
+ * hpx_ctx_mark records event `slot` (0..15); hpx_ctx_elapsed_ms waits for `slot_end` and returns the GPU time between
+ * two recorded slots.  dvren::Renderer fills its RenderStats from these (reference renderer.hpp:41-48 uses host clocks). */
+HP_API hp_status hpx_ctx_mark(const hp_ctx* ctx, uint32_t slot);
+HP_API hp_status hpx_ctx_elapsed_ms(const hp_ctx* ctx, uint32_t slot_begin, uint32_t slot_end, float* out_ms);
 /* Blocking device-to-host copy on the context's stream, for binding languages without a CUDA
  * runtime of their own (reading back the DEVICE views hp_graph_execute / hpx_frame_image return). */
 HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void* device_src, size_t bytes);
@@ -83,6 +88,9 @@ HP_API hp_status hpx_copy_to_host(const hp_ctx* ctx, void* host_dst, const void*
 HP_API hp_status hpx_device_alloc(const hp_ctx* ctx, size_t bytes, void** out_device_ptr);
 HP_API void      hpx_device_free(const hp_ctx* ctx, void* device_ptr);
 HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const void* host_src, size_t bytes);
+/* Page-lock / release a caller-owned host range (direct DMA for the HOST-memspace copies of this library). */
+HP_API hp_status hpx_host_register(const hp_ctx* ctx, void* host_ptr, size_t bytes);
+HP_API void      hpx_host_unregister(const hp_ctx* ctx, void* host_ptr);
 /* Last CUDA/runtime error text recorded on this thread ("" if none). */
 HP_API const char* hpx_last_error(void);
 

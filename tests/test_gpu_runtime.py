@@ -246,3 +246,15 @@ def test_cube_sample_and_touched_voxel_counters_match_the_oracle(ctx):
         ref_touched = (ref["sigma_grad"] != 0) | (ref["color_grad"].reshape(-1, 3) != 0).any(axis=1)
         assert abs(int(touched.sum()) - int(ref_touched.sum())) <= 0.001 * ref_touched.sum() + 2   # exact zeros may differ by rounding
         frame.close(); grid.close(); plan.close()
+
+
+def test_cxx_surface_selftest():
+    """diff-volume-renderer_b200/apps/dvren_bench.cpp `selftest`: dvren::DenseGridField::UpdateValues reaches the staged
+    path (fused == staged == fresh field), RenderStats carry CUDA-event stage times, Backward stats exist, the host
+    gradient mirrors are lazy but correct, and a Renderer survives the release of its Context."""
+    import os
+    import subprocess
+    exe = os.path.join(U.REPO, "diff-volume-renderer_b200", "dvren_bench")
+    assert os.path.exists(exe), f"{exe} is not built (__graft_entry__.build())"
+    r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "selftest ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
