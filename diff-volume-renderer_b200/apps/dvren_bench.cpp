@@ -5,11 +5,18 @@
 //   dvren_bench bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup>
 //       times Forward+Backward per step on the host clock (every host<->device copy inside) and prints ONE JSON line:
 //       bench.py reports it as e2e.renderer next to the pinned C-ABI end-to-end number.
+//   dvren_bench shard <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas>
+//       ONE frame rendered by <gpus> GPUs of this box with NO Python: one host thread per GPU, hpx_comm (NCCL) +
+//       hpx_shard_step (interleaved tile rows, signalled backward, slab all-reduces behind it).  Rank 0 first checks
+//       the reduced gradient against a plain single-GPU backward, then all ranks time <iters> steps (CUDA events, max
+//       over ranks).  Prints ONE JSON line.
 //   dvren_bench selftest
 //       small end-to-end checks of the C++ surface that need a GPU: UpdateValues reaches the staged path, RenderStats
 //       carry GPU (CUDA-event) stage times, objects outlive their context.  Exit code 0 = pass.
 //
 // The synthetic volume / camera / dL/dI are those of SURVEY 8(d) (same integer hash as python/synth.py).
+#include <atomic>
+#include <barrier>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
@@ -17,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "dvren/core/context.hpp"
@@ -177,13 +185,164 @@ int run_selftest() {
     return 0;
 }
 
+// ---- one frame over several GPUs, C ABI only ----------------------------------------------------------------------
+struct ShardArgs {
+    int n; uint32_t w, steps; bool strat; int iters, warmup, gpus; uint32_t groups, reserve; int max_ctas;
+};
+
+struct ShardShared {
+    uint8_t id[HPX_COMM_ID_BYTES];
+    const dvren::DenseGridConfig* volume;
+    const std::vector<float>* dl;
+    std::vector<double> ms, ms_no_reduce;
+    std::vector<int> status;
+    double verify = -1.0;
+    uint64_t samples = 0;
+    uint32_t usable_sms = 0, total_sms = 0;
+    int nccl_version = 0;
+};
+
+#define SCHECK(expr)                                                                                     \
+    do {                                                                                                 \
+        const hp_status st__ = (expr);                                                                   \
+        if (st__ != HP_STATUS_SUCCESS) {                                                                 \
+            std::fprintf(stderr, "rank %d: %s -> %d (%s)\n", rank, #expr, static_cast<int>(st__), hpx_last_error()); \
+            sh.status[rank] = 1;                                                                         \
+            return;                                                                                      \
+        }                                                                                                \
+    } while (0)
+
+void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& sync) {
+    hpx_ctx_ext2 ext{HPX_CTX_EXT2_MAGIC, rank, nullptr, a.reserve, 0u};
+    hp_ctx_desc cd{};
+    cd.reserved = &ext;
+    hp_ctx* ctx = nullptr;
+    SCHECK(hp_ctx_create(&cd, &ctx));
+    hp_plan_desc pd{};
+    {
+        const dvren::PlanDescriptor d = bench_plan(a.w, a.w, a.steps, a.strat);
+        pd.width = d.width; pd.height = d.height; pd.t_near = d.t_near; pd.t_far = d.t_far; pd.seed = d.seed;
+        pd.sampling.dt = d.sampling.dt; pd.sampling.max_steps = d.sampling.max_steps;
+        pd.sampling.mode = a.strat ? HP_SAMPLING_STRATIFIED : HP_SAMPLING_FIXED;
+        pd.camera.model = HP_CAMERA_PINHOLE;
+        for (int i = 0; i < 9; ++i) pd.camera.K[i] = d.camera.K[static_cast<size_t>(i)];
+        for (int i = 0; i < 12; ++i) pd.camera.c2w[i] = d.camera.c2w[static_cast<size_t>(i)];
+    }
+    hp_plan* plan = nullptr;
+    SCHECK(hp_plan_create(ctx, &pd, &plan));
+    hpx_grid* grid = nullptr;
+    SCHECK(hpx_grid_create_raw(ctx, a.n, a.n, a.n, sh.volume->sigma.data(), sh.volume->color.data(), HP_MEMSPACE_HOST, HP_INTERP_LINEAR,
+                               HP_OOB_ZERO, nullptr, nullptr, &grid));
+    hpx_comm* comm = nullptr;
+    SCHECK(hpx_comm_create(ctx, sh.id, rank, a.gpus, a.max_ctas, &comm));
+    std::vector<float> weights(a.groups);
+    for (uint32_t g = 0; g < a.groups; ++g) weights[g] = a.groups == 1 ? 1.0f : std::pow(0.72f, static_cast<float>(g));   // small last group
+    hpx_shard* shard = nullptr;
+    SCHECK(hpx_shard_create(comm, plan, grid, weights.data(), a.groups, &shard));
+    void* d_dl = nullptr;
+    SCHECK(hpx_device_alloc(ctx, sh.dl->size() * 4, &d_dl));
+    SCHECK(hpx_copy_to_device(ctx, d_dl, sh.dl->data(), sh.dl->size() * 4));
+    const uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
+
+    // correctness first: the reduced gradient of one sharded step against a plain single-GPU backward (rank 0)
+    SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+    SCHECK(hpx_ctx_synchronize(ctx));
+    hpx_frame* own = nullptr;
+    SCHECK(hpx_shard_frame(shard, &own));
+    hpx_counts counts{};
+    SCHECK(hpx_frame_counts(own, &counts));
+    static std::atomic<uint64_t> total_samples{0};
+    total_samples += counts.samples;
+    sync.arrive_and_wait();
+    if (rank == 0) {
+        const size_t v = static_cast<size_t>(a.n) * a.n * a.n;
+        std::vector<float> sg(v), cg(v * 3), sg1(v), cg1(v * 3);
+        SCHECK(hpx_grid_read_grad(grid, sg.data(), cg.data(), nullptr, HP_MEMSPACE_HOST));
+        hpx_frame* full = nullptr;
+        SCHECK(hpx_frame_create(plan, &full));
+        SCHECK(hpx_forward(full, grid));
+        SCHECK(hpx_backward(full, grid, static_cast<const float*>(d_dl), HP_MEMSPACE_DEVICE, flags));
+        SCHECK(hpx_grid_read_grad(grid, sg1.data(), cg1.data(), nullptr, HP_MEMSPACE_HOST));
+        hpx_frame_release(full);
+        double peak_s = 0, peak_c = 0, worst = 0;
+        for (size_t i = 0; i < v; ++i) peak_s = std::fmax(peak_s, std::fabs(sg1[i]));
+        for (size_t i = 0; i < 3 * v; ++i) peak_c = std::fmax(peak_c, std::fabs(cg1[i]));
+        for (size_t i = 0; i < v; ++i)
+            worst = std::fmax(worst, std::fabs(static_cast<double>(sg[i]) - sg1[i]) / std::fmax(std::fabs(sg1[i]), 1e-3 * peak_s));
+        for (size_t i = 0; i < 3 * v; ++i)
+            worst = std::fmax(worst, std::fabs(static_cast<double>(cg[i]) - cg1[i]) / std::fmax(std::fabs(cg1[i]), 1e-3 * peak_c));
+        sh.verify = worst;
+        sh.samples = total_samples.load();
+        hpx_ctx_sm_counts(ctx, &sh.usable_sms, &sh.total_sms);
+        int32_t r = 0, w = 0, ver = 0;
+        hpx_comm_info(comm, &r, &w, &ver);
+        sh.nccl_version = ver;
+    }
+    for (int pass = 0; pass < 2; ++pass) {   // pass 0: the real step; pass 1: the same without its collectives
+        SCHECK(hpx_shard_set_reduce(shard, pass == 0 ? 1 : 0));
+        for (int i = 0; i < a.warmup; ++i) SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+        SCHECK(hpx_ctx_synchronize(ctx));
+        sync.arrive_and_wait();
+        SCHECK(hpx_ctx_mark(ctx, 14));
+        for (int i = 0; i < a.iters; ++i) SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+        SCHECK(hpx_ctx_mark(ctx, 15));
+        float ms = 0.0f;
+        SCHECK(hpx_ctx_elapsed_ms(ctx, 14, 15, &ms));
+        (pass == 0 ? sh.ms : sh.ms_no_reduce)[rank] = ms / a.iters;
+        sync.arrive_and_wait();
+    }
+    hpx_shard_release(shard);
+    hpx_comm_release(comm);
+    hpx_device_free(ctx, d_dl);
+    hpx_grid_release(grid);
+    hp_plan_release(plan);
+    hp_ctx_release(ctx);
+}
+
+int run_shard(const ShardArgs& a) {
+    ShardShared sh;
+    if (a.gpus > 1) {
+        const hp_status st = hpx_comm_unique_id(sh.id);
+        CHECK(st == HP_STATUS_SUCCESS, "hpx_comm_unique_id: %s", hpx_last_error());
+    }
+    const dvren::DenseGridConfig volume = hashed_volume(a.n, 2.0f);
+    const std::vector<float> dl = hashed_image_grad(static_cast<size_t>(a.w) * a.w);
+    sh.volume = &volume;
+    sh.dl = &dl;
+    sh.ms.assign(a.gpus, 0.0); sh.ms_no_reduce.assign(a.gpus, 0.0); sh.status.assign(a.gpus, 0);
+    std::barrier<> sync(a.gpus);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < a.gpus; ++r) threads.emplace_back([&, r] {
+        shard_rank(r, a, sh, sync);
+        if (sh.status[r] != 0) std::_Exit(3);   // a failed rank would leave the others waiting at the barrier
+    });
+    for (auto& t : threads) t.join();
+    double ms = 0, ms0 = 0;
+    for (int r = 0; r < a.gpus; ++r) { ms = std::fmax(ms, sh.ms[r]); ms0 = std::fmax(ms0, sh.ms_no_reduce[r]); }
+    const double total = static_cast<double>(a.w) * a.w * a.steps;
+    std::printf("{\"mode\": \"shard\", \"gpus\": %d, \"groups\": %u, \"reserve_sms\": %u, \"usable_sms\": %u, \"total_sms\": %u, "
+                "\"max_ctas\": %d, \"nccl_version\": %d, \"ms_per_step\": %.4f, \"ms_per_step_without_collectives\": %.4f, "
+                "\"msamples_per_s\": %.1f, \"samples\": %.0f, \"verify_max_rel_err_vs_single_gpu\": %.3e}\n",
+                a.gpus, a.groups, a.reserve, sh.usable_sms, sh.total_sms, a.max_ctas, sh.nccl_version, ms, ms0, total / (ms * 1e-3) / 1e6,
+                total, sh.verify);
+    CHECK(sh.verify >= 0.0 && sh.verify <= 1e-4, "sharded gradient differs from the single-GPU one: %.3e", sh.verify);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
+    if (argc >= 12 && std::string(argv[1]) == "shard") {
+        ShardArgs a{std::atoi(argv[2]), static_cast<uint32_t>(std::atoi(argv[3])), static_cast<uint32_t>(std::atoi(argv[4])),
+                    std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]),
+                    static_cast<uint32_t>(std::atoi(argv[9])), static_cast<uint32_t>(std::atoi(argv[10])), std::atoi(argv[11])};
+        return run_shard(a);
+    }
     if (argc >= 2 && std::string(argv[1]) == "selftest") return run_selftest();
     if (argc >= 8 && std::string(argv[1]) == "bench")
         return run_bench(std::atoi(argv[2]), static_cast<uint32_t>(std::atoi(argv[3])), static_cast<uint32_t>(std::atoi(argv[4])),
                          std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]));
-    std::fprintf(stderr, "usage: %s selftest | bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup>\n", argv[0]);
+    std::fprintf(stderr, "usage: %s selftest | bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> | "
+                         "shard <grid n> <width> <steps> <stratified> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas>\n", argv[0]);
     return 2;
 }

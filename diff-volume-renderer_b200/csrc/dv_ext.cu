@@ -19,6 +19,7 @@ using namespace dv;
 namespace {
 
 constexpr size_t kCameraFloats = 16;
+constexpr uint32_t kMaxRowGroups = 16;   // LeanBuffers::group_end
 constexpr size_t kStageVoxels = size_t(1) << 25;  // 32 Mi voxels per staging chunk (512 MiB)
 
 hp_status grid_alloc(hpx_grid* g) {
@@ -176,6 +177,15 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
                                     hp_memspace memspace) {
     DV_RANGE("hpx_grid_read_grad");
     if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    return hpx_grid_read_grad_range(g, 0, g->voxels, sigma_grad, color_grad, camera16, memspace);
+}
+
+// Voxels [first, first + count) of the REFERENCE order (z slowest, x fastest): sigma_grad[count], color_grad[3 * count].
+// Lets every rank of a sharded job hand ITS share of the summed gradient to the host over its own PCIe link.
+HP_API hp_status hpx_grid_read_grad_range(hpx_grid* g, size_t first, size_t count, float* sigma_grad, float* color_grad,
+                                          float* camera16, hp_memspace memspace) {
+    DV_RANGE("hpx_grid_read_grad_range");
+    if (g == nullptr || first > g->voxels || count > g->voxels - first) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(g->ctx);
     DV_TRY(grid_ensure_grad(g));
     cudaStream_t s = g->ctx->stream;
@@ -183,13 +193,13 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
     const ScatterParams lay = scatter_params(*g);   // strides of the gradient block
     const uint32_t unx = static_cast<uint32_t>(g->nx), uny = static_cast<uint32_t>(g->ny);
     if (memspace == HP_MEMSPACE_DEVICE) {
-        DV_CUDA(launch_unpack_grad(s, packed, sigma_grad, color_grad, 0, g->voxels, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
+        DV_CUDA(launch_unpack_grad(s, packed, sigma_grad, color_grad, first, count, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
         if (camera16) DV_CUDA(cudaMemcpyAsync(camera16, g->d_grad + g->voxels * 4, kCameraFloats * sizeof(float),
                                               cudaMemcpyDeviceToDevice, s));
         return HP_STATUS_SUCCESS;
     }
     // HOST: un-interleave chunk by chunk through a staging buffer the grid keeps (no per-call malloc)
-    const size_t chunk = std::min<size_t>(g->voxels, kStageVoxels);
+    const size_t chunk = std::min<size_t>(std::max<size_t>(count, 1), kStageVoxels);
     if (g->d_unpacked == nullptr || g->unpacked_voxels < chunk) {
         cudaFree(g->d_unpacked);
         g->d_unpacked = nullptr;
@@ -197,10 +207,10 @@ HP_API hp_status hpx_grid_read_grad(hpx_grid* g, float* sigma_grad, float* color
         g->unpacked_voxels = chunk;
     }
     float* d_sig = sigma_grad ? g->d_unpacked : nullptr;
-    float* d_col = color_grad ? g->d_unpacked + chunk : nullptr;
-    for (size_t off = 0; off < g->voxels && (sigma_grad || color_grad); off += chunk) {
-        const size_t n = std::min(chunk, g->voxels - off);
-        DV_CUDA(launch_unpack_grad(s, packed, d_sig, d_col, off, n, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
+    float* d_col = color_grad ? g->d_unpacked + g->unpacked_voxels : nullptr;
+    for (size_t off = 0; off < count && (sigma_grad || color_grad); off += chunk) {
+        const size_t n = std::min(chunk, count - off);
+        DV_CUDA(launch_unpack_grad(s, packed, d_sig, d_col, first + off, n, unx, uny, lay.box_sx, lay.box_sy, lay.box_sz));
         if (sigma_grad) DV_CUDA(cudaMemcpyAsync(sigma_grad + off, d_sig, n * 4, cudaMemcpyDeviceToHost, s));
         if (color_grad) DV_CUDA(cudaMemcpyAsync(color_grad + 3 * off, d_col, n * 12, cudaMemcpyDeviceToHost, s));
     }
@@ -336,7 +346,7 @@ HP_API hp_status hpx_frame_create(const hp_plan* plan, hpx_frame** out_frame) {
     f->buf.live_total = static_cast<unsigned long long*>(frame_take(f, sizeof(unsigned long long), &st));
     f->d_dL_dI = static_cast<float*>(frame_take(f, rays * 12, &st));
     f->d_box_miss = static_cast<unsigned int*>(frame_take(f, sizeof(unsigned int), &st));
-    f->d_group_done = static_cast<unsigned int*>(frame_take(f, 8 * sizeof(unsigned int), &st));
+    f->d_group_done = static_cast<unsigned int*>(frame_take(f, kMaxRowGroups * sizeof(unsigned int), &st));
     if (st == HP_STATUS_SUCCESS) {
         const cudaError_t e = cudaMemset(f->d_box_miss, 0, sizeof(unsigned int));
         if (e != cudaSuccess) st = cuda_fail(e, "cudaMemset(frame)");
@@ -629,7 +639,7 @@ HP_API hp_status hpx_backward_signalled(hpx_frame* f, hpx_grid* g, const float* 
                                         uint32_t* out_expected) {
     DV_RANGE("hpx_backward_signalled");
     DV_TRY(frame_check_grid(f, g));
-    if (dL_dI == nullptr || group_end_rows == nullptr || n_groups == 0 || n_groups > 8 || out_expected == nullptr)
+    if (dL_dI == nullptr || group_end_rows == nullptr || n_groups == 0 || n_groups > kMaxRowGroups || out_expected == nullptr)
         return HP_STATUS_INVALID_ARGUMENT;
     if (!f->forward_done) return HP_STATUS_INVALID_ARGUMENT;
     const RoiParams& roi = f->h_params.roi;
@@ -664,7 +674,7 @@ HP_API hp_status hpx_frame_reset_group_counters(hpx_frame* f, uint32_t** out_dev
     DV_RANGE("hpx_frame_reset_group_counters");
     if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     DV_ENTER(f->ctx);
-    DV_CUDA(cudaMemsetAsync(f->d_group_done, 0, 8 * sizeof(unsigned int), f->ctx->stream));
+    DV_CUDA(cudaMemsetAsync(f->d_group_done, 0, kMaxRowGroups * sizeof(unsigned int), f->ctx->stream));
     if (out_device_counters) *out_device_counters = f->d_group_done;
     return HP_STATUS_SUCCESS;
 }

@@ -36,7 +36,7 @@ struct LeanBuffers {
     // slabs that group finished while later rows are still running -- one launch, no per-group launch tails.
     unsigned int* group_done = nullptr;
     uint32_t group_count = 0;
-    uint32_t group_end[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // exclusive end (owned tile rows) of each group
+    uint32_t group_end[16] = {};                        // exclusive end (owned tile rows) of each group
 };
 
 // Fills `table[uniform_count]` with the per-step values above (plain IEEE float arithmetic, no contraction).

@@ -32,6 +32,9 @@ struct hp_ctx {
     int requested_ordinal = -1;
     cudaStream_t user_stream = nullptr;
     bool has_user_stream = false;
+    uint32_t reserve_sms = 0;                        // hpx_ctx_ext2: SMs kept out of this context's green context
+    mutable void* green_ctx = nullptr;               // CUgreenCtx owning the SMs the stream may use
+    mutable uint32_t usable_sms = 0, total_sms = 0;
     // lazily initialised
     mutable bool ready = false;
     mutable bool failed = false;
@@ -103,7 +106,7 @@ struct hpx_frame {
     float* d_dL_dI = nullptr;     // [rays][3]
     double* d_cam_partials = nullptr;
     unsigned int* d_box_miss = nullptr;   // contributions hpx_backward_box had to drop (must stay 0)
-    unsigned int* d_group_done = nullptr; // [8] completion counters of hpx_backward_signalled
+    unsigned int* d_group_done = nullptr; // [16] completion counters of hpx_backward_signalled
     size_t device_bytes = 0;
     uint64_t rays = 0, samples = 0;
     bool forward_done = false;

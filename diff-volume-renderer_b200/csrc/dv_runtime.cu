@@ -12,6 +12,8 @@
 #include <cstring>
 #include <new>
 
+#include <cuda.h>   // types of the green-context driver API; the entry points are looked up at run time
+
 #include "dv_objects.h"
 
 namespace dv {
@@ -35,8 +37,106 @@ hp_status cuda_fail(cudaError_t err, const char* what) {
     }
 }
 
+// ---- SM reservation (hpx_ctx_ext2.reserve_sms): a green context over all but `reserve` SMs ------------------------
+namespace {
+struct GreenApi {
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+    CUresult (*DeviceGetDevResource)(CUdevice, CUdevResource*, CUdevResourceType) = nullptr;
+    CUresult (*DevSmResourceSplitByCount)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int,
+                                          unsigned int) = nullptr;
+    CUresult (*DevResourceGenerateDesc)(CUdevResourceDesc*, CUdevResource*, unsigned int) = nullptr;
+    CUresult (*GreenCtxCreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int) = nullptr;
+    CUresult (*GreenCtxDestroy)(CUgreenCtx) = nullptr;
+    CUresult (*GreenCtxStreamCreate)(CUstream*, CUgreenCtx, unsigned int, int) = nullptr;
+    bool ok = false;
+};
+
+template <typename F>
+bool driver_fn(const char* name, F& out) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    out = reinterpret_cast<F>(p);
+    return true;
+}
+
+const GreenApi& green_api() {
+    static const GreenApi api = [] {
+        GreenApi a;
+        a.ok = driver_fn("cuDeviceGet", a.DeviceGet) && driver_fn("cuDeviceGetDevResource", a.DeviceGetDevResource) &&
+               driver_fn("cuDevSmResourceSplitByCount", a.DevSmResourceSplitByCount) &&
+               driver_fn("cuDevResourceGenerateDesc", a.DevResourceGenerateDesc) && driver_fn("cuGreenCtxCreate", a.GreenCtxCreate) &&
+               driver_fn("cuGreenCtxDestroy", a.GreenCtxDestroy) && driver_fn("cuGreenCtxStreamCreate", a.GreenCtxStreamCreate);
+        return a;
+    }();
+    return api;
+}
+
+// Creates ctx->green_ctx over (total - reserve) SMs (rounded DOWN to the partition granularity so that at least `reserve`
+// SMs stay free) and ctx->stream inside it.
+hp_status create_green_stream(const hp_ctx* ctx) {
+    const GreenApi& g = green_api();
+    if (!g.ok) {
+        set_last_error("SM reservation needs the green-context driver API (CUDA 12.4+)");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_CUDA(cudaFree(nullptr));   // the primary context exists
+    CUdevice dev;
+    CUdevResource all{}, part{}, rest{};
+    if (g.DeviceGet(&dev, ctx->device) != CUDA_SUCCESS || g.DeviceGetDevResource(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) {
+        set_last_error("cuDeviceGetDevResource failed");
+        return HP_STATUS_INTERNAL_ERROR;
+    }
+    const unsigned int total = all.sm.smCount;
+    ctx->total_sms = total;
+    if (ctx->reserve_sms >= total) {
+        set_last_error("reserve_sms leaves no SM for the context");
+        return HP_STATUS_INVALID_ARGUMENT;
+    }
+    // the split rounds a request UP to the partition granularity (8 SMs on sm_90+): start from the largest multiple of 8
+    // that leaves `reserve` SMs free and step down until the partition really does
+    unsigned int want = (total - ctx->reserve_sms) / 8u * 8u;
+    CUresult rc = CUDA_ERROR_INVALID_VALUE;
+    while (want >= 8u) {
+        unsigned int groups = 1;
+        rc = g.DevSmResourceSplitByCount(&part, &groups, &all, &rest, 0u, want);
+        if (rc != CUDA_SUCCESS || groups != 1) break;
+        if (part.sm.smCount + ctx->reserve_sms <= total) break;
+        want -= 8u;
+    }
+    if (rc != CUDA_SUCCESS || part.sm.smCount == 0 || total - part.sm.smCount < ctx->reserve_sms) {
+        set_last_error("cuDevSmResourceSplitByCount could not set " + std::to_string(ctx->reserve_sms) + " SMs aside (driver error " +
+                       std::to_string(static_cast<int>(rc)) + ")");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    CUdevResourceDesc desc = nullptr;
+    CUgreenCtx green = nullptr;
+    if ((rc = g.DevResourceGenerateDesc(&desc, &part, 1)) != CUDA_SUCCESS ||
+        (rc = g.GreenCtxCreate(&green, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM)) != CUDA_SUCCESS) {
+        set_last_error("cuGreenCtxCreate failed with driver error " + std::to_string(static_cast<int>(rc)));
+        return HP_STATUS_INTERNAL_ERROR;
+    }
+    CUstream stream = nullptr;
+    if ((rc = g.GreenCtxStreamCreate(&stream, green, CU_STREAM_NON_BLOCKING, 0)) != CUDA_SUCCESS) {
+        g.GreenCtxDestroy(green);
+        set_last_error("cuGreenCtxStreamCreate failed with driver error " + std::to_string(static_cast<int>(rc)));
+        return HP_STATUS_INTERNAL_ERROR;
+    }
+    ctx->green_ctx = green;
+    ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+    ctx->owns_stream = true;
+    ctx->usable_sms = part.sm.smCount;
+    return HP_STATUS_SUCCESS;
+}
+}  // namespace
+
 static void destroy_device_state(const hp_ctx* ctx) {
     if (ctx->owns_stream && ctx->stream != nullptr) cudaStreamDestroy(ctx->stream);
+    if (ctx->green_ctx != nullptr && green_api().ok) green_api().GreenCtxDestroy(static_cast<CUgreenCtx>(ctx->green_ctx));
+    ctx->green_ctx = nullptr;
     cudaFree(ctx->d_status);
     cudaFree(ctx->d_total);
     if (ctx->h_status != nullptr) cudaFreeHost(ctx->h_status);
@@ -75,7 +175,19 @@ hp_status ensure_device(const hp_ctx* ctx) {
         DV_CUDA(cudaSetDevice(dev));
         // all or nothing: a failure half way rolls back what was created, so that a retry starts clean (no leak)
         cudaError_t err = cudaSuccess;
-        if (ctx->has_user_stream) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) ctx->total_sms = ctx->usable_sms = static_cast<uint32_t>(sms);
+        if (ctx->reserve_sms != 0) {
+            if (ctx->has_user_stream) {
+                set_last_error("hpx_ctx_ext2.reserve_sms needs a library-owned stream (stream must be NULL)");
+                return HP_STATUS_INVALID_ARGUMENT;
+            }
+            const hp_status gs = create_green_stream(ctx);
+            if (gs != HP_STATUS_SUCCESS) {
+                destroy_device_state(ctx);
+                return gs;
+            }
+        } else if (ctx->has_user_stream) {
             ctx->stream = ctx->user_stream;
             ctx->owns_stream = false;
         } else {
@@ -353,12 +465,13 @@ HP_API hp_status hp_ctx_create(const hp_ctx_desc* desc, hp_ctx** out_ctx) {
     }
     if (ctx->desc.reserved != nullptr) {
         const auto* ext = static_cast<const hpx_ctx_ext*>(ctx->desc.reserved);
-        if (ext->magic == HPX_CTX_EXT_MAGIC) {
+        if (ext->magic == HPX_CTX_EXT_MAGIC || ext->magic == HPX_CTX_EXT2_MAGIC) {
             if (ext->device_ordinal >= 0) ctx->requested_ordinal = ext->device_ordinal;
             if (ext->stream != nullptr) {
                 ctx->user_stream = static_cast<cudaStream_t>(ext->stream);
                 ctx->has_user_stream = true;
             }
+            if (ext->magic == HPX_CTX_EXT2_MAGIC) ctx->reserve_sms = static_cast<const hpx_ctx_ext2*>(ctx->desc.reserved)->reserve_sms;
         }
         ctx->desc.reserved = nullptr;  // not ours to hand back later
     }
@@ -458,6 +571,14 @@ HP_API hp_status hpx_copy_to_device(const hp_ctx* ctx, void* device_dst, const v
     DV_ENTER(ctx);
     DV_CUDA(cudaMemcpyAsync(device_dst, host_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     DV_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_ctx_sm_counts(const hp_ctx* ctx, uint32_t* out_usable, uint32_t* out_total) {
+    DV_RANGE("hpx_ctx_sm_counts");
+    DV_ENTER(ctx);
+    if (out_usable != nullptr) *out_usable = ctx->usable_sms;
+    if (out_total != nullptr) *out_total = ctx->total_sms;
     return HP_STATUS_SUCCESS;
 }
 

@@ -21,12 +21,19 @@ PKG_DIR = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(PKG_DIR, "libdvren_hp.so")
 
 HPX_CTX_EXT_MAGIC = 0x42323030
+HPX_CTX_EXT2_MAGIC = 0x42323031
+HPX_COMM_ID_BYTES = 128
 HPX_BACKWARD_GRID, HPX_BACKWARD_CAMERA, HPX_BACKWARD_ZERO = 1, 2, 4
 HPX_BACKWARD_SCATTER_PER_RAY, HPX_BACKWARD_SCATTER_MERGED, HPX_BACKWARD_DETERMINISTIC = 0x10, 0x20, 0x40
 
 
 class hpx_ctx_ext(C.Structure):
     _fields_ = [("magic", C.c_uint32), ("device_ordinal", C.c_int32), ("stream", C.c_void_p)]
+
+
+class hpx_ctx_ext2(C.Structure):
+    _fields_ = [("magic", C.c_uint32), ("device_ordinal", C.c_int32), ("stream", C.c_void_p),
+                ("reserve_sms", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class hpx_counts(C.Structure):
@@ -56,6 +63,7 @@ HPX_FUNCTIONS = {
     "hpx_grid_zero_grad": (C.c_int, [C.c_void_p]),
     "hpx_grid_grad_buffer": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]),
     "hpx_grid_read_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "hpx_grid_read_grad_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hpx_grid_release": (None, [C.c_void_p]),
     "hpx_frame_create": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
     "hpx_frame_bytes": (C.c_size_t, [C.c_void_p]),
@@ -83,6 +91,19 @@ HPX_FUNCTIONS = {
     "hpx_frame_replay": (C.c_int, [C.c_void_p]),
     "hpx_frame_grad_input": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
     "hpx_frame_release": (None, [C.c_void_p]),
+    "hpx_ctx_sm_counts": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32)]),
+    "hpx_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "hpx_comm_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, P(C.c_void_p)]),
+    "hpx_comm_release": (None, [C.c_void_p]),
+    "hpx_comm_info": (C.c_int, [C.c_void_p, P(C.c_int32), P(C.c_int32), P(C.c_int32)]),
+    "hpx_comm_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "hpx_grid_allreduce_grad": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hpx_shard_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, P(C.c_float), C.c_uint32, P(C.c_void_p)]),
+    "hpx_shard_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
+    "hpx_shard_frame": (C.c_int, [C.c_void_p, P(C.c_void_p)]),
+    "hpx_shard_set_reduce": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hpx_shard_layout": (C.c_int, [C.c_void_p, P(C.c_int32), P(C.c_uint32), P(C.c_uint32), P(C.c_int32)]),
+    "hpx_shard_release": (None, [C.c_void_p]),
 }
 
 _lib = None
@@ -124,15 +145,41 @@ def _vec3(v):
 class Context:
     """hp_ctx bound to a device ordinal and (optionally) a caller stream."""
 
-    def __init__(self, device: int = -1, stream: int = 0):
+    def __init__(self, device: int = -1, stream: int = 0, reserve_sms: int = 0):
+        """reserve_sms > 0: the context's kernels stay off that many SMs (green context; the library then owns the
+        stream -- `stream` must be 0 -- and `self.stream` returns it)."""
         self.lib = load()
-        self._ext = hpx_ctx_ext(HPX_CTX_EXT_MAGIC, device, stream or None)
+        if reserve_sms:
+            self._ext = hpx_ctx_ext2(HPX_CTX_EXT2_MAGIC, device, None, reserve_sms, 0)
+        else:
+            self._ext = hpx_ctx_ext(HPX_CTX_EXT_MAGIC, device, stream or None)
         desc = A.hp_ctx_desc(0, None, C.cast(C.pointer(self._ext), C.c_void_p))
         self.handle = C.c_void_p()
         check("hp_ctx_create", self.lib.hp_ctx_create(C.byref(desc), C.byref(self.handle)))
 
     def synchronize(self):
         check("hpx_ctx_synchronize", self.lib.hpx_ctx_synchronize(self.handle))
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t the context enqueues on (creates the device state on first use)."""
+        dev, st = C.c_int32(), C.c_void_p()
+        check("hpx_ctx_device", self.lib.hpx_ctx_device(self.handle, C.byref(dev), C.byref(st)))
+        return st.value or 0
+
+    def sm_counts(self):
+        """(SMs this context's kernels may use, SMs of the GPU)."""
+        a, b = C.c_uint32(), C.c_uint32()
+        check("hpx_ctx_sm_counts", self.lib.hpx_ctx_sm_counts(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def mark(self, slot: int):
+        check("hpx_ctx_mark", self.lib.hpx_ctx_mark(self.handle, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        check("hpx_ctx_elapsed_ms", self.lib.hpx_ctx_elapsed_ms(self.handle, a, b, C.byref(ms)))
+        return ms.value
 
     def wait_counter(self, device_counter_ptr: int, value: int):
         """This context's stream waits (without occupying an SM) until *device_counter_ptr >= value."""
@@ -343,4 +390,79 @@ class Frame:
     def close(self):
         if self.handle:
             self.lib.hpx_frame_release(self.handle)
+            self.handle = C.c_void_p()
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL rendezvous id (rank 0 makes it, the others receive it by any means)."""
+    buf = (C.c_uint8 * HPX_COMM_ID_BYTES)()
+    check("hpx_comm_unique_id", load().hpx_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Comm:
+    """hpx_comm: one rank of the NCCL communicator behind the C ABI (world 1 = no NCCL)."""
+
+    def __init__(self, ctx: Context, unique_id: Optional[bytes], rank: int, world: int, max_ctas: int = 0):
+        self.ctx, self.lib, self.rank, self.world = ctx, ctx.lib, rank, world
+        self.handle = C.c_void_p()
+        ident = (C.c_uint8 * HPX_COMM_ID_BYTES).from_buffer_copy(unique_id) if unique_id else None
+        check("hpx_comm_create", self.lib.hpx_comm_create(ctx.handle, ident, rank, world, max_ctas, C.byref(self.handle)))
+
+    def nccl_version(self) -> int:
+        v = C.c_int32()
+        check("hpx_comm_info", self.lib.hpx_comm_info(self.handle, None, None, C.byref(v)))
+        return v.value
+
+    def allreduce_grad(self, grid: Grid):
+        check("hpx_grid_allreduce_grad", self.lib.hpx_grid_allreduce_grad(self.handle, grid.handle))
+
+    def allreduce(self, device_ptr: int, floats: int):
+        check("hpx_comm_allreduce", self.lib.hpx_comm_allreduce(self.handle, int(device_ptr), floats))
+
+    def close(self):
+        if self.handle:
+            self.lib.hpx_comm_release(self.handle)
+            self.handle = C.c_void_p()
+
+
+class _BorrowedFrame(Frame):
+    """The frame a shard owns (never released from Python)."""
+
+    def __init__(self, plan: Plan, handle):
+        self.plan, self.lib, self.handle = plan, plan.lib, handle
+
+    def close(self):
+        self.handle = C.c_void_p()
+
+
+class Shard:
+    """hpx_shard: ONE frame rendered by all ranks of a communicator, all-reduce hidden behind the backward."""
+
+    def __init__(self, comm: Comm, plan: Plan, grid: Grid, group_weights):
+        self.comm, self.lib, self.plan, self.grid = comm, comm.lib, plan, grid
+        self.handle = C.c_void_p()
+        w = (C.c_float * len(group_weights))(*[float(v) for v in group_weights])
+        check("hpx_shard_create", self.lib.hpx_shard_create(comm.handle, plan.handle, grid.handle, w, len(group_weights),
+                                                            C.byref(self.handle)))
+        fh = C.c_void_p()
+        check("hpx_shard_frame", self.lib.hpx_shard_frame(self.handle, C.byref(fh)))
+        self.frame = _BorrowedFrame(plan, fh)
+
+    def step(self, dL_dI_device_ptr: int, flags: int = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO):
+        check("hpx_shard_step", self.lib.hpx_shard_step(self.handle, int(dL_dI_device_ptr), flags))
+
+    def set_reduce(self, enabled: bool):
+        check("hpx_shard_set_reduce", self.lib.hpx_shard_set_reduce(self.handle, 1 if enabled else 0))
+
+    def layout(self):
+        axis, n = C.c_int32(), C.c_uint32()
+        rows, ranges = (C.c_uint32 * 16)(), (C.c_int32 * 32)()
+        check("hpx_shard_layout", self.lib.hpx_shard_layout(self.handle, C.byref(axis), C.byref(n), rows, ranges))
+        return {"slow_axis": "xyz"[axis.value], "group_rows": [int(rows[i]) for i in range(n.value)],
+                "slab_ranges": [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(n.value)]}
+
+    def close(self):
+        if self.handle:
+            self.lib.hpx_shard_release(self.handle)
             self.handle = C.c_void_p()

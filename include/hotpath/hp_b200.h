@@ -50,6 +50,21 @@ typedef struct hpx_ctx_ext {
     void*    stream;         /* cudaStream_t to enqueue on; NULL: library-owned stream */
 } hpx_ctx_ext;
 
+/* Extended form (magic HPX_CTX_EXT2_MAGIC): additionally keeps `reserve_sms` streaming multiprocessors of the GPU OUT of
+ * this context's reach: the context's stream is created in a CUDA green context that owns the remaining SMs (rounded to
+ * the hardware's partition granularity, 8 SMs on sm_90+), so kernels of this library never occupy the reserved ones.
+ * A collective running next to a long rendering launch (hpx_shard_step) then always finds free SMs for its CTAs
+ * instead of waiting for the launch to drain.  Requires stream == NULL (the library creates the stream).
+ * hpx_ctx_sm_counts reports what was provisioned. */
+#define HPX_CTX_EXT2_MAGIC 0x42323031u
+typedef struct hpx_ctx_ext2 {
+    uint32_t magic;          /* HPX_CTX_EXT2_MAGIC */
+    int32_t  device_ordinal;
+    void*    stream;
+    uint32_t reserve_sms;    /* 0: use the whole GPU */
+    uint32_t flags;          /* 0 */
+} hpx_ctx_ext2;
+
 typedef struct hpx_grid  hpx_grid;
 typedef struct hpx_frame hpx_frame;
 
@@ -76,6 +91,8 @@ typedef struct hpx_counts {
 /* ---- context helpers ---------------------------------------------------- */
 HP_API hp_status hpx_ctx_synchronize(const hp_ctx* ctx);
 HP_API hp_status hpx_ctx_device(const hp_ctx* ctx, int32_t* out_ordinal, void** out_stream);
+/* SMs the context's kernels can run on / SMs of the GPU (differ when hpx_ctx_ext2.reserve_sms took effect). */
+HP_API hp_status hpx_ctx_sm_counts(const hp_ctx* ctx, uint32_t* out_usable, uint32_t* out_total);
 /* Device-side stage timing (CUDA events on the context's stream) for callers that do not link a CUDA runtime:
  * hpx_ctx_mark records event `slot` (0..15); hpx_ctx_elapsed_ms waits for `slot_end` and returns the GPU time between
  * two recorded slots.  dvren::Renderer fills its RenderStats from these (reference renderer.hpp:41-48 uses host clocks). */
@@ -122,6 +139,10 @@ HP_API hp_status hpx_grid_grad_buffer(hpx_grid* grid, float** out_device_ptr, si
  * in `memspace`.  Blocks until done when the destination is HOST. */
 HP_API hp_status hpx_grid_read_grad(hpx_grid* grid, float* sigma_grad, float* color_grad,
                                     float* camera16, hp_memspace memspace);
+/* Same for voxels [first, first + count) of the reference order (sigma_grad[count], color_grad[3 * count]): every rank of
+ * a sharded job can hand its share of the summed gradient to the host over its own PCIe link. */
+HP_API hp_status hpx_grid_read_grad_range(hpx_grid* grid, size_t first, size_t count, float* sigma_grad, float* color_grad,
+                                          float* camera16, hp_memspace memspace);
 /* DenseGridField::AccumulateSampleGradients on the GPU (reference src/fields/dense_grid.cpp:171-309):
  * scatter per-sample gradients (positions (M,3), grad_sigma (M), grad_color (M,3) in `memspace`)
  * into the packed gradient grid with the grid's bbox / interpolation / OOB policy. */
@@ -208,6 +229,48 @@ HP_API hp_status hpx_frame_capture(hpx_frame* frame, hpx_grid* grid, uint32_t ba
 HP_API hp_status hpx_frame_replay(hpx_frame* frame);
 HP_API hp_status hpx_frame_grad_input(hpx_frame* frame, float** out_device_dL_dI);
 HP_API void      hpx_frame_release(hpx_frame* frame);
+
+/* ---- multi-GPU: one process (or thread) per GPU, NCCL over NVLink ---------------------------------------------------
+ * The reference is single-device.  Rays are independent, so the path shards with no forward
+ * collective; the one exchange is the sum of the packed gradient block.  NCCL is loaded at run time
+ * (libnccl.so.2, or the path in DVREN_NCCL_LIBRARY): without it these calls return HP_STATUS_UNSUPPORTED and the rest
+ * of the library is unaffected.
+ *
+ *   hpx_comm_unique_id      rank 0 creates the 128-byte rendezvous id and hands it to the other ranks by any means
+ *   hpx_comm_create         rank `rank` of `world` on ctx's GPU; world == 1 is valid (no NCCL involved).  max_ctas > 0 caps
+ *                           the CTAs of NCCL's kernels (use the SMs hpx_ctx_ext2.reserve_sms left free)
+ *   hpx_grid_allreduce_grad data parallelism over views: sum of the whole gradient block after the local backward passes
+ *   hpx_shard_*             ONE frame rendered by all ranks (strong scaling): rank r marches the CTA tile rows t with
+ *                           t % world == r; the gradient block is laid out with the axis the image rows advance along as
+ *                           its slowest one; ONE backward launch signals per group of rows and a high-priority side stream
+ *                           all-reduces in place the slabs each finished group leaves behind while later rows still render.
+ *                           group_weights: relative heights of the row groups (NULL = equal); keep the last one small,
+ *                           only its slabs are reduced after the kernel.  Linear OOB-zero fields with the unit scatter box. */
+#define HPX_COMM_ID_BYTES 128
+typedef struct hpx_comm  hpx_comm;
+typedef struct hpx_shard hpx_shard;
+HP_API hp_status hpx_comm_unique_id(uint8_t out_id[HPX_COMM_ID_BYTES]);
+HP_API hp_status hpx_comm_create(const hp_ctx* ctx, const uint8_t id[HPX_COMM_ID_BYTES], int32_t rank, int32_t world,
+                                 int32_t max_ctas, hpx_comm** out_comm);
+HP_API void      hpx_comm_release(hpx_comm* comm);
+HP_API hp_status hpx_comm_info(const hpx_comm* comm, int32_t* out_rank, int32_t* out_world, int32_t* out_nccl_version);
+/* In-place sum over the ranks, ordered after the work already on the context's stream; that stream continues after it. */
+HP_API hp_status hpx_comm_allreduce(hpx_comm* comm, float* device_buf, size_t floats);
+HP_API hp_status hpx_grid_allreduce_grad(hpx_comm* comm, hpx_grid* grid);
+HP_API hp_status hpx_shard_create(hpx_comm* comm, const hp_plan* full_frame_plan, hpx_grid* grid, const float* group_weights,
+                                  uint32_t n_groups, hpx_shard** out_shard);
+/* [HPX_BACKWARD_ZERO: clear the gradient block, overlapped with the forward] -> forward -> signalled backward -> slab
+ * all-reduces.  dL_dI_device: (rays of the WHOLE frame, 3) on the device.  Afterwards every rank holds the summed gradient. */
+HP_API hp_status hpx_shard_step(hpx_shard* shard, const float* dL_dI_device, uint32_t flags);
+/* The rank's frame (image planes of its tile rows, counts).  Owned by the shard. */
+HP_API hp_status hpx_shard_frame(hpx_shard* shard, hpx_frame** out_frame);
+/* Timing experiments: run the step without its collectives. */
+HP_API hp_status hpx_shard_set_reduce(hpx_shard* shard, int32_t enabled);
+/* Slowest axis of the gradient block, number of row groups, image rows and touched slab range [lo, hi) per group
+ * (arrays of 16 / 32 entries; any pointer may be NULL). */
+HP_API hp_status hpx_shard_layout(const hpx_shard* shard, int32_t* out_slow_axis, uint32_t* out_groups,
+                                  uint32_t* out_group_rows, int32_t* out_slab_ranges);
+HP_API void      hpx_shard_release(hpx_shard* shard);
 
 #ifdef __cplusplus
 }

@@ -309,7 +309,44 @@ def ref_lib() -> C.CDLL:
                                     C.c_uint32, C.c_int, f32p, f32p, f32p, f32p, f32p, C.c_void_p, f32p,
                                     f32p, f32p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        _ref.ref_worker_create.restype = C.c_void_p
+        _ref.ref_worker_create.argtypes = [C.POINTER(C.c_int32 * 3), f32p, f32p, C.c_uint32, C.c_uint32]
+        _ref.ref_worker_destroy.restype = None
+        _ref.ref_worker_destroy.argtypes = [C.c_void_p]
+        _ref.ref_worker_run.restype = C.c_int
+        _ref.ref_worker_run.argtypes = [C.c_void_p, C.POINTER(A.hp_plan_desc), f32p, C.POINTER(C.c_uint64),
+                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]
     return _ref
+
+
+class RefWorker:
+    """One host thread's handle on the unmodified reference's hot-path calls (oracle/ref_shim.cpp: ref_worker_*):
+    hp_ray -> hp_samp_int_fused -> hp_img, then hp_diff -> DenseGridField::AccumulateSampleGradients, for ROI bands of a
+    plan.  sigma / color are SHARED between workers (the reference's fields view them); each worker owns the gradient
+    vectors its scatter writes (4 floats per voxel, plus the reference field's own zero-filled value copy)."""
+
+    def __init__(self, sigma: np.ndarray, color: np.ndarray, interp=A.HP_INTERP_LINEAR, oob=A.HP_OOB_ZERO):
+        assert sigma.dtype == np.float32 and color.dtype == np.float32 and sigma.flags.c_contiguous and color.flags.c_contiguous
+        self._keep = (sigma, color)
+        nz, ny, nx = sigma.shape
+        r3 = (C.c_int32 * 3)(nx, ny, nz)
+        self.handle = ref_lib().ref_worker_create(C.byref(r3), _p(sigma), _p(color), interp, oob)
+        if not self.handle:
+            raise RuntimeError("ref_worker_create failed")
+
+    def run(self, desc, dL_dI=None):
+        """Returns (sample_count, forward_ms, backward_ms) of one band (`desc` = unresolved plan descriptor with its ROI)."""
+        dl = np.ascontiguousarray(dL_dI, np.float32) if dL_dI is not None else None
+        n, f, b = C.c_uint64(0), C.c_double(0), C.c_double(0)
+        rc = ref_lib().ref_worker_run(self.handle, C.byref(desc), _p(dl), C.byref(n), C.byref(f), C.byref(b))
+        if rc != 0:
+            raise RuntimeError(f"ref_worker_run -> {rc}")
+        return n.value, f.value, b.value
+
+    def close(self):
+        if self.handle:
+            ref_lib().ref_worker_destroy(self.handle)
+            self.handle = None
 
 
 def ref_scatter(res, bmin, bmax, interp, oob, positions, gsig, gcol):

@@ -7,13 +7,16 @@
 // dvren::Renderer (reference include/dvren/fields/dense_grid.hpp:24-75,
 // include/dvren/render/renderer.hpp:68-149) so Python can reach them via ctypes.
 #include <chrono>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
+#include <new>
 #include <span>
 #include <vector>
 
 #include "dvren/core/context.hpp"
 #include "dvren/core/plan.hpp"
+#include "dvren/core/tensor_utils.hpp"
 #include "dvren/fields/dense_grid.hpp"
 #include "dvren/render/renderer.hpp"
 
@@ -138,6 +141,102 @@ int ref_render(const hp_plan_desc* desc, const int32_t res[3], const float* sigm
         if (camera_grad12) std::memcpy(camera_grad12, bwd.camera.data(), 12 * sizeof(float));
     }
     return 0;
+}
+
+// ---- bench.py --impl reference / cpu_baseline: the hot-path calls themselves, per host thread ----------------------
+// One worker per thread: hp.h fields that VIEW the caller's shared grid arrays (reference hp_runtime.cpp:259-339 keeps a
+// view, so the threads share one copy of the values), plus a DenseGridField that receives the gradient scatter.  A run is
+// the reference's own call sequence for one ROI band -- hp_ray -> hp_samp_int_fused -> hp_img, then hp_diff ->
+// DenseGridField::AccumulateSampleGradients (reference src/render/renderer.cpp:259-365,415-427) -- timed WITHOUT
+// Renderer's whole-grid bookkeeping (ZeroGradients and the V-sized result copies, renderer.cpp:424,441-442): that cost is
+// per call, not per sample, and would dominate a bounded band of a 512^3 grid while it vanishes in the full frame.
+struct RefWorker {
+    dvren::Context ctx;
+    hp_field* fs{nullptr};
+    hp_field* fc{nullptr};
+    dvren::DenseGridField scatter;
+    std::vector<std::byte> ws, ws_img, ws_diff;
+    std::vector<float> rays_f;
+    std::vector<uint32_t> rays_u;
+};
+
+void* ref_worker_create(const int32_t res[3], const float* sigma, const float* color, uint32_t interp, uint32_t oob) {
+    RefWorker* w = new (std::nothrow) RefWorker();
+    if (w == nullptr) return nullptr;
+    if (!dvren::Context::Create({}, w->ctx).ok()) { delete w; return nullptr; }
+    const int64_t nx = res[0], ny = res[1], nz = res[2];
+    hp_tensor st = dvren::MakeHostTensor(static_cast<void*>(const_cast<float*>(sigma)), HP_DTYPE_F32, {nz, ny, nx});
+    hp_tensor ct = dvren::MakeHostTensor(static_cast<void*>(const_cast<float*>(color)), HP_DTYPE_F32, {nz, ny, nx, 3});
+    if (hp_field_create_grid_sigma(w->ctx.handle(), &st, interp, oob, &w->fs) != HP_STATUS_SUCCESS ||
+        hp_field_create_grid_color(w->ctx.handle(), &ct, interp, oob, &w->fc) != HP_STATUS_SUCCESS) {
+        delete w;
+        return nullptr;
+    }
+    dvren::DenseGridConfig cfg{};
+    cfg.resolution = {res[0], res[1], res[2]};
+    const size_t voxels = static_cast<size_t>(nx) * ny * nz;
+    cfg.sigma.assign(voxels, 0.0f);   // the scatter never reads the values (dense_grid.cpp:171-309)
+    cfg.color.assign(voxels * 3, 0.0f);
+    cfg.interp = static_cast<hp_interp_mode>(interp);
+    cfg.oob = static_cast<hp_oob_policy>(oob);
+    if (!dvren::DenseGridField::Create(w->ctx, cfg, w->scatter).ok()) { delete w; return nullptr; }
+    w->scatter.ZeroGradients();
+    return w;
+}
+
+void ref_worker_destroy(void* handle) {
+    RefWorker* w = static_cast<RefWorker*>(handle);
+    if (w == nullptr) return;
+    if (w->fs) hp_field_release(w->fs);
+    if (w->fc) hp_field_release(w->fc);
+    delete w;
+}
+
+int ref_worker_run(void* handle, const hp_plan_desc* desc, const float* dL_dI, uint64_t* sample_count,
+                   double* forward_ms, double* backward_ms) {
+    RefWorker* w = static_cast<RefWorker*>(handle);
+    if (w == nullptr || desc == nullptr) return -1;
+    hp_plan* plan = nullptr;
+    if (hp_plan_create(w->ctx.handle(), desc, &plan) != HP_STATUS_SUCCESS) return -2;
+    hp_plan_desc d{};
+    hp_plan_get_desc(plan, &d);
+    const size_t n = static_cast<size_t>(d.roi.width) * d.roi.height, cap = d.max_samples;
+    const size_t pixels = static_cast<size_t>(d.width) * d.height;
+    w->rays_f.resize(n * 8);
+    w->rays_u.resize(n);
+    w->ws.resize(cap * 32 + (n + 1) * 4 + n * 24 + cap * 16 + 256);
+    w->ws_img.resize(pixels * 28 + 256);
+    hp_rays_t rays{};
+    rays.origins.data = w->rays_f.data();
+    rays.directions.data = w->rays_f.data() + n * 3;
+    rays.t_near.data = w->rays_f.data() + n * 6;
+    rays.t_far.data = w->rays_f.data() + n * 7;
+    rays.pixel_ids.data = w->rays_u.data();
+    for (hp_tensor* t : {&rays.origins, &rays.directions, &rays.t_near, &rays.t_far, &rays.pixel_ids}) t->memspace = HP_MEMSPACE_HOST;
+    hp_samp_t samp{};
+    hp_intl_t intl{};
+    hp_img_t img{};
+    int rc = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    if (hp_ray(plan, nullptr, &rays, nullptr, 0) != HP_STATUS_SUCCESS) rc = -3;
+    if (rc == 0 && hp_samp_int_fused(plan, w->fs, w->fc, &rays, &samp, &intl, w->ws.data(), w->ws.size()) != HP_STATUS_SUCCESS) rc = -4;
+    if (rc == 0 && hp_img(plan, &intl, &rays, &img, w->ws_img.data(), w->ws_img.size()) != HP_STATUS_SUCCESS) rc = -5;
+    if (forward_ms) *forward_ms = MsSince(t0);
+    const size_t m = rc == 0 && samp.dt.rank >= 1 ? static_cast<size_t>(samp.dt.shape[0]) : 0;
+    if (sample_count) *sample_count = m;
+    if (rc == 0 && dL_dI != nullptr) {
+        w->ws_diff.resize(m * 16 + 256);
+        hp_tensor g = dvren::MakeHostTensor(static_cast<void*>(const_cast<float*>(dL_dI)), HP_DTYPE_F32, {static_cast<int64_t>(n), 3});
+        hp_grads_t grads{};
+        t0 = std::chrono::steady_clock::now();
+        if (hp_diff(plan, &g, &samp, &intl, &grads, w->ws_diff.data(), w->ws_diff.size()) != HP_STATUS_SUCCESS) rc = -6;
+        if (rc == 0 && !w->scatter.AccumulateSampleGradients(samp, std::span<const float>(static_cast<const float*>(grads.sigma.data), m),
+                                                             std::span<const float>(static_cast<const float*>(grads.color.data), m * 3)).ok())
+            rc = -7;
+        if (backward_ms) *backward_ms = MsSince(t0);
+    }
+    hp_plan_release(plan);
+    return rc;
 }
 
 }  // extern "C"
