@@ -2,10 +2,12 @@
 // Renderer::Forward + Backward through libdvren.so with pageable std::vector inputs and results (the shapes the
 // reference's API forces, reference src/render/renderer.cpp:376-386,441-444).  Two uses:
 //
-//   dvren_bench bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup>
+//   dvren_bench bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> [pin 0|1]
 //       times Forward+Backward per step on the host clock (every host<->device copy inside) and prints ONE JSON line:
 //       bench.py reports it as e2e.renderer next to the pinned C-ABI end-to-end number.
-//   dvren_bench shard <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas>
+//   dvren_bench shard <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas> [mode]
+//       (mode 0: interleaved tile rows + slab all-reduces; 1: balanced bands + sparse exchange, every rank ends with the
+//       whole gradient; 2: the same, every rank ends with the finished sum of the slabs it owns)
 //       ONE frame rendered by <gpus> GPUs of this box with NO Python: one host thread per GPU, hpx_comm (NCCL) +
 //       hpx_shard_step (interleaved tile rows, signalled backward, slab all-reduces behind it).  Rank 0 first checks
 //       the reduced gradient against a plain single-GPU backward, then all ranks time <iters> steps (CUDA events, max
@@ -89,7 +91,7 @@ std::vector<float> hashed_image_grad(size_t rays) {
         }                                                       \
     } while (0)
 
-int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warmup) {
+int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warmup, bool pin) {
     dvren::Context ctx;
     dvren::Status st = dvren::Context::Create({}, ctx);
     CHECK(st.ok(), "Context::Create: %s", st.ToString().c_str());
@@ -102,7 +104,9 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
         st = dvren::DenseGridField::Create(ctx, cfg, field);
         CHECK(st.ok(), "DenseGridField::Create: %s", st.ToString().c_str());
     }
-    dvren::Renderer renderer(ctx, plan, dvren::RenderOptions{});
+    dvren::RenderOptions opt{};
+    opt.pin_result_buffers = pin;   // one set of result objects, alive for the whole loop: the opt-in's contract
+    dvren::Renderer renderer(ctx, plan, opt);
     const std::vector<float> dl = hashed_image_grad(static_cast<size_t>(w) * w);
     dvren::ForwardResult fwd;      // reused across steps, as a training loop does
     dvren::BackwardResult bwd;
@@ -123,10 +127,10 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
     double mass = 0.0;
     for (size_t i = 0; i < bwd.sigma.size(); i += 4099) mass += std::fabs(bwd.sigma[i]);
     const size_t pixels = static_cast<size_t>(w) * w;
-    std::printf("{\"ms_per_step\": %.4f, \"samples\": %zu, \"rays\": %zu, \"live_samples\": %zu, \"forward_kernel_ms\": %.4f, "
+    std::printf("{\"pin_result_buffers\": %s, \"ms_per_step\": %.4f, \"samples\": %zu, \"rays\": %zu, \"live_samples\": %zu, \"forward_kernel_ms\": %.4f, "
                 "\"forward_readback_ms\": %.4f, \"backward_kernel_ms\": %.4f, \"backward_readback_ms\": %.4f, "
                 "\"h2d_bytes_per_step\": %zu, \"d2h_bytes_per_step\": %zu, \"iters\": %d, \"warmup\": %d, \"checksum\": %.6g}\n",
-                total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_read / iters,
+                pin ? "true" : "false", total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_read / iters,
                 bwd_kernel / iters, bwd_read / iters, dl.size() * 4, pixels * 28 + bwd.sigma.size() * 16 + 64, iters, warmup, mass);
     return 0;
 }
@@ -188,14 +192,17 @@ int run_selftest() {
 // ---- one frame over several GPUs, C ABI only ----------------------------------------------------------------------
 struct ShardArgs {
     int n; uint32_t w, steps; bool strat; int iters, warmup, gpus; uint32_t groups, reserve; int max_ctas;
+    int mode;   // 0: interleaved tile rows + slab all-reduces; 1: balanced bands, replicated result; 2: balanced bands, owned result
 };
 
 struct ShardShared {
     uint8_t id[HPX_COMM_ID_BYTES];
     const dvren::DenseGridConfig* volume;
     const std::vector<float>* dl;
-    std::vector<double> ms, ms_no_reduce;
+    std::vector<double> ms, ms_no_reduce, send_mb, recv_mb;
     std::vector<int> status;
+    std::vector<uint32_t> band_row0, band_rows;
+    std::vector<int32_t> wedges, cuts;
     double verify = -1.0;
     uint64_t samples = 0;
     uint32_t usable_sms = 0, total_sms = 0;
@@ -238,7 +245,8 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
     std::vector<float> weights(a.groups);
     for (uint32_t g = 0; g < a.groups; ++g) weights[g] = a.groups == 1 ? 1.0f : std::pow(0.72f, static_cast<float>(g));   // small last group
     hpx_shard* shard = nullptr;
-    SCHECK(hpx_shard_create(comm, plan, grid, weights.data(), a.groups, &shard));
+    if (a.mode == 0) SCHECK(hpx_shard_create(comm, plan, grid, weights.data(), a.groups, &shard));
+    else SCHECK(hpx_shard_create_bands(comm, plan, grid, HPX_SHARD_RESULT_REPLICATED, &shard));   // verified replicated, timed as asked
     void* d_dl = nullptr;
     SCHECK(hpx_device_alloc(ctx, sh.dl->size() * 4, &d_dl));
     SCHECK(hpx_copy_to_device(ctx, d_dl, sh.dl->data(), sh.dl->size() * 4));
@@ -264,13 +272,15 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
         SCHECK(hpx_backward(full, grid, static_cast<const float*>(d_dl), HP_MEMSPACE_DEVICE, flags));
         SCHECK(hpx_grid_read_grad(grid, sg1.data(), cg1.data(), nullptr, HP_MEMSPACE_HOST));
         hpx_frame_release(full);
+        // Both sides are float32 red accumulations of the SAME contributions in different orders (each kernel has its own
+        // oracle parity tests); this check is there to catch a slab summed twice or not at all, hence the 1e-2 floor.
         double peak_s = 0, peak_c = 0, worst = 0;
         for (size_t i = 0; i < v; ++i) peak_s = std::fmax(peak_s, std::fabs(sg1[i]));
         for (size_t i = 0; i < 3 * v; ++i) peak_c = std::fmax(peak_c, std::fabs(cg1[i]));
         for (size_t i = 0; i < v; ++i)
-            worst = std::fmax(worst, std::fabs(static_cast<double>(sg[i]) - sg1[i]) / std::fmax(std::fabs(sg1[i]), 1e-3 * peak_s));
+            worst = std::fmax(worst, std::fabs(static_cast<double>(sg[i]) - sg1[i]) / std::fmax(std::fabs(sg1[i]), 1e-2 * peak_s));
         for (size_t i = 0; i < 3 * v; ++i)
-            worst = std::fmax(worst, std::fabs(static_cast<double>(cg[i]) - cg1[i]) / std::fmax(std::fabs(cg1[i]), 1e-3 * peak_c));
+            worst = std::fmax(worst, std::fabs(static_cast<double>(cg[i]) - cg1[i]) / std::fmax(std::fabs(cg1[i]), 1e-2 * peak_c));
         sh.verify = worst;
         sh.samples = total_samples.load();
         hpx_ctx_sm_counts(ctx, &sh.usable_sms, &sh.total_sms);
@@ -278,6 +288,17 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
         hpx_comm_info(comm, &r, &w, &ver);
         sh.nccl_version = ver;
     }
+    if (a.mode != 0 && rank == 0) {
+        sh.band_row0.resize(a.gpus); sh.band_rows.resize(a.gpus); sh.wedges.resize(2 * a.gpus); sh.cuts.resize(a.gpus + 1);
+        hpx_shard_bands(shard, sh.band_row0.data(), sh.band_rows.data(), sh.wedges.data(), sh.cuts.data(), nullptr, nullptr);
+    }
+    if (a.mode != 0) {
+        size_t out = 0, in = 0;
+        hpx_shard_bands(shard, nullptr, nullptr, nullptr, nullptr, &out, &in);
+        sh.send_mb[rank] = out * 4.0 / 1e6;
+        sh.recv_mb[rank] = in * 4.0 / 1e6;
+    }
+    if (a.mode == 2) SCHECK(hpx_shard_set_result(shard, HPX_SHARD_RESULT_OWNED));
     for (int pass = 0; pass < 2; ++pass) {   // pass 0: the real step; pass 1: the same without its collectives
         SCHECK(hpx_shard_set_reduce(shard, pass == 0 ? 1 : 0));
         for (int i = 0; i < a.warmup; ++i) SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
@@ -310,6 +331,7 @@ int run_shard(const ShardArgs& a) {
     sh.volume = &volume;
     sh.dl = &dl;
     sh.ms.assign(a.gpus, 0.0); sh.ms_no_reduce.assign(a.gpus, 0.0); sh.status.assign(a.gpus, 0);
+    sh.send_mb.assign(a.gpus, 0.0); sh.recv_mb.assign(a.gpus, 0.0);
     std::barrier<> sync(a.gpus);
     std::vector<std::thread> threads;
     for (int r = 0; r < a.gpus; ++r) threads.emplace_back([&, r] {
@@ -320,7 +342,21 @@ int run_shard(const ShardArgs& a) {
     double ms = 0, ms0 = 0;
     for (int r = 0; r < a.gpus; ++r) { ms = std::fmax(ms, sh.ms[r]); ms0 = std::fmax(ms0, sh.ms_no_reduce[r]); }
     const double total = static_cast<double>(a.w) * a.w * a.steps;
-    std::printf("{\"mode\": \"shard\", \"gpus\": %d, \"groups\": %u, \"reserve_sms\": %u, \"usable_sms\": %u, \"total_sms\": %u, "
+    auto list = [](const char* key, const auto& v) {
+        std::printf("\"%s\": [", key);
+        for (size_t i = 0; i < v.size(); ++i) std::printf("%s%.6g", i ? ", " : "", static_cast<double>(v[i]));
+        std::printf("], ");
+    };
+    std::printf("{");
+    list("ms_per_rank", sh.ms); list("ms_per_rank_without_collectives", sh.ms_no_reduce);
+    if (a.mode != 0) {
+        list("band_row0", sh.band_row0); list("band_rows", sh.band_rows); list("wedges", sh.wedges); list("owner_cuts", sh.cuts);
+        list("send_mb", sh.send_mb); list("recv_mb", sh.recv_mb);
+    }
+    std::printf("\"sharding\": \"%s\", ", a.mode == 0 ? "interleaved tile rows, slab all-reduces behind a signalled backward"
+                                           : a.mode == 1 ? "balanced bands, sparse exchange, replicated result"
+                                                         : "balanced bands, sparse exchange, owned result (reduce-scatter)");
+    std::printf("\"mode\": \"shard\", \"gpus\": %d, \"groups\": %u, \"reserve_sms\": %u, \"usable_sms\": %u, \"total_sms\": %u, "
                 "\"max_ctas\": %d, \"nccl_version\": %d, \"ms_per_step\": %.4f, \"ms_per_step_without_collectives\": %.4f, "
                 "\"msamples_per_s\": %.1f, \"samples\": %.0f, \"verify_max_rel_err_vs_single_gpu\": %.3e}\n",
                 a.gpus, a.groups, a.reserve, sh.usable_sms, sh.total_sms, a.max_ctas, sh.nccl_version, ms, ms0, total / (ms * 1e-3) / 1e6,
@@ -335,14 +371,15 @@ int main(int argc, char** argv) {
     if (argc >= 12 && std::string(argv[1]) == "shard") {
         ShardArgs a{std::atoi(argv[2]), static_cast<uint32_t>(std::atoi(argv[3])), static_cast<uint32_t>(std::atoi(argv[4])),
                     std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]), std::atoi(argv[8]),
-                    static_cast<uint32_t>(std::atoi(argv[9])), static_cast<uint32_t>(std::atoi(argv[10])), std::atoi(argv[11])};
+                    static_cast<uint32_t>(std::atoi(argv[9])), static_cast<uint32_t>(std::atoi(argv[10])), std::atoi(argv[11]),
+                    argc >= 13 ? std::atoi(argv[12]) : 0};
         return run_shard(a);
     }
     if (argc >= 2 && std::string(argv[1]) == "selftest") return run_selftest();
     if (argc >= 8 && std::string(argv[1]) == "bench")
         return run_bench(std::atoi(argv[2]), static_cast<uint32_t>(std::atoi(argv[3])), static_cast<uint32_t>(std::atoi(argv[4])),
-                         std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]));
-    std::fprintf(stderr, "usage: %s selftest | bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> | "
-                         "shard <grid n> <width> <steps> <stratified> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas>\n", argv[0]);
+                         std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]), argc >= 9 && std::atoi(argv[8]) != 0);
+    std::fprintf(stderr, "usage: %s selftest | bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> [pin 0|1] | "
+                         "shard <grid n> <width> <steps> <stratified> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas> [mode 0|1|2]\n", argv[0]);
     return 2;
 }

@@ -44,6 +44,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
@@ -73,11 +76,15 @@ const NcclApi& nccl() {
         a.CommInitRankConfig = reinterpret_cast<decltype(a.CommInitRankConfig)>(sym("ncclCommInitRankConfig"));
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(sym("ncclCommDestroy"));
         a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(sym("ncclAllReduce"));
+        a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
+        a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
+        a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
         a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
         a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(sym("ncclGetVersion"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GroupStart && a.GroupEnd && a.GetErrorString;
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Send && a.Recv && a.Broadcast && a.GroupStart &&
+               a.GroupEnd && a.GetErrorString;
         if (!a.ok) a.why = "the NCCL library lacks a required symbol";
         return a;
     }();
@@ -134,6 +141,17 @@ struct hpx_shard {
     std::vector<uint32_t> group_rows;                                // image rows per group
     cudaEvent_t ev_zero = nullptr;
     bool reduce = true;
+    // ---- band mode (hpx_shard_create_bands) ----
+    bool bands = false;
+    int result = HPX_SHARD_RESULT_REPLICATED;
+    std::vector<uint32_t> band_row0, band_rows;                     // per rank: first image row (inside the ROI), rows
+    std::vector<std::pair<int32_t, int32_t>> wedges;                // per rank: slabs its rows can touch [lo, hi)
+    std::vector<int32_t> cuts;                                      // world + 1: rank r owns slabs [cuts[r], cuts[r + 1])
+    struct Xfer { int peer; int32_t lo, hi; size_t staging_off; };  // slab range, offset (floats) in `staging`
+    std::vector<Xfer> sends, recvs;
+    float* staging = nullptr;
+    int32_t hull_lo = 0, hull_hi = 0;                               // slabs ANY rank can touch
+    size_t dl_offset_floats = 0;                                    // this rank's rows inside the frame's dL/dI
 };
 
 namespace {
@@ -181,6 +199,78 @@ std::vector<std::vector<std::pair<int32_t, int32_t>>> final_slab_runs(const std:
             else runs.emplace_back(s, s + 1);
         }
         out.push_back(std::move(runs));
+    }
+    return out;
+}
+
+
+// ---- band mode helpers ------------------------------------------------------------------------------------------
+// dst[i] += src[i] (float4 lanes; counts are multiples of 4 floats: a slab is nx * ny * 4 floats)
+__global__ void add_slabs_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 a = dst[i];
+        const float4 b = __ldg(src + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        dst[i] = a;
+    }
+}
+
+// Marching work of one image row, in samples: steps of its rays that lie inside the unit cube (what the kernels spend
+// their time on; steps outside are skipped by range) plus a small constant per ray.  Host restatement of make_ray /
+// cube_interval on every 4th pixel -- an ESTIMATE that only places the band boundaries, no result depends on it.
+double row_work(const FrameParams& p, uint32_t gy, uint32_t x0, uint32_t w) {
+    const CameraParams& c = p.cam;
+    const MarchParams& m = p.march;
+    const float t_last = std::min(m.t_far, m.t_near + static_cast<float>(m.uniform_count) * m.dt);
+    double work = 0.0;
+    uint32_t n = 0;
+    for (uint32_t px = x0; px < x0 + w; px += 4, ++n) {
+        float qx = (static_cast<float>(px) + 0.5f - c.cx) / c.fx, qy = (static_cast<float>(gy) + 0.5f - c.cy) / c.fy;
+        if (c.ortho) qx = qy = 0.0f;
+        const float v[3] = {c.r00 * qx + c.r01 * qy + c.r02, c.r10 * qx + c.r11 * qy + c.r12, c.r20 * qx + c.r21 * qy + c.r22};
+        const float len = std::sqrt(std::max(v[0] * v[0] + v[1] * v[1] + v[2] * v[2], 1e-30f));
+        const float o[3] = {c.ox, c.oy, c.oz};
+        float t_in = m.t_near, t_out = t_last;
+        for (int i = 0; i < 3 && t_in < t_out; ++i) {
+            const float d = v[i] / len;
+            if (std::fabs(d) > 1e-12f) {
+                const float a = (0.0f - o[i]) / d, b = (1.0f - o[i]) / d;
+                t_in = std::max(t_in, std::min(a, b));
+                t_out = std::min(t_out, std::max(a, b));
+            } else if (o[i] < 0.0f || o[i] > 1.0f) {
+                t_out = t_in;
+            }
+        }
+        work += 8.0 + (t_out > t_in && m.dt > 0.0f ? static_cast<double>((t_out - t_in) / m.dt) : 0.0);
+    }
+    return n != 0 ? work * static_cast<double>(w) / n : 0.0;
+}
+
+// Contiguous bands of CTA tile rows with (nearly) equal work.
+std::vector<RowBand> balanced_bands(const FrameParams& p, const hp_plan_desc& d, uint32_t world) {
+    const uint32_t unit = kTileH * kWarpsY, h = d.roi.height;
+    const uint32_t units = (h + unit - 1) / unit;
+    std::vector<double> cum(units + 1, 0.0);
+    for (uint32_t u = 0; u < units; ++u) {
+        double w = 0.0;
+        for (uint32_t r = u * unit; r < std::min(h, (u + 1) * unit); r += 2)   // every 2nd row of the unit
+            w += row_work(p, d.roi.y + r, d.roi.x, d.roi.width);
+        cum[u + 1] = cum[u] + w;
+    }
+    std::vector<RowBand> out;
+    uint32_t prev = 0;
+    for (uint32_t b = 0; b < world; ++b) {
+        uint32_t cut = units;
+        if (b + 1 < world) {
+            const double target = cum[units] * (b + 1) / world;
+            cut = static_cast<uint32_t>(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+            if (cut > 0 && target - cum[cut - 1] < cum[cut] - target) --cut;   // nearer boundary
+            cut = std::min(units, std::max(prev, cut));
+        }
+        const uint32_t r0 = std::min(prev * unit, h), r1 = std::min(cut * unit, h);
+        out.push_back(RowBand{r0, r1 - r0});   // y0 relative to the ROI
+        prev = cut;
     }
     return out;
 }
@@ -369,6 +459,246 @@ HP_API hp_status hpx_shard_create(hpx_comm* c, const hp_plan* full_plan, hpx_gri
     return HP_STATUS_SUCCESS;
 }
 
+
+// ---- one frame over all ranks, contiguous bands -------------------------------------------------------------------
+// Rank r renders a contiguous band of image rows; the bands are cut so that every rank has the same marching work
+// (balanced_bands).  A band's rays stay inside a wedge of the volume, so with the gradient block laid out slab by slab
+// along the world axis the image rows advance along, rank r's backward touches ONE contiguous slab range (its wedge) --
+// about 2 / world of the grid -- and the exchange is sparse: every slab has an owner (cuts between neighbouring
+// wedges); a rank sends the parts of its wedge it does not own to their owners (point-to-point, a few hundred MB at
+// 512^3 / 8 GPUs instead of a 2.1 GB all-reduce), the owners add what they receive in rank order (deterministic).
+// HPX_SHARD_RESULT_OWNED stops there: rank r holds the finished sum of slabs [cuts[r], cuts[r+1]) -- the hand-over for a
+// slab-sharded optimiser.  HPX_SHARD_RESULT_REPLICATED then broadcasts every owned range, so that all ranks hold the
+// whole summed gradient (what an all-reduce leaves behind).
+HP_API hp_status hpx_shard_create_bands(hpx_comm* c, const hp_plan* full_plan, hpx_grid* g, uint32_t result,
+                                        hpx_shard** out_shard) {
+    DV_RANGE("hpx_shard_create_bands");
+    if (c == nullptr || full_plan == nullptr || g == nullptr || out_shard == nullptr ||
+        (result != HPX_SHARD_RESULT_OWNED && result != HPX_SHARD_RESULT_REPLICATED))
+        return HP_STATUS_INVALID_ARGUMENT;
+    if (full_plan->ctx != c->ctx || g->ctx != c->ctx) {
+        set_last_error("communicator, plan and grid must come from one context");
+        return HP_STATUS_INVALID_ARGUMENT;
+    }
+    if (!g->linear || g->clamp || scatter_params(*g).unit_bbox == 0u) {
+        set_last_error("hpx_shard needs a linear OOB-zero field whose scatter box is the unit cube (hpx_frame_bounds)");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_ENTER(c->ctx);
+    hpx_shard* s = new (std::nothrow) hpx_shard();
+    if (s == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    s->comm = c;
+    s->grid = g;
+    s->bands = true;
+    s->result = static_cast<int>(result);
+    auto fail = [&](hp_status st) {
+        hpx_shard_release(s);
+        return st;
+    };
+    const hp_plan_desc& d = full_plan->desc;
+    const float down[3] = {std::fabs(d.camera.c2w[1]), std::fabs(d.camera.c2w[5]), std::fabs(d.camera.c2w[9])};
+    s->slow_axis = down[0] > down[1] ? (down[0] > down[2] ? 0 : 2) : (down[1] >= down[2] ? 1 : 2);
+    hp_status st = hpx_grid_set_grad_layout(g, s->slow_axis, &s->slab_floats, &s->n_slabs);
+    if (st != HP_STATUS_SUCCESS) return fail(st);
+    if (cudaEventCreateWithFlags(&s->ev_zero, cudaEventDisableTiming) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event"));
+
+    const int world = c->world, me = c->rank;
+    const std::vector<RowBand> bands = balanced_bands(frame_params_from_plan(*full_plan), d, static_cast<uint32_t>(world));
+    // every rank derives every band's wedge itself (same inputs, same code: all ranks agree without talking)
+    for (int r = 0; r < world; ++r) {
+        s->band_row0.push_back(bands[r].y0);
+        s->band_rows.push_back(bands[r].rows);
+        std::pair<int32_t, int32_t> wedge(0, 0);
+        if (bands[r].rows != 0) {
+            hp_plan_desc bd = d;
+            bd.roi.y = d.roi.y + bands[r].y0;
+            bd.roi.height = bands[r].rows;
+            bd.max_rays = 0;
+            bd.max_samples = 0;
+            hp_plan* band_plan = nullptr;
+            hpx_frame* frame = nullptr;
+            int32_t box[6] = {0, 0, 0, 0, 0, 0};
+            st = hp_plan_create(c->ctx, &bd, &band_plan);
+            if (st == HP_STATUS_SUCCESS) st = hpx_frame_create(band_plan, &frame);
+            if (st == HP_STATUS_SUCCESS) st = hpx_frame_bounds(frame, g, box);
+            if (st == HP_STATUS_SUCCESS && r == me) {
+                // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
+                st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
+                s->plan = band_plan;
+                s->frame = frame;
+                s->dl_offset_floats = static_cast<size_t>(bands[r].y0) * d.roi.width * 3;
+            } else {
+                hpx_frame_release(frame);
+                hp_plan_release(band_plan);
+            }
+            if (st != HP_STATUS_SUCCESS) return fail(st);
+            if (box[3 + s->slow_axis] > 0) wedge = {box[s->slow_axis], box[s->slow_axis] + box[3 + s->slow_axis]};
+        }
+        s->wedges.push_back(wedge);
+    }
+    // owners: cut half way through the overlap (or gap) of neighbouring wedges; empty wedges inherit their predecessor's end
+    s->cuts.assign(static_cast<size_t>(world) + 1, 0);
+    s->cuts[static_cast<size_t>(world)] = s->n_slabs;
+    int32_t prev_hi = 0;
+    s->hull_lo = s->n_slabs;
+    s->hull_hi = 0;
+    for (int r = 0; r < world; ++r) {
+        const bool empty = s->wedges[r].first >= s->wedges[r].second;
+        const int32_t lo = empty ? prev_hi : s->wedges[r].first, hi = empty ? prev_hi : s->wedges[r].second;
+        if (r > 0) s->cuts[r] = std::min(s->n_slabs, std::max(s->cuts[r - 1], (lo + prev_hi) / 2));
+        if (!empty) {
+            s->hull_lo = std::min(s->hull_lo, lo);
+            s->hull_hi = std::max(s->hull_hi, hi);
+        }
+        prev_hi = std::max(prev_hi, hi);
+    }
+    if (s->hull_hi < s->hull_lo) s->hull_lo = s->hull_hi = 0;
+    auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
+        return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
+    };
+    size_t staging_floats = 0;
+    for (int o = 0; o < world; ++o) {
+        if (o == me) continue;
+        const auto out = overlap(me, o);
+        if (out.first < out.second) s->sends.push_back(hpx_shard::Xfer{o, out.first, out.second, 0});
+        const auto in = overlap(o, me);
+        if (in.first < in.second) {
+            s->recvs.push_back(hpx_shard::Xfer{o, in.first, in.second, staging_floats});
+            staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
+        }
+    }
+    if (staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
+        return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)"));
+    *out_shard = s;
+    return HP_STATUS_SUCCESS;
+}
+
+// Host-only (works without a GPU): the bands hpx_shard_create_bands cuts for `world` ranks.
+HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, uint32_t* out_row0, uint32_t* out_rows, double* out_work) {
+    DV_RANGE("hpx_plan_balanced_bands");
+    if (plan == nullptr || world == 0 || world > 4096 || out_row0 == nullptr || out_rows == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    const FrameParams p = frame_params_from_plan(*plan);
+    const std::vector<RowBand> bands = balanced_bands(p, plan->desc, world);
+    for (uint32_t r = 0; r < world; ++r) {
+        out_row0[r] = bands[r].y0;
+        out_rows[r] = bands[r].rows;
+        if (out_work != nullptr) {
+            double w = 0.0;
+            for (uint32_t y = bands[r].y0; y < bands[r].y0 + bands[r].rows; ++y) w += row_work(p, plan->desc.roi.y + y, plan->desc.roi.x, plan->desc.roi.width);
+            out_work[r] = w;
+        }
+    }
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_shard_set_result(hpx_shard* s, uint32_t result) {
+    DV_RANGE("hpx_shard_set_result");
+    if (s == nullptr || !s->bands || (result != HPX_SHARD_RESULT_OWNED && result != HPX_SHARD_RESULT_REPLICATED))
+        return HP_STATUS_INVALID_ARGUMENT;
+    s->result = static_cast<int>(result);
+    return HP_STATUS_SUCCESS;
+}
+
+HP_API hp_status hpx_shard_bands(const hpx_shard* s, uint32_t* out_row0, uint32_t* out_rows, int32_t* out_wedges, int32_t* out_cuts,
+                                 size_t* out_send_floats, size_t* out_recv_floats) {
+    DV_RANGE("hpx_shard_bands");
+    if (s == nullptr || !s->bands) return HP_STATUS_INVALID_ARGUMENT;
+    for (size_t r = 0; r < s->band_rows.size(); ++r) {
+        if (out_row0) out_row0[r] = s->band_row0[r];
+        if (out_rows) out_rows[r] = s->band_rows[r];
+        if (out_wedges) {
+            out_wedges[2 * r] = s->wedges[r].first;
+            out_wedges[2 * r + 1] = s->wedges[r].second;
+        }
+    }
+    if (out_cuts) std::copy(s->cuts.begin(), s->cuts.end(), out_cuts);
+    size_t out = 0, in = 0;
+    for (const auto& x : s->sends) out += static_cast<size_t>(x.hi - x.lo) * s->slab_floats;
+    for (const auto& x : s->recvs) in += static_cast<size_t>(x.hi - x.lo) * s->slab_floats;
+    if (out_send_floats) *out_send_floats = out;
+    if (out_recv_floats) *out_recv_floats = in;
+    return HP_STATUS_SUCCESS;
+}
+
+// The slabs this rank owns, as they lie in the gradient block (hpx_grid_set_grad_layout order, {dr,dg,db,dsigma} per
+// voxel): [first_slab, first_slab + slabs) x slab_floats floats at *out_device_ptr.
+HP_API hp_status hpx_shard_owned(const hpx_shard* s, float** out_device_ptr, int32_t* out_first_slab, int32_t* out_slabs,
+                                 size_t* out_slab_floats, int32_t* out_slow_axis) {
+    DV_RANGE("hpx_shard_owned");
+    if (s == nullptr || !s->bands) return HP_STATUS_INVALID_ARGUMENT;
+    float* block = nullptr;
+    size_t floats = 0;
+    DV_TRY(hpx_grid_grad_buffer(s->grid, &block, &floats));
+    const int32_t lo = s->cuts[static_cast<size_t>(s->comm->rank)], hi = s->cuts[static_cast<size_t>(s->comm->rank) + 1];
+    if (out_device_ptr) *out_device_ptr = block + static_cast<size_t>(lo) * s->slab_floats;
+    if (out_first_slab) *out_first_slab = lo;
+    if (out_slabs) *out_slabs = hi - lo;
+    if (out_slab_floats) *out_slab_floats = s->slab_floats;
+    if (out_slow_axis) *out_slow_axis = s->slow_axis;
+    return HP_STATUS_SUCCESS;
+}
+
+static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t flags) {
+    hpx_comm* c = s->comm;
+    cudaStream_t main = c->ctx->stream, side = c->side;
+    const int me = c->rank;
+    float* block = nullptr;
+    size_t floats = 0;
+    DV_TRY(hpx_grid_grad_buffer(s->grid, &block, &floats));
+    const size_t S = s->slab_floats;
+    if (flags & HPX_BACKWARD_ZERO) {
+        // only what this rank can write or must hand out as a finished sum: its wedge and the slabs it owns; cleared on the
+        // side stream while the forward kernel runs
+        const int32_t lo = std::min(s->wedges[me].first < s->wedges[me].second ? s->wedges[me].first : s->cuts[me], s->cuts[me]);
+        const int32_t hi = std::max(s->wedges[me].first < s->wedges[me].second ? s->wedges[me].second : s->cuts[me + 1], s->cuts[me + 1]);
+        DV_CUDA(cudaEventRecord(c->ev_main, main));
+        DV_CUDA(cudaStreamWaitEvent(side, c->ev_main, 0));
+        if (hi > lo) DV_CUDA(cudaMemsetAsync(block + static_cast<size_t>(lo) * S, 0, static_cast<size_t>(hi - lo) * S * sizeof(float), side));
+        DV_CUDA(cudaMemsetAsync(block + floats - 16, 0, 16 * sizeof(float), side));
+        DV_CUDA(cudaEventRecord(s->ev_zero, side));
+    }
+    if (s->frame != nullptr) DV_TRY(hpx_forward(s->frame, s->grid));
+    if (flags & HPX_BACKWARD_ZERO) DV_CUDA(cudaStreamWaitEvent(main, s->ev_zero, 0));
+    if (s->frame != nullptr)
+        DV_TRY(hpx_backward(s->frame, s->grid, dL_dI_device + s->dl_offset_floats, HP_MEMSPACE_DEVICE, flags & ~HPX_BACKWARD_ZERO));
+    if (c->world == 1 || !s->reduce) return HP_STATUS_SUCCESS;
+    // ---- sparse reduce-scatter: wedge parts to their owners
+    if (!s->sends.empty() || !s->recvs.empty()) {
+        DV_NCCL(nccl().GroupStart());
+        ncclResult_t r = ncclSuccess;
+        for (const auto& x : s->sends)
+            if (r == ncclSuccess)
+                r = nccl().Send(block + static_cast<size_t>(x.lo) * S, static_cast<size_t>(x.hi - x.lo) * S, ncclFloat32, x.peer, c->comm, main);
+        for (const auto& x : s->recvs)
+            if (r == ncclSuccess)
+                r = nccl().Recv(s->staging + x.staging_off, static_cast<size_t>(x.hi - x.lo) * S, ncclFloat32, x.peer, c->comm, main);
+        const ncclResult_t e = nccl().GroupEnd();
+        if (r != ncclSuccess) return nccl_fail(r, "ncclSend/ncclRecv(slabs)");
+        if (e != ncclSuccess) return nccl_fail(e, "ncclGroupEnd(slabs)");
+        for (const auto& x : s->recvs) {   // ascending peer order: the sum does not depend on arrival order
+            const size_t n4 = static_cast<size_t>(x.hi - x.lo) * S / 4;
+            add_slabs_kernel<<<static_cast<unsigned>(std::min<size_t>((n4 + 255) / 256, 148 * 8)), 256, 0, main>>>(
+                reinterpret_cast<float4*>(block + static_cast<size_t>(x.lo) * S), reinterpret_cast<const float4*>(s->staging + x.staging_off), n4);
+        }
+        DV_CUDA(cudaGetLastError());
+    }
+    if (flags & HPX_BACKWARD_CAMERA) DV_NCCL(nccl().AllReduce(block + floats - 16, block + floats - 16, 16, ncclFloat32, ncclSum, c->comm, main));
+    if (s->result != HPX_SHARD_RESULT_REPLICATED) return HP_STATUS_SUCCESS;
+    // ---- all-gather of the finished sums: every owner broadcasts its slabs inside the touched hull
+    DV_NCCL(nccl().GroupStart());
+    ncclResult_t r = ncclSuccess;
+    for (int o = 0; o < c->world && r == ncclSuccess; ++o) {
+        const int32_t lo = std::max(s->cuts[o], s->hull_lo), hi = std::min(s->cuts[o + 1], s->hull_hi);
+        if (lo >= hi) continue;
+        float* p = block + static_cast<size_t>(lo) * S;
+        r = nccl().Broadcast(p, p, static_cast<size_t>(hi - lo) * S, ncclFloat32, o, c->comm, main);
+    }
+    const ncclResult_t e = nccl().GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(r, "ncclBroadcast(slabs)");
+    if (e != ncclSuccess) return nccl_fail(e, "ncclGroupEnd(broadcast)");
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API void hpx_shard_release(hpx_shard* s) {
     DV_RANGE("hpx_shard_release");
     if (s == nullptr) return;
@@ -378,6 +708,7 @@ HP_API void hpx_shard_release(hpx_shard* s) {
         cudaStreamSynchronize(s->comm->ctx->stream);
         if (s->comm->side != nullptr) cudaStreamSynchronize(s->comm->side);
         if (s->ev_zero != nullptr) cudaEventDestroy(s->ev_zero);
+        cudaFree(s->staging);
     }
     hpx_frame_release(s->frame);
     hp_plan_release(s->plan);
@@ -424,6 +755,7 @@ HP_API hp_status hpx_shard_step(hpx_shard* s, const float* dL_dI_device, uint32_
     if (s == nullptr || dL_dI_device == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     hpx_comm* c = s->comm;
     DV_ENTER(c->ctx);
+    if (s->bands) return band_step(s, dL_dI_device, flags);
     cudaStream_t main = c->ctx->stream, side = c->side;
     const bool collect = c->world > 1 && s->reduce;
     if (flags & HPX_BACKWARD_ZERO) {

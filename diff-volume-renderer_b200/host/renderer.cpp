@@ -61,8 +61,10 @@ struct Renderer::Impl {
     hp_samp_t samp{};
     hp_intl_t intl{};
 
-    // Result vectors the caller hands in again and again (a training loop reuses its ForwardResult / BackwardResult)
-    // are page-locked the second time they are seen: from then on the read-back is direct DMA into the vector.
+    // RenderOptions::pin_result_buffers: result vectors the caller hands in again and again (a training loop reuses
+    // its ForwardResult / BackwardResult) are page-locked the second time they are seen: from then on the read-back is
+    // direct DMA into the vector.  Never done unasked: a vector freed while registered (a ForwardResult local to a
+    // frame loop, reference tests/render/test_smoke_animation.cpp:324) would leave a stale registration behind.
     std::vector<std::pair<void*, size_t>> seen, pinned;
 
     ~Impl() {
@@ -71,8 +73,10 @@ struct Renderer::Impl {
         for (void* p : {d_rays, d_ws, d_img, d_grads, d_dl}) hpx_device_free(ctx, p);
     }
 
+    bool pin_enabled{false};   // RenderOptions::pin_result_buffers
+
     void PinIfRepeated(void* ptr, size_t bytes) {
-        if (ptr == nullptr || bytes < (size_t(1) << 20)) return;   // small results are not worth a registration
+        if (!pin_enabled || ptr == nullptr || bytes < (size_t(1) << 20)) return;   // small results are not worth a registration
         for (auto it = pinned.begin(); it != pinned.end(); ++it) {
             if (it->first == ptr && it->second >= bytes) return;
             if (it->first == ptr) {   // same address, grown: register afresh
@@ -105,6 +109,7 @@ struct Renderer::Impl {
 Renderer::Renderer(const Context& ctx, const Plan& plan, RenderOptions options)
     : ctx_(&ctx), plan_(&plan), options_(options), impl_(new Impl()) {
     impl_->ctx = ctx.handle();
+    impl_->pin_enabled = options.pin_result_buffers;
 }
 
 Renderer::~Renderer() { delete impl_; }

@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libdvren_hp.so")
 HPX_CTX_EXT_MAGIC = 0x42323030
 HPX_CTX_EXT2_MAGIC = 0x42323031
 HPX_COMM_ID_BYTES = 128
+HPX_SHARD_RESULT_OWNED, HPX_SHARD_RESULT_REPLICATED = 1, 2
 HPX_BACKWARD_GRID, HPX_BACKWARD_CAMERA, HPX_BACKWARD_ZERO = 1, 2, 4
 HPX_BACKWARD_SCATTER_PER_RAY, HPX_BACKWARD_SCATTER_MERGED, HPX_BACKWARD_DETERMINISTIC = 0x10, 0x20, 0x40
 
@@ -104,6 +105,11 @@ HPX_FUNCTIONS = {
     "hpx_shard_set_reduce": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_shard_layout": (C.c_int, [C.c_void_p, P(C.c_int32), P(C.c_uint32), P(C.c_uint32), P(C.c_int32)]),
     "hpx_shard_release": (None, [C.c_void_p]),
+    "hpx_shard_create_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_void_p)]),
+    "hpx_shard_set_result": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "hpx_plan_balanced_bands": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_uint32), P(C.c_double)]),
+    "hpx_shard_bands": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_size_t)]),
+    "hpx_shard_owned": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_int32)]),
 }
 
 _lib = None

@@ -27,6 +27,11 @@ struct RenderOptions {
     // additive: fill BackwardResult::camera with d/d c2w (the reference leaves it zero,
     // src/render/renderer.cpp:408,443) and expose d/d {fx,fy,cx,cy} via intrinsics_gradient()
     bool camera_gradients{false};
+    // additive: page-lock the caller's result vectors (ForwardResult / BackwardResult members of >= 1 MiB) the second
+    // time the same buffer is handed in, so that the read-back is direct DMA into them.  OPT-IN, because the renderer
+    // cannot see a vector being freed: only for callers that reuse ONE set of result objects and keep them alive (and
+    // un-resized) for as long as the Renderer lives -- a training loop.  Off: results are copied into pageable memory.
+    bool pin_result_buffers{false};
 };
 
 struct WorkspaceInfo {

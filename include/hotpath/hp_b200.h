@@ -270,6 +270,36 @@ HP_API hp_status hpx_shard_set_reduce(hpx_shard* shard, int32_t enabled);
  * (arrays of 16 / 32 entries; any pointer may be NULL). */
 HP_API hp_status hpx_shard_layout(const hpx_shard* shard, int32_t* out_slow_axis, uint32_t* out_groups,
                                   uint32_t* out_group_rows, int32_t* out_slab_ranges);
+/* ---- the same frame in contiguous, work-balanced bands with a SPARSE exchange ---------------------------------------
+ * hpx_shard_create_bands: rank r renders one contiguous band of image rows; the bands are cut so that every rank has the
+ * same marching work (in-cube samples of its rays).  The rays of a band stay inside a wedge of the volume, so with the
+ * gradient block laid out slab by slab along the world axis the image rows advance along, a rank's backward touches one
+ * contiguous slab range (about 2 / world of the grid) and nothing else.  Every slab has an OWNER (cut half way through
+ * the overlap of neighbouring wedges).  hpx_shard_step then runs: clear wedge + owned slabs -> forward -> backward ->
+ * the parts of the wedge the rank does not own go point-to-point to their owners, which add them in rank order.
+ *   HPX_SHARD_RESULT_OWNED       stops there: rank r holds the finished sum of ITS slabs (hpx_shard_owned) -- a reduce-scatter,
+ *                                the hand-over for a slab-sharded optimiser; a few hundred MB exchanged at 512^3 / 8 GPUs
+ *   HPX_SHARD_RESULT_REPLICATED  additionally broadcasts every owned range: all ranks hold the whole summed gradient, as after
+ *                                an all-reduce (hpx_grid_read_grad / hpx_grid_grad_buffer as usual)
+ * Same field restrictions as hpx_shard_create.  All ranks must pass the same plan, grid shape and result mode. */
+#define HPX_SHARD_RESULT_OWNED      1u
+#define HPX_SHARD_RESULT_REPLICATED 2u
+HP_API hp_status hpx_shard_create_bands(hpx_comm* comm, const hp_plan* full_frame_plan, hpx_grid* grid, uint32_t result,
+                                        hpx_shard** out_shard);
+HP_API hp_status hpx_shard_set_result(hpx_shard* shard, uint32_t result);
+/* Host-only (works without a GPU): the bands hpx_shard_create_bands cuts for `world` ranks -- first row inside the ROI and
+ * rows per rank, multiples of the 8-row CTA tile; out_work (may be NULL): estimated marching work per band in samples. */
+HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, uint32_t* out_row0, uint32_t* out_rows,
+                                         double* out_work);
+/* Per rank (arrays of `world` entries; any pointer may be NULL): first image row inside the plan's ROI and rows of its band,
+ * wedge [lo, hi) in slabs (2 * world ints), owner cuts (world + 1 ints: rank r owns slabs [cuts[r], cuts[r + 1])); floats
+ * this rank sends / receives per step in the reduce-scatter part. */
+HP_API hp_status hpx_shard_bands(const hpx_shard* shard, uint32_t* out_row0, uint32_t* out_rows, int32_t* out_wedges,
+                                 int32_t* out_cuts, size_t* out_send_floats, size_t* out_recv_floats);
+/* Device view of the slabs this rank owns inside the gradient block ({dr,dg,db,dsigma} per voxel, slab order of
+ * hpx_grid_set_grad_layout with *out_slow_axis slowest): slabs [first, first + count) x slab_floats floats. */
+HP_API hp_status hpx_shard_owned(const hpx_shard* shard, float** out_device_ptr, int32_t* out_first_slab, int32_t* out_slabs,
+                                 size_t* out_slab_floats, int32_t* out_slow_axis);
 HP_API void      hpx_shard_release(hpx_shard* shard);
 
 #ifdef __cplusplus

@@ -163,3 +163,45 @@ def test_two_rank_gloo_sharded_step_matches_unsharded():
     assert res[0] == "ok", res
     assert res[1], "sharded image differs from the unsharded one (must be bit-exact)"
     assert res[2] and res[3], "sample counts do not add up"
+
+
+# ---- balanced bands of the C library (host-only entry point, no GPU needed) ---------------------
+@pytest.mark.parametrize("width,height,steps,world,roi", [(2048, 2048, 1024, 8, None), (1024, 1024, 512, 4, None), (1024, 1024, 512, 2, None),
+                                                          (320, 200, 64, 3, (16, 24, 256, 150)), (64, 20, 16, 8, None)])
+def test_library_balanced_bands(width, height, steps, world, roi):
+    """hpx_plan_balanced_bands (what hpx_shard_create_bands cuts): contiguous, complete, on CTA tile rows, and equal
+    in marching work -- in-cube steps of the band's rays, recounted here from the oracle's ray generator."""
+    import dvren_b200 as D
+    ctx = D.Context(device=0)
+    desc = S.bench_plan(width, height, steps, stratified=False, roi=roi)
+    plan = D.Plan(ctx, desc)
+    row0, rows, work = (C.c_uint32 * world)(), (C.c_uint32 * world)(), (C.c_double * world)()
+    D.check("hpx_plan_balanced_bands", ctx.lib.hpx_plan_balanced_bands(plan.handle, world, row0, rows, work))
+    h = plan.desc.roi.height
+    y = 0
+    for r in range(world):
+        assert row0[r] == y
+        assert rows[r] % 8 == 0 or row0[r] + rows[r] == h
+        y += rows[r]
+    assert y == h
+    # independent recount on a coarse pixel lattice: slab-method cube interval of pinhole rays from the same camera
+    d = plan.desc
+    K, c2w = np.array(d.camera.K[:], np.float64), np.array(d.camera.c2w[:], np.float64).reshape(3, 4)
+    ys = np.arange(d.roi.y, d.roi.y + h, dtype=np.float64)
+    xs = np.arange(d.roi.x, d.roi.x + d.roi.width, 8, dtype=np.float64)
+    qx, qy = np.meshgrid((xs + 0.5 - K[2]) / K[0], (ys + 0.5 - K[5]) / K[4])
+    v = np.stack([qx, qy, np.ones_like(qx)], -1) @ c2w[:, :3].T
+    v /= np.linalg.norm(v, axis=-1, keepdims=True)
+    o = c2w[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a, b = (0.0 - o) / v, (1.0 - o) / v
+    t_in = np.maximum(np.minimum(a, b).max(-1), d.t_near)
+    t_out = np.minimum(np.maximum(a, b).min(-1), min(d.t_far, d.t_near + d.sampling.max_steps * d.sampling.dt))
+    per_row = (np.clip(t_out - t_in, 0, None) / d.sampling.dt + 8.0).sum(-1)
+    mine = np.array([per_row[row0[r]:row0[r] + rows[r]].sum() for r in range(world)])
+    lib = np.array(work[:])
+    busy = mine > 0
+    np.testing.assert_allclose(lib[busy] / lib[busy].sum(), mine[busy] / mine[busy].sum(), rtol=0.03, atol=1e-3)
+    if h >= 64 * world:   # enough tile rows to balance: nobody more than 6 % above the mean
+        assert mine.max() <= 1.06 * mine.mean()
+    plan.close(); ctx.close()
