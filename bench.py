@@ -1,16 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- Msamples/s of the dvren hot path (fused forward + backward to the dense grid).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
 
-A "step" is one pass of the hot path over one batch of synthetic input: ray generation ->
-fused march / integrate / compose -> reverse-march backward with grid scatter (-> NCCL all-reduce
-of the packed gradient block when N > 1).  Default workload = BASELINE.json configs[1]:
-256^3 grid, 1024x1024, stratified sampling, 512 steps (537 M samples), on one B200.  For N > 1
-every rank renders its own view of an N-view batch against a replicated grid (weak scaling) and
-the ranks all-reduce the gradients; `value` counts the samples of all ranks.
+A "step" is one pass of the hot path over one batch of synthetic input: ray generation -> fused
+march / integrate / compose -> reverse-march backward with the grid scatter (-> exchange of the
+gradient sums when N > 1).
 
-Prints ONE JSON line (see README / DESIGN.md section "Measurement" for every key).
+Default workload for EVERY N = BASELINE.json configs[2], the configuration the scaling target is
+quoted on: ONE 2048x2048 frame over a 512^3 grid, fixed sampling, 1024 steps (2^32 samples per
+step).  N = 1 runs it on one B200 (it fits: 2.1 GB grid + 2.1 GB gradient + 2.1 GB checkpoints);
+N > 1 is STRONG scaling of that same frame through the library's band sharding (hpx_shard_*,
+include/hotpath/hp_b200.h): work-balanced row bands, grid replicated, sparse slab exchange.  The
+N = 1 line also carries the numbers of BASELINE configs[1] (256^3 / 1024^2 / stratified, the round-1
+default) under "c2".
+
+Prints ONE JSON line (README / DESIGN.md section "Measurement" explain every key).
 """
 from __future__ import annotations
 
@@ -33,7 +38,8 @@ def emit(line: dict):
 
 
 REPO = os.path.dirname(os.path.abspath(__file__))
-sys.path[:0] = [os.path.join(REPO, "diff-volume-renderer_b200", "python")]
+PKG = os.path.join(REPO, "diff-volume-renderer_b200")
+sys.path[:0] = [os.path.join(PKG, "python")]
 
 CONFIGS = {
     # name: grid n, image W, steps, stratified, description
@@ -52,17 +58,23 @@ CONFIGS = {
 }
 METRIC = "Msamples/s fwd+bwd (fused forward + backward adjoint to the dense sigma/color grid)"
 UNIT = "Msamples/s"
-# algorithmic bytes per live sample: 8 corners x 16 B gathered; + 8 x 16 B gradient reds
-BYTES_FWD_PER_SAMPLE = 128
-BYTES_BWD_PER_SAMPLE = 256
 
 
 def read_peaks():
+    """Roofline denominators: HBM from the driver's MEASURED_PEAKS.json (fallback: B200_PROFILING.md), the SM-side ones
+    from this repo's own probe (tools/mem_probe.cu, results committed as profiles/r01_mem_probe.json)."""
+    out = {"hbm_gbs": 6650.0, "hbm_source": "fallback (B200_PROFILING.md)"}
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            out["hbm_gbs"], out["hbm_source"] = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    with open(os.path.join(REPO, "profiles", "r01_mem_probe.json")) as f:
+        probe = json.load(f)
+    out["l2_gather_gbs"] = next(r["gbs"] for r in probe["gather_random_16B"] if r["footprint_mb"] == 64)
+    out["l1_gather_gbs"] = max(r["gbs"] for r in probe["gather_warp_local_16B"])
+    out["red_lane_gops"] = max(r["gops"] for r in probe["red_v4_f32"])
+    out["sm_side_source"] = "profiles/r01_mem_probe.json (tools/mem_probe.cu on a B200: 16-B gathers, L2-resident 64 MB random / warp-local window)"
+    return out
 
 
 class ClockSampler:
@@ -126,100 +138,209 @@ class ClockSampler:
 class CudaArrayView:
     """Exposes a raw device pointer to torch (zero copy) via __cuda_array_interface__."""
 
-    def __init__(self, ptr: int, n_floats: int):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
-def run_ours(args):
+def device_hashed_volume(torch, n, kind, dev, seed=1234):
+    """synth.hashed_volume (u(i, s) = top 24 bits of mix64((s ^ i) + GOLDEN) / 2^24) evaluated on the GPU with
+    wrapping int64 arithmetic -- identical bytes, seconds instead of minutes of host hashing at 512^3."""
+    def lsr(x, k):
+        return (x >> k) & ((1 << (64 - k)) - 1)
+
+    def s64(v):
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def unit(idx, s):
+        x = (idx ^ s) + s64(0x9E3779B97F4A7C15)
+        x = (x ^ lsr(x, 30)) * s64(0xBF58476D1CE4E5B9)
+        x = (x ^ lsr(x, 27)) * s64(0x94D049BB133111EB)
+        x = x ^ lsr(x, 31)
+        return lsr(x, 40).to(torch.float32) * (1.0 / 16777216.0)
+
+    idx = torch.arange(n * n * n, dtype=torch.int64, device=dev)
+    scale = {"thin": 2.0, "dense": 40.0}[kind]
+    sigma = (unit(idx, seed) * scale).reshape(n, n, n).contiguous()
+    color = torch.stack([unit(idx, seed + 1 + c) for c in range(3)], dim=-1).reshape(n, n, n, 3).contiguous()
+    return sigma, color
+
+
+def make_grid(D, S, torch, ctx, n, kind, dev):
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import dvren_b200 as D
-    import synth as S
-
-    cfg = CONFIGS[args.config]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus != world:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL's kernels on a HIGH-PRIORITY stream: when a collective is issued while a long rendering kernel still has
-        # CTAs queued (overlapped strong scaling), its few CTAs get the next free slots instead of waiting for the tail
-        opts = dist.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-
-    import sharding as SH
-
-    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
-    sigma, color = S.hashed_volume(n, "thin")       # no early termination: live samples == samples
-    ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
-    rows_mode = args.sharding == "rows" and world > 1
-    if args.sharding in ("pipeline", "signalled", "views-overlap"):
-        return run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank)
-    if rows_mode:
-        # strong scaling: ONE frame cut into row bands (SURVEY 8e), global pixel ids + global ray-index base
-        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
-        band = SH.row_bands(full, world)[rank]
-        plan = D.Plan(ctx, SH.band_desc(full, band))
-    else:
-        # weak scaling: every rank renders its own view of a `world`-view batch.  The views sit 2.5 degrees apart on an arc
-        # centred on the canonical camera, so that per-rank work is (nearly) the same: kernel time depends on the view
-        # direction relative to the grid's x-fastest layout (profiles/README.md: 2.25 ms at 0 deg, 2.83 ms at 90 deg)
-        # and a full orbit would measure that spread, not the scaling.
-        plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank - (world - 1) / 2.0, views=144))
-    grid = D.Grid(ctx, sigma, color)
+    if not getattr(make_grid, "checked", False):   # the device generator against the numpy one, once
+        a, b = device_hashed_volume(torch, 8, kind, dev)
+        ha, hb = S.hashed_volume(8, kind)
+        assert np.array_equal(a.cpu().numpy(), ha) and np.array_equal(b.cpu().numpy(), hb), "device volume generator drifted"
+        make_grid.checked = True
+    sigma, color = device_hashed_volume(torch, n, kind, dev)
+    torch.cuda.synchronize()
+    grid = D.Grid(ctx, sigma.data_ptr(), color.data_ptr(), device_shape=(n, n, n))
+    ctx.synchronize()
     del sigma, color
+    torch.cuda.empty_cache()
+    return grid
+
+
+def roofline(cfg_name, bwd_kernel, fwd_ms, bwd_ms, cube, live, rays, touched, peaks):
+    """Three levels, each a fraction that stays <= ~1 and can be recomputed from this object + profiles/:
+      hbm  compulsory HBM bytes (the touched voxels once per pass) / time / measured HBM copy bandwidth
+      l2   SURVEY 8d two-level model: algorithmic gather/red bytes / the measured L2-resident gather bandwidth -> T_roof;
+           frac = T_roof / T_measured.  > 1 means L1 absorbs the re-touches of a pixel tile (it does).
+      l1   the same algorithmic bytes, counted for IN-CUBE samples only (samples outside the cube gather nothing),
+           / time / the warp-local 16-B gather ceiling of tools/mem_probe -- the level that binds (ncu: L1/LSU data pipe)
+    """
+    tj, l1_pct = {}, {}
+    tpath = os.path.join(REPO, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f).get(cfg_name, {})
+        l1_pct = tj.get("_l1_wavefront_pct", {})
+    wf = tj.get("_wavefronts_per_request", {})
+
+    def level(ms, alg_per_sample, per_ray, hbm_bytes, kernel):
+        t = ms * 1e-3
+        alg_cube = alg_per_sample * cube + per_ray * rays
+        traffic = tj.get(kernel)
+        o = {"kernel": kernel, "ms": ms,
+             "algorithmic_bytes_per_launch": alg_cube,
+             "l1": {"achieved_gbs": alg_cube / t / 1e9, "peak_gbs": peaks["l1_gather_gbs"], "frac": alg_cube / t / 1e9 / peaks["l1_gather_gbs"],
+                    "lsu_data_pipe_pct_ncu": l1_pct.get(kernel), "wavefronts_per_request_ncu": wf.get(kernel)},
+             "l2": {"t_roof_ms": alg_cube / (peaks["l2_gather_gbs"] * 1e9) * 1e3, "peak_gbs": peaks["l2_gather_gbs"],
+                    "frac": alg_cube / (peaks["l2_gather_gbs"] * 1e9) / t},
+             "hbm": {"compulsory_bytes": hbm_bytes, "achieved_gbs": hbm_bytes / t / 1e9, "peak_gbs": peaks["hbm_gbs"],
+                     "frac": hbm_bytes / t / 1e9 / peaks["hbm_gbs"], "traffic_ncu": traffic,
+                     "traffic_over_compulsory": (traffic / hbm_bytes) if traffic else None}}
+        return o
+
+    fwd = level(fwd_ms, 128, 24, 16 * touched + 24 * rays, "lean_forward_kernel")
+    bwd = level(bwd_ms, 256, 12, 48 * touched + 12 * rays, bwd_kernel)
+    return {"bound": "l1_lsu", "kernel": bwd_kernel, "achieved": bwd["l1"]["achieved_gbs"], "peak": peaks["l1_gather_gbs"],
+            "unit": "GB/s", "frac": bwd["l1"]["frac"], "traffic": bwd["hbm"]["traffic_ncu"],
+            "peak_source": "warp-local 16-B gather ceiling measured by tools/mem_probe.cu (" + peaks["sm_side_source"] + "); HBM: " + peaks["hbm_source"],
+            "units_per_launch": {"in_cube_live_samples": cube, "live_samples": live, "rays": rays, "touched_voxels": touched},
+            "algorithmic_bytes_per_unit": "SURVEY 8(d): forward 128 B per in-cube live sample (8 corners x 16 B) + 24 B per ray; "
+                                          "backward 256 B per in-cube live sample (128 B re-gather + 8 x 16 B reds) + 12 B per ray; "
+                                          "compulsory HBM: 16 B per touched voxel forward, 48 B backward",
+            "note": "neither kernel is HBM-bound (hbm.frac of a few percent): a pixel tile re-touches the same voxels and L1 "
+                    "absorbs it, so the binding level is the SM's L1/LSU data pipe (ncu: lsu_data_pipe_pct_ncu)",
+            "backward": bwd, "forward": fwd}
+
+
+def renderer_e2e(cfg, iters=5, warmup=2):
+    """The drop-in path a reference caller links: dvren::Renderer::Forward + Backward through libdvren.so with std::vector
+    results (apps/dvren_bench.cpp), pageable as the reference's results are, and with the opt-in result pinning."""
+    exe = os.path.join(PKG, "dvren_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "dvren_bench not built"}
+    out = {}
+    for key, pin in (("pageable", 0), ("pinned_opt_in", 1)):
+        try:
+            r = subprocess.run([exe, "bench", str(cfg["grid"]), str(cfg["width"]), str(cfg["steps"]), "1" if cfg["stratified"] else "0",
+                                str(iters), str(warmup), str(pin)], capture_output=True, text=True, timeout=600)
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            out[key] = {"value": j["samples"] / (j["ms_per_step"] * 1e-3) / 1e6, "ms_per_step": j["ms_per_step"],
+                        "forward_kernel_ms": j["forward_kernel_ms"], "forward_readback_ms": j["forward_readback_ms"],
+                        "backward_kernel_ms": j["backward_kernel_ms"], "backward_readback_ms": j["backward_readback_ms"],
+                        "d2h_bytes_per_step": j["d2h_bytes_per_step"], "h2d_bytes_per_step": j["h2d_bytes_per_step"]}
+        except Exception as e:   # never let the side measurement kill the bench line
+            out[key] = {"error": repr(e)[:200]}
+    out["what"] = "dvren::Renderer::Forward + Backward (C++ surface, host clock, every host<->device copy inside), " + cfg["workload"]
+    return out
+
+
+class Env:
+    """Process-wide plumbing: torch.distributed for rendezvous / barriers / max-over-ranks, one CUDA stream, one hp_ctx."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import dvren_b200 as D
+        self.torch, self.dist, self.D = torch, dist, D
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if args.gpus != self.world and self.world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        torch.cuda.set_stream(self.stream)
+        self.ctx = D.Context(device=self.local_rank, stream=self.stream.cuda_stream)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, k, warm, sampler=None):
+        """W untimed steps, then EXACTLY k steps between CUDA events on the launching stream, barrier + synchronize on both
+        sides, max over ranks.  Returns total milliseconds."""
+        torch = self.torch
+        for _ in range(warm):
+            fn()
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler is not None:
+            sampler.mark_begin()
+        a.record(self.stream)
+        for _ in range(k):
+            fn()
+        b.record(self.stream)
+        self.barrier()
+        if sampler is not None:
+            sampler.mark_end()
+        ms = torch.tensor([a.elapsed_time(b)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def close(self):
+        self.ctx.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def measure_single(env, cfg, cfg_name, args, sampler=None, with_renderer=False):
+    """One GPU, one frame: resident step, end-to-end step through the C ABI with HOST buffers, per-kernel times, roofline."""
+    import hp_abi as A
+    import synth as S
+    torch, D, ctx, dev, stream = env.torch, env.D, env.ctx, env.dev, env.stream
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"]))
+    grid = make_grid(D, S, torch, ctx, n, "thin", dev)      # thin: no early termination, live samples == samples
     frame = D.Frame(plan)
-    if rows_mode:
-        frame.set_view(None, plan.desc.seed, band.ray_index_base)
     n_rays = plan.n_rays
     g_host = torch.from_numpy(S.hashed_image_grad(n_rays)).pin_memory()
     g_dev = g_host.to(dev, non_blocking=True)
     grad_ptr, grad_floats = grid.grad_buffer()
-    grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
     img = frame.image_ptrs()
     pixels = W * W
-    reducer = SH.GradientAllReduce(grad_view) if world > 1 else None
     planes = [torch.as_tensor(CudaArrayView(img.image.data, pixels * 3), device=dev),
               torch.as_tensor(CudaArrayView(img.trans.data, pixels), device=dev),
               torch.as_tensor(CudaArrayView(img.opacity.data, pixels), device=dev),
               torch.as_tensor(CudaArrayView(img.depth.data, pixels), device=dev)]
     planes_host = [torch.empty(p.shape, dtype=p.dtype).pin_memory() for p in planes]
     flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    lib = ctx.lib
 
     def step_resident():
         frame.forward(grid)
         frame.backward(grid, g_dev.data_ptr(), flags, device=True)
-        if reducer is not None:
-            reducer()
 
-    # e2e: the same step through the C ABI with HOST buffers (pinned), i.e. what dvren::Renderer
-    # Forward/Backward move per step (reference renderer.hpp:50-66): dL/dI host->device; image planes
-    # and the un-interleaved sigma / colour gradient grids device->host.  The image planes are read from
-    # the frame's device views (hpx_frame_image) on a side stream while the backward runs; the gradient
-    # read blocks.
-    import ctypes as C
-    import hp_abi as A
-    lib = ctx.lib
+    # e2e: the same step through the C ABI with HOST buffers (pinned) -- what dvren::Renderer Forward/Backward move per
+    # step (reference renderer.hpp:50-66): dL/dI host->device; image planes and the un-interleaved sigma / colour gradient
+    # grids device->host.  The image planes are read on a side stream while the backward runs; the gradient read blocks.
     sg_host = torch.empty(grid.voxels, dtype=torch.float32).pin_memory()
     cg_host = torch.empty(grid.voxels * 3, dtype=torch.float32).pin_memory()
     cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
     mask_host = torch.empty(pixels, dtype=torch.int32).pin_memory()
-
     side = torch.cuda.Stream(device=dev)
     fwd_done = torch.cuda.Event()
     mask_dev = torch.as_tensor(CudaArrayView(img.hitmask.data, pixels), device=dev).view(torch.int32)
 
     def read_planes_async():
-        """Image planes device -> pinned host on a side stream, so that the copy runs under the backward kernel."""
         fwd_done.record(stream)
         with torch.cuda.stream(side):
             side.wait_event(fwd_done)
@@ -231,271 +352,301 @@ def run_ours(args):
         D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
         read_planes_async()
         D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
-        if reducer is not None:
-            reducer()
         D.check("hpx_grid_read_grad", lib.hpx_grid_read_grad(grid.handle, sg_host.data_ptr(), cg_host.data_ptr(),
                                                              cam_host.data_ptr(), A.HP_MEMSPACE_HOST))
         stream.wait_stream(side)
 
     def step_e2e_device_grads():
-        """Same, but the gradient block stays in HBM for a device-side optimiser (hpx_grid_grad_buffer): host
-        traffic is dL/dI in, the five image planes out."""
+        """Same, but the gradient block stays in HBM for a device-side optimiser (hpx_grid_grad_buffer)."""
         D.check("hpx_forward", lib.hpx_forward(frame.handle, grid.handle))
         read_planes_async()
         D.check("hpx_backward", lib.hpx_backward(frame.handle, grid.handle, g_host.data_ptr(), A.HP_MEMSPACE_HOST, flags))
-        if reducer is not None:
-            reducer()
         stream.wait_stream(side)
         ctx.synchronize()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k, warm, sampler=None):
-        for _ in range(warm):
-            fn()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if sampler is not None:
-            sampler.mark_begin()
-        a.record(stream)
-        for _ in range(k):
-            fn()
-        b.record(stream)
-        barrier()
-        if sampler is not None:
-            sampler.mark_end()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    total_ms = timed(step_resident, args.steps, args.warmup, sampler if rank == 0 else None)
-    clocks = sampler.stop() if rank == 0 else None
+    k = args.steps
+    total_ms = env.timed(step_resident, k, args.warmup, sampler)
     counts = frame.counts()
     samples, live = counts["samples"], counts["live_samples"]
-    e2e_ms = timed(step_e2e, args.steps, max(args.warmup, 1))
-    e2e_dev_ms = timed(step_e2e_device_grads, args.steps, 1)
-    # kernel-level timing for the roofline lines (same stream, CUDA events, after the runs above)
-    fwd_ms = timed(lambda: frame.forward(grid), args.steps, 1)
-    bwd_ms = timed(lambda: frame.backward(grid, g_dev.data_ptr(), D.HPX_BACKWARD_GRID, device=True), args.steps, 1)
-
-    ms_per_step = total_ms / args.steps
-    total_samples = samples
-    if world > 1:
-        ts = torch.tensor([samples], dtype=torch.int64, device=dev)
-        dist.all_reduce(ts)
-        total_samples = int(ts.item())
-    value = total_samples / (ms_per_step * 1e-3) / 1e6
-    e2e_value = total_samples / (e2e_ms / args.steps * 1e-3) / 1e6
-    peak, peak_src = read_peaks()
-    bwd_bytes = BYTES_BWD_PER_SAMPLE * live + 12 * n_rays
-    fwd_bytes = BYTES_FWD_PER_SAMPLE * live + 24 * n_rays
-    bwd_gbs = bwd_bytes / (bwd_ms / args.steps * 1e-3) / 1e9
-    fwd_gbs = fwd_bytes / (fwd_ms / args.steps * 1e-3) / 1e9
+    cube = frame.cube_samples(grid)
+    touched = grid.touched_voxels()
+    e2e_ms = env.timed(step_e2e, k, max(1, min(args.warmup, 2)))
+    e2e_dev_ms = env.timed(step_e2e_device_grads, k, 1)
+    fwd_ms = env.timed(lambda: frame.forward(grid), k, 1)
+    bwd_ms = env.timed(lambda: frame.backward(grid, g_dev.data_ptr(), D.HPX_BACKWARD_GRID, device=True), k, 1)
     bwd_kernel = "lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged" else "lean_backward_kernel"
-    traffic = fwd_traffic = None
-    l1_pct = {}
-    tpath = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tj = json.load(f).get(args.config, {})
-        traffic, fwd_traffic = tj.get(bwd_kernel), tj.get("lean_forward_kernel")
-        l1_pct = tj.get("_l1_wavefront_pct", {})
-
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if rows_mode else "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
-                   "rays_per_gpu": n_rays, "samples_per_gpu_step": samples, "live_samples_per_gpu_step": live,
-                   "parallelism": (f"one frame in {world} row bands" if rows_mode else f"{world} views (2.5 deg apart), one per GPU") +
-                                  ", grid replicated, one NCCL all-reduce of the packed gradient block per step"
-                                  if world > 1 else "single GPU",
-                   "allreduce_bytes": int(grad_floats * 4) if world > 1 else 0,
-                   "l2": "inputs larger than L2 (packed grid %d MB + gradient grid %d MB vs 126 MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(g_host.numel() * 4),
-                "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4 + grad_floats * 4),
-                "ms_per_step": e2e_ms / args.steps,
-                "note": "full dvren::Renderer result contract: image planes AND un-interleaved sigma/colour gradient grids "
-                        "copied to host every step (PCIe-bound)",
-                "device_resident_gradients": {
-                    "value": total_samples / (e2e_dev_ms / args.steps * 1e-3) / 1e6, "ms_per_step": e2e_dev_ms / args.steps,
-                    "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4)}},
-        "gpu_launches": 2 * args.steps,
-        "clocks": clocks,
-        "fwd": {"ms": fwd_ms / args.steps, "msamples_s": samples / (fwd_ms / args.steps * 1e-3) / 1e6},
-        "bwd": {"ms": bwd_ms / args.steps, "msamples_s": samples / (bwd_ms / args.steps * 1e-3) / 1e6},
-        "roofline": {"bound": "hbm", "kernel": bwd_kernel, "achieved": bwd_gbs, "peak": peak,
-                     "unit": "GB/s", "frac": bwd_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bwd_bytes,
-                     "note": "algorithmic bytes (SURVEY 8d) are gather/scatter bytes at the L1/L2 level: 256 B per live "
-                             "sample for the backward, 128 B for the forward; a pixel tile re-touches the same voxels, "
-                             "so caches absorb them and frac > 1.  Measured DRAM bytes per launch are in `traffic`; "
-                             "the binding resource is the SM's L1/LSU data pipe (l1_wavefront_pct_of_peak, from the ncu "
-                             "capture under profiles/), see DESIGN.md section 5",
-                     "l1_wavefront_pct_of_peak": l1_pct.get(bwd_kernel),
-                     "hbm_frac_of_peak": (traffic / (bwd_ms / args.steps * 1e-3) / 1e9 / peak) if traffic else None,
-                     "forward_kernel": {"kernel": "lean_forward_kernel", "achieved": fwd_gbs, "frac": fwd_gbs / peak,
-                                        "algorithmic_bytes_per_launch": fwd_bytes, "traffic": fwd_traffic,
-                                        "l1_wavefront_pct_of_peak": l1_pct.get("lean_forward_kernel")}},
+    peaks = read_peaks()
+    d2h = int(sum(p.numel() for p in planes_host) * 4 + pixels * 4 + grad_floats * 4)
+    out = {
+        "workload": cfg["workload"], "value": samples / (total_ms / k * 1e-3) / 1e6, "ms_per_step": total_ms / k,
+        "rays": n_rays, "samples": samples, "live_samples": live, "in_cube_live_samples": cube, "touched_voxels": touched,
+        "fwd": {"ms": fwd_ms / k, "msamples_s": samples / (fwd_ms / k * 1e-3) / 1e6},
+        "bwd": {"ms": bwd_ms / k, "msamples_s": samples / (bwd_ms / k * 1e-3) / 1e6, "kernel": bwd_kernel},
+        "e2e": {"value": samples / (e2e_ms / k * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(g_host.numel() * 4),
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / k,
+                "note": "C ABI with pinned HOST buffers, full dvren::Renderer result contract: image planes AND un-interleaved "
+                        "sigma/colour gradient grids copied to host every step (PCIe-bound)",
+                "device_resident_gradients": {"value": samples / (e2e_dev_ms / k * 1e-3) / 1e6, "ms_per_step": e2e_dev_ms / k,
+                                              "d2h_bytes_per_step": int(sum(p.numel() for p in planes_host) * 4 + pixels * 4)}},
+        "roofline": roofline(cfg_name, bwd_kernel, fwd_ms / k, bwd_ms / k, cube, live, n_rays, touched, peaks),
+        "l2": "inputs larger than L2 (packed grid %d MB + gradient grid %d MB vs 126 MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20),
     }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    frame.close(); grid.close(); plan.close()
+    del sg_host, cg_host, planes_host, g_host, g_dev
+    torch.cuda.empty_cache()
+    if with_renderer:
+        out["e2e"]["renderer"] = renderer_e2e(cfg)
+    return out
+
+
+def base_line(env, args, cfg, value, ms_per_step, scaling):
+    return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic"}
+
+
+def run_single(env, args):
+    cfg = CONFIGS[args.config]
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    m = measure_single(env, cfg, args.config, args, sampler, with_renderer=args.config == "c2")
+    clocks = sampler.stop()
+    line = base_line(env, args, cfg, m["value"], m["ms_per_step"], "strong")
+    line["config"] = {"workload": m["workload"], "volume": "hashed thin (sigma = 2u, no early termination)", "rays": m["rays"],
+                      "samples_per_step": m["samples"], "live_samples_per_step": m["live_samples"],
+                      "in_cube_live_samples_per_step": m["in_cube_live_samples"], "parallelism": "single GPU", "l2": m["l2"]}
+    line.update({"e2e": m["e2e"], "gpu_launches": 2 * args.steps, "clocks": clocks, "fwd": m["fwd"], "bwd": m["bwd"],
+                 "roofline": m["roofline"]})
+    if args.config == "c3" and not args.no_c2:
+        c2 = measure_single(env, CONFIGS["c2"], "c2", args, None, with_renderer=True)
+        line["c2"] = {k: c2[k] for k in ("workload", "value", "ms_per_step", "fwd", "bwd", "e2e", "roofline", "samples",
+                                         "in_cube_live_samples", "touched_voxels")}
+    if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
-    if rank == 0:
-        emit(line)
-    frame.close(); grid.close(); plan.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    emit(line)
 
 
-def run_pipelined(args, cfg, ctx, sigma, color, stream, dev, world, rank):
-    """Strong scaling of ONE frame with the gradient all-reduce hidden behind the rendering (sharding.PipelinedFrame):
-    row groups, interleaved tile rows inside a group, per-group voxel boxes reduced on a side stream."""
+def run_sharded(env, args):
+    """N > 1: ONE frame of the configuration, strong scaling, through the library's sharding (hp_b200.h hpx_comm / hpx_shard):
+    work-balanced contiguous row bands (default) or interleaved tile rows; grid replicated."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import dvren_b200 as D
-    import sharding as SH
     import synth as S
-
+    torch, dist, D, ctx, dev, stream = env.torch, env.dist, env.D, env.ctx, env.dev, env.stream
+    world, rank = env.world, env.rank
+    cfg = CONFIGS[args.config]
     n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
-    weak = args.sharding == "views-overlap"
-    if weak:   # every rank its own view (2.5 degrees apart, like the default weak-scaling run), all-reduce hidden behind the backward
-        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=rank - (world - 1) / 2.0, views=144)
-    else:
-        full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
-    grid = D.Grid(ctx, sigma, color)
-    del sigma, color
+    # rendezvous: rank 0's NCCL id travels over torch.distributed
+    uid = torch.zeros(D.HPX_COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(D.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    comm = D.Comm(ctx, bytes(uid.cpu().numpy().tobytes()), rank, world)
+    full = S.bench_plan(W, W, steps, stratified=cfg["stratified"])
+    plan = D.Plan(ctx, full)
+    grid = make_grid(D, S, torch, ctx, n, "thin", dev)
+    bands = args.sharding == "bands"
+    shard = D.Shard(comm, plan, grid, bands="replicated") if bands else \
+        D.Shard(comm, plan, grid, [0.72 ** g for g in range(args.groups)])
+    layout = shard.layout()
     g_host = torch.from_numpy(S.hashed_image_grad(W * W)).pin_memory()
     g_dev = g_host.to(dev, non_blocking=True)
-    groups = [float(v) for v in args.group_split.split(",")] if args.group_split else args.groups
-    if weak:
-        pf = SH.SignalledFrame(D, ctx, grid, full, groups, world, rank, dev, stream, interleave=False)
-    else:
-        cls = SH.SignalledFrame if args.sharding == "signalled" else SH.PipelinedFrame
-        pf = cls(D, ctx, grid, full, groups, world, rank, dev, stream)
-    flags = D.HPX_BACKWARD_GRID
-    cam_host = torch.empty(16, dtype=torch.float32).pin_memory()
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    grad_ptr, grad_floats = grid.grad_buffer()
+    block = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
 
     def step():
-        pf.step(g_dev.data_ptr(), flags)
+        shard.step(g_dev.data_ptr(), flags)
 
-    def step_e2e():
-        g_dev.copy_(g_host, non_blocking=True)
-        pf.step(g_dev.data_ptr(), flags)
-        cam_host.copy_(pf.block[-16:], non_blocking=True)
-        (pf.frame if hasattr(pf, "frame") else pf.parts[0]["frame"]).read()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k, warm):
-        for _ in range(warm):
-            fn()
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
-        for _ in range(k):
-            fn()
-        b.record(stream)
-        barrier()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
-    # correctness first: the pipelined, all-reduced gradient against a plain single-GPU full-frame backward (rank 0)
+    # correctness first: every rank must hold the gradient a single GPU computes for the whole frame (rank 0 checks)
     step()
-    barrier()
+    env.barrier()
     verify = None
-    if rank == 0 and not weak:   # (weak mode sums DIFFERENT views: no single-GPU frame to compare with)
-        got = pf.block.clone()
-        plan = D.Plan(ctx, full)
-        frame = D.Frame(plan)
-        frame.forward(grid)
-        frame.backward(grid, g_dev.data_ptr(), D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO, device=True)
+    if rank == 0:
+        got = block.clone()
+        fplan = D.Plan(ctx, full)
+        frame = D.Frame(fplan)
+        gref = make_grid(D, S, torch, ctx, n, "thin", dev)
+        gref.set_grad_layout("xyz".index(layout["slow_axis"]))
+        frame.forward(gref)
+        frame.backward(gref, g_dev.data_ptr(), flags, device=True)
         torch.cuda.synchronize()
-        ref = pf.block
+        rptr, rfloats = gref.grad_buffer()
+        ref = torch.as_tensor(CudaArrayView(rptr, rfloats), device=dev)
+        # both are float32 red accumulations of the same contributions in different orders (each kernel has its own oracle
+        # parity tests, tests/test_gpu_lean.py); this catches a slab summed twice or not at all, hence the 1e-2 floor
         scale = torch.maximum(ref.abs(), 1e-2 * ref.abs().max())
         verify = float(((got - ref).abs() / scale).max().item())
-        frame.close(); plan.close()
-    barrier()
+        del got, ref
+        frame.close(); gref.close(); fplan.close()
+        torch.cuda.empty_cache()
+    env.barrier()
 
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    sampler = ClockSampler(env.local_rank)
     if rank == 0:
         sampler.start()
-    total_ms = timed(step, args.steps, args.warmup)
+    k = args.steps
+    results = {}
+    # the headline is the all-reduce contract of SURVEY 8(e): after the step EVERY rank holds the whole summed gradient
+    total_ms = env.timed(step, k, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = timed(step_e2e, args.steps, 1)
-    pf.reduce = False                      # the same step without the collectives: what the all-reduce still costs
-    no_reduce_ms = timed(step, args.steps, 1)
-    pf.reduce = True
-    samples = torch.tensor([pf.samples], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(samples)
-    total = int(samples.item())
-    ms_per_step = total_ms / args.steps
-    line = {"metric": METRIC, "value": total / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
-                       "parallelism": f"one frame, {len(pf.ranges)} row groups ({args.sharding}), tile rows interleaved over {world} GPUs; gradient "
-                                      f"block laid out with axis {'xyz'[pf.slow_axis]} slowest, the slabs a finished group leaves "
-                                      "behind all-reduced in place on a side stream while the next group renders",
-                       "slab_ranges": pf.ranges,
-                       "group_rows": [b.rows for b in pf.bands] if hasattr(pf, "bands") else [p["band"].rows for p in pf.parts], "allreduce_bytes": grid.voxels * 16,
-                       "verify_max_rel_err_vs_single_gpu": verify,
-                       "ms_per_step_without_collectives": no_reduce_ms / args.steps,
-                       "l2": "inputs larger than L2"},
-            "e2e": {"value": total / (e2e_ms / args.steps * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(g_host.numel() * 4), "d2h_bytes_per_step": 64 + W * W * 28,
-                    "note": "gradient block stays in HBM (device-side optimiser)"},
-            "gpu_launches": (2 if hasattr(pf, "frame") else 2 * len(pf.parts)) * args.steps, "clocks": clocks}
+    results["replicated"] = total_ms / k
+    total = W * W * steps
+    frame = shard.frame
+    my_samples = frame.counts()["samples"] if frame is not None else 0
+    ts = torch.tensor([my_samples], dtype=torch.int64, device=dev)
+    dist.all_reduce(ts)
+    assert int(ts.item()) == total, (int(ts.item()), total)
+    if bands:
+        shard.set_result("owned")       # reduce-scatter contract: every rank holds the finished sum of the slabs it owns
+        results["owned"] = env.timed(step, k, 1) / k
+    shard.set_reduce(False)
+    results["without_exchange"] = env.timed(step, k, 1) / k
+    shard.set_reduce(True)
+
+    # e2e (owned result, what a slab-sharded optimiser on the host side would consume): per step every rank copies ITS
+    # rows of dL/dI host->device, runs the step, and reads ITS band of the image planes and ITS owned slabs device->host
+    e2e = None
+    if bands:
+        row0, rows = layout["band_row0"][rank], layout["band_rows"][rank]
+        optr, first, count, slab_floats = shard.owned()
+        owned_dev = torch.as_tensor(CudaArrayView(optr, max(count * slab_floats, 1)), device=dev)[:count * slab_floats]
+        owned_host = torch.empty(count * slab_floats, dtype=torch.float32).pin_memory()
+        img = frame.image_ptrs() if frame is not None else None
+        lo, hi = row0 * W, (row0 + rows) * W
+        planes, hosts = [], []
+        if img is not None and rows:
+            for ptr, ch, ts_ in ((img.image.data, 3, "<f4"), (img.trans.data, 1, "<f4"), (img.opacity.data, 1, "<f4"),
+                                 (img.depth.data, 1, "<f4"), (img.hitmask.data, 1, "<u4")):
+                t = torch.as_tensor(CudaArrayView(ptr, W * W * ch, "<f4"), device=dev)[lo * ch:hi * ch]
+                planes.append(t)
+                hosts.append(torch.empty(t.shape, dtype=t.dtype).pin_memory())
+        g_rows_host = g_host.reshape(-1)[lo * 3:hi * 3]
+        g_rows_dev = g_dev.reshape(-1)[lo * 3:hi * 3]
+
+        def step_e2e():
+            g_rows_dev.copy_(g_rows_host, non_blocking=True)
+            shard.step(g_dev.data_ptr(), flags)
+            owned_host.copy_(owned_dev, non_blocking=True)
+            for h, d in zip(hosts, planes):
+                h.copy_(d, non_blocking=True)
+            stream.synchronize()
+
+        e2e_ms = env.timed(step_e2e, k, 1) / k
+        h2d = torch.tensor([g_rows_host.numel() * 4], dtype=torch.int64, device=dev)
+        d2h = torch.tensor([owned_host.numel() * 4 + sum(h.numel() for h in hosts) * 4], dtype=torch.int64, device=dev)
+        dist.all_reduce(h2d)
+        dist.all_reduce(d2h)
+        e2e = {"value": total / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
+               "note": "all ranks together: every rank moves its own rows of dL/dI in and its band of the image planes + the "
+                       "finished gradient sums of the slabs it owns out (packed {dr,dg,db,dsigma} slabs), over its own PCIe link"}
+        shard.set_result("replicated")
+
+    # continuity with round 1: weak scaling of configs[1] (one view of SURVEY 8d's orbit per GPU, whole-block all-reduce in
+    # the library)
+    weak = None
+    if not args.no_c2:
+        weak = run_weak_views(env, args, comm)
+
+    ms = results["replicated"]
+    line = base_line(env, args, cfg, total / (ms * 1e-3) / 1e6, ms, "strong")
+    line["config"] = {
+        "workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
+        "samples_per_step": total,
+        "parallelism": (f"ONE frame in {world} contiguous row bands cut for equal marching work (hpx_shard_create_bands), grid "
+                        "replicated; the gradient block is laid out in slabs along world axis " + layout["slow_axis"] +
+                        ", a band's backward touches one slab wedge; wedge parts go point-to-point (NCCL send/recv over "
+                        "NVLink) to the slab owners, which add them in rank order; then every owner broadcasts its sums: all "
+                        "ranks hold the whole summed gradient, as after an all-reduce") if bands else
+                       (f"ONE frame, tile rows interleaved over {world} GPUs, {args.groups} row groups, slab all-reduces behind a "
+                        "device-signalled backward (hpx_shard_create)"),
+        "layout": layout, "verify_max_rel_err_vs_single_gpu": verify,
+        "ms_per_step_without_exchange": results["without_exchange"],
+        "exchange_bytes_sent_by_rank0": layout.get("send_bytes"), "l2": "inputs larger than L2"}
+    if "owned" in results:
+        line["owned_result"] = {"value": total / (results["owned"] * 1e-3) / 1e6, "ms_per_step": results["owned"],
+                                "what": "same step, stopping at the reduce-scatter: every rank holds the finished sum of the slabs "
+                                        "it owns (hand-over to a slab-sharded optimiser); no broadcast of the sums"}
+    if e2e is not None:
+        line["e2e"] = e2e
+    line["gpu_launches"] = 2 * args.steps
+    line["clocks"] = clocks
+    if weak is not None:
+        line["c2_weak"] = weak
     if rank == 0:
         emit(line)
-    pf.close(); grid.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    shard.close(); comm.close(); grid.close(); plan.close()
 
 
-def run_view_batch(args):
-    """Config 4: a batch of views through ONE captured CUDA graph (forward + backward to the grid AND the camera);
-    the view changes between replays through the frame's device parameter block.  N > 1: views split across ranks."""
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    import dvren_b200 as D
-    import sharding as SH
+def run_weak_views(env, args, comm):
+    """configs[1] weak scaling: rank j renders view j of SURVEY 8(d)'s orbit (360 deg * j / N about the cube centre), then
+    hpx_grid_allreduce_grad sums the whole 268 MB gradient block in the library."""
     import synth as S
+    torch, dist, D, ctx, dev = env.torch, env.dist, env.D, env.ctx, env.dev
+    cfg = CONFIGS["c2"]
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=True, view=env.rank, views=env.world))
+    grid = make_grid(D, S, torch, ctx, n, "thin", dev)
+    frame = D.Frame(plan)
+    g_dev = torch.from_numpy(S.hashed_image_grad(W * W)).to(dev)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    ptr, floats = grid.grad_buffer()
+    block = torch.as_tensor(CudaArrayView(ptr, floats), device=dev)
 
+    def local():
+        frame.forward(grid)
+        frame.backward(grid, g_dev.data_ptr(), flags, device=True)
+
+    def step():
+        local()
+        comm.allreduce_grad(grid)
+
+    # the all-reduced block must equal the sum of the per-view gradients (checked through two independent reductions:
+    # the library's NCCL call against torch.distributed's on a copy)
+    local()
+    mine = block.clone()
+    dist.all_reduce(mine)
+    step()
+    env.barrier()
+    scale = torch.maximum(mine.abs(), 1e-3 * mine.abs().max())
+    err = ((block - mine).abs() / scale).max()
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    ms = env.timed(step, args.steps, 2) / args.steps
+    ms_local = env.timed(local, args.steps, 1) / args.steps
+    total = env.world * W * W * steps
+    out = {"workload": cfg["workload"] + f"; {env.world} views on the orbit of SURVEY 8(d), one per GPU, whole-block all-reduce "
+                                         "(hpx_grid_allreduce_grad)",
+           "scaling": "weak", "value": total / (ms * 1e-3) / 1e6, "ms_per_step": ms, "ms_per_step_without_allreduce": ms_local,
+           "allreduce_bytes": floats * 4, "allreduced_block_vs_sum_of_views_max_rel_err": float(err.item())}
+    del mine, block
+    frame.close(); grid.close(); plan.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_view_batch(env, args):
+    """Configs 4 / 5: a batch of views through ONE captured CUDA graph (forward + backward to the grid [+ camera]); the
+    view changes between replays through the frame's device parameter block.  N > 1: views split across ranks, gradient
+    block all-reduced by the library."""
+    import numpy as np
+    import synth as S
+    torch, dist, D, ctx, dev, stream = env.torch, env.dist, env.D, env.ctx, env.dev, env.stream
+    world, rank = env.world, env.rank
     cfg = CONFIGS[args.config]
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
     n, W, steps, views = cfg["grid"], cfg["width"], cfg["steps"], cfg["views"]
-    ctx = D.Context(device=local_rank, stream=stream.cuda_stream)
-    my_views = SH.views_of_rank(views, world, rank)
+    comm = None
+    if world > 1:
+        uid = torch.zeros(D.HPX_COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(D.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = D.Comm(ctx, bytes(uid.cpu().numpy().tobytes()), rank, world)
+    per = (views + world - 1) // world
+    my_views = list(range(rank * per, min(views, (rank + 1) * per)))
     descs = [S.bench_plan(W, W, steps, stratified=cfg["stratified"], view=v, views=views) for v in my_views]
     plan = D.Plan(ctx, descs[0])
     if cfg.get("device_volume"):
-        # too large to hash on the host in reasonable time: a seeded device generator (same seed on every rank = replicas)
-        gen = torch.Generator(device=dev).manual_seed(1234)
+        gen = torch.Generator(device=dev).manual_seed(1234)   # same seed on every rank = replicas
         sigma = torch.rand((n, n, n), generator=gen, device=dev, dtype=torch.float32) * 2.0
         color = torch.rand((n, n, n, 3), generator=gen, device=dev, dtype=torch.float32)
         torch.cuda.synchronize()
@@ -504,16 +655,13 @@ def run_view_batch(args):
         del sigma, color
         torch.cuda.empty_cache()
     else:
-        sigma, color = S.hashed_volume(n, "thin")
-        grid = D.Grid(ctx, sigma, color)
-        del sigma, color
+        grid = make_grid(D, S, torch, ctx, n, "thin", dev)
     frame = D.Frame(plan)
     g_host = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).pin_memory()
     g_frame = torch.as_tensor(CudaArrayView(frame.grad_input_ptr(), plan.n_rays * 3), device=dev)
     g_frame.copy_(g_host.reshape(-1), non_blocking=True)
     grad_ptr, grad_floats = grid.grad_buffer()
     grad_view = torch.as_tensor(CudaArrayView(grad_ptr, grad_floats), device=dev)
-    reducer = SH.GradientAllReduce(grad_view) if world > 1 else None
     flags = D.HPX_BACKWARD_GRID | (D.HPX_BACKWARD_CAMERA if cfg.get("camera", True) else 0)
     frame.capture(grid, flags)
     cams = [d.camera for d in descs]
@@ -524,64 +672,51 @@ def run_view_batch(args):
         for v, cam in zip(my_views, cams):
             frame.set_view(cam, 42 + v, 0)
             frame.replay()
-        if reducer is not None:
-            reducer()
+        if comm is not None:
+            comm.allreduce_grad(grid)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(stream)
-    for _ in range(args.steps):
-        step()
-    b.record(stream)
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([a.elapsed_time(b)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(ms.item()) / args.steps
-    samples = views * plan.n_rays * steps
-    # e2e: per step the cameras go in (tiny) and the camera gradients + the last image come out; the grid gradient stays in HBM
-    a.record(stream)
-    for _ in range(args.steps):
+    def step_e2e():
         step()
         cam_host.copy_(grad_view[-16:], non_blocking=True)
         frame.read()
-    b.record(stream)
-    barrier()
-    e2e_ms = a.elapsed_time(b) / args.steps
-    line = {"metric": METRIC + (" + camera adjoint" if cfg.get("camera", True) else ""), "value": samples / (ms_per_step * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["workload"], "views": views, "views_per_gpu": len(my_views),
-                       "volume": "device-generated uniform (sigma = 2u)" if cfg.get("device_volume") else "hashed thin (sigma = 2u)",
-                       "samples_per_step": samples, "allreduce_bytes": int(grad_floats * 4) if world > 1 else 0,
-                       "backward_kernel": ("lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged"
-                                           else "lean_backward_kernel") + (" (+ camera adjoint)" if cfg.get("camera", True) else ""),
-                       "l2": "inputs larger than L2 (grid %d MB + gradient %d MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)},
-            "e2e": {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": len(my_views) * 128, "d2h_bytes_per_step": 64 + W * W * 28},
-            "gpu_launches": 4 * len(my_views) * args.steps, "clocks": clocks,
-            "ms_per_view": ms_per_step / len(my_views)}
+
+    sampler = ClockSampler(env.local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_per_step = env.timed(step, args.steps, args.warmup, sampler if rank == 0 else None) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = env.timed(step_e2e, args.steps, 1) / args.steps
+    samples = views * plan.n_rays * steps
+    line = base_line(env, args, cfg, samples / (ms_per_step * 1e-3) / 1e6, ms_per_step, "strong")
+    line["metric"] = METRIC + (" + camera adjoint" if cfg.get("camera", True) else "")
+    line["config"] = {"workload": cfg["workload"], "views": views, "views_per_gpu": len(my_views),
+                      "volume": "device-generated uniform (sigma = 2u)" if cfg.get("device_volume") else "hashed thin (sigma = 2u)",
+                      "samples_per_step": samples, "allreduce_bytes": int(grad_floats * 4) if world > 1 else 0,
+                      "backward_kernel": ("lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged"
+                                          else "lean_backward_kernel") + (" (+ camera adjoint)" if cfg.get("camera", True) else ""),
+                      "l2": "inputs larger than L2 (grid %d MB + gradient %d MB)" % (n ** 3 * 16 >> 20, n ** 3 * 16 >> 20)}
+    line["e2e"] = {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms,
+                   "h2d_bytes_per_step": len(my_views) * 128, "d2h_bytes_per_step": 64 + W * W * 28}
+    line.update({"gpu_launches": 4 * len(my_views) * args.steps, "clocks": clocks, "ms_per_view": ms_per_step / max(len(my_views), 1)})
     if rank == 0:
         emit(line)
-    frame.close(); grid.close(); plan.close(); ctx.close()
-    if world > 1:
-        dist.destroy_process_group()
+    frame.close(); grid.close(); plan.close()
+    if comm is not None:
+        comm.close()
 
 
-def cpu_baseline(cfg, rows: int, threads: int):
-    """The reference's own CPU implementation (oracle/_ref, unmodified, via dvren::Renderer) -- or the
-    oracle port when that library is absent -- timed on a band of `rows` image rows per thread."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline(cfg, rows: int, threads: int, repeats: int = 1):
+    """The reference's own CPU implementation of the path (oracle/_ref: the UNMODIFIED reference compiled here; its hp_ray ->
+    hp_samp_int_fused -> hp_img, hp_diff -> DenseGridField::AccumulateSampleGradients call sequence, oracle/ref_shim.cpp
+    ref_worker_*) -- or the oracle port when that library is absent -- on `threads` host threads, each rendering a band of
+    `rows` image rows of the same workload around the image centre."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import numpy as np
 
@@ -594,25 +729,27 @@ def cpu_baseline(cfg, rows: int, threads: int):
     if not use_ref:
         O.build_oracle()
     results = [None] * threads
-    y_start = (W - rows * threads) // 2
+    y_start = max(0, (W - rows * threads) // 2)
+    workers = [O.RefWorker(sigma, color) for _ in range(threads)] if use_ref else None
 
     def work(t):
         y0 = y_start + t * rows
         desc = S.bench_plan(W, W, steps, stratified=cfg["stratified"], roi=(0, y0, W, rows))
         dl = S.hashed_image_grad(W * rows)
-        t0 = time.perf_counter()
-        if use_ref:
-            r = O.ref_render(desc, sigma, color, dl)
-            assert r["status"] == 0, r["status"]
-            ms = r["forward_ms"] + r["backward_ms"]
-            cnt = r["sample_count"]
-        else:
-            st, rd = O.plan_resolve(desc)
-            gs, gc = O.make_grid(sigma, 1), O.make_grid(color, 3)
-            r = O.render(rd, gs, gc, dl, per_ray=False, frames=True)
-            ms = (time.perf_counter() - t0) * 1e3
-            cnt = r["sample_count"]
-        results[t] = (cnt, ms, (time.perf_counter() - t0) * 1e3)
+        cnt, ms = 0, 0.0
+        for _ in range(repeats):
+            if use_ref:
+                c, f, b = workers[t].run(desc, dl)
+                cnt += c
+                ms += f + b
+            else:
+                t0 = time.perf_counter()
+                st, rd = O.plan_resolve(desc)
+                gs, gc = O.make_grid(sigma, 1), O.make_grid(color, 3)
+                r = O.render(rd, gs, gc, dl, per_ray=False, frames=True)
+                ms += (time.perf_counter() - t0) * 1e3
+                cnt += r["sample_count"]
+        results[t] = (cnt, ms)
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -621,22 +758,25 @@ def cpu_baseline(cfg, rows: int, threads: int):
     for th in ths:
         th.join()
     wall = time.perf_counter() - t0
+    if workers:
+        for w in workers:
+            w.close()
     total = sum(r[0] for r in results)
-    # throughput of the hot path itself: samples / (forward + backward time), slowest thread
-    busy_ms = max(r[1] for r in results)
+    busy_ms = max(r[1] for r in results)   # throughput of the hot path itself: samples / (forward + backward time), slowest thread
     return {"value": total / (busy_ms * 1e-3) / 1e6, "unit": UNIT, "cores": threads,
             "kind": "reference" if use_ref else "port",
-            "sample": f"{threads} band(s) of {rows} rows x {W} px x {steps} steps = {total} samples, "
-                      f"Renderer::Forward+Backward time {busy_ms:.0f} ms (wall incl. setup {wall:.1f} s)"}
+            "sample": f"{threads} band(s) of {rows} rows x {W} px x {steps} steps x {repeats} = {total} samples, reference hp_ray -> "
+                      f"hp_samp_int_fused -> hp_img -> hp_diff -> AccumulateSampleGradients time {busy_ms:.0f} ms (wall {wall:.1f} s)"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation on all host threads, rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """--impl reference: the reference's CPU implementation on all host threads the process may use, rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     cfg = CONFIGS[args.config]
-    threads = max(1, min(os.cpu_count() or 1, args.cpu_threads))
+    threads = host_threads() if args.cpu_threads <= 0 else min(host_threads(), args.cpu_threads)
+    if cfg["grid"] >= 512:
+        threads = min(threads, 24)   # every worker owns a 4.3 GB gradient target at 512^3 (reference DenseGridField)
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(cfg, rows=1, threads=threads)
     t0 = time.perf_counter()
@@ -647,7 +787,7 @@ def run_reference(args):
     base["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -657,28 +797,32 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--cpu-rows", type=int, default=32, help="image rows of the cpu_baseline sample")
-    ap.add_argument("--cpu-rows-ref", type=int, default=8, help="rows per thread per step for --impl reference")
-    ap.add_argument("--cpu-threads", type=int, default=16)
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-rows", type=int, default=16, help="image rows of the cpu_baseline sample")
+    ap.add_argument("--cpu-rows-ref", type=int, default=2, help="rows per thread per step for --impl reference")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="host threads of --impl reference (0 = all the process may use)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sharding", default="views", choices=["views", "rows", "pipeline", "signalled", "views-overlap"],
-                    help="N > 1: one view per GPU (weak scaling, default); one frame cut into row bands (strong); or one "
-                         "frame in row groups with interleaved tile rows and the all-reduce overlapped (strong, pipelined)")
-    ap.add_argument("--groups", type=int, default=2, help="equal row groups of --sharding pipeline")
-    ap.add_argument("--group-split", default="", help="relative heights of the row groups instead, e.g. 0.75,0.25")
+    ap.add_argument("--no-c2", action="store_true", help="skip the configs[1] continuity numbers")
+    ap.add_argument("--sharding", default="bands", choices=["bands", "interleaved"],
+                    help="N > 1: work-balanced row bands with a sparse slab exchange (default), or interleaved tile rows with slab "
+                         "all-reduces behind a device-signalled backward")
+    ap.add_argument("--groups", type=int, default=4, help="row groups of --sharding interleaved")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "ours":
-        args.warmup = 3   # timing rule: at least 3 warm-up steps
     if args.impl == "reference":
-        run_reference(args)
-    elif "views" in CONFIGS[args.config]:
-        run_view_batch(args)
+        return run_reference(args)
+    if args.warmup < 3:
+        args.warmup = 3   # timing rule: at least 3 warm-up steps
+    env = Env(args)
+    if "views" in CONFIGS[args.config]:
+        run_view_batch(env, args)
+    elif env.world == 1:
+        run_single(env, args)
     else:
-        run_ours(args)
+        run_sharded(env, args)
+    env.close()
 
 
 if __name__ == "__main__":

@@ -258,16 +258,31 @@ std::vector<RowBand> balanced_bands(const FrameParams& p, const hp_plan_desc& d,
             w += row_work(p, d.roi.y + r, d.roi.x, d.roi.width);
         cum[u + 1] = cum[u] + w;
     }
+    // smallest cap such that `world` contiguous bands of at most `cap` work cover all units (binary search over the cap,
+    // greedy packing as the feasibility test): minimises the work of the busiest rank
+    auto bands_needed = [&](double cap, std::vector<uint32_t>* cuts) {
+        uint32_t n = 0, start = 0;
+        while (start < units) {
+            uint32_t end = start + 1;   // at least one unit per band
+            while (end < units && cum[end + 1] - cum[start] <= cap) ++end;
+            if (cuts) cuts->push_back(end);
+            start = end;
+            ++n;
+        }
+        return n;
+    };
+    double lo = 0.0, hi = cum[units];
+    for (uint32_t u = 0; u < units; ++u) lo = std::max(lo, cum[u + 1] - cum[u]);
+    for (int it = 0; it < 50 && hi - lo > 1e-6 * hi; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (bands_needed(mid, nullptr) <= world) hi = mid; else lo = mid;
+    }
+    std::vector<uint32_t> cuts;
+    bands_needed(hi, &cuts);
     std::vector<RowBand> out;
     uint32_t prev = 0;
     for (uint32_t b = 0; b < world; ++b) {
-        uint32_t cut = units;
-        if (b + 1 < world) {
-            const double target = cum[units] * (b + 1) / world;
-            cut = static_cast<uint32_t>(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
-            if (cut > 0 && target - cum[cut - 1] < cum[cut] - target) --cut;   // nearer boundary
-            cut = std::min(units, std::max(prev, cut));
-        }
+        const uint32_t cut = b < cuts.size() ? (b + 1 == world ? units : cuts[b]) : units;
         const uint32_t r0 = std::min(prev * unit, h), r1 = std::min(cut * unit, h);
         out.push_back(RowBand{r0, r1 - r0});   // y0 relative to the ROI
         prev = cut;
@@ -524,6 +539,11 @@ HP_API hp_status hpx_shard_create_bands(hpx_comm* c, const hp_plan* full_plan, h
             if (st == HP_STATUS_SUCCESS && r == me) {
                 // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
                 st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
+                // end the launches with the band's CHEAP rows (short tail): last row first when the rays get longer downwards
+                const FrameParams fp = frame_params_from_plan(*full_plan);
+                const double first = row_work(fp, d.roi.y + bands[r].y0, d.roi.x, d.roi.width);
+                const double last = row_work(fp, d.roi.y + bands[r].y0 + bands[r].rows - 1, d.roi.x, d.roi.width);
+                if (st == HP_STATUS_SUCCESS) st = hpx_frame_set_row_order(frame, last > first ? 1 : 0);
                 s->plan = band_plan;
                 s->frame = frame;
                 s->dl_offset_floats = static_cast<size_t>(bands[r].y0) * d.roi.width * 3;

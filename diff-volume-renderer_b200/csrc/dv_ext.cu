@@ -574,6 +574,16 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_
     return HP_STATUS_SUCCESS;
 }
 
+// Order in which the CTAs of this frame's launches take its tile rows (RoiParams::tile_row_reverse).  Results do not
+// depend on it.  Not combined with hpx_backward_signalled, whose row groups count in dispatch order.
+HP_API hp_status hpx_frame_set_row_order(hpx_frame* f, int32_t last_row_first) {
+    DV_RANGE("hpx_frame_set_row_order");
+    if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    f->h_params.roi.tile_row_reverse = last_row_first != 0 ? 1u : 0u;
+    f->params_dirty = true;
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_box[6]) {
     DV_RANGE("hpx_frame_bounds");
     DV_TRY(frame_check_grid(f, g));

@@ -345,7 +345,7 @@ FrameParams frame_params_from_plan(const hp_plan& plan) {
     p.march.uniform_count = plan.uniform_count;
     p.march.seed = d.seed;
     p.march.ray_index_base = 0;
-    p.roi = RoiParams{d.roi.x, d.roi.y, d.roi.width, d.roi.height, d.width, d.height, 1u, 0u};
+    p.roi = RoiParams{d.roi.x, d.roi.y, d.roi.width, d.roi.height, d.width, d.height, 1u, 0u, 0u};
     return p;
 }
 

@@ -37,6 +37,10 @@ struct RoiParams {
     // Interleaving the tile rows of one frame over the GPUs of a box gives every rank the same mix of short and long
     // rays (strong scaling, diff-volume-renderer_b200/python/sharding.py).
     uint32_t tile_row_stride, tile_row_phase;
+    // 1: CTAs take the (owned) tile rows last-to-first.  CTAs are dispatched in blockIdx order, so the rows a launch ends
+    // with decide its tail: a band of a sharded frame whose rays get LONGER towards its last row (the upper half of a
+    // perspective image) finishes with its most expensive rows and idles SMs; reversed, it finishes with the cheap ones.
+    uint32_t tile_row_reverse;
 };
 
 struct FrameParams {

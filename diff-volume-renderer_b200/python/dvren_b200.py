@@ -74,6 +74,7 @@ HPX_FUNCTIONS = {
     "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "hpx_backward_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
     "hpx_frame_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "hpx_frame_set_row_order": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
@@ -443,17 +444,27 @@ class _BorrowedFrame(Frame):
 
 
 class Shard:
-    """hpx_shard: ONE frame rendered by all ranks of a communicator, all-reduce hidden behind the backward."""
+    """hpx_shard: ONE frame rendered by all ranks of a communicator.
 
-    def __init__(self, comm: Comm, plan: Plan, grid: Grid, group_weights):
-        self.comm, self.lib, self.plan, self.grid = comm, comm.lib, plan, grid
+    bands=None   interleaved tile rows, slab all-reduces hidden behind a device-signalled backward (hpx_shard_create)
+    bands="replicated" | "owned"   contiguous work-balanced bands with a sparse point-to-point exchange
+                 (hpx_shard_create_bands); "owned": every rank ends with the finished sum of the slabs it owns."""
+
+    RESULTS = {"owned": HPX_SHARD_RESULT_OWNED, "replicated": HPX_SHARD_RESULT_REPLICATED}
+
+    def __init__(self, comm: Comm, plan: Plan, grid: Grid, group_weights=(1.0,), bands: Optional[str] = None):
+        self.comm, self.lib, self.plan, self.grid, self.bands = comm, comm.lib, plan, grid, bands
         self.handle = C.c_void_p()
-        w = (C.c_float * len(group_weights))(*[float(v) for v in group_weights])
-        check("hpx_shard_create", self.lib.hpx_shard_create(comm.handle, plan.handle, grid.handle, w, len(group_weights),
-                                                            C.byref(self.handle)))
+        if bands is None:
+            w = (C.c_float * len(group_weights))(*[float(v) for v in group_weights])
+            check("hpx_shard_create", self.lib.hpx_shard_create(comm.handle, plan.handle, grid.handle, w, len(group_weights),
+                                                                C.byref(self.handle)))
+        else:
+            check("hpx_shard_create_bands", self.lib.hpx_shard_create_bands(comm.handle, plan.handle, grid.handle,
+                                                                            self.RESULTS[bands], C.byref(self.handle)))
         fh = C.c_void_p()
         check("hpx_shard_frame", self.lib.hpx_shard_frame(self.handle, C.byref(fh)))
-        self.frame = _BorrowedFrame(plan, fh)
+        self.frame = _BorrowedFrame(plan, fh) if fh.value else None
 
     def step(self, dL_dI_device_ptr: int, flags: int = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO):
         check("hpx_shard_step", self.lib.hpx_shard_step(self.handle, int(dL_dI_device_ptr), flags))
@@ -461,12 +472,32 @@ class Shard:
     def set_reduce(self, enabled: bool):
         check("hpx_shard_set_reduce", self.lib.hpx_shard_set_reduce(self.handle, 1 if enabled else 0))
 
+    def set_result(self, result: str):
+        check("hpx_shard_set_result", self.lib.hpx_shard_set_result(self.handle, self.RESULTS[result]))
+
     def layout(self):
+        if self.bands is not None:
+            n = self.comm.world
+            row0, rows = (C.c_uint32 * n)(), (C.c_uint32 * n)()
+            wedges, cuts = (C.c_int32 * (2 * n))(), (C.c_int32 * (n + 1))()
+            out, inn = C.c_size_t(), C.c_size_t()
+            check("hpx_shard_bands", self.lib.hpx_shard_bands(self.handle, row0, rows, wedges, cuts, C.byref(out), C.byref(inn)))
+            axis = C.c_int32()
+            check("hpx_shard_owned", self.lib.hpx_shard_owned(self.handle, None, None, None, None, C.byref(axis)))
+            return {"slow_axis": "xyz"[axis.value], "band_row0": list(row0), "band_rows": list(rows),
+                    "wedges": [(int(wedges[2 * i]), int(wedges[2 * i + 1])) for i in range(n)], "owner_cuts": list(cuts),
+                    "send_bytes": out.value * 4, "recv_bytes": inn.value * 4}
         axis, n = C.c_int32(), C.c_uint32()
         rows, ranges = (C.c_uint32 * 16)(), (C.c_int32 * 32)()
         check("hpx_shard_layout", self.lib.hpx_shard_layout(self.handle, C.byref(axis), C.byref(n), rows, ranges))
         return {"slow_axis": "xyz"[axis.value], "group_rows": [int(rows[i]) for i in range(n.value)],
                 "slab_ranges": [(int(ranges[2 * i]), int(ranges[2 * i + 1])) for i in range(n.value)]}
+
+    def owned(self):
+        """(device pointer, first slab, slabs, floats per slab) of the slabs this rank owns inside the gradient block."""
+        ptr, first, count, sf = C.c_void_p(), C.c_int32(), C.c_int32(), C.c_size_t()
+        check("hpx_shard_owned", self.lib.hpx_shard_owned(self.handle, C.byref(ptr), C.byref(first), C.byref(count), C.byref(sf), None))
+        return ptr.value or 0, first.value, count.value, sf.value
 
     def close(self):
         if self.handle:
