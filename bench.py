@@ -555,9 +555,9 @@ def run_sharded(env, args):
         "samples_per_step": total,
         "parallelism": (f"ONE frame in {world} contiguous row bands cut for equal marching work (hpx_shard_create_bands), grid "
                         "replicated; the gradient block is laid out in slabs along world axis " + layout["slow_axis"] +
-                        ", a band's backward touches one slab wedge; wedge parts go point-to-point (NCCL send/recv over "
-                        "NVLink) to the slab owners, which add them in rank order; then every owner broadcasts its sums: all "
-                        "ranks hold the whole summed gradient, as after an all-reduce") if bands else
+                        ", a band's backward touches one slab wedge; the wedge parts a rank does not own are added by their "
+                        "owners in rank order (" + layout.get("exchange", "") + "); then every rank fetches the finished sums of "
+                        "all owners: all ranks hold the whole summed gradient, as after an all-reduce") if bands else
                        (f"ONE frame, tile rows interleaved over {world} GPUs, {args.groups} row groups, slab all-reduces behind a "
                         "device-signalled backward (hpx_shard_create)"),
         "layout": layout, "verify_max_rel_err_vs_single_gpu": verify,
@@ -608,9 +608,10 @@ def run_weak_views(env, args, comm):
     dist.all_reduce(mine)
     step()
     env.barrier()
-    scale = torch.maximum(mine.abs(), 1e-3 * mine.abs().max())
+    scale = torch.maximum(mine.abs(), 1e-2 * mine.abs().max())   # two float32 reductions in different orders
     err = ((block - mine).abs() / scale).max()
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    assert float(err.item()) < 1e-3, f"all-reduced gradient block differs from the sum of the per-view gradients: {float(err.item()):.3e}"
     ms = env.timed(step, args.steps, 2) / args.steps
     ms_local = env.timed(local, args.steps, 1) / args.steps
     total = env.world * W * W * steps

@@ -203,6 +203,7 @@ struct ShardShared {
     std::vector<int> status;
     std::vector<uint32_t> band_row0, band_rows;
     std::vector<int32_t> wedges, cuts;
+    int direct = 0;
     double verify = -1.0;
     uint64_t samples = 0;
     uint32_t usable_sms = 0, total_sms = 0;
@@ -293,6 +294,9 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
         hpx_shard_bands(shard, sh.band_row0.data(), sh.band_rows.data(), sh.wedges.data(), sh.cuts.data(), nullptr, nullptr);
     }
     if (a.mode != 0) {
+        int32_t direct = 0;
+        hpx_shard_exchange_is_direct(shard, &direct);
+        if (rank == 0) sh.direct = direct;
         size_t out = 0, in = 0;
         hpx_shard_bands(shard, nullptr, nullptr, nullptr, nullptr, &out, &in);
         sh.send_mb[rank] = out * 4.0 / 1e6;
@@ -353,6 +357,7 @@ int run_shard(const ShardArgs& a) {
         list("band_row0", sh.band_row0); list("band_rows", sh.band_rows); list("wedges", sh.wedges); list("owner_cuts", sh.cuts);
         list("send_mb", sh.send_mb); list("recv_mb", sh.recv_mb);
     }
+    if (a.mode != 0) std::printf("\"exchange\": \"%s\", ", sh.direct ? "own kernels over peer memory" : "nccl");
     std::printf("\"sharding\": \"%s\", ", a.mode == 0 ? "interleaved tile rows, slab all-reduces behind a signalled backward"
                                            : a.mode == 1 ? "balanced bands, sparse exchange, replicated result"
                                                          : "balanced bands, sparse exchange, owned result (reduce-scatter)");

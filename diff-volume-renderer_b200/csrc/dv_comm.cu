@@ -16,6 +16,7 @@
 //                     waiting for the rendering launch to drain (profiles/README.md, round 1: that wait exposed the
 //                     whole 2.1 GB all-reduce at 8 GPUs).
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types and enumerators only; every function is resolved with dlsym
 
 #include <algorithm>
@@ -47,6 +48,7 @@ struct NcclApi {
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*GetVersion)(int*) = nullptr;
@@ -79,11 +81,12 @@ const NcclApi& nccl() {
         a.Send = reinterpret_cast<decltype(a.Send)>(sym("ncclSend"));
         a.Recv = reinterpret_cast<decltype(a.Recv)>(sym("ncclRecv"));
         a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(sym("ncclBroadcast"));
+        a.AllGather = reinterpret_cast<decltype(a.AllGather)>(sym("ncclAllGather"));
         a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(sym("ncclGroupStart"));
         a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(sym("ncclGroupEnd"));
         a.GetVersion = reinterpret_cast<decltype(a.GetVersion)>(sym("ncclGetVersion"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(sym("ncclGetErrorString"));
-        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Send && a.Recv && a.Broadcast && a.GroupStart &&
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.Send && a.Recv && a.Broadcast && a.AllGather && a.GroupStart &&
                a.GroupEnd && a.GetErrorString;
         if (!a.ok) a.why = "the NCCL library lacks a required symbol";
         return a;
@@ -152,6 +155,12 @@ struct hpx_shard {
     float* staging = nullptr;
     int32_t hull_lo = 0, hull_hi = 0;                               // slabs ANY rank can touch
     size_t dl_offset_floats = 0;                                    // this rank's rows inside the frame's dL/dI
+    // direct exchange: every rank's gradient block mapped into this GPU's address space (same process: peer access;
+    // other processes: CUDA IPC), read by this rank's own kernels over NVLink
+    bool direct = false;
+    std::vector<float*> peer_block;                                 // per rank (own entry = own block)
+    std::vector<void*> ipc_opened;
+    int* d_flag = nullptr;                                          // 1 int: payload of the cross-GPU barrier
 };
 
 namespace {
@@ -214,6 +223,127 @@ __global__ void add_slabs_kernel(float4* __restrict__ dst, const float4* __restr
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         dst[i] = a;
     }
+}
+
+
+// dst[i] += src[i] / dst[i] = src[i] with src in ANOTHER GPU's memory (mapped peer pointer): 16-byte loads over NVLink,
+// four in flight per thread before the first use, so that a 148-SM grid keeps several MB of reads outstanding.
+template <bool kAdd>
+__global__ void __launch_bounds__(256) peer_pull_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = src[i + k * stride];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (kAdd) {
+                float4 a = dst[i + k * stride];
+                a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
+                dst[i + k * stride] = a;
+            } else {
+                dst[i + k * stride] = v[k];
+            }
+        }
+    }
+    for (; i < n4; i += stride) {
+        const float4 v = src[i];
+        if (kAdd) {
+            float4 a = dst[i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            dst[i] = a;
+        } else {
+            dst[i] = v;
+        }
+    }
+}
+
+struct PeerInfo {
+    cudaIpcMemHandle_t handle;
+    unsigned long long ptr;
+    long long pid;
+    int device;
+    int ok;
+};
+
+// Maps every rank's gradient block into this GPU's address space.  Collective: all ranks call it; returns with
+// s->direct == true on ALL ranks or on none (any rank that cannot map a peer vetoes).
+hp_status map_peer_blocks(hpx_shard* s) {
+    hpx_comm* c = s->comm;
+    const int world = c->world, me = c->rank;
+    cudaStream_t main = c->ctx->stream;
+    float* block = nullptr;
+    size_t floats = 0;
+    DV_TRY(hpx_grid_grad_buffer(s->grid, &block, &floats));
+    DV_CUDA(cudaMalloc(&s->d_flag, sizeof(int)));
+    DV_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int), main));
+    s->peer_block.assign(static_cast<size_t>(world), nullptr);
+    s->peer_block[static_cast<size_t>(me)] = block;
+    if (world == 1) return HP_STATUS_SUCCESS;
+    const char* env = std::getenv("DVREN_SHARD_EXCHANGE");
+    int ok = (env != nullptr && std::strcmp(env, "nccl") == 0) ? 0 : 1;
+    PeerInfo mine{};
+    mine.ptr = reinterpret_cast<unsigned long long>(block);
+    mine.pid = static_cast<long long>(getpid());
+    mine.device = c->ctx->device;
+    if (ok && cudaIpcGetMemHandle(&mine.handle, block) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+    mine.ok = ok;
+    PeerInfo* d_all = nullptr;
+    DV_CUDA(cudaMalloc(&d_all, sizeof(PeerInfo) * world));
+    std::vector<PeerInfo> all(static_cast<size_t>(world));
+    hp_status st = HP_STATUS_SUCCESS;
+    do {
+        if (cudaMemcpyAsync(d_all + me, &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice, main) != cudaSuccess) { st = cuda_fail(cudaGetLastError(), "peer info"); break; }
+        const ncclResult_t r = nccl().AllGather(d_all + me, d_all, sizeof(PeerInfo), ncclChar, c->comm, main);
+        if (r != ncclSuccess) { st = nccl_fail(r, "ncclAllGather(peer info)"); break; }
+        if (cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * world, cudaMemcpyDeviceToHost, main) != cudaSuccess ||
+            cudaStreamSynchronize(main) != cudaSuccess) { st = cuda_fail(cudaGetLastError(), "peer info"); break; }
+    } while (false);
+    cudaFree(d_all);
+    if (st != HP_STATUS_SUCCESS) return st;
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == me) continue;
+        if (!all[r].ok) { ok = 0; break; }
+        if (all[r].pid == mine.pid) {   // another thread of this process: plain peer access
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, c->ctx->device, all[r].device) != cudaSuccess || !can) { cudaGetLastError(); ok = 0; break; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(all[r].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ok = 0; break; }
+            cudaGetLastError();
+            s->peer_block[static_cast<size_t>(r)] = reinterpret_cast<float*>(all[r].ptr);
+        } else {
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+            s->ipc_opened.push_back(p);
+            s->peer_block[static_cast<size_t>(r)] = static_cast<float*>(p);
+        }
+    }
+    // unanimous or not at all
+    int* d_ok = s->d_flag;
+    DV_CUDA(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, main));
+    DV_NCCL(nccl().AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, c->comm, main));
+    int all_ok = 0;
+    DV_CUDA(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, main));
+    DV_CUDA(cudaStreamSynchronize(main));
+    s->direct = all_ok != 0;
+    return HP_STATUS_SUCCESS;
+}
+
+// Cross-GPU barrier in stream order: returns (on the stream) once every rank's stream has reached it.
+hp_status stream_barrier(hpx_shard* s) {
+    hpx_comm* c = s->comm;
+    DV_NCCL(nccl().AllReduce(s->d_flag, s->d_flag, 1, ncclInt32, ncclMax, c->comm, c->ctx->stream));
+    return HP_STATUS_SUCCESS;
+}
+
+template <bool kAdd>
+cudaError_t launch_peer_pull(cudaStream_t stream, float* dst, const float* src, size_t floats) {
+    const size_t n4 = floats / 4;
+    if (n4 == 0) return cudaSuccess;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((n4 + 1023) / 1024, 148 * 8));
+    peer_pull_kernel<kAdd><<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n4);
+    return cudaGetLastError();
 }
 
 // Marching work of one image row, in samples: steps of its rays that lie inside the unit cube (what the kernels spend
@@ -587,7 +717,9 @@ HP_API hp_status hpx_shard_create_bands(hpx_comm* c, const hp_plan* full_plan, h
             staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
         }
     }
-    if (staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
+    st = map_peer_blocks(s);
+    if (st != HP_STATUS_SUCCESS) return fail(st);
+    if (!s->direct && staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
         return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)"));
     *out_shard = s;
     return HP_STATUS_SUCCESS;
@@ -608,6 +740,14 @@ HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, ui
             out_work[r] = w;
         }
     }
+    return HP_STATUS_SUCCESS;
+}
+
+// 1: the exchange runs as this library's own kernels over mapped peer memory; 0: NCCL point-to-point + broadcast.
+HP_API hp_status hpx_shard_exchange_is_direct(const hpx_shard* s, int32_t* out_direct) {
+    DV_RANGE("hpx_shard_exchange_is_direct");
+    if (s == nullptr || out_direct == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    *out_direct = s->direct ? 1 : 0;
     return HP_STATUS_SUCCESS;
 }
 
@@ -682,7 +822,31 @@ static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t fla
     if (s->frame != nullptr)
         DV_TRY(hpx_backward(s->frame, s->grid, dL_dI_device + s->dl_offset_floats, HP_MEMSPACE_DEVICE, flags & ~HPX_BACKWARD_ZERO));
     if (c->world == 1 || !s->reduce) return HP_STATUS_SUCCESS;
-    // ---- sparse reduce-scatter: wedge parts to their owners
+    if (s->direct) {
+        // ---- own kernels over peer memory (NVLink): every owner PULLS the wedge parts of its slabs out of its neighbours'
+        // gradient blocks and adds them in rank order -- no staging copy, no separate add pass.
+        DV_TRY(stream_barrier(s));   // every rank's backward has finished: the blocks hold the final partial sums
+        for (const auto& x : s->recvs)
+            DV_CUDA(launch_peer_pull<true>(main, block + static_cast<size_t>(x.lo) * S,
+                                           s->peer_block[static_cast<size_t>(x.peer)] + static_cast<size_t>(x.lo) * S,
+                                           static_cast<size_t>(x.hi - x.lo) * S));
+        if (flags & HPX_BACKWARD_CAMERA)
+            DV_NCCL(nccl().AllReduce(block + floats - 16, block + floats - 16, 16, ncclFloat32, ncclSum, c->comm, main));
+        if (s->result == HPX_SHARD_RESULT_REPLICATED) {
+            DV_TRY(stream_barrier(s));   // every owner has finished its sums
+            for (int k = 1; k < c->world; ++k) {   // start at different owners: no two ranks hammer the same peer at once
+                const int o = (me + k) % c->world;
+                const int32_t lo = std::max(s->cuts[o], s->hull_lo), hi = std::min(s->cuts[o + 1], s->hull_hi);
+                if (lo >= hi) continue;
+                DV_CUDA(launch_peer_pull<false>(main, block + static_cast<size_t>(lo) * S,
+                                                s->peer_block[static_cast<size_t>(o)] + static_cast<size_t>(lo) * S,
+                                                static_cast<size_t>(hi - lo) * S));
+            }
+        }
+        return stream_barrier(s);        // nobody still reads this rank's block when it is cleared for the next step
+    }
+    // ---- NCCL fallback (DVREN_SHARD_EXCHANGE=nccl, or a peer's block cannot be mapped): sparse reduce-scatter with
+    // point-to-point sends into a staging buffer
     if (!s->sends.empty() || !s->recvs.empty()) {
         DV_NCCL(nccl().GroupStart());
         ncclResult_t r = ncclSuccess;
@@ -729,6 +893,8 @@ HP_API void hpx_shard_release(hpx_shard* s) {
         if (s->comm->side != nullptr) cudaStreamSynchronize(s->comm->side);
         if (s->ev_zero != nullptr) cudaEventDestroy(s->ev_zero);
         cudaFree(s->staging);
+        cudaFree(s->d_flag);
+        for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     }
     hpx_frame_release(s->frame);
     hp_plan_release(s->plan);

@@ -108,6 +108,7 @@ HPX_FUNCTIONS = {
     "hpx_shard_release": (None, [C.c_void_p]),
     "hpx_shard_create_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_void_p)]),
     "hpx_shard_set_result": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "hpx_shard_exchange_is_direct": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "hpx_plan_balanced_bands": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_uint32), P(C.c_double)]),
     "hpx_shard_bands": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_size_t)]),
     "hpx_shard_owned": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_int32)]),
@@ -484,7 +485,10 @@ class Shard:
             check("hpx_shard_bands", self.lib.hpx_shard_bands(self.handle, row0, rows, wedges, cuts, C.byref(out), C.byref(inn)))
             axis = C.c_int32()
             check("hpx_shard_owned", self.lib.hpx_shard_owned(self.handle, None, None, None, None, C.byref(axis)))
-            return {"slow_axis": "xyz"[axis.value], "band_row0": list(row0), "band_rows": list(rows),
+            direct = C.c_int32()
+            check("hpx_shard_exchange_is_direct", self.lib.hpx_shard_exchange_is_direct(self.handle, C.byref(direct)))
+            return {"exchange": "own kernels over mapped peer memory (NVLink)" if direct.value else "NCCL send/recv + broadcast",
+                    "slow_axis": "xyz"[axis.value], "band_row0": list(row0), "band_rows": list(rows),
                     "wedges": [(int(wedges[2 * i]), int(wedges[2 * i + 1])) for i in range(n)], "owner_cuts": list(cuts),
                     "send_bytes": out.value * 4, "recv_bytes": inn.value * 4}
         axis, n = C.c_int32(), C.c_uint32()

@@ -291,6 +291,13 @@ HP_API hp_status hpx_shard_layout(const hpx_shard* shard, int32_t* out_slow_axis
 HP_API hp_status hpx_shard_create_bands(hpx_comm* comm, const hp_plan* full_frame_plan, hpx_grid* grid, uint32_t result,
                                         hpx_shard** out_shard);
 HP_API hp_status hpx_shard_set_result(hpx_shard* shard, uint32_t result);
+/* How the band exchange runs.  1 (default when every rank can map every other rank's gradient block -- peer access inside
+ * one process, CUDA IPC between processes of one node): the library's OWN kernels over peer memory: after a stream-ordered
+ * cross-GPU barrier every owner pulls the wedge parts of its slabs out of its neighbours' blocks over NVLink and adds them
+ * in rank order (no staging copy, no separate add pass; the replicated result pulls the finished sums the same way).
+ * 0 (environment DVREN_SHARD_EXCHANGE=nccl, or mapping failed on some rank): NCCL send/recv into a staging buffer + an add
+ * kernel, NCCL broadcasts for the replicated result. */
+HP_API hp_status hpx_shard_exchange_is_direct(const hpx_shard* shard, int32_t* out_direct);
 /* Host-only (works without a GPU): the bands hpx_shard_create_bands cuts for `world` ranks -- first row inside the ROI and
  * rows per rank, multiples of the 8-row CTA tile; out_work (may be NULL): estimated marching work per band in samples. */
 HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, uint32_t* out_row0, uint32_t* out_rows,

@@ -258,3 +258,71 @@ def test_cxx_surface_selftest():
     assert os.path.exists(exe), f"{exe} is not built (__graft_entry__.build())"
     r = subprocess.run([exe, "selftest"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "selftest ok" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_balanced_bands_sum_to_the_whole_frame(ctx):
+    """What hpx_shard_create_bands gives each rank, replayed on ONE GPU: the bands of hpx_plan_balanced_bands rendered one
+    after the other (ROI sub-plan, global ray-index base for the stratified jitter, every other band with its tile rows
+    taken last-to-first) reproduce the whole frame's image planes bit for bit and sum to its gradient; the voxel wedges
+    of hpx_frame_bounds contain everything a band's backward writes."""
+    W, Hh, steps, world = 96, 80, 64, 3
+    desc = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=7)
+    sig, col = S.hashed_volume(20, "dense", seed=5)
+    dl = S.hashed_image_grad(W * Hh)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_DETERMINISTIC
+    grid = D.Grid(ctx, sig, col)
+    whole = _render(ctx, grid, desc, dl, flags | D.HPX_BACKWARD_ZERO)
+
+    plan = D.Plan(ctx, desc)
+    row0, rows = (C.c_uint32 * world)(), (C.c_uint32 * world)()
+    D.check("hpx_plan_balanced_bands", ctx.lib.hpx_plan_balanced_bands(plan.handle, world, row0, rows, None))
+    assert sum(rows) == Hh and all(r > 0 for r in rows)
+    grid.zero_grad()
+    image = np.zeros((Hh, W, 3), np.float32)
+    samples = 0
+    for r in range(world):
+        bd = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=7, roi=(0, int(row0[r]), W, int(rows[r])))
+        bplan = D.Plan(ctx, bd)
+        frame = D.Frame(bplan)
+        frame.set_view(None, desc.seed, int(row0[r]) * W)
+        D.check("hpx_frame_set_row_order", ctx.lib.hpx_frame_set_row_order(frame.handle, r % 2))
+        box = (C.c_int32 * 6)()
+        D.check("hpx_frame_bounds", ctx.lib.hpx_frame_bounds(frame.handle, grid.handle, box))
+        frame.forward(grid)
+        out = frame.read()
+        image[row0[r]:row0[r] + rows[r]] = out["image"][row0[r]:row0[r] + rows[r]]
+        samples += frame.counts()["samples"]
+        before = grid.read_grad()[0].reshape(20, 20, 20).copy()
+        frame.backward(grid, dl[int(row0[r]) * W:(int(row0[r]) + int(rows[r])) * W], flags)
+        delta = grid.read_grad()[0].reshape(20, 20, 20) - before           # [z][y][x]
+        zs, ys, xs = np.nonzero(delta)
+        if len(zs):
+            assert xs.min() >= box[0] and xs.max() < box[0] + box[3]
+            assert ys.min() >= box[1] and ys.max() < box[1] + box[4]
+            assert zs.min() >= box[2] and zs.max() < box[2] + box[5]
+        frame.close(); bplan.close()
+    assert samples == whole["samples"]
+    U.assert_bits(image, whole["image"], "bands vs whole frame: image")
+    sg, cg, _ = grid.read_grad()
+    # deterministic (fixed-point) accumulation: the band sums differ from the whole frame's only by the float conversion of
+    # each band's integer total
+    U.assert_close(sg, whole["sigma_grad"], 1e-5, "bands vs whole frame: sigma gradient", floor_frac=1e-3)
+    U.assert_close(cg, whole["color_grad"], 1e-5, "bands vs whole frame: colour gradient", floor_frac=1e-3)
+    plan.close(); grid.close()
+
+
+def test_sharded_frame_on_two_gpus():
+    """hpx_comm + hpx_shard_* with NO Python in the loop (apps/dvren_bench.cpp `shard`: one host thread per GPU): interleaved
+    tile rows with slab all-reduces, balanced bands with the replicated and with the owned result -- each verified inside
+    the tool against a single-GPU backward of the whole frame."""
+    import os
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    exe = os.path.join(U.REPO, "diff-volume-renderer_b200", "dvren_bench")
+    assert os.path.exists(exe), f"{exe} is not built (__graft_entry__.build())"
+    for mode, env in ((0, {}), (1, {}), (2, {}), (1, {"DVREN_SHARD_EXCHANGE": "nccl"})):
+        r = subprocess.run([exe, "shard", "96", "384", "192", "1", "2", "1", "2", "3", "0", "0", str(mode)], capture_output=True,
+                           text=True, timeout=300, env={**os.environ, **env})
+        assert r.returncode == 0 and '"verify_max_rel_err_vs_single_gpu"' in r.stdout, (mode, env, r.stdout[-2000:], r.stderr[-2000:])
