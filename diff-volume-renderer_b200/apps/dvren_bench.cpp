@@ -253,6 +253,15 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
     SCHECK(hpx_copy_to_device(ctx, d_dl, sh.dl->data(), sh.dl->size() * 4));
     const uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
 
+    if (a.mode != 0) {   // untimed start-up: bands re-cut from the measured per-rank time until they stop moving
+        for (int round = 0; round < 4; ++round) {
+            SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+            SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+            int32_t changed = 0;
+            SCHECK(hpx_shard_rebalance(shard, &changed));
+            if (!changed) break;
+        }
+    }
     // correctness first: the reduced gradient of one sharded step against a plain single-GPU backward (rank 0)
     SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
     SCHECK(hpx_ctx_synchronize(ctx));

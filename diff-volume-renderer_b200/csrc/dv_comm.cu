@@ -161,6 +161,12 @@ struct hpx_shard {
     std::vector<float*> peer_block;                                 // per rank (own entry = own block)
     std::vector<void*> ipc_opened;
     int* d_flag = nullptr;                                          // 1 int: payload of the cross-GPU barrier
+    // measured rebalancing (hpx_shard_rebalance)
+    hp_plan_desc full_desc{};
+    FrameParams full_params{};
+    std::vector<double> unit_cost;                                  // estimated work per CTA tile row, rescaled by measurements
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;                   // around this rank's forward + backward
+    bool timed = false;
 };
 
 namespace {
@@ -378,16 +384,22 @@ double row_work(const FrameParams& p, uint32_t gy, uint32_t x0, uint32_t w) {
 }
 
 // Contiguous bands of CTA tile rows with (nearly) equal work.
-std::vector<RowBand> balanced_bands(const FrameParams& p, const hp_plan_desc& d, uint32_t world) {
+// Estimated marching work of every CTA tile row (8 image rows) of the plan's ROI.
+std::vector<double> unit_costs(const FrameParams& p, const hp_plan_desc& d) {
     const uint32_t unit = kTileH * kWarpsY, h = d.roi.height;
     const uint32_t units = (h + unit - 1) / unit;
-    std::vector<double> cum(units + 1, 0.0);
-    for (uint32_t u = 0; u < units; ++u) {
-        double w = 0.0;
+    std::vector<double> cost(units, 0.0);
+    for (uint32_t u = 0; u < units; ++u)
         for (uint32_t r = u * unit; r < std::min(h, (u + 1) * unit); r += 2)   // every 2nd row of the unit
-            w += row_work(p, d.roi.y + r, d.roi.x, d.roi.width);
-        cum[u + 1] = cum[u] + w;
-    }
+            cost[u] += row_work(p, d.roi.y + r, d.roi.x, d.roi.width);
+    return cost;
+}
+
+std::vector<RowBand> partition_units(const std::vector<double>& cost, uint32_t h, uint32_t world) {
+    const uint32_t unit = kTileH * kWarpsY;
+    const uint32_t units = static_cast<uint32_t>(cost.size());
+    std::vector<double> cum(units + 1, 0.0);
+    for (uint32_t u = 0; u < units; ++u) cum[u + 1] = cum[u] + cost[u];
     // smallest cap such that `world` contiguous bands of at most `cap` work cover all units (binary search over the cap,
     // greedy packing as the feasibility test): minimises the work of the busiest rank
     auto bands_needed = [&](double cap, std::vector<uint32_t>* cuts) {
@@ -418,6 +430,10 @@ std::vector<RowBand> balanced_bands(const FrameParams& p, const hp_plan_desc& d,
         prev = cut;
     }
     return out;
+}
+
+std::vector<RowBand> balanced_bands(const FrameParams& p, const hp_plan_desc& d, uint32_t world) {
+    return partition_units(unit_costs(p, d), d.roi.height, world);
 }
 
 }  // namespace
@@ -605,6 +621,118 @@ HP_API hp_status hpx_shard_create(hpx_comm* c, const hp_plan* full_plan, hpx_gri
 }
 
 
+// (Re)builds everything that follows from the band cuts: this rank's frame, every rank's wedge, the owner cuts and the
+// transfer lists.  Every rank derives all of it from the same inputs with the same code: the ranks agree without talking.
+static hp_status band_configure(hpx_shard* s) {
+    hpx_comm* c = s->comm;
+    hpx_grid* g = s->grid;
+    const hp_plan_desc& d = s->full_desc;
+    const int world = c->world, me = c->rank;
+    cudaStream_t main = c->ctx->stream;
+    DV_CUDA(cudaStreamSynchronize(main));
+    hpx_frame_release(s->frame);
+    hp_plan_release(s->plan);
+    s->frame = nullptr;
+    s->plan = nullptr;
+    cudaFree(s->staging);
+    s->staging = nullptr;
+    s->band_row0.clear(); s->band_rows.clear(); s->wedges.clear(); s->sends.clear(); s->recvs.clear();
+    s->timed = false;
+    const std::vector<RowBand> bands = partition_units(s->unit_cost, d.roi.height, static_cast<uint32_t>(world));
+    hp_status st = HP_STATUS_SUCCESS;
+    for (int r = 0; r < world; ++r) {
+        s->band_row0.push_back(bands[r].y0);
+        s->band_rows.push_back(bands[r].rows);
+        std::pair<int32_t, int32_t> wedge(0, 0);
+        if (bands[r].rows != 0) {
+            hp_plan_desc bd = d;
+            bd.roi.y = d.roi.y + bands[r].y0;
+            bd.roi.height = bands[r].rows;
+            bd.max_rays = 0;
+            bd.max_samples = 0;
+            hp_plan* band_plan = nullptr;
+            hpx_frame* frame = nullptr;
+            int32_t box[6] = {0, 0, 0, 0, 0, 0};
+            st = hp_plan_create(c->ctx, &bd, &band_plan);
+            if (st == HP_STATUS_SUCCESS) st = hpx_frame_create(band_plan, &frame);
+            if (st == HP_STATUS_SUCCESS) st = hpx_frame_bounds(frame, g, box);
+            if (st == HP_STATUS_SUCCESS && r == me) {
+                // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
+                st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
+                // end the launches with the band's CHEAP rows (short tail): last row first when the rays get longer downwards
+                const double first = row_work(s->full_params, d.roi.y + bands[r].y0, d.roi.x, d.roi.width);
+                const double last = row_work(s->full_params, d.roi.y + bands[r].y0 + bands[r].rows - 1, d.roi.x, d.roi.width);
+                if (st == HP_STATUS_SUCCESS) st = hpx_frame_set_row_order(frame, last > first ? 1 : 0);
+                s->plan = band_plan;
+                s->frame = frame;
+                s->dl_offset_floats = static_cast<size_t>(bands[r].y0) * d.roi.width * 3;
+            } else {
+                hpx_frame_release(frame);
+                hp_plan_release(band_plan);
+            }
+            if (st != HP_STATUS_SUCCESS) return st;
+            if (box[3 + s->slow_axis] > 0) wedge = {box[s->slow_axis], box[s->slow_axis] + box[3 + s->slow_axis]};
+        }
+        s->wedges.push_back(wedge);
+    }
+    s->hull_lo = s->n_slabs;
+    s->hull_hi = 0;
+    for (int r = 0; r < world; ++r) {
+        if (s->wedges[r].first >= s->wedges[r].second) continue;
+        s->hull_lo = std::min(s->hull_lo, s->wedges[r].first);
+        s->hull_hi = std::max(s->hull_hi, s->wedges[r].second);
+    }
+    if (s->hull_hi < s->hull_lo) s->hull_lo = s->hull_hi = 0;
+    // Owners.  Rank o pulls, for every slab it owns, the partial sums of every OTHER rank whose wedge contains the slab.
+    // The cuts are chosen so that the busiest owner receives as little as possible (binary search over the cap, owners
+    // take slabs greedily while their inbound volume stays below it): where many wedges overlap the owned ranges get
+    // narrower.  An owner's range starts inside or before its own wedge, so most of what it owns it has rendered itself.
+    std::vector<int32_t> cover(static_cast<size_t>(s->n_slabs) + 1, 0);   // cover[y] = ranks whose wedge contains slab y
+    for (int r = 0; r < world; ++r)
+        for (int32_t y = s->wedges[r].first; y < s->wedges[r].second; ++y) ++cover[static_cast<size_t>(y)];
+    auto inbound = [&](int o, int32_t y) {   // what owning slab y costs rank o
+        const bool mine = y >= s->wedges[o].first && y < s->wedges[o].second;
+        return cover[static_cast<size_t>(y)] - (mine ? 1 : 0);
+    };
+    auto cuts_for = [&](long long cap, std::vector<int32_t>* out) {
+        int32_t y = 0;
+        for (int o = 0; o < world; ++o) {
+            if (out) (*out)[static_cast<size_t>(o)] = y;
+            long long got = 0;
+            // an owner may not run past the end of its own wedge unless it is the last one (keeps ownership local)
+            const int32_t stop = o + 1 == world ? s->n_slabs : std::max(y, s->wedges[o].second);
+            while (y < stop && got + inbound(o, y) <= cap) got += inbound(o, y++);
+        }
+        if (out) (*out)[static_cast<size_t>(world)] = s->n_slabs;
+        return y >= s->n_slabs;
+    };
+    long long lo = 0, hi = static_cast<long long>(s->n_slabs) * world;
+    while (lo < hi) {
+        const long long mid = (lo + hi) / 2;
+        if (cuts_for(mid, nullptr)) hi = mid; else lo = mid + 1;
+    }
+    s->cuts.assign(static_cast<size_t>(world) + 1, 0);
+    cuts_for(hi, &s->cuts);
+    auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
+        return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
+    };
+    size_t staging_floats = 0;
+    for (int o = 0; o < world; ++o) {
+        if (o == me) continue;
+        const auto out = overlap(me, o);
+        if (out.first < out.second) s->sends.push_back(hpx_shard::Xfer{o, out.first, out.second, 0});
+        const auto in = overlap(o, me);
+        if (in.first < in.second) {
+            s->recvs.push_back(hpx_shard::Xfer{o, in.first, in.second, staging_floats});
+            staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
+        }
+    }
+    if (!s->direct && staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)");
+    return HP_STATUS_SUCCESS;
+}
+
+
 // ---- one frame over all ranks, contiguous bands -------------------------------------------------------------------
 // Rank r renders a contiguous band of image rows; the bands are cut so that every rank has the same marching work
 // (balanced_bands).  A band's rays stay inside a wedge of the volume, so with the gradient block laid out slab by slab
@@ -647,81 +775,68 @@ HP_API hp_status hpx_shard_create_bands(hpx_comm* c, const hp_plan* full_plan, h
     if (st != HP_STATUS_SUCCESS) return fail(st);
     if (cudaEventCreateWithFlags(&s->ev_zero, cudaEventDisableTiming) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event"));
 
-    const int world = c->world, me = c->rank;
-    const std::vector<RowBand> bands = balanced_bands(frame_params_from_plan(*full_plan), d, static_cast<uint32_t>(world));
-    // every rank derives every band's wedge itself (same inputs, same code: all ranks agree without talking)
-    for (int r = 0; r < world; ++r) {
-        s->band_row0.push_back(bands[r].y0);
-        s->band_rows.push_back(bands[r].rows);
-        std::pair<int32_t, int32_t> wedge(0, 0);
-        if (bands[r].rows != 0) {
-            hp_plan_desc bd = d;
-            bd.roi.y = d.roi.y + bands[r].y0;
-            bd.roi.height = bands[r].rows;
-            bd.max_rays = 0;
-            bd.max_samples = 0;
-            hp_plan* band_plan = nullptr;
-            hpx_frame* frame = nullptr;
-            int32_t box[6] = {0, 0, 0, 0, 0, 0};
-            st = hp_plan_create(c->ctx, &bd, &band_plan);
-            if (st == HP_STATUS_SUCCESS) st = hpx_frame_create(band_plan, &frame);
-            if (st == HP_STATUS_SUCCESS) st = hpx_frame_bounds(frame, g, box);
-            if (st == HP_STATUS_SUCCESS && r == me) {
-                // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
-                st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
-                // end the launches with the band's CHEAP rows (short tail): last row first when the rays get longer downwards
-                const FrameParams fp = frame_params_from_plan(*full_plan);
-                const double first = row_work(fp, d.roi.y + bands[r].y0, d.roi.x, d.roi.width);
-                const double last = row_work(fp, d.roi.y + bands[r].y0 + bands[r].rows - 1, d.roi.x, d.roi.width);
-                if (st == HP_STATUS_SUCCESS) st = hpx_frame_set_row_order(frame, last > first ? 1 : 0);
-                s->plan = band_plan;
-                s->frame = frame;
-                s->dl_offset_floats = static_cast<size_t>(bands[r].y0) * d.roi.width * 3;
-            } else {
-                hpx_frame_release(frame);
-                hp_plan_release(band_plan);
-            }
-            if (st != HP_STATUS_SUCCESS) return fail(st);
-            if (box[3 + s->slow_axis] > 0) wedge = {box[s->slow_axis], box[s->slow_axis] + box[3 + s->slow_axis]};
-        }
-        s->wedges.push_back(wedge);
-    }
-    // owners: cut half way through the overlap (or gap) of neighbouring wedges; empty wedges inherit their predecessor's end
-    s->cuts.assign(static_cast<size_t>(world) + 1, 0);
-    s->cuts[static_cast<size_t>(world)] = s->n_slabs;
-    int32_t prev_hi = 0;
-    s->hull_lo = s->n_slabs;
-    s->hull_hi = 0;
-    for (int r = 0; r < world; ++r) {
-        const bool empty = s->wedges[r].first >= s->wedges[r].second;
-        const int32_t lo = empty ? prev_hi : s->wedges[r].first, hi = empty ? prev_hi : s->wedges[r].second;
-        if (r > 0) s->cuts[r] = std::min(s->n_slabs, std::max(s->cuts[r - 1], (lo + prev_hi) / 2));
-        if (!empty) {
-            s->hull_lo = std::min(s->hull_lo, lo);
-            s->hull_hi = std::max(s->hull_hi, hi);
-        }
-        prev_hi = std::max(prev_hi, hi);
-    }
-    if (s->hull_hi < s->hull_lo) s->hull_lo = s->hull_hi = 0;
-    auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
-        return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
-    };
-    size_t staging_floats = 0;
-    for (int o = 0; o < world; ++o) {
-        if (o == me) continue;
-        const auto out = overlap(me, o);
-        if (out.first < out.second) s->sends.push_back(hpx_shard::Xfer{o, out.first, out.second, 0});
-        const auto in = overlap(o, me);
-        if (in.first < in.second) {
-            s->recvs.push_back(hpx_shard::Xfer{o, in.first, in.second, staging_floats});
-            staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
-        }
-    }
+    s->full_desc = d;
+    s->full_params = frame_params_from_plan(*full_plan);
+    s->unit_cost = unit_costs(s->full_params, d);
+    if (cudaEventCreate(&s->ev_t0) != cudaSuccess || cudaEventCreate(&s->ev_t1) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "event"));
     st = map_peer_blocks(s);
+    if (st == HP_STATUS_SUCCESS) st = band_configure(s);
     if (st != HP_STATUS_SUCCESS) return fail(st);
-    if (!s->direct && staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
-        return fail(cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)"));
     *out_shard = s;
+    return HP_STATUS_SUCCESS;
+}
+
+// Collective.  Re-cuts the bands from MEASURED time: every rank contributes the GPU time of its last step's forward +
+// backward; a band that took longer than its share has the estimated work of its rows scaled up by that ratio (and vice
+// versa), and the rows are partitioned again.  The estimate (in-cube steps per ray) does not know that tile rows differ
+// in cache behaviour and idle lanes; two or three rounds during warm-up bring the ranks within a few percent.
+// out_changed: 1 when the bands moved (frames, wedges and owner cuts were rebuilt; hpx_shard_frame / hpx_shard_owned /
+// hpx_shard_bands must be queried again).
+HP_API hp_status hpx_shard_rebalance(hpx_shard* s, int32_t* out_changed) {
+    DV_RANGE("hpx_shard_rebalance");
+    if (s == nullptr || !s->bands) return HP_STATUS_INVALID_ARGUMENT;
+    if (out_changed) *out_changed = 0;
+    hpx_comm* c = s->comm;
+    if (c->world == 1 || !s->timed) return HP_STATUS_SUCCESS;
+    DV_ENTER(c->ctx);
+    cudaStream_t main = c->ctx->stream;
+    DV_CUDA(cudaStreamSynchronize(main));
+    float ms = 0.0f;
+    if (s->frame != nullptr) DV_CUDA(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
+    const int world = c->world;
+    float* d_ms = nullptr;
+    DV_CUDA(cudaMalloc(&d_ms, sizeof(float) * world));
+    std::vector<float> all(static_cast<size_t>(world), 0.0f);
+    hp_status st = HP_STATUS_SUCCESS;
+    if (cudaMemcpyAsync(d_ms + c->rank, &ms, sizeof(float), cudaMemcpyHostToDevice, main) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "rebalance");
+    if (st == HP_STATUS_SUCCESS) {
+        const ncclResult_t r = nccl().AllGather(d_ms + c->rank, d_ms, 1, ncclFloat32, c->comm, main);
+        if (r != ncclSuccess) st = nccl_fail(r, "ncclAllGather(step times)");
+    }
+    if (st == HP_STATUS_SUCCESS && (cudaMemcpyAsync(all.data(), d_ms, sizeof(float) * world, cudaMemcpyDeviceToHost, main) != cudaSuccess ||
+                                    cudaStreamSynchronize(main) != cudaSuccess))
+        st = cuda_fail(cudaGetLastError(), "rebalance");
+    cudaFree(d_ms);
+    if (st != HP_STATUS_SUCCESS) return st;
+    const uint32_t unit = kTileH * kWarpsY;
+    double t_sum = 0.0, w_sum = 0.0;
+    std::vector<double> w(static_cast<size_t>(world), 0.0);
+    for (int r = 0; r < world; ++r) {
+        for (uint32_t u = s->band_row0[r] / unit; u < (s->band_row0[r] + s->band_rows[r] + unit - 1) / unit && u < s->unit_cost.size(); ++u) w[r] += s->unit_cost[u];
+        if (s->band_rows[r] != 0) { t_sum += all[r]; w_sum += w[r]; }
+    }
+    if (!(t_sum > 0.0) || !(w_sum > 0.0)) return HP_STATUS_SUCCESS;
+    for (int r = 0; r < world; ++r) {
+        if (s->band_rows[r] == 0 || !(w[r] > 0.0) || !(all[r] > 0.0f)) continue;
+        const double ratio = std::min(1.25, std::max(0.8, (all[r] / t_sum) / (w[r] / w_sum)));   // measured share / estimated share
+        for (uint32_t u = s->band_row0[r] / unit; u < (s->band_row0[r] + s->band_rows[r] + unit - 1) / unit && u < s->unit_cost.size(); ++u) s->unit_cost[u] *= ratio;
+    }
+    const std::vector<RowBand> bands = partition_units(s->unit_cost, s->full_desc.roi.height, static_cast<uint32_t>(world));
+    bool same = true;
+    for (int r = 0; r < world; ++r) same = same && bands[r].y0 == s->band_row0[r] && bands[r].rows == s->band_rows[r];
+    if (same) return HP_STATUS_SUCCESS;
+    DV_TRY(band_configure(s));
+    if (out_changed) *out_changed = 1;
     return HP_STATUS_SUCCESS;
 }
 
@@ -817,10 +932,13 @@ static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t fla
         DV_CUDA(cudaMemsetAsync(block + floats - 16, 0, 16 * sizeof(float), side));
         DV_CUDA(cudaEventRecord(s->ev_zero, side));
     }
+    DV_CUDA(cudaEventRecord(s->ev_t0, main));
     if (s->frame != nullptr) DV_TRY(hpx_forward(s->frame, s->grid));
     if (flags & HPX_BACKWARD_ZERO) DV_CUDA(cudaStreamWaitEvent(main, s->ev_zero, 0));
     if (s->frame != nullptr)
         DV_TRY(hpx_backward(s->frame, s->grid, dL_dI_device + s->dl_offset_floats, HP_MEMSPACE_DEVICE, flags & ~HPX_BACKWARD_ZERO));
+    DV_CUDA(cudaEventRecord(s->ev_t1, main));
+    s->timed = true;
     if (c->world == 1 || !s->reduce) return HP_STATUS_SUCCESS;
     if (s->direct) {
         // ---- own kernels over peer memory (NVLink): every owner PULLS the wedge parts of its slabs out of its neighbours'
@@ -894,6 +1012,8 @@ HP_API void hpx_shard_release(hpx_shard* s) {
         if (s->ev_zero != nullptr) cudaEventDestroy(s->ev_zero);
         cudaFree(s->staging);
         cudaFree(s->d_flag);
+        if (s->ev_t0 != nullptr) cudaEventDestroy(s->ev_t0);
+        if (s->ev_t1 != nullptr) cudaEventDestroy(s->ev_t1);
         for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     }
     hpx_frame_release(s->frame);

@@ -108,6 +108,7 @@ HPX_FUNCTIONS = {
     "hpx_shard_release": (None, [C.c_void_p]),
     "hpx_shard_create_bands": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_void_p)]),
     "hpx_shard_set_result": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "hpx_shard_rebalance": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "hpx_shard_exchange_is_direct": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "hpx_plan_balanced_bands": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_uint32), P(C.c_double)]),
     "hpx_shard_bands": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_size_t)]),
@@ -469,6 +470,17 @@ class Shard:
 
     def step(self, dL_dI_device_ptr: int, flags: int = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO):
         check("hpx_shard_step", self.lib.hpx_shard_step(self.handle, int(dL_dI_device_ptr), flags))
+
+    def rebalance(self) -> bool:
+        """Collective: re-cut the bands from the measured time of the last step; True when they moved (self.frame is then
+        a new frame)."""
+        changed = C.c_int32()
+        check("hpx_shard_rebalance", self.lib.hpx_shard_rebalance(self.handle, C.byref(changed)))
+        if changed.value:
+            fh = C.c_void_p()
+            check("hpx_shard_frame", self.lib.hpx_shard_frame(self.handle, C.byref(fh)))
+            self.frame = _BorrowedFrame(self.plan, fh) if fh.value else None
+        return bool(changed.value)
 
     def set_reduce(self, enabled: bool):
         check("hpx_shard_set_reduce", self.lib.hpx_shard_set_reduce(self.handle, 1 if enabled else 0))

@@ -291,6 +291,12 @@ HP_API hp_status hpx_shard_layout(const hpx_shard* shard, int32_t* out_slow_axis
 HP_API hp_status hpx_shard_create_bands(hpx_comm* comm, const hp_plan* full_frame_plan, hpx_grid* grid, uint32_t result,
                                         hpx_shard** out_shard);
 HP_API hp_status hpx_shard_set_result(hpx_shard* shard, uint32_t result);
+/* Collective (every rank calls it, after at least one hpx_shard_step).  Re-cuts the bands from MEASURED time: every rank
+ * contributes the GPU time of its last step's forward + backward; bands that took longer than their share get fewer rows.
+ * (The work estimate -- in-cube steps per ray -- does not see cache behaviour or idle lanes; two or three rounds during
+ * warm-up bring the ranks within a few percent.)  *out_changed = 1 when the bands moved: this rank's frame, the wedges and
+ * the owner cuts were rebuilt, so hpx_shard_frame / hpx_shard_owned / hpx_shard_bands must be queried again. */
+HP_API hp_status hpx_shard_rebalance(hpx_shard* shard, int32_t* out_changed);
 /* How the band exchange runs.  1 (default when every rank can map every other rank's gradient block -- peer access inside
  * one process, CUDA IPC between processes of one node): the library's OWN kernels over peer memory: after a stream-ordered
  * cross-GPU barrier every owner pulls the wedge parts of its slabs out of its neighbours' blocks over NVLink and adds them
