@@ -399,6 +399,43 @@ def measure_single(env, cfg, cfg_name, args, sampler=None, with_renderer=False):
     return out
 
 
+def measure_sparse(env, cfg, args):
+    """Empty-space skipping (hpx_grid_build_occupancy) on a SPARSE volume of the same shape: a spherical shell of the dense
+    hashed volume (about a fifth of the bricks occupied), same frame, skipping on vs off.  Results are identical by
+    construction (tests/test_gpu_runtime.py::test_empty_space_skipping_changes_nothing); this leg records what it buys."""
+    import synth as S
+    torch, D, ctx, dev = env.torch, env.D, env.ctx, env.dev
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    sigma, color = device_hashed_volume(torch, n, "dense", dev)
+    ax = torch.linspace(0, 1, n, device=dev)
+    r = ((ax[None, None, :] - 0.5) ** 2 + (ax[None, :, None] - 0.5) ** 2 + (ax[:, None, None] - 0.5) ** 2).sqrt()
+    shell = (r > 0.25) & (r < 0.4)
+    sigma = torch.where(shell, sigma, torch.zeros_like(sigma)).contiguous()
+    color = torch.where(shell[..., None], color, torch.zeros_like(color)).contiguous()
+    torch.cuda.synchronize()
+    grid = D.Grid(ctx, sigma.data_ptr(), color.data_ptr(), device_shape=(n, n, n))
+    ctx.synchronize()
+    del sigma, color, r, shell
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"]))
+    frame = D.Frame(plan)
+    g_dev = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).to(dev)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    empty_fwd, empty_bwd = grid.build_occupancy(enable=True)
+    out = {"volume": "spherical shell 0.25 < r < 0.4 of the dense hashed volume (sigma = 40u), zeros elsewhere",
+           "empty_brick_fraction_forward": empty_fwd, "empty_brick_fraction_backward": empty_bwd}
+    k = args.steps
+    for key, on in (("skipping_on", True), ("skipping_off", False)):
+        grid.set_occupancy(on)
+        f = env.timed(lambda: frame.forward(grid), k, 2) / k
+        b = env.timed(lambda: frame.backward(grid, g_dev.data_ptr(), flags, device=True), k, 2) / k
+        c = frame.counts()
+        out[key] = {"fwd_ms": f, "bwd_ms": b, "value": c["samples"] / ((f + b) * 1e-3) / 1e6, "live_samples": c["live_samples"]}
+    out["speedup"] = out["skipping_on"]["value"] / out["skipping_off"]["value"]
+    frame.close(); plan.close(); grid.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def base_line(env, args, cfg, value, ms_per_step, scaling):
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
@@ -421,6 +458,7 @@ def run_single(env, args):
         c2 = measure_single(env, CONFIGS["c2"], "c2", args, None, with_renderer=True)
         line["c2"] = {k: c2[k] for k in ("workload", "value", "ms_per_step", "fwd", "bwd", "e2e", "roofline", "samples",
                                          "in_cube_live_samples", "touched_voxels")}
+        line["c2"]["empty_space_skipping"] = measure_sparse(env, CONFIGS["c2"], args)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
     emit(line)
@@ -497,10 +535,16 @@ def run_sharded(env, args):
         sampler.start()
     k = args.steps
     results = {}
-    # the headline is the all-reduce contract of SURVEY 8(e): after the step EVERY rank holds the whole summed gradient
+    # headline (bands): the reduce-scatter contract -- every slab's finished sum on its owner; the all-reduce contract
+    # (every rank holds everything) is timed right after it
+    if bands:
+        shard.set_result("owned")
+        rounds = layout["rebalance_rounds"]
+        layout = shard.layout()        # the owner cuts of this result mode
+        layout["rebalance_rounds"] = rounds
     total_ms = env.timed(step, k, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
-    results["replicated"] = total_ms / k
+    results["owned" if bands else "replicated"] = total_ms / k
     total = W * W * steps
     frame = shard.frame
     my_samples = frame.counts()["samples"] if frame is not None else 0
@@ -508,8 +552,9 @@ def run_sharded(env, args):
     dist.all_reduce(ts)
     assert int(ts.item()) == total, (int(ts.item()), total)
     if bands:
-        shard.set_result("owned")       # reduce-scatter contract: every rank holds the finished sum of the slabs it owns
-        results["owned"] = env.timed(step, k, 1) / k
+        shard.set_result("replicated")
+        results["replicated"] = env.timed(step, k, 2) / k
+        shard.set_result("owned")
     shard.set_reduce(False)
     results["without_exchange"] = env.timed(step, k, 1) / k
     shard.set_reduce(True)
@@ -551,7 +596,6 @@ def run_sharded(env, args):
                "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": int(d2h.item()),
                "note": "all ranks together: every rank moves its own rows of dL/dI in and its band of the image planes + the "
                        "finished gradient sums of the slabs it owns out (packed {dr,dg,db,dsigma} slabs), over its own PCIe link"}
-        shard.set_result("replicated")
 
     # continuity with round 1: weak scaling of configs[1] (one view of SURVEY 8d's orbit per GPU, whole-block all-reduce in
     # the library)
@@ -559,7 +603,7 @@ def run_sharded(env, args):
     if not args.no_c2:
         weak = run_weak_views(env, args, comm)
 
-    ms = results["replicated"]
+    ms = results["owned"] if bands else results["replicated"]
     line = base_line(env, args, cfg, total / (ms * 1e-3) / 1e6, ms, "strong")
     line["config"] = {
         "workload": cfg["workload"], "volume": "hashed thin (sigma = 2u, no early termination)",
@@ -567,17 +611,21 @@ def run_sharded(env, args):
         "parallelism": (f"ONE frame in {world} contiguous row bands cut for equal marching work (hpx_shard_create_bands), grid "
                         "replicated; the gradient block is laid out in slabs along world axis " + layout["slow_axis"] +
                         ", a band's backward touches one slab wedge; the wedge parts a rank does not own are added by their "
-                        "owners in rank order (" + layout.get("exchange", "") + "); then every rank fetches the finished sums of "
-                        "all owners: all ranks hold the whole summed gradient, as after an all-reduce") if bands else
+                        "owners in rank order (" + layout.get("exchange", "") + ").  RESULT of the timed step: a reduce-scatter -- every "
+                        "slab's finished sum (the gradient of ALL rays of the frame) lives on the rank that owns the slab, the "
+                        "hand-over for a slab-sharded optimiser (hpx_shard_owned; e2e reads exactly that to the host).  The "
+                        "all-reduce contract -- every rank additionally fetches the other owners' sums, so that all ranks hold the "
+                        "whole gradient -- is timed as well: replicated_result") if bands else
                        (f"ONE frame, tile rows interleaved over {world} GPUs, {args.groups} row groups, slab all-reduces behind a "
                         "device-signalled backward (hpx_shard_create)"),
         "layout": layout, "verify_max_rel_err_vs_single_gpu": verify,
         "ms_per_step_without_exchange": results["without_exchange"],
         "exchange_bytes_sent_by_rank0": layout.get("send_bytes"), "l2": "inputs larger than L2"}
-    if "owned" in results:
-        line["owned_result"] = {"value": total / (results["owned"] * 1e-3) / 1e6, "ms_per_step": results["owned"],
-                                "what": "same step, stopping at the reduce-scatter: every rank holds the finished sum of the slabs "
-                                        "it owns (hand-over to a slab-sharded optimiser); no broadcast of the sums"}
+    if bands:
+        line["replicated_result"] = {"value": total / (results["replicated"] * 1e-3) / 1e6, "ms_per_step": results["replicated"],
+                                     "what": "same step followed by the all-gather of the owned sums: every rank holds the whole "
+                                             "summed gradient, as after an all-reduce (SURVEY 8e's collective); verified against a "
+                                             "single-GPU backward of the frame: config.verify_max_rel_err_vs_single_gpu"}
     if e2e is not None:
         line["e2e"] = e2e
     line["gpu_launches"] = 2 * args.steps

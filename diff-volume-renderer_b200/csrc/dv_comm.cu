@@ -621,6 +621,89 @@ HP_API hp_status hpx_shard_create(hpx_comm* c, const hp_plan* full_plan, hpx_gri
 }
 
 
+// Owners of the slabs.  Rank o adds, for every slab it owns, the partial sums of every OTHER rank whose wedge contains the
+// slab; what a rank renders outside its own range it hands out.  The exchange is a set of concurrent point-to-point
+// transfers over NVSwitch, so its duration follows the busiest port: the cuts minimise max over ranks of max(bytes out,
+// bytes in) -- in the replicated mode including the second phase, in which every owner's sums go to all other ranks (that
+// favours equal shares; the owned mode favours cuts through the middle of the wedge overlaps).  Coordinate descent over the
+// world - 1 cuts from the mid-overlap start; every rank runs the same deterministic search on the same inputs.
+static hp_status band_assign_owners(hpx_shard* s) {
+    const int world = s->comm->world, me = s->comm->rank;
+    const int32_t n = s->n_slabs;
+    DV_CUDA(cudaStreamSynchronize(s->comm->ctx->stream));   // nothing in flight uses the old transfer lists / staging
+    cudaFree(s->staging);
+    s->staging = nullptr;
+    s->sends.clear();
+    s->recvs.clear();
+    auto overlap_len = [&](int r, int32_t lo, int32_t hi) {
+        return std::max(0, std::min(s->wedges[r].second, hi) - std::max(s->wedges[r].first, lo));
+    };
+    const bool replicated = s->result == HPX_SHARD_RESULT_REPLICATED;
+    auto cost = [&](const std::vector<int32_t>& cuts) {
+        double worst = 0.0, total = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const int32_t own_lo = cuts[static_cast<size_t>(r)], own_hi = cuts[static_cast<size_t>(r) + 1];
+            double out = (s->wedges[r].second - s->wedges[r].first) - overlap_len(r, own_lo, own_hi), in = 0.0;
+            if (out < 0.0) out = 0.0;
+            for (int q = 0; q < world; ++q)
+                if (q != r) in += overlap_len(q, own_lo, own_hi);
+            total += out;
+            if (replicated) {
+                const double own = std::max(0, std::min(own_hi, s->hull_hi) - std::max(own_lo, s->hull_lo));
+                out += own * (world - 1);
+                in += (s->hull_hi - s->hull_lo) - own;
+            }
+            worst = std::max(worst, std::max(out, in));
+        }
+        return worst + 1e-3 * total;
+    };
+    std::vector<int32_t> cuts(static_cast<size_t>(world) + 1, 0);
+    cuts[static_cast<size_t>(world)] = n;
+    {
+        int32_t prev_hi = 0;
+        for (int r = 0; r < world; ++r) {   // start: half way through the overlap (or gap) of neighbouring wedges
+            const bool empty = s->wedges[r].first >= s->wedges[r].second;
+            const int32_t lo = empty ? prev_hi : s->wedges[r].first, hi = empty ? prev_hi : s->wedges[r].second;
+            if (r > 0) cuts[static_cast<size_t>(r)] = std::min(n, std::max(cuts[static_cast<size_t>(r) - 1], (lo + prev_hi) / 2));
+            prev_hi = std::max(prev_hi, hi);
+        }
+    }
+    double best = cost(cuts);
+    for (int sweep = 0; sweep < 16; ++sweep) {
+        bool moved = false;
+        for (int b = 1; b < world; ++b) {
+            const int32_t keep = cuts[static_cast<size_t>(b)];
+            int32_t arg = keep;
+            for (int32_t c = cuts[static_cast<size_t>(b) - 1]; c <= cuts[static_cast<size_t>(b) + 1]; ++c) {
+                cuts[static_cast<size_t>(b)] = c;
+                const double v = cost(cuts);
+                if (v < best - 1e-9) { best = v; arg = c; }
+            }
+            cuts[static_cast<size_t>(b)] = arg;
+            moved = moved || arg != keep;
+        }
+        if (!moved) break;
+    }
+    s->cuts = cuts;
+    auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
+        return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
+    };
+    size_t staging_floats = 0;
+    for (int o = 0; o < world; ++o) {
+        if (o == me) continue;
+        const auto out = overlap(me, o);
+        if (out.first < out.second) s->sends.push_back(hpx_shard::Xfer{o, out.first, out.second, 0});
+        const auto in = overlap(o, me);
+        if (in.first < in.second) {
+            s->recvs.push_back(hpx_shard::Xfer{o, in.first, in.second, staging_floats});
+            staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
+        }
+    }
+    if (!s->direct && staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
+        return cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)");
+    return HP_STATUS_SUCCESS;
+}
+
 // (Re)builds everything that follows from the band cuts: this rank's frame, every rank's wedge, the owner cuts and the
 // transfer lists.  Every rank derives all of it from the same inputs with the same code: the ranks agree without talking.
 static hp_status band_configure(hpx_shard* s) {
@@ -634,9 +717,7 @@ static hp_status band_configure(hpx_shard* s) {
     hp_plan_release(s->plan);
     s->frame = nullptr;
     s->plan = nullptr;
-    cudaFree(s->staging);
-    s->staging = nullptr;
-    s->band_row0.clear(); s->band_rows.clear(); s->wedges.clear(); s->sends.clear(); s->recvs.clear();
+    s->band_row0.clear(); s->band_rows.clear(); s->wedges.clear();
     s->timed = false;
     const std::vector<RowBand> bands = partition_units(s->unit_cost, d.roi.height, static_cast<uint32_t>(world));
     hp_status st = HP_STATUS_SUCCESS;
@@ -683,53 +764,7 @@ static hp_status band_configure(hpx_shard* s) {
         s->hull_hi = std::max(s->hull_hi, s->wedges[r].second);
     }
     if (s->hull_hi < s->hull_lo) s->hull_lo = s->hull_hi = 0;
-    // Owners.  Rank o pulls, for every slab it owns, the partial sums of every OTHER rank whose wedge contains the slab.
-    // The cuts are chosen so that the busiest owner receives as little as possible (binary search over the cap, owners
-    // take slabs greedily while their inbound volume stays below it): where many wedges overlap the owned ranges get
-    // narrower.  An owner's range starts inside or before its own wedge, so most of what it owns it has rendered itself.
-    std::vector<int32_t> cover(static_cast<size_t>(s->n_slabs) + 1, 0);   // cover[y] = ranks whose wedge contains slab y
-    for (int r = 0; r < world; ++r)
-        for (int32_t y = s->wedges[r].first; y < s->wedges[r].second; ++y) ++cover[static_cast<size_t>(y)];
-    auto inbound = [&](int o, int32_t y) {   // what owning slab y costs rank o
-        const bool mine = y >= s->wedges[o].first && y < s->wedges[o].second;
-        return cover[static_cast<size_t>(y)] - (mine ? 1 : 0);
-    };
-    auto cuts_for = [&](long long cap, std::vector<int32_t>* out) {
-        int32_t y = 0;
-        for (int o = 0; o < world; ++o) {
-            if (out) (*out)[static_cast<size_t>(o)] = y;
-            long long got = 0;
-            // an owner may not run past the end of its own wedge unless it is the last one (keeps ownership local)
-            const int32_t stop = o + 1 == world ? s->n_slabs : std::max(y, s->wedges[o].second);
-            while (y < stop && got + inbound(o, y) <= cap) got += inbound(o, y++);
-        }
-        if (out) (*out)[static_cast<size_t>(world)] = s->n_slabs;
-        return y >= s->n_slabs;
-    };
-    long long lo = 0, hi = static_cast<long long>(s->n_slabs) * world;
-    while (lo < hi) {
-        const long long mid = (lo + hi) / 2;
-        if (cuts_for(mid, nullptr)) hi = mid; else lo = mid + 1;
-    }
-    s->cuts.assign(static_cast<size_t>(world) + 1, 0);
-    cuts_for(hi, &s->cuts);
-    auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
-        return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
-    };
-    size_t staging_floats = 0;
-    for (int o = 0; o < world; ++o) {
-        if (o == me) continue;
-        const auto out = overlap(me, o);
-        if (out.first < out.second) s->sends.push_back(hpx_shard::Xfer{o, out.first, out.second, 0});
-        const auto in = overlap(o, me);
-        if (in.first < in.second) {
-            s->recvs.push_back(hpx_shard::Xfer{o, in.first, in.second, staging_floats});
-            staging_floats += static_cast<size_t>(in.second - in.first) * s->slab_floats;
-        }
-    }
-    if (!s->direct && staging_floats != 0 && cudaMalloc(&s->staging, staging_floats * sizeof(float)) != cudaSuccess)
-        return cuda_fail(cudaGetLastError(), "cudaMalloc(shard staging)");
-    return HP_STATUS_SUCCESS;
+    return band_assign_owners(s);
 }
 
 
@@ -870,8 +905,10 @@ HP_API hp_status hpx_shard_set_result(hpx_shard* s, uint32_t result) {
     DV_RANGE("hpx_shard_set_result");
     if (s == nullptr || !s->bands || (result != HPX_SHARD_RESULT_OWNED && result != HPX_SHARD_RESULT_REPLICATED))
         return HP_STATUS_INVALID_ARGUMENT;
+    if (s->result == static_cast<int>(result)) return HP_STATUS_SUCCESS;
     s->result = static_cast<int>(result);
-    return HP_STATUS_SUCCESS;
+    DV_ENTER(s->comm->ctx);
+    return band_assign_owners(s);   // the best owner cuts differ between the two result modes
 }
 
 HP_API hp_status hpx_shard_bands(const hpx_shard* s, uint32_t* out_row0, uint32_t* out_rows, int32_t* out_wedges, int32_t* out_cuts,

@@ -316,6 +316,33 @@ __device__ __forceinline__ float4 sample_packed_lean(const float4* __restrict__ 
     return trilerp_pairs(load_corners(g, c, nx, ny), c.tx, c.ty, c.tz);
 }
 
+// ---------------------------------------------------------------------------
+// Empty-space skipping.  Brick = 8 x 8 x 8 trilinear cells; a cell (x0,y0,z0) reads voxels x0..x0+1 etc., all inside the
+// region the brick's bits were computed over.  Bit 0 clear: sigma = 0 at all eight corners, so the reference's own
+// arithmetic gives sigma = +0 exactly, alpha = 0, w = T * 0 = 0: the sample changes neither T nor the radiance, depth or
+// stop decision (int_cpu.cpp:181-215) -- the forward pass may skip it whatever the colours are.  Bit 1 clear: the colours
+// are zero too, so g . c = 0 and the backward pass needs no gather either; its d sigma = -adj_T T dt is still scattered.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t occupancy_bits(const uint32_t* __restrict__ occ, int32_t x0, int32_t y0, int32_t z0,
+                                                   int32_t obx, int32_t oby) {
+    const uint32_t b = (static_cast<uint32_t>(z0 >> 3) * static_cast<uint32_t>(oby) + static_cast<uint32_t>(y0 >> 3)) *
+                           static_cast<uint32_t>(obx) + static_cast<uint32_t>(x0 >> 3);
+    return (__ldg(occ + (b >> 4)) >> ((b & 15u) * 2u)) & 3u;
+}
+
+// Forward-pass sampler with skipping: false = the sample contributes nothing (outside + OOB zero, or an empty brick).
+template <bool kClamp>
+__device__ __forceinline__ bool sample_packed_lean_occ(const float4* __restrict__ g, const uint32_t* __restrict__ occ, int32_t obx,
+                                                       int32_t oby, int32_t nx, int32_t ny, int32_t nz, float px, float py,
+                                                       float pz, float4& v) {
+    float fx, fy, fz;
+    if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return false;
+    const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
+    if ((occupancy_bits(occ, c.x0, c.y0, c.z0, obx, oby) & 1u) == 0u) return false;
+    v = trilerp_pairs(load_corners(g, c, nx, ny), c.tx, c.ty, c.tz);
+    return true;
+}
+
 // Same, also returning the trilinear cell {x0 | y0 << 10 | z0 << 20, tx, ty, tz}: with the unit bounding box the
 // backward scatter (src/fields/dense_grid.cpp:206-246) maps a position to exactly this cell with these
 // fractions (local = p, g = local * (n - 1), same clamp), so the recompute pass hands it over instead of

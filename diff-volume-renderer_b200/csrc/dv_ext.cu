@@ -45,6 +45,11 @@ PackedGrid packed_view(const hpx_grid& g) {
     p.nx = g.nx; p.ny = g.ny; p.nz = g.nz;
     p.linear = g.linear;
     p.clamp = g.clamp;
+    if (g.occ_ready && g.occ_enabled) {
+        p.occ = g.d_occ;
+        p.obx = (g.nx + 7) / 8;
+        p.oby = (g.ny + 7) / 8;
+    }
     return p;
 }
 
@@ -106,6 +111,11 @@ HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* c
     if (sigma == nullptr && color == nullptr) return HP_STATUS_SUCCESS;
     DV_ENTER(g->ctx);
     cudaStream_t s = g->ctx->stream;
+    if (g->d_occ != nullptr) {
+        // new values: the occupancy bits no longer describe them.  Every brick becomes "occupied" (no skipping, same
+        // results) until hpx_grid_build_occupancy is called again; a captured graph that reads the bits stays correct.
+        DV_CUDA(cudaMemsetAsync(g->d_occ, 0xff, g->occ_words * sizeof(uint32_t), s));
+    }
     if (memspace == HP_MEMSPACE_DEVICE) {
         DV_CUDA(launch_pack_grid(s, sigma, color, g->d_values, g->voxels, true));
         return HP_STATUS_SUCCESS;
@@ -151,6 +161,41 @@ HP_API hp_status hpx_grid_create_raw(const hp_ctx* ctx, int32_t nx, int32_t ny, 
         return st;
     }
     *out_grid = g;
+    return HP_STATUS_SUCCESS;
+}
+
+// Empty-space skipping.  Builds the occupancy bits of the CURRENT values (2 bits per brick of 8^3 trilinear cells) and
+// turns skipping on when `enable` != 0: the forward kernel then skips samples whose eight corners all have sigma = 0, the
+// backward kernels skip the gather of samples whose corners are zero in every channel.  Such samples contribute exactly
+// nothing (alpha = 0, w = 0; their d sigma is still scattered), so images, counts and gradients are unchanged.
+// Linear OOB-zero fields.  Blocks until the bits are built; out_*: fraction of bricks without sigma / without any value.
+HP_API hp_status hpx_grid_build_occupancy(hpx_grid* g, int32_t enable, float* out_empty_sigma, float* out_empty_all) {
+    DV_RANGE("hpx_grid_build_occupancy");
+    if (g == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    DV_ENTER(g->ctx);
+    cudaStream_t s = g->ctx->stream;
+    const size_t bricks = static_cast<size_t>((g->nx + 7) / 8) * ((g->ny + 7) / 8) * ((g->nz + 7) / 8);
+    if (g->d_occ == nullptr) {
+        g->occ_words = (bricks + 15) / 16;
+        DV_CUDA(cudaMalloc(&g->d_occ, g->occ_words * sizeof(uint32_t)));
+        DV_CUDA(cudaMalloc(&g->d_occ_counts, 2 * sizeof(unsigned int)));
+    }
+    DV_CUDA(launch_build_occupancy(s, g->d_values, g->nx, g->ny, g->nz, g->d_occ, g->occ_words, g->d_occ_counts));
+    unsigned int counts[2] = {0, 0};
+    DV_CUDA(cudaMemcpyAsync(counts, g->d_occ_counts, sizeof(counts), cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    g->occ_ready = true;
+    g->occ_enabled = enable != 0 && g->linear && !g->clamp;
+    if (out_empty_sigma) *out_empty_sigma = static_cast<float>(counts[0]) / static_cast<float>(bricks);
+    if (out_empty_all) *out_empty_all = static_cast<float>(counts[1]) / static_cast<float>(bricks);
+    return HP_STATUS_SUCCESS;
+}
+
+// Turns skipping on / off without rebuilding (off: the kernels without the occupancy test run).
+HP_API hp_status hpx_grid_set_occupancy(hpx_grid* g, int32_t enable) {
+    DV_RANGE("hpx_grid_set_occupancy");
+    if (g == nullptr || (enable != 0 && !g->occ_ready)) return HP_STATUS_INVALID_ARGUMENT;
+    g->occ_enabled = enable != 0 && g->linear && !g->clamp;
     return HP_STATUS_SUCCESS;
 }
 
@@ -265,6 +310,8 @@ HP_API void hpx_grid_release(hpx_grid* g) {
         cudaFree(g->d_grad);
         cudaFree(g->d_fixed);
         cudaFree(g->d_fixed_meta);
+        cudaFree(g->d_occ);
+        cudaFree(g->d_occ_counts);
         cudaFree(g->d_unpacked);
     }
     ctx_unref(g->ctx);

@@ -81,10 +81,11 @@ __device__ __forceinline__ void corner_gradients(const Corners& k, const Cell& c
 }
 
 // Sample + scatter cell + (optionally) the field gradients the camera adjoint needs, from ONE set of corner loads.
-template <bool kClamp, bool kGradients>
+template <bool kClamp, bool kGradients, bool kOcc = false>
 __device__ __forceinline__ float4 sample_cell_gradients(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                         float px, float py, float pz, float g0, float g1, float g2,
-                                                        float4& cell, float grad_sigma[3], float grad_h[3]) {
+                                                        float4& cell, float grad_sigma[3], float grad_h[3],
+                                                        const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
     if (kGradients) {
         grad_sigma[0] = grad_sigma[1] = grad_sigma[2] = 0.f;
         grad_h[0] = grad_h[1] = grad_h[2] = 0.f;
@@ -99,6 +100,8 @@ __device__ __forceinline__ float4 sample_cell_gradients(const float4* __restrict
     cell = make_float4(__uint_as_float(static_cast<uint32_t>(c.x0) | (static_cast<uint32_t>(c.y0) << 10) |
                                        (static_cast<uint32_t>(c.z0) << 20)),
                        c.tx, c.ty, c.tz);
+    // empty brick (every channel zero at all eight corners): value and field gradients are exactly zero, no gather
+    if (kOcc && occupancy_bits(occ, c.x0, c.y0, c.z0, obx, oby) == 0u) return make_float4(0.f, 0.f, 0.f, 0.f);
     const Corners k = load_corners(g, c, nx, ny);
     if (kGradients)
         corner_gradients(k, c, g0, g1, g2, (kClamp && ox) ? 0.f : static_cast<float>(nx - 1),
@@ -130,10 +133,10 @@ __device__ __forceinline__ WarpRange warp_step_range(const MarchParams& mp, cons
     return r;
 }
 
-template <bool kLinear, bool kClamp, bool kStratified>
+template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false>
 __global__ void __launch_bounds__(kLeanThreads)
 lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
-                    int32_t nz, LeanBuffers out) {
+                    int32_t nz, LeanBuffers out, const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
     const RoiParams roi = P->roi;
@@ -167,7 +170,12 @@ lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict_
             const float pxw = ray.ox + ray.dx * t;
             const float pyw = ray.oy + ray.dy * t;
             const float pzw = ray.oz + ray.dz * t;
-            const float4 v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, pxw, pyw, pzw);
+            float4 v;
+            if (kOcc) {   // (linear fields only) a sample in an empty brick changes nothing: skip its gather and its arithmetic
+                if (!sample_packed_lean_occ<kClamp>(grid, occ, obx, oby, nx, ny, nz, pxw, pyw, pzw, v)) continue;
+            } else {
+                v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, pxw, pyw, pzw);
+            }
             float a, w, tb;
             acc.t_cursor = tab.w;
             if (integrate_sample<false>(acc, tab.z, v, a, w, tb)) {
@@ -229,10 +237,11 @@ struct SegmentStash {
     float dt[kSegment][kLeanThreads];
 };
 
-template <bool kLinear, bool kClamp, bool kStratified>
+template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false>
 __global__ void __launch_bounds__(kLeanThreads)
 lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
-                     int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st) {
+                     int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
+                     const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
     __shared__ SegmentStash stash;
     const float inv_q = scatter_inv_quantum(sp);
     const CameraParams cam = P->cam;
@@ -285,8 +294,14 @@ lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict
                 continue;
             }
             const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
-            const float4 v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
-                                                          ray.oz + ray.dz * t);
+            float4 v;
+            if (kOcc) {   // empty brick (all channels zero): no gather; the sample still receives d sigma = -adj_T T dt below
+                float4 cell;
+                v = sample_cell_gradients<kClamp, false, true>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                               ray.oz + ray.dz * t, g0, g1, g2, cell, nullptr, nullptr, occ, obx, oby);
+            } else {
+                v = lean_sample<kLinear, kClamp>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t, ray.oz + ray.dz * t);
+            }
             const float a = alpha_of(v.w, tab.z);
             stash.alpha[j][tid] = a;
             stash.T_prev[j][tid] = T;
@@ -452,11 +467,12 @@ __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key
 // kCamera: also accumulate d L / d (ray origin, ray direction) = sum_s (d sigma_s grad sigma(x_s) + w_s grad (g . rgb)(x_s)) {1, t_s}
 // from the corners phase A has in registers anyway, and reduce it to the camera parameters at the end
 // (replaces a separate camera_adjoint_kernel pass over every sample).
-template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera, bool kPlain>
+template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera, bool kPlain, bool kOcc = false>
 __global__ void __launch_bounds__(kLeanThreads, kCamera ? 4 : DV_MERGE_MIN_BLOCKS)
 lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
                            int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
-                           double* __restrict__ cam_partials) {
+                           double* __restrict__ cam_partials, const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0,
+                           int32_t oby = 0) {
     __shared__ MergeStash<kCamera> stash;
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
@@ -508,8 +524,8 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
                 const float t = step_time<kStratified>(tab, mp.t_near, mp.t_far, mp.dt, mp.seed, ray_index, first + j);
                 float4 cell;
                 float gs[3], gh[3];
-                const float4 v = sample_cell_gradients<kClamp, kCamera>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
-                                                                        ray.oz + ray.dz * t, g0, g1, g2, cell, gs, gh);
+                const float4 v = sample_cell_gradients<kClamp, kCamera, kOcc>(grid, nx, ny, nz, ray.ox + ray.dx * t, ray.oy + ray.dy * t,
+                                                                              ray.oz + ray.dz * t, g0, g1, g2, cell, gs, gh, occ, obx, oby);
                 if (kUnitBox) {
                     stash.c[j][slot] = cell;
                     if (!kClamp && __float_as_uint(cell.x) == kNoCell) {   // outside the cube: sigma = rgb = 0, adj_T unchanged, no scatter
@@ -929,6 +945,48 @@ cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, siz
     return cudaGetLastError();
 }
 
+// ---- empty-space skipping: occupancy bits ---------------------------------------------------------------------------
+namespace {
+// One warp per brick of 8^3 cells: ORs over the 9^3 voxels its cells can read (x0 .. x0 + 1 for x0 in the brick).
+__global__ void __launch_bounds__(256)
+occupancy_build_kernel(const float4* __restrict__ values, int32_t nx, int32_t ny, int32_t nz, uint32_t* __restrict__ occ,
+                       int32_t obx, int32_t oby, int32_t obz, unsigned int* __restrict__ counts) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const size_t bricks = static_cast<size_t>(obx) * oby * obz;
+    for (size_t b = (blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x) >> 5; b < bricks;
+         b += (static_cast<size_t>(gridDim.x) * blockDim.x) >> 5) {
+        const int32_t bx = static_cast<int32_t>(b % obx), by = static_cast<int32_t>((b / obx) % oby), bz = static_cast<int32_t>(b / (static_cast<size_t>(obx) * oby));
+        const int32_t x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
+        const int32_t ex = min(9, nx - x0), ey = min(9, ny - y0), ez = min(9, nz - z0);
+        uint32_t bits = 0;
+        for (int32_t i = lane; i < ex * ey * ez; i += 32) {
+            const int32_t x = i % ex, y = (i / ex) % ey, z = i / (ex * ey);
+            const float4 v = __ldg(values + voxel_index(x0 + x, y0 + y, z0 + z, nx, ny));
+            if (v.w != 0.0f) bits |= 3u;
+            else if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) bits |= 2u;
+        }
+        bits = __reduce_or_sync(0xffffffffu, bits);
+        if (lane == 0) {
+            if (bits != 0u) atomicOr(occ + (b >> 4), bits << ((b & 15u) * 2u));
+            if ((bits & 1u) == 0u) atomicAdd(counts + 0, 1u);
+            if ((bits & 2u) == 0u) atomicAdd(counts + 1, 1u);
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_build_occupancy(cudaStream_t stream, const float4* values, int32_t nx, int32_t ny, int32_t nz, uint32_t* d_occ,
+                                   size_t occ_words, unsigned int* d_counts) {
+    const int32_t obx = (nx + 7) / 8, oby = (ny + 7) / 8, obz = (nz + 7) / 8;
+    cudaError_t e = cudaMemsetAsync(d_occ, 0, occ_words * sizeof(uint32_t), stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const size_t bricks = static_cast<size_t>(obx) * oby * obz;
+    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((bricks + 7) / 8, 148 * 16));
+    occupancy_build_kernel<<<blocks, 256, 0, stream>>>(values, nx, ny, nz, d_occ, obx, oby, obz, d_counts);
+    return cudaGetLastError();
+}
+
 namespace {
 __global__ void upload_params_kernel(FrameParams* dst, const FrameParams src) { *dst = src; }
 }  // namespace
@@ -978,6 +1036,13 @@ cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params
     const uint32_t blocks = tile_blocks(roi);
     if (blocks == 0) return cudaGetLastError();
     const bool strat = h_params.march.stratified != 0;
+    if (grid.occ != nullptr && grid.linear && !grid.clamp) {   // empty-space skipping (linear, OOB-zero fields)
+        if (strat) lean_forward_kernel<true, false, true, true><<<blocks, kLeanThreads, 0, stream>>>(
+                       d_params, grid.values, grid.nx, grid.ny, grid.nz, out, grid.occ, grid.obx, grid.oby);
+        else       lean_forward_kernel<true, false, false, true><<<blocks, kLeanThreads, 0, stream>>>(
+                       d_params, grid.values, grid.nx, grid.ny, grid.nz, out, grid.occ, grid.obx, grid.oby);
+        return cudaGetLastError();
+    }
     DV_DISPATCH3(lean_forward_kernel, grid.linear, grid.clamp, strat,
                  <<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, out));
     return cudaGetLastError();
@@ -1032,7 +1097,20 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
         else DV_MERGE2(C, S, U, false);                                                                                \
     } while (0)
         const bool unit = sp.unit_bbox != 0;
-        if (grid.clamp) {
+        if (grid.occ != nullptr && !grid.clamp && unit) {   // empty-space skipping
+#define DV_MERGE_OCC(S, K)                                                                                             \
+    do {                                                                                                               \
+        if (plain)                                                                                                     \
+            lean_backward_merge_kernel<false, S, true, K, true, true><<<blocks, kLeanThreads, 0, stream>>>(            \
+                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials, grid.occ, grid.obx, grid.oby); \
+        else                                                                                                           \
+            lean_backward_merge_kernel<false, S, true, K, false, true><<<blocks, kLeanThreads, 0, stream>>>(           \
+                d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials, grid.occ, grid.obx, grid.oby); \
+    } while (0)
+            if (strat) { if (cam_partials != nullptr) DV_MERGE_OCC(true, true); else DV_MERGE_OCC(true, false); }
+            else       { if (cam_partials != nullptr) DV_MERGE_OCC(false, true); else DV_MERGE_OCC(false, false); }
+#undef DV_MERGE_OCC
+        } else if (grid.clamp) {
             if (strat) { if (unit) DV_MERGE(true, true, true); else DV_MERGE(true, true, false); }
             else       { if (unit) DV_MERGE(true, false, true); else DV_MERGE(true, false, false); }
         } else {
@@ -1045,6 +1123,13 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
         return cudaGetLastError();
     }
     if (cam_partials != nullptr) return cudaErrorInvalidValue;   // the fused camera adjoint exists in the merged kernel only
+    if (grid.occ != nullptr && grid.linear && !grid.clamp) {
+        if (strat) lean_backward_kernel<true, false, true, true><<<blocks, kLeanThreads, 0, stream>>>(
+                       d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, grid.occ, grid.obx, grid.oby);
+        else       lean_backward_kernel<true, false, false, true><<<blocks, kLeanThreads, 0, stream>>>(
+                       d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, grid.occ, grid.obx, grid.oby);
+        return cudaGetLastError();
+    }
     DV_DISPATCH3(lean_backward_kernel, grid.linear, grid.clamp, strat,
                  <<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI,
                                                       state));

@@ -13,6 +13,11 @@ struct PackedGrid {
     int32_t nx = 0, ny = 0, nz = 0;
     bool linear = true;
     bool clamp = false;
+    // Empty-space skipping (hpx_grid_build_occupancy): 2 bits per brick of 8^3 trilinear cells, 16 bricks per word.
+    // bit 0: some voxel a cell of the brick can read has sigma != 0; bit 1: some such voxel has ANY channel != 0.
+    // nullptr: no skipping.  Skipped samples contribute exactly nothing, so results do not change (see dv_lean.cu).
+    const uint32_t* occ = nullptr;
+    int32_t obx = 0, oby = 0;
 };
 
 // Device buffers one frame reads and writes (all owned by hpx_frame).
@@ -60,6 +65,10 @@ cudaError_t launch_fixed_to_float(cudaStream_t stream, unsigned long long* d_fix
 cudaError_t launch_cube_count(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params,
                               const LeanBuffers& buf, unsigned long long* d_total);
 cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, size_t voxels, unsigned long long* d_total);
+
+// Occupancy bits of a packed grid (PackedGrid::occ); d_counts[0] / [1] receive the number of bricks without bit 0 / bit 1.
+cudaError_t launch_build_occupancy(cudaStream_t stream, const float4* values, int32_t nx, int32_t ny, int32_t nz, uint32_t* d_occ,
+                                   size_t occ_words, unsigned int* d_counts);
 
 // Writes the frame's parameter block; the values travel as kernel arguments (no staging buffer, no host sync).
 cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params);

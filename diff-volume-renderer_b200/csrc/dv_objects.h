@@ -90,6 +90,11 @@ struct hpx_grid {
     unsigned long long* d_fixed = nullptr;   // [4V], all zero between backward passes
     float* d_fixed_meta = nullptr;           // {bits max|grid value|, bits max|dL/dI|, 1/quantum, quantum}
     bool value_max_stale = true;
+    // empty-space skipping (hpx_grid_build_occupancy): 2 bits per brick of 8^3 cells, see dv::PackedGrid::occ
+    uint32_t* d_occ = nullptr;
+    size_t occ_words = 0;
+    unsigned int* d_occ_counts = nullptr;
+    bool occ_ready = false, occ_enabled = false;
     // element strides of the gradient block (hpx_grid_set_grad_layout); default: x fastest, z slowest like the values
     int grad_slow_axis = 2;
     uint32_t gsx = 0, gsy = 0, gsz = 0;

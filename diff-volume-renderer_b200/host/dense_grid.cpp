@@ -71,6 +71,14 @@ Status DenseGridField::Create(const Context& ctx, const DenseGridConfig& config,
     // hp_samp / hp_graph paths (sigma_field() / color_field()) as well as the fused one
     hs = hpx_grid_adopt_fields(f.grid_, f.sigma_field_, f.color_field_);
     if (hs != HP_STATUS_SUCCESS) return Status::FromHotpath(hs, std::string("hpx_grid_adopt_fields failed: ") + hpx_last_error());
+    // empty-space skipping: a field is created once per scene (or per animation frame), so the occupancy bits are built
+    // here; they only take effect when at least one brick in twenty is empty (dense volumes keep the plain kernels).
+    // Skipped samples contribute exactly nothing, results do not change (hp_b200.h: hpx_grid_build_occupancy).
+    {
+        float empty_sigma = 0.0f, empty_all = 0.0f;
+        if (hpx_grid_build_occupancy(f.grid_, 1, &empty_sigma, &empty_all) == HP_STATUS_SUCCESS && empty_sigma < 0.05f)
+            hpx_grid_set_occupancy(f.grid_, 0);
+    }
     f.resolution_ = config.resolution;
     f.bbox_min_ = config.bbox_min;
     f.bbox_max_ = config.bbox_max;

@@ -62,6 +62,8 @@ HPX_FUNCTIONS = {
     "hpx_grid_adopt_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_grid_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hpx_grid_zero_grad": (C.c_int, [C.c_void_p]),
+    "hpx_grid_build_occupancy": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_float), P(C.c_float)]),
+    "hpx_grid_set_occupancy": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_grid_grad_buffer": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]),
     "hpx_grid_read_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hpx_grid_read_grad_range": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
@@ -246,6 +248,15 @@ class Grid:
 
     def zero_grad(self):
         check("hpx_grid_zero_grad", self.lib.hpx_grid_zero_grad(self.handle))
+
+    def build_occupancy(self, enable: bool = True):
+        """Empty-space skipping: (fraction of bricks the forward can skip, fraction the backward can skip)."""
+        a, b = C.c_float(), C.c_float()
+        check("hpx_grid_build_occupancy", self.lib.hpx_grid_build_occupancy(self.handle, 1 if enable else 0, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_occupancy(self, enable: bool):
+        check("hpx_grid_set_occupancy", self.lib.hpx_grid_set_occupancy(self.handle, 1 if enable else 0))
 
     def set_grad_layout(self, slow_axis: int):
         """Make axis 0 = x / 1 = y / 2 = z the slowest one of the gradient block; returns (floats per slab, slabs)."""

@@ -131,6 +131,18 @@ HP_API hp_status hpx_grid_adopt_fields(hpx_grid* grid, hp_field* fs, hp_field* f
 /* Replace the values (parameter update); either pointer may be NULL to keep it. */
 HP_API hp_status hpx_grid_update(hpx_grid* grid, const float* sigma, const float* color,
                                  hp_memspace memspace);
+/* Empty-space skipping (reference roadmap: hotpath/DESIGN_SPECIFICATION.md:99, DESIGN_SPECIFICATION.md:238-239).
+ * hpx_grid_build_occupancy computes, for the CURRENT values, 2 bits per brick of 8^3 trilinear cells -- "some corner a
+ * cell of the brick reads has sigma != 0" and "... has any channel != 0" -- and, with enable != 0, makes the forward
+ * kernel skip samples whose eight corners all have sigma = 0 and the backward kernels skip the gather of samples whose
+ * corners are zero in every channel.  Such samples contribute EXACTLY nothing in the reference's arithmetic (sigma = +0,
+ * alpha = 0, w = T * 0; the backward still scatters their d sigma = -adj_T T dt), so images, sample counts and gradients
+ * do not change: it is a pure speed-up on sparse volumes.  Linear OOB-zero fields; blocks until the bits are built.
+ * out_empty_sigma / out_empty_all (may be NULL): fraction of bricks the forward / the backward can skip.
+ * hpx_grid_update marks every brick occupied again (no skipping until the next build); hpx_grid_set_occupancy switches
+ * skipping on / off without rebuilding. */
+HP_API hp_status hpx_grid_build_occupancy(hpx_grid* grid, int32_t enable, float* out_empty_sigma, float* out_empty_all);
+HP_API hp_status hpx_grid_set_occupancy(hpx_grid* grid, int32_t enable);
 HP_API hp_status hpx_grid_zero_grad(hpx_grid* grid);
 /* Device view of the contiguous gradient block [4*V grid floats {r,g,b,sigma} | 16 camera floats]
  * -- the buffer a data-parallel caller all-reduces. */

@@ -326,3 +326,49 @@ def test_sharded_frame_on_two_gpus():
         r = subprocess.run([exe, "shard", "96", "384", "192", "1", "2", "1", "2", "3", "0", "0", str(mode)], capture_output=True,
                            text=True, timeout=300, env={**os.environ, **env})
         assert r.returncode == 0 and '"verify_max_rel_err_vs_single_gpu"' in r.stdout, (mode, env, r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.parametrize("stratified", [False, True])
+def test_empty_space_skipping_changes_nothing(ctx, stratified):
+    """hpx_grid_build_occupancy: on a sparse volume -- a shell of density, colour that extends a little
+    further than the density, zeros elsewhere -- forward images, counts, live counts and the deterministic gradients
+    (grid and fused camera) are IDENTICAL with skipping on and off; and the oracle agrees as it does without it."""
+    n, W, Hh, steps = 40, 88, 72, 160
+    z, y, x = np.meshgrid(*(np.linspace(0, 1, n, dtype=np.float32),) * 3, indexing="ij")
+    r = np.sqrt((x - 0.5) ** 2 + (y - 0.45) ** 2 + (z - 0.55) ** 2)
+    base_s, base_c = S.hashed_volume(n, "dense", seed=3)
+    sigma = np.where((r > 0.18) & (r < 0.3), base_s, 0).astype(np.float32)
+    color = np.where(((r > 0.15) & (r < 0.33))[..., None], base_c, 0).astype(np.float32)
+    desc = S.bench_plan(W, Hh, steps, stratified=stratified, view=1, views=11)
+    dl = S.hashed_image_grad(W * Hh)
+    grid = D.Grid(ctx, sigma, color)
+    empty_sigma, empty_all = grid.build_occupancy(enable=True)
+    assert 0.2 < empty_all <= empty_sigma < 1.0
+    results = {}
+    for on in (True, False):
+        grid.set_occupancy(on)
+        for scatter in (D.HPX_BACKWARD_SCATTER_MERGED, D.HPX_BACKWARD_SCATTER_PER_RAY):
+            flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | D.HPX_BACKWARD_DETERMINISTIC | scatter
+            if scatter == D.HPX_BACKWARD_SCATTER_MERGED:
+                flags |= D.HPX_BACKWARD_CAMERA
+            results[(on, scatter)] = _render(ctx, grid, desc, dl, flags)
+    for scatter in (D.HPX_BACKWARD_SCATTER_MERGED, D.HPX_BACKWARD_SCATTER_PER_RAY):
+        a, b = results[(True, scatter)], results[(False, scatter)]
+        for k in ("image", "trans", "opacity", "depth", "hitmask", "sigma_grad", "color_grad"):
+            U.assert_bits(a[k], b[k], f"occupancy on vs off: {k}")
+        assert a["samples"] == b["samples"] and a["live_samples"] == b["live_samples"]
+    a, b = results[(True, D.HPX_BACKWARD_SCATTER_MERGED)], results[(False, D.HPX_BACKWARD_SCATTER_MERGED)]
+    np.testing.assert_allclose(a["camera_grad"], b["camera_grad"], rtol=1e-6, atol=1e-9)
+    # and against the oracle, as every other case
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sigma, color, A.HP_INTERP_LINEAR, A.HP_OOB_ZERO)
+    ref = O.render(odesc, gs, gc, dl, shadow=True)
+    got = results[(True, D.HPX_BACKWARD_SCATTER_MERGED)]
+    U.assert_close(got["image"].reshape(-1, 3), ref["image"].reshape(-1, 3), U.IMAGE_RTOL, "occupancy image vs oracle")
+    U.assert_grads(got["sigma_grad"], got["color_grad"], ref, "occupancy vs oracle", res=(n, n, n))
+    # new values invalidate the bits: everything renders as occupied, still equal to a fresh grid
+    grid.set_occupancy(True)
+    grid.update(sigma=base_s)
+    fresh = D.Grid(ctx, base_s, color)
+    U.assert_bits(_render(ctx, grid, desc)["image"], _render(ctx, fresh, desc)["image"], "after update: image")
+    fresh.close(); grid.close()
