@@ -10,6 +10,7 @@
 
 #include <cfloat>
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
@@ -196,7 +197,21 @@ __device__ __forceinline__ uint32_t voxel_index32(int32_t x, int32_t y, int32_t 
 
 struct Corners { float4 v000, v100, v010, v110, v001, v101, v011, v111; };
 
-__device__ __forceinline__ Corners load_corners(const float4* __restrict__ g, const Cell& c, int32_t nx, int32_t ny) {
+// Storage of one packed voxel: float4 {r,g,b,sigma} (16 B, the default) or four IEEE halfs (8 B, hpx_grid_set_storage).
+// Half storage changes what is STORED, not the arithmetic: a voxel is widened to float4 exactly on load and everything
+// downstream is the same fp32 code, so a half grid renders exactly like an fp32 grid holding the rounded values.
+struct HalfVoxel { uint2 bits; };   // {r, g} | {b, sigma}
+
+__device__ __forceinline__ float4 load_voxel(const float4* __restrict__ g, uint32_t i) { return __ldg(g + i); }
+__device__ __forceinline__ float4 load_voxel(const HalfVoxel* __restrict__ g, uint32_t i) {
+    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(g) + i);
+    const float2 rg = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 bs = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    return make_float4(rg.x, rg.y, bs.x, bs.y);
+}
+
+template <class V>
+__device__ __forceinline__ Corners load_corners(const V* __restrict__ g, const Cell& c, int32_t nx, int32_t ny) {
     const uint32_t i000 = voxel_index32(c.x0, c.y0, c.z0, nx, ny);
     const uint32_t ox = static_cast<uint32_t>(c.x1 - c.x0);                                       // 0 or 1
     const uint32_t oy = static_cast<uint32_t>(c.y1 - c.y0) * static_cast<uint32_t>(nx);           // 0 or one row
@@ -210,16 +225,16 @@ __device__ __forceinline__ Corners load_corners(const float4* __restrict__ g, co
         return k;
     }
 #endif
-    k.v000 = __ldg(g + i000);           k.v100 = __ldg(g + (i000 + ox));
-    k.v010 = __ldg(g + (i000 + oy));      k.v110 = __ldg(g + (i000 + oy + ox));
-    k.v001 = __ldg(g + (i000 + oz));      k.v101 = __ldg(g + (i000 + oz + ox));
-    k.v011 = __ldg(g + (i000 + oz + oy)); k.v111 = __ldg(g + (i000 + oz + oy + ox));
+    k.v000 = load_voxel(g, i000);           k.v100 = load_voxel(g, i000 + ox);
+    k.v010 = load_voxel(g, i000 + oy);      k.v110 = load_voxel(g, i000 + oy + ox);
+    k.v001 = load_voxel(g, i000 + oz);      k.v101 = load_voxel(g, i000 + oz + ox);
+    k.v011 = load_voxel(g, i000 + oz + oy); k.v111 = load_voxel(g, i000 + oz + oy + ox);
     return k;
 }
 
 // Packed {r,g,b,sigma} gather: 8 x 16-byte loads through the read-only path.
-template <bool kLinear, bool kClamp, bool kExactColor = true>
-__device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+template <bool kLinear, bool kClamp, bool kExactColor = true, class V = float4>
+__device__ __forceinline__ float4 sample_packed(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                 float px, float py, float pz) {
     float fx, fy, fz;
     if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,7 +242,7 @@ __device__ __forceinline__ float4 sample_packed(const float4* __restrict__ g, in
         const int32_t ix = static_cast<int32_t>(roundf(fx));
         const int32_t iy = static_cast<int32_t>(roundf(fy));
         const int32_t iz = static_cast<int32_t>(roundf(fz));
-        return __ldg(g + voxel_index32(ix, iy, iz, nx, ny));
+        return load_voxel(g, voxel_index32(ix, iy, iz, nx, ny));
     }
     const Cell c = make_cell(fx, fy, fz, nx, ny, nz);
     const Corners k = load_corners(g, c, nx, ny);
@@ -307,8 +322,8 @@ __device__ __forceinline__ float4 trilerp_pairs(const Corners& k, float tx, floa
     return o;
 }
 
-template <bool kClamp>
-__device__ __forceinline__ float4 sample_packed_lean(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+template <bool kClamp, class V>
+__device__ __forceinline__ float4 sample_packed_lean(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                      float px, float py, float pz) {
     float fx, fy, fz;
     if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) return make_float4(0.f, 0.f, 0.f, 0.f);
@@ -331,8 +346,8 @@ __device__ __forceinline__ uint32_t occupancy_bits(const uint32_t* __restrict__ 
 }
 
 // Forward-pass sampler with skipping: false = the sample contributes nothing (outside + OOB zero, or an empty brick).
-template <bool kClamp>
-__device__ __forceinline__ bool sample_packed_lean_occ(const float4* __restrict__ g, const uint32_t* __restrict__ occ, int32_t obx,
+template <bool kClamp, class V>
+__device__ __forceinline__ bool sample_packed_lean_occ(const V* __restrict__ g, const uint32_t* __restrict__ occ, int32_t obx,
                                                        int32_t oby, int32_t nx, int32_t ny, int32_t nz, float px, float py,
                                                        float pz, float4& v) {
     float fx, fy, fz;
@@ -347,8 +362,8 @@ __device__ __forceinline__ bool sample_packed_lean_occ(const float4* __restrict_
 // backward scatter (src/fields/dense_grid.cpp:206-246) maps a position to exactly this cell with these
 // fractions (local = p, g = local * (n - 1), same clamp), so the recompute pass hands it over instead of
 // deriving it a second time.  Outside + OOB-zero: key = 0xffffffff.
-template <bool kClamp>
-__device__ __forceinline__ float4 sample_packed_lean_cell(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+template <bool kClamp, class V>
+__device__ __forceinline__ float4 sample_packed_lean_cell(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                           float px, float py, float pz, float4& cell) {
     float fx, fy, fz;
     if (!grid_coords(px, py, pz, kClamp, nx, ny, nz, fx, fy, fz)) {

@@ -42,6 +42,7 @@ hp_status grid_ensure_grad(hpx_grid* g) {
 PackedGrid packed_view(const hpx_grid& g) {
     PackedGrid p;
     p.values = g.d_values;
+    p.half_values = g.d_half;
     p.nx = g.nx; p.ny = g.ny; p.nz = g.nz;
     p.linear = g.linear;
     p.clamp = g.clamp;
@@ -116,8 +117,11 @@ HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* c
         // results) until hpx_grid_build_occupancy is called again; a captured graph that reads the bits stays correct.
         DV_CUDA(cudaMemsetAsync(g->d_occ, 0xff, g->occ_words * sizeof(uint32_t), s));
     }
+    const bool half = g->d_half != nullptr;
+    char* const half_base = static_cast<char*>(g->d_half);
     if (memspace == HP_MEMSPACE_DEVICE) {
-        DV_CUDA(launch_pack_grid(s, sigma, color, g->d_values, g->voxels, true));
+        if (half) DV_CUDA(launch_pack_grid_half(s, sigma, color, half_base, g->voxels));
+        else DV_CUDA(launch_pack_grid(s, sigma, color, g->d_values, g->voxels, true));
         return HP_STATUS_SUCCESS;
     }
     // HOST: stream the arrays through a bounded staging buffer and interleave on the device
@@ -130,7 +134,8 @@ HP_API hp_status hpx_grid_update(hpx_grid* g, const float* sigma, const float* c
         const size_t n = std::min(chunk, g->voxels - off);
         if (sigma) DV_CUDA(cudaMemcpyAsync(d_sig, sigma + off, n * 4, cudaMemcpyHostToDevice, s));
         if (color) DV_CUDA(cudaMemcpyAsync(d_col, color + 3 * off, n * 12, cudaMemcpyHostToDevice, s));
-        DV_CUDA(launch_pack_grid(s, d_sig, d_col, g->d_values + off, n, true));
+        if (half) DV_CUDA(launch_pack_grid_half(s, d_sig, d_col, half_base + off * 8, n));
+        else DV_CUDA(launch_pack_grid(s, d_sig, d_col, g->d_values + off, n, true));
     }
     DV_CUDA(cudaStreamSynchronize(s));  // the caller may free its buffers; scratch is released
     return HP_STATUS_SUCCESS;
@@ -180,7 +185,8 @@ HP_API hp_status hpx_grid_build_occupancy(hpx_grid* g, int32_t enable, float* ou
         DV_CUDA(cudaMalloc(&g->d_occ, g->occ_words * sizeof(uint32_t)));
         DV_CUDA(cudaMalloc(&g->d_occ_counts, 2 * sizeof(unsigned int)));
     }
-    DV_CUDA(launch_build_occupancy(s, g->d_values, g->nx, g->ny, g->nz, g->d_occ, g->occ_words, g->d_occ_counts));
+    DV_CUDA(launch_build_occupancy(s, g->d_half != nullptr ? static_cast<const float4*>(g->d_half) : g->d_values, g->nx, g->ny, g->nz,
+                                   g->d_occ, g->occ_words, g->d_occ_counts, g->d_half != nullptr));
     unsigned int counts[2] = {0, 0};
     DV_CUDA(cudaMemcpyAsync(counts, g->d_occ_counts, sizeof(counts), cudaMemcpyDeviceToHost, s));
     DV_CUDA(cudaStreamSynchronize(s));
@@ -188,6 +194,40 @@ HP_API hp_status hpx_grid_build_occupancy(hpx_grid* g, int32_t enable, float* ou
     g->occ_enabled = enable != 0 && g->linear && !g->clamp;
     if (out_empty_sigma) *out_empty_sigma = static_cast<float>(counts[0]) / static_cast<float>(bricks);
     if (out_empty_all) *out_empty_all = static_cast<float>(counts[1]) / static_cast<float>(bricks);
+    return HP_STATUS_SUCCESS;
+}
+
+// Storage precision of the packed VALUES (the gradient block stays fp32).  HPX_STORAGE_F16 keeps four IEEE halfs per voxel
+// (8 B instead of 16: half the gather bytes, half the HBM footprint -- a 1024^3 grid drops from 17.2 GB to 8.6 GB).  The
+// values are rounded to half ONCE (round to nearest even); a voxel is widened back to fp32 exactly when it is loaded and
+// all arithmetic stays the fp32 code of dv_device.cuh, so the grid renders and differentiates exactly like an fp32 grid
+// that holds the rounded values (that grid, through the oracle, is the parity twin: tests/test_gpu_runtime.py).
+// Linear OOB-zero grids with the unit scatter box and no adopted hp_fields (the staged hp.h calls read fp32 views).
+HP_API hp_status hpx_grid_set_storage(hpx_grid* g, uint32_t storage) {
+    DV_RANGE("hpx_grid_set_storage");
+    if (g == nullptr || (storage != HPX_STORAGE_F32 && storage != HPX_STORAGE_F16)) return HP_STATUS_INVALID_ARGUMENT;
+    const bool want_half = storage == HPX_STORAGE_F16;
+    if (want_half == (g->d_half != nullptr)) return HP_STATUS_SUCCESS;
+    if (want_half && (!g->linear || g->clamp || scatter_params(*g).unit_bbox == 0u || !g->views.empty())) {
+        set_last_error("half storage needs a linear OOB-zero grid with the unit scatter box and no adopted fields");
+        return HP_STATUS_UNSUPPORTED;
+    }
+    DV_ENTER(g->ctx);
+    cudaStream_t s = g->ctx->stream;
+    if (want_half) {
+        DV_CUDA(cudaMalloc(&g->d_half, std::max<size_t>(g->voxels, 1) * 8));
+        DV_CUDA(launch_convert_storage(s, g->d_values, g->d_half, g->voxels, true));
+        DV_CUDA(cudaStreamSynchronize(s));
+        cudaFree(g->d_values);
+        g->d_values = nullptr;
+    } else {
+        DV_CUDA(cudaMalloc(&g->d_values, std::max<size_t>(g->voxels, 1) * sizeof(float4)));
+        DV_CUDA(launch_convert_storage(s, g->d_values, g->d_half, g->voxels, false));
+        DV_CUDA(cudaStreamSynchronize(s));
+        cudaFree(g->d_half);
+        g->d_half = nullptr;
+    }
+    g->value_max_stale = true;
     return HP_STATUS_SUCCESS;
 }
 
@@ -307,6 +347,7 @@ HP_API void hpx_grid_release(hpx_grid* g) {
         scope.enter(g->ctx);
         cudaStreamSynchronize(g->ctx->stream);
         cudaFree(g->d_values);
+        cudaFree(g->d_half);
         cudaFree(g->d_grad);
         cudaFree(g->d_fixed);
         cudaFree(g->d_fixed_meta);
@@ -324,6 +365,10 @@ HP_API hp_status hpx_grid_adopt_fields(hpx_grid* g, hp_field* fs, hp_field* fc) 
     DV_RANGE("hpx_grid_adopt_fields");
     if (g == nullptr || (fs == nullptr && fc == nullptr)) return HP_STATUS_INVALID_ARGUMENT;
     if ((fs && fs->kind != FieldKind::kDenseSigma) || (fc && fc->kind != FieldKind::kDenseColor)) return HP_STATUS_INVALID_ARGUMENT;
+    if (g->d_half != nullptr) {
+        set_last_error("a grid stored as halfs cannot back hp_fields (the staged hp.h calls read fp32 views)");
+        return HP_STATUS_UNSUPPORTED;
+    }
     for (hp_field* f : {fs, fc}) {
         if (f == nullptr) continue;
         if (f->ctx != g->ctx || f->nx != g->nx || f->ny != g->ny || f->nz != g->nz ||
@@ -545,7 +590,8 @@ static hp_status enqueue_backward(hpx_frame* f, hpx_grid* g, const float* d_dL_d
             uint32_t* meta_bits = reinterpret_cast<uint32_t*>(g->d_fixed_meta);
             if (g->value_max_stale || capturing) {
                 DV_CUDA(cudaMemsetAsync(meta_bits, 0, sizeof(uint32_t), s));
-                DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits, true));
+                if (g->d_half != nullptr) DV_CUDA(launch_abs_max_half(s, g->d_half, g->voxels, meta_bits));
+                else DV_CUDA(launch_abs_max(s, reinterpret_cast<const float*>(g->d_values), g->voxels * 4, meta_bits, true));
                 if (!capturing) g->value_max_stale = false;
             }
             DV_CUDA(cudaMemsetAsync(meta_bits + 1, 0, sizeof(uint32_t), s));

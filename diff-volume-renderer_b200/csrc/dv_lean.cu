@@ -50,11 +50,11 @@ __device__ __forceinline__ TilePixel tile_pixel(const RoiParams& roi) {
     return p;
 }
 
-template <bool kLinear, bool kClamp>
-__device__ __forceinline__ float4 lean_sample(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz, float px,
+template <bool kLinear, bool kClamp, class V>
+__device__ __forceinline__ float4 lean_sample(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz, float px,
                                               float py, float pz) {
     if (kLinear) return sample_packed_lean<kClamp>(g, nx, ny, nz, px, py, pz);
-    return sample_packed<false, kClamp, false>(g, nx, ny, nz, px, py, pz);
+    return sample_packed<false, kClamp, false, V>(g, nx, ny, nz, px, py, pz);
 }
 
 // d/d(position) of sigma and of h = g . rgb inside one trilinear cell: differences of the lerped
@@ -81,8 +81,8 @@ __device__ __forceinline__ void corner_gradients(const Corners& k, const Cell& c
 }
 
 // Sample + scatter cell + (optionally) the field gradients the camera adjoint needs, from ONE set of corner loads.
-template <bool kClamp, bool kGradients, bool kOcc = false>
-__device__ __forceinline__ float4 sample_cell_gradients(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+template <bool kClamp, bool kGradients, bool kOcc = false, class V = float4>
+__device__ __forceinline__ float4 sample_cell_gradients(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                         float px, float py, float pz, float g0, float g1, float g2,
                                                         float4& cell, float grad_sigma[3], float grad_h[3],
                                                         const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
@@ -133,9 +133,9 @@ __device__ __forceinline__ WarpRange warp_step_range(const MarchParams& mp, cons
     return r;
 }
 
-template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false>
+template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false, class V = float4>
 __global__ void __launch_bounds__(kLeanThreads)
-lean_forward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
+lean_forward_kernel(const FrameParams* __restrict__ P, const V* __restrict__ grid, int32_t nx, int32_t ny,
                     int32_t nz, LeanBuffers out, const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
     const CameraParams cam = P->cam;
     const MarchParams mp = P->march;
@@ -237,9 +237,9 @@ struct SegmentStash {
     float dt[kSegment][kLeanThreads];
 };
 
-template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false>
+template <bool kLinear, bool kClamp, bool kStratified, bool kOcc = false, class V = float4>
 __global__ void __launch_bounds__(kLeanThreads)
-lean_backward_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
+lean_backward_kernel(const FrameParams* __restrict__ P, const V* __restrict__ grid, int32_t nx, int32_t ny,
                      int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
                      const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0, int32_t oby = 0) {
     __shared__ SegmentStash stash;
@@ -467,9 +467,9 @@ __device__ __forceinline__ void flush_cell(const ScatterParams& sp, uint32_t key
 // kCamera: also accumulate d L / d (ray origin, ray direction) = sum_s (d sigma_s grad sigma(x_s) + w_s grad (g . rgb)(x_s)) {1, t_s}
 // from the corners phase A has in registers anyway, and reduce it to the camera parameters at the end
 // (replaces a separate camera_adjoint_kernel pass over every sample).
-template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera, bool kPlain, bool kOcc = false>
+template <bool kClamp, bool kStratified, bool kUnitBox, bool kCamera, bool kPlain, bool kOcc = false, class V = float4>
 __global__ void __launch_bounds__(kLeanThreads, kCamera ? 4 : DV_MERGE_MIN_BLOCKS)
-lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
+lean_backward_merge_kernel(const FrameParams* __restrict__ P, const V* __restrict__ grid, int32_t nx, int32_t ny,
                            int32_t nz, ScatterParams sp, const float* __restrict__ dL_dI, LeanBuffers st,
                            double* __restrict__ cam_partials, const uint32_t* __restrict__ occ = nullptr, int32_t obx = 0,
                            int32_t oby = 0) {
@@ -656,8 +656,8 @@ lean_backward_merge_kernel(const FrameParams* __restrict__ P, const float4* __re
 
 // ---- camera adjoint ---------------------------------------------------------
 // value is not needed, only d/d(position) of sigma and of h = g . rgb
-template <bool kClamp>
-__device__ __forceinline__ void field_gradients(const float4* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
+template <bool kClamp, class V>
+__device__ __forceinline__ void field_gradients(const V* __restrict__ g, int32_t nx, int32_t ny, int32_t nz,
                                                 float px, float py, float pz, float g0, float g1, float g2,
                                                 float4& value, float grad_sigma[3], float grad_h[3]) {
     grad_sigma[0] = grad_sigma[1] = grad_sigma[2] = 0.f;
@@ -674,9 +674,9 @@ __device__ __forceinline__ void field_gradients(const float4* __restrict__ g, in
                      grad_sigma, grad_h);
 }
 
-template <bool kClamp, bool kStratified>
+template <bool kClamp, bool kStratified, class V = float4>
 __global__ void __launch_bounds__(kLeanThreads)
-camera_adjoint_kernel(const FrameParams* __restrict__ P, const float4* __restrict__ grid, int32_t nx, int32_t ny,
+camera_adjoint_kernel(const FrameParams* __restrict__ P, const V* __restrict__ grid, int32_t nx, int32_t ny,
                       int32_t nz, const float* __restrict__ dL_dI, const uint32_t* __restrict__ live_counts,
                       const float4* __restrict__ steps, double* __restrict__ partials) {
     const CameraParams cam = P->cam;
@@ -948,8 +948,9 @@ cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, siz
 // ---- empty-space skipping: occupancy bits ---------------------------------------------------------------------------
 namespace {
 // One warp per brick of 8^3 cells: ORs over the 9^3 voxels its cells can read (x0 .. x0 + 1 for x0 in the brick).
+template <class V>
 __global__ void __launch_bounds__(256)
-occupancy_build_kernel(const float4* __restrict__ values, int32_t nx, int32_t ny, int32_t nz, uint32_t* __restrict__ occ,
+occupancy_build_kernel(const V* __restrict__ values, int32_t nx, int32_t ny, int32_t nz, uint32_t* __restrict__ occ,
                        int32_t obx, int32_t oby, int32_t obz, unsigned int* __restrict__ counts) {
     const uint32_t lane = threadIdx.x & 31u;
     const size_t bricks = static_cast<size_t>(obx) * oby * obz;
@@ -961,7 +962,7 @@ occupancy_build_kernel(const float4* __restrict__ values, int32_t nx, int32_t ny
         uint32_t bits = 0;
         for (int32_t i = lane; i < ex * ey * ez; i += 32) {
             const int32_t x = i % ex, y = (i / ex) % ey, z = i / (ex * ey);
-            const float4 v = __ldg(values + voxel_index(x0 + x, y0 + y, z0 + z, nx, ny));
+            const float4 v = load_voxel(values, voxel_index32(x0 + x, y0 + y, z0 + z, nx, ny));
             if (v.w != 0.0f) bits |= 3u;
             else if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) bits |= 2u;
         }
@@ -976,14 +977,74 @@ occupancy_build_kernel(const float4* __restrict__ values, int32_t nx, int32_t ny
 }  // namespace
 
 cudaError_t launch_build_occupancy(cudaStream_t stream, const float4* values, int32_t nx, int32_t ny, int32_t nz, uint32_t* d_occ,
-                                   size_t occ_words, unsigned int* d_counts) {
+                                   size_t occ_words, unsigned int* d_counts, bool values_are_half) {
     const int32_t obx = (nx + 7) / 8, oby = (ny + 7) / 8, obz = (nz + 7) / 8;
     cudaError_t e = cudaMemsetAsync(d_occ, 0, occ_words * sizeof(uint32_t), stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(d_counts, 0, 2 * sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
     const size_t bricks = static_cast<size_t>(obx) * oby * obz;
     const unsigned blocks = static_cast<unsigned>(std::min<size_t>((bricks + 7) / 8, 148 * 16));
-    occupancy_build_kernel<<<blocks, 256, 0, stream>>>(values, nx, ny, nz, d_occ, obx, oby, obz, d_counts);
+    if (values_are_half)
+        occupancy_build_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const HalfVoxel*>(values), nx, ny, nz, d_occ, obx, oby, obz, d_counts);
+    else
+        occupancy_build_kernel<<<blocks, 256, 0, stream>>>(values, nx, ny, nz, d_occ, obx, oby, obz, d_counts);
+    return cudaGetLastError();
+}
+
+// ---- half storage ------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ HalfVoxel to_half_voxel(float4 v) {
+    HalfVoxel h;
+    const __half2 rg = __floats2half2_rn(v.x, v.y), bs = __floats2half2_rn(v.z, v.w);
+    h.bits.x = *reinterpret_cast<const uint32_t*>(&rg);
+    h.bits.y = *reinterpret_cast<const uint32_t*>(&bs);
+    return h;
+}
+
+__global__ void convert_storage_kernel(float4* __restrict__ f32, HalfVoxel* __restrict__ half, size_t voxels, bool to_half) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        if (to_half) half[i] = to_half_voxel(f32[i]);
+        else f32[i] = load_voxel(half, static_cast<uint32_t>(i));
+    }
+}
+
+// hpx_grid_update on a half grid: channels the caller does not pass keep their stored values
+__global__ void pack_grid_half_kernel(const float* __restrict__ sigma, const float* __restrict__ color, HalfVoxel* __restrict__ half, size_t voxels) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 v = (sigma == nullptr || color == nullptr) ? load_voxel(half, static_cast<uint32_t>(i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (color != nullptr) { v.x = color[3 * i]; v.y = color[3 * i + 1]; v.z = color[3 * i + 2]; }
+        if (sigma != nullptr) v.w = sigma[i];
+        half[i] = to_half_voxel(v);
+    }
+}
+
+__global__ void abs_max_half_kernel(const HalfVoxel* __restrict__ half, size_t voxels, uint32_t* __restrict__ out_bits) {
+    float m = 0.0f;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < voxels; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = load_voxel(half, static_cast<uint32_t>(i));
+        const float a = fmaxf(fabsf(v.x), fmaxf(fabsf(v.y), fabsf(v.z)));
+        if (a < CUDART_INF_F) m = fmaxf(m, a);
+    }
+    const uint32_t bits = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) atomicMax(out_bits, bits);
+}
+}  // namespace
+
+cudaError_t launch_convert_storage(cudaStream_t stream, const float4* f32, void* half, size_t voxels, bool to_half) {
+    if (voxels == 0) return cudaSuccess;
+    convert_storage_kernel<<<148 * 8, 256, 0, stream>>>(const_cast<float4*>(f32), static_cast<HalfVoxel*>(half), voxels, to_half);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_grid_half(cudaStream_t stream, const float* sigma, const float* color, void* half, size_t voxels) {
+    if (voxels == 0) return cudaSuccess;
+    pack_grid_half_kernel<<<148 * 8, 256, 0, stream>>>(sigma, color, static_cast<HalfVoxel*>(half), voxels);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_abs_max_half(cudaStream_t stream, const void* half, size_t voxels, uint32_t* d_out_bits) {
+    if (voxels == 0) return cudaSuccess;
+    abs_max_half_kernel<<<148 * 8, 256, 0, stream>>>(static_cast<const HalfVoxel*>(half), voxels, d_out_bits);
     return cudaGetLastError();
 }
 
@@ -1036,6 +1097,16 @@ cudaError_t launch_lean_forward(cudaStream_t stream, const FrameParams* d_params
     const uint32_t blocks = tile_blocks(roi);
     if (blocks == 0) return cudaGetLastError();
     const bool strat = h_params.march.stratified != 0;
+    if (grid.half_values != nullptr) {   // half storage: linear OOB-zero grids (hpx_grid_set_storage checks)
+        const HalfVoxel* hv = static_cast<const HalfVoxel*>(grid.half_values);
+        const bool occ = grid.occ != nullptr;
+#define DV_FWD_HALF(S, O) lean_forward_kernel<true, false, S, O, HalfVoxel><<<blocks, kLeanThreads, 0, stream>>>(      \
+        d_params, hv, grid.nx, grid.ny, grid.nz, out, grid.occ, grid.obx, grid.oby)
+        if (strat) { if (occ) DV_FWD_HALF(true, true); else DV_FWD_HALF(true, false); }
+        else       { if (occ) DV_FWD_HALF(false, true); else DV_FWD_HALF(false, false); }
+#undef DV_FWD_HALF
+        return cudaGetLastError();
+    }
     if (grid.occ != nullptr && grid.linear && !grid.clamp) {   // empty-space skipping (linear, OOB-zero fields)
         if (strat) lean_forward_kernel<true, false, true, true><<<blocks, kLeanThreads, 0, stream>>>(
                        d_params, grid.values, grid.nx, grid.ny, grid.nz, out, grid.occ, grid.obx, grid.oby);
@@ -1097,7 +1168,21 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
         else DV_MERGE2(C, S, U, false);                                                                                \
     } while (0)
         const bool unit = sp.unit_bbox != 0;
-        if (grid.occ != nullptr && !grid.clamp && unit) {   // empty-space skipping
+        if (grid.half_values != nullptr) {
+            if (grid.clamp || !unit) return cudaErrorInvalidValue;   // hpx_grid_set_storage refuses such grids
+            const HalfVoxel* hv = static_cast<const HalfVoxel*>(grid.half_values);
+            const bool occ = grid.occ != nullptr, cam = cam_partials != nullptr;
+#define DV_MERGE_HALF(S, K, PL, O)                                                                                     \
+    lean_backward_merge_kernel<false, S, true, K, PL, O, HalfVoxel><<<blocks, kLeanThreads, 0, stream>>>(             \
+        d_params, hv, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, cam_partials, grid.occ, grid.obx, grid.oby)
+#define DV_MERGE_HALF3(S, K, PL) do { if (occ) DV_MERGE_HALF(S, K, PL, true); else DV_MERGE_HALF(S, K, PL, false); } while (0)
+#define DV_MERGE_HALF2(S, K) do { if (plain) DV_MERGE_HALF3(S, K, true); else DV_MERGE_HALF3(S, K, false); } while (0)
+            if (strat) { if (cam) DV_MERGE_HALF2(true, true); else DV_MERGE_HALF2(true, false); }
+            else       { if (cam) DV_MERGE_HALF2(false, true); else DV_MERGE_HALF2(false, false); }
+#undef DV_MERGE_HALF2
+#undef DV_MERGE_HALF3
+#undef DV_MERGE_HALF
+        } else if (grid.occ != nullptr && !grid.clamp && unit) {   // empty-space skipping
 #define DV_MERGE_OCC(S, K)                                                                                             \
     do {                                                                                                               \
         if (plain)                                                                                                     \
@@ -1123,6 +1208,16 @@ cudaError_t launch_lean_backward(cudaStream_t stream, const FrameParams* d_param
         return cudaGetLastError();
     }
     if (cam_partials != nullptr) return cudaErrorInvalidValue;   // the fused camera adjoint exists in the merged kernel only
+    if (grid.half_values != nullptr) {
+        const HalfVoxel* hv = static_cast<const HalfVoxel*>(grid.half_values);
+        const bool occ = grid.occ != nullptr;
+#define DV_BWD_HALF(S, O) lean_backward_kernel<true, false, S, O, HalfVoxel><<<blocks, kLeanThreads, 0, stream>>>(     \
+        d_params, hv, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, grid.occ, grid.obx, grid.oby)
+        if (strat) { if (occ) DV_BWD_HALF(true, true); else DV_BWD_HALF(true, false); }
+        else       { if (occ) DV_BWD_HALF(false, true); else DV_BWD_HALF(false, false); }
+#undef DV_BWD_HALF
+        return cudaGetLastError();
+    }
     if (grid.occ != nullptr && grid.linear && !grid.clamp) {
         if (strat) lean_backward_kernel<true, false, true, true><<<blocks, kLeanThreads, 0, stream>>>(
                        d_params, grid.values, grid.nx, grid.ny, grid.nz, sp, d_dL_dI, state, grid.occ, grid.obx, grid.oby);
@@ -1142,6 +1237,13 @@ cudaError_t launch_camera_adjoint(cudaStream_t stream, const FrameParams* d_para
     const uint32_t blocks = tile_blocks(h_params.roi);
     if (blocks == 0 || !grid.linear) return cudaSuccess;  // nearest-neighbour fields have zero spatial gradient
     const bool strat = h_params.march.stratified != 0;
+    if (grid.half_values != nullptr) {
+        const HalfVoxel* hv = static_cast<const HalfVoxel*>(grid.half_values);
+        if (strat) camera_adjoint_kernel<false, true, HalfVoxel><<<blocks, kLeanThreads, 0, stream>>>(d_params, hv, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
+        else       camera_adjoint_kernel<false, false, HalfVoxel><<<blocks, kLeanThreads, 0, stream>>>(d_params, hv, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
+        camera_reduce_kernel<<<1, 512, 0, stream>>>(d_partials, blocks, d_cam16);
+        return cudaGetLastError();
+    }
     if (grid.clamp) {
         if (strat) camera_adjoint_kernel<true, true><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);
         else       camera_adjoint_kernel<true, false><<<blocks, kLeanThreads, 0, stream>>>(d_params, grid.values, grid.nx, grid.ny, grid.nz, d_dL_dI, d_live, d_steps, d_partials);

@@ -10,6 +10,7 @@ namespace dv {
 // Packed {r,g,b,sigma} grid resident in HBM.
 struct PackedGrid {
     const float4* values = nullptr;
+    const void* half_values = nullptr;   // HalfVoxel[V] instead of `values` (hpx_grid_set_storage): linear OOB-zero grids only
     int32_t nx = 0, ny = 0, nz = 0;
     bool linear = true;
     bool clamp = false;
@@ -67,8 +68,14 @@ cudaError_t launch_cube_count(cudaStream_t stream, const FrameParams* d_params, 
 cudaError_t launch_touched_voxels(cudaStream_t stream, const float4* d_grad, size_t voxels, unsigned long long* d_total);
 
 // Occupancy bits of a packed grid (PackedGrid::occ); d_counts[0] / [1] receive the number of bricks without bit 0 / bit 1.
+// Half storage (dv_device.cuh HalfVoxel): conversion both ways, parameter update, |rgb| maximum for the deterministic quantum.
+cudaError_t launch_convert_storage(cudaStream_t stream, const float4* f32, void* half, size_t voxels, bool to_half);
+cudaError_t launch_pack_grid_half(cudaStream_t stream, const float* sigma, const float* color, void* half, size_t voxels);
+cudaError_t launch_abs_max_half(cudaStream_t stream, const void* half, size_t voxels, uint32_t* d_out_bits);
+
+// values_are_half: `values` is really HalfVoxel[V]
 cudaError_t launch_build_occupancy(cudaStream_t stream, const float4* values, int32_t nx, int32_t ny, int32_t nz, uint32_t* d_occ,
-                                   size_t occ_words, unsigned int* d_counts);
+                                   size_t occ_words, unsigned int* d_counts, bool values_are_half = false);
 
 // Writes the frame's parameter block; the values travel as kernel arguments (no staging buffer, no host sync).
 cudaError_t launch_upload_params(cudaStream_t stream, FrameParams* d_params, const FrameParams& h_params);

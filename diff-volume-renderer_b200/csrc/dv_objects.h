@@ -80,7 +80,8 @@ struct hpx_grid {
     int32_t nx = 0, ny = 0, nz = 0;
     bool linear = true, clamp = false;
     float bmin[3] = {0.f, 0.f, 0.f}, bmax[3] = {1.f, 1.f, 1.f};
-    float4* d_values = nullptr;   // [V] {r,g,b,sigma}
+    float4* d_values = nullptr;   // [V] {r,g,b,sigma}; nullptr while the grid is stored as halfs
+    void* d_half = nullptr;       // [V] dv::HalfVoxel (hpx_grid_set_storage(HPX_STORAGE_F16)): 8 B per voxel instead of 16
     float* d_grad = nullptr;      // [4V + 16]: packed gradient grid, then camera gradient
     float* d_unpacked = nullptr;  // [V + 3V] staging for un-interleaved read-back (lazily allocated)
     size_t unpacked_voxels = 0;

@@ -62,6 +62,7 @@ HPX_FUNCTIONS = {
     "hpx_grid_adopt_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_grid_update": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "hpx_grid_zero_grad": (C.c_int, [C.c_void_p]),
+    "hpx_grid_set_storage": (C.c_int, [C.c_void_p, C.c_uint32]),
     "hpx_grid_build_occupancy": (C.c_int, [C.c_void_p, C.c_int32, P(C.c_float), P(C.c_float)]),
     "hpx_grid_set_occupancy": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_grid_grad_buffer": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_size_t)]),
@@ -248,6 +249,10 @@ class Grid:
 
     def zero_grad(self):
         check("hpx_grid_zero_grad", self.lib.hpx_grid_zero_grad(self.handle))
+
+    def set_storage(self, half: bool):
+        """Store the packed values as four halfs per voxel (8 B) instead of four floats (16 B); arithmetic stays fp32."""
+        check("hpx_grid_set_storage", self.lib.hpx_grid_set_storage(self.handle, 1 if half else 0))
 
     def build_occupancy(self, enable: bool = True):
         """Empty-space skipping: (fraction of bricks the forward can skip, fraction the backward can skip)."""

@@ -143,6 +143,15 @@ HP_API hp_status hpx_grid_update(hpx_grid* grid, const float* sigma, const float
  * skipping on / off without rebuilding. */
 HP_API hp_status hpx_grid_build_occupancy(hpx_grid* grid, int32_t enable, float* out_empty_sigma, float* out_empty_all);
 HP_API hp_status hpx_grid_set_occupancy(hpx_grid* grid, int32_t enable);
+/* Storage precision of the packed VALUES (the gradient block stays fp32).  HPX_STORAGE_F16: four IEEE halfs per voxel, 8 B
+ * instead of 16 -- half the gather bytes and half the HBM footprint (1024^3: 8.6 GB instead of 17.2 GB).  The values are
+ * rounded to half once; voxels are widened back to fp32 exactly on load and all arithmetic stays fp32, so the grid behaves
+ * EXACTLY like an fp32 grid holding the rounded values: against that twin the usual tolerances hold (counts bit-exact,
+ * image 1e-5, gradients 1e-4); against the unrounded grid the difference is the storage rounding (2^-11 relative per
+ * value).  Linear OOB-zero grids with the unit scatter box and no adopted hp_fields. */
+#define HPX_STORAGE_F32 0u
+#define HPX_STORAGE_F16 1u
+HP_API hp_status hpx_grid_set_storage(hpx_grid* grid, uint32_t storage);
 HP_API hp_status hpx_grid_zero_grad(hpx_grid* grid);
 /* Device view of the contiguous gradient block [4*V grid floats {r,g,b,sigma} | 16 camera floats]
  * -- the buffer a data-parallel caller all-reduces. */

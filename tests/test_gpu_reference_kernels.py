@@ -108,7 +108,8 @@ def test_reference_cuda_kernels_side_by_side():
             setattr(grads, k, _dev_tensor(v))
         assert ours.lib.hp_diff(plan, C.byref(g), C.byref(samp), C.byref(intl), C.byref(grads), None, 0) == 0
 
-    cudart = torch.cuda.cudart()
+    cudart = C.CDLL("libcudart.so.12")     # torch has loaded it; the reference's buffers live in the same primary context
+    cudart.cudaFree.argtypes = [C.c_void_p]
     kept = {}
 
     def ref_diff(keep=False):
@@ -116,10 +117,10 @@ def test_reference_cuda_kernels_side_by_side():
         assert ref.hp_diff(rplan, C.byref(g), C.byref(samp), C.byref(intl), C.byref(grads), None, 0) == 0
         if keep:
             sync()
-            out = torch.empty(m, device=dev), torch.empty(m, 3, device=dev)
-            for dst, src in zip(out, (grads.sigma, grads.color)):
-                cudart.cudaMemcpy(dst.data_ptr(), src.data, dst.numel() * 4, 3)   # cudaMemcpyDeviceToDevice
-            kept["sigma"], kept["color"] = out[0].cpu().numpy(), out[1].cpu().numpy()
+            for key, src, shape in (("sigma", grads.sigma, (m,)), ("color", grads.color, (m, 3))):
+                host = np.zeros(shape, np.float32)
+                assert ours.lib.hpx_copy_to_host(ours.ctx, host.ctypes.data, src.data, host.nbytes) == 0
+                kept[key] = host
         for t in (grads.sigma, grads.color, grads.camera):
             if t.data:
                 cudart.cudaFree(t.data)
@@ -128,6 +129,7 @@ def test_reference_cuda_kernels_side_by_side():
     ref_diff(keep=True)
     sync()
     # the reference's own CPU <-> CUDA gate (hp_runner.cpp:2580-2594, rel 1e-3)
+    assert np.abs(kept["sigma"]).max() > 0
     U.assert_close(gsig.cpu().numpy(), kept["sigma"], 1e-3, "diff.sigma vs reference backward_kernel", floor_frac=1e-3)
     U.assert_close(gcol.cpu().numpy(), kept["color"], 1e-3, "diff.color vs reference backward_kernel", floor_frac=1e-3)
     diff_ms = {"ours_diff_kernel": _best(ours_diff, sync), "reference_backward_kernel": _best(ref_diff, sync)}

@@ -372,3 +372,58 @@ def test_empty_space_skipping_changes_nothing(ctx, stratified):
     fresh = D.Grid(ctx, base_s, color)
     U.assert_bits(_render(ctx, grid, desc)["image"], _render(ctx, fresh, desc)["image"], "after update: image")
     fresh.close(); grid.close()
+
+
+@pytest.mark.parametrize("stratified,scatter", [(True, D.HPX_BACKWARD_SCATTER_MERGED), (False, D.HPX_BACKWARD_SCATTER_PER_RAY)])
+def test_half_storage_equals_the_oracle_on_the_rounded_grid(ctx, stratified, scatter):
+    """hpx_grid_set_storage(HPX_STORAGE_F16): values are rounded to IEEE half once, widened exactly on
+    load, and all arithmetic stays fp32 -- so the parity twin is the ORACLE run on the rounded values, at the usual gates
+    (counts and hit mask bit-exact, image 1e-5, grid gradients 1e-4 with the float64 adjudication, camera 1e-4).  Against
+    the unrounded grid the image differs by the storage rounding only (<= 2^-10 relative, checked loosely)."""
+    n, W, Hh, steps = 28, 72, 60, 128
+    sig, col = S.hashed_volume(n, "dense", seed=21)
+    sig16, col16 = sig.astype(np.float16).astype(np.float32), col.astype(np.float16).astype(np.float32)
+    desc = S.bench_plan(W, Hh, steps, stratified=stratified, view=2, views=13)
+    dl = S.hashed_image_grad(W * Hh)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO | scatter
+    if scatter == D.HPX_BACKWARD_SCATTER_MERGED:
+        flags |= D.HPX_BACKWARD_CAMERA
+    grid = D.Grid(ctx, sig, col)
+    full = _render(ctx, grid, desc)
+    grid.set_storage(half=True)
+    got = _render(ctx, grid, desc, dl, flags)
+    st, odesc = O.plan_resolve(desc)
+    gs, gc = U.oracle_grids(sig16, col16, A.HP_INTERP_LINEAR, A.HP_OOB_ZERO)
+    ref = O.render(odesc, gs, gc, dl, shadow=True)
+    assert got["samples"] == ref["sample_count"]
+    U.assert_bits(got["hitmask"], ref["hitmask"], "half storage: hitmask")
+    for k in ("image", "trans", "opacity", "depth"):
+        U.assert_close(got[k], ref[k], U.IMAGE_RTOL, f"half storage vs oracle on the rounded grid: {k}")
+    U.assert_grads(got["sigma_grad"], got["color_grad"], ref, "half storage vs oracle on the rounded grid", res=(n, n, n))
+    np.testing.assert_allclose(got["image"], full["image"], rtol=0, atol=2e-3 * float(np.abs(full["image"]).max()))
+    # the same through a grid that was created from the rounded values and never converted: bit for bit
+    twin = D.Grid(ctx, sig16, col16)
+    same = _render(ctx, twin, desc, dl, flags | D.HPX_BACKWARD_DETERMINISTIC)
+    det = _render(ctx, grid, desc, dl, flags | D.HPX_BACKWARD_DETERMINISTIC)
+    for k in ("image", "trans", "opacity", "depth", "sigma_grad", "color_grad"):
+        U.assert_bits(det[k], same[k], f"half storage vs fp32 grid of the rounded values: {k}")
+    # parameter update on a half grid (one channel set kept), occupancy on a half grid, and the way back
+    grid.update(sigma=sig * np.float32(0.5))
+    twin.update(sigma=(sig * np.float32(0.5)).astype(np.float16).astype(np.float32))
+    U.assert_bits(_render(ctx, grid, desc)["image"], _render(ctx, twin, desc)["image"], "half storage after update")
+    grid.build_occupancy(enable=True)
+    U.assert_bits(_render(ctx, grid, desc)["image"], _render(ctx, twin, desc)["image"], "half storage + occupancy")
+    grid.set_storage(half=False)
+    U.assert_bits(_render(ctx, grid, desc)["image"], _render(ctx, twin, desc)["image"], "back to fp32 storage")
+    twin.close(); grid.close()
+
+
+def test_half_storage_is_refused_where_it_cannot_hold(ctx):
+    sig, col = S.hashed_volume(8, "thin")
+    for kw in (dict(oob=A.HP_OOB_CLAMP), dict(interp=A.HP_INTERP_NEAREST), dict(bbox_min=(-1, -1, -1), bbox_max=(2, 2, 2))):
+        g = D.Grid(ctx, sig, col, **kw)
+        assert ctx.lib.hpx_grid_set_storage(g.handle, 1) == A.HP_STATUS_UNSUPPORTED
+        g.close()
+    g = D.Grid(ctx, sig, col)
+    assert ctx.lib.hpx_grid_set_storage(g.handle, 7) == A.HP_STATUS_INVALID_ARGUMENT
+    g.close()

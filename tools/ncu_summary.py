@@ -39,6 +39,13 @@ METRICS = [
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1 LSU wavefronts % of peak"),
     ("l1tex__t_bytes_pipe_lsu_mem_global_op_ld.sum", "L1 global-load bytes"),
     ("l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum", "L1 red accesses"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "global-load requests (warp-wide instructions)"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "global-load wavefronts"),
+    ("l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "global-red requests"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_red.sum", "global-red wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
+    ("l1tex__data_pipe_lsu_wavefronts.sum", "LSU data-pipe wavefronts (all)"),
+    ("smsp__inst_executed_op_global_red.sum", "global-red warp instructions"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput % of peak"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
     ("smsp__inst_executed.sum", "warp instructions"),
@@ -87,6 +94,7 @@ def main():
               "profiler (cold caches, serialised) -- bench.py times the same kernels live with CUDA events.", ""]
     traffic = {}
     l1pct = {}
+    wpr = {}
     for r in rows:
         name = r[col["Kernel Name"]]
         short = re.sub(r"^void\s+", "", name)
@@ -110,10 +118,21 @@ def main():
         rd = num(r[col["dram__bytes_read.sum"]]) * UNIT_SCALE.get(units[col["dram__bytes_read.sum"]], 1)
         wr = num(r[col["dram__bytes_write.sum"]]) * UNIT_SCALE.get(units[col["dram__bytes_write.sum"]], 1)
         base = re.sub(r"<.*$", "", short)
-        traffic[base] = int(rd + wr)
+        if rd == rd and wr == wr:   # (a kernel ncu could not replay fully has NaN here)
+            traffic[base] = int(rd + wr)
         k = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
         if k in col:
             l1pct[base] = num(r[col[k]])
+        # LSU data-pipe wavefronts of the launch = utilisation x elapsed L1 cycles summed over the SMs (the raw page carries
+        # the percentage only); per warp-wide global load: 4 is the floor for 16-byte lanes (512 B / 128 B per wavefront)
+        kc, kr, ks = "l1tex__cycles_elapsed.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"
+        if k in col and kc in col and kr in col and num(r[col[kr]]) > 0 and num(r[col[k]]) == num(r[col[k]]):
+            total = num(r[col[k]]) / 100.0 * num(r[col[kc]])
+            shared = num(r[col[ks]]) if ks in col else 0.0
+            wpr[base] = (total - shared) / num(r[col[kr]])
+            lines.insert(len(lines) - 1, f"| LSU data-pipe wavefronts, derived (`{k}` x `{kc}`) | {total:.4g} |")
+            lines.insert(len(lines) - 1, f"| of which shared memory | {shared:.4g} ({100 * shared / total:.0f} %) |")
+            lines.insert(len(lines) - 1, f"| global-memory data-pipe wavefronts (loads + reds) per warp-wide global LOAD (floor 4 for 16-byte lanes) | {wpr[base]:.2f} |")
     os.makedirs(os.path.dirname(os.path.abspath(args.out_md)), exist_ok=True)
     with open(args.out_md, "w") as f:
         f.write("\n".join(lines))
@@ -125,6 +144,7 @@ def main():
                 data = json.load(f)
         data.setdefault(args.traffic_key, {}).update(traffic)
         data[args.traffic_key].setdefault("_l1_wavefront_pct", {}).update(l1pct)
+        data[args.traffic_key].setdefault("_wavefronts_per_request", {}).update(wpr)
         data[args.traffic_key]["_source"] = os.path.basename(args.out_md)
         with open(tpath, "w") as f:
             json.dump(data, f, indent=1, sort_keys=True)
