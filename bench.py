@@ -33,8 +33,19 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+def _finite(x):
+    """JSON has no NaN / Infinity: they become null."""
+    if isinstance(x, float) and (x != x or x in (float("inf"), float("-inf"))):
+        return None
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    return x
+
+
 def emit(line: dict):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(_REAL_STDOUT, (json.dumps(_finite(line), allow_nan=False) + "\n").encode())
 
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -436,6 +447,30 @@ def measure_sparse(env, cfg, args):
     return out
 
 
+def measure_half(env, cfg, args):
+    """Half-precision grid storage (hpx_grid_set_storage): the same thin volume and frame with the values kept as four
+    halfs per voxel (8 B gathers instead of 16 B; arithmetic stays fp32, results = an fp32 grid of the rounded values)."""
+    import synth as S
+    torch, D, ctx, dev = env.torch, env.D, env.ctx, env.dev
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    grid = make_grid(D, S, torch, ctx, n, "thin", dev)
+    grid.set_storage(half=True)
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"]))
+    frame = D.Frame(plan)
+    g_dev = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).to(dev)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    k = args.steps
+    f = env.timed(lambda: frame.forward(grid), k, 2) / k
+    b = env.timed(lambda: frame.backward(grid, g_dev.data_ptr(), flags, device=True), k, 2) / k
+    c = frame.counts()
+    out = {"fwd_ms": f, "bwd_ms": b, "value": c["samples"] / ((f + b) * 1e-3) / 1e6, "grid_bytes": n ** 3 * 8,
+           "what": "values stored as IEEE half {r,g,b,sigma} (8 B per voxel), widened exactly on load, fp32 arithmetic; gradient "
+                   "block stays fp32; parity twin: the oracle on the rounded grid (tests/test_gpu_runtime.py)"}
+    frame.close(); plan.close(); grid.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def base_line(env, args, cfg, value, ms_per_step, scaling):
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
@@ -459,6 +494,7 @@ def run_single(env, args):
         line["c2"] = {k: c2[k] for k in ("workload", "value", "ms_per_step", "fwd", "bwd", "e2e", "roofline", "samples",
                                          "in_cube_live_samples", "touched_voxels")}
         line["c2"]["empty_space_skipping"] = measure_sparse(env, CONFIGS["c2"], args)
+        line["c2"]["half_storage"] = measure_half(env, CONFIGS["c2"], args)
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
     emit(line)

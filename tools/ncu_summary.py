@@ -121,7 +121,7 @@ def main():
         if rd == rd and wr == wr:   # (a kernel ncu could not replay fully has NaN here)
             traffic[base] = int(rd + wr)
         k = "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"
-        if k in col:
+        if k in col and num(r[col[k]]) == num(r[col[k]]):
             l1pct[base] = num(r[col[k]])
         # LSU data-pipe wavefronts of the launch = utilisation x elapsed L1 cycles summed over the SMs (the raw page carries
         # the percentage only); per warp-wide global load: 4 is the floor for 16-byte lanes (512 B / 128 B per wavefront)
