@@ -265,6 +265,65 @@ __global__ void __launch_bounds__(256) peer_pull_kernel(float4* __restrict__ dst
     }
 }
 
+// ---- exchange kernels: ONE launch per phase, all peers at once ---------------------------------------------------------
+// Reduce phase: the owner walks the slabs it owns; for every element it adds, in ascending rank order (the sum never
+// depends on timing), the partial sums of every peer whose wedge contains the slab.  The loads from the different peers
+// of an element are independent and issued back to back, so all NVLink ports that feed this GPU are busy at once, and
+// the owner's own block is read and written once instead of once per peer.
+constexpr int kMaxPeers = 16;
+struct PullTable {
+    const float4* src[kMaxPeers];   // peer block (mapped into this GPU's address space)
+    int32_t lo[kMaxPeers], hi[kMaxPeers];   // slabs of that peer's wedge inside this rank's owned range
+    int32_t n;
+    int32_t first_slab;             // blockIdx.y = 0
+};
+
+__global__ void __launch_bounds__(256) peer_reduce_kernel(float4* __restrict__ block, PullTable t, size_t slab4) {
+    const int32_t y = t.first_slab + static_cast<int32_t>(blockIdx.y);
+    uint32_t mask = 0;
+    for (int p = 0; p < t.n; ++p)
+        if (y >= t.lo[p] && y < t.hi[p]) mask |= 1u << p;
+    if (mask == 0u) return;
+    const size_t base = static_cast<size_t>(y) * slab4;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < slab4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 v[kMaxPeers];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < t.n && (mask >> p) & 1u) v[p] = t.src[p][base + i];
+        float4 a = block[base + i];
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < t.n && (mask >> p) & 1u) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+        block[base + i] = a;
+    }
+}
+
+// Gather phase (replicated result): every slab of the touched hull this rank does not own is copied from its owner.
+struct OwnerTable {
+    const float4* src[kMaxPeers];   // by rank
+    int32_t cuts[kMaxPeers + 1];
+    int32_t world, me, first_slab;
+};
+
+__global__ void __launch_bounds__(256) peer_gather_kernel(float4* __restrict__ block, OwnerTable t, size_t slab4) {
+    const int32_t y = t.first_slab + static_cast<int32_t>(blockIdx.y);
+    int owner = 0;
+    while (owner + 1 < t.world && y >= t.cuts[owner + 1]) ++owner;
+    if (owner == t.me) return;
+    const float4* __restrict__ src = t.src[owner] + static_cast<size_t>(y) * slab4;
+    float4* __restrict__ dst = block + static_cast<size_t>(y) * slab4;
+    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+    size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    for (; i + 3 * stride < slab4; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = src[i + k * stride];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[i + k * stride] = v[k];
+    }
+    for (; i < slab4; i += stride) dst[i] = src[i];
+}
+
 struct PeerInfo {
     cudaIpcMemHandle_t handle;
     unsigned long long ptr;
@@ -288,7 +347,7 @@ hp_status map_peer_blocks(hpx_shard* s) {
     s->peer_block[static_cast<size_t>(me)] = block;
     if (world == 1) return HP_STATUS_SUCCESS;
     const char* env = std::getenv("DVREN_SHARD_EXCHANGE");
-    int ok = (env != nullptr && std::strcmp(env, "nccl") == 0) ? 0 : 1;
+    int ok = (env != nullptr && std::strcmp(env, "nccl") == 0) || world > kMaxPeers ? 0 : 1;
     PeerInfo mine{};
     mine.ptr = reinterpret_cast<unsigned long long>(block);
     mine.pid = static_cast<long long>(getpid());
@@ -981,22 +1040,35 @@ static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t fla
         // ---- own kernels over peer memory (NVLink): every owner PULLS the wedge parts of its slabs out of its neighbours'
         // gradient blocks and adds them in rank order -- no staging copy, no separate add pass.
         DV_TRY(stream_barrier(s));   // every rank's backward has finished: the blocks hold the final partial sums
-        for (const auto& x : s->recvs)
-            DV_CUDA(launch_peer_pull<true>(main, block + static_cast<size_t>(x.lo) * S,
-                                           s->peer_block[static_cast<size_t>(x.peer)] + static_cast<size_t>(x.lo) * S,
-                                           static_cast<size_t>(x.hi - x.lo) * S));
+        const size_t slab4 = S / 4;
+        const unsigned bx = static_cast<unsigned>(std::max<size_t>(1, std::min<size_t>((slab4 + 1023) / 1024, 64)));
+        if (!s->recvs.empty() && s->cuts[me + 1] > s->cuts[me]) {
+            PullTable t{};
+            t.n = 0;
+            for (const auto& x : s->recvs) {   // ascending peer order = order of the additions
+                if (t.n >= kMaxPeers) break;
+                t.src[t.n] = reinterpret_cast<const float4*>(s->peer_block[static_cast<size_t>(x.peer)]);
+                t.lo[t.n] = x.lo;
+                t.hi[t.n] = x.hi;
+                ++t.n;
+            }
+            t.first_slab = s->cuts[me];
+            peer_reduce_kernel<<<dim3(bx, static_cast<unsigned>(s->cuts[me + 1] - s->cuts[me])), 256, 0, main>>>(
+                reinterpret_cast<float4*>(block), t, slab4);
+            DV_CUDA(cudaGetLastError());
+        }
         if (flags & HPX_BACKWARD_CAMERA)
             DV_NCCL(nccl().AllReduce(block + floats - 16, block + floats - 16, 16, ncclFloat32, ncclSum, c->comm, main));
-        if (s->result == HPX_SHARD_RESULT_REPLICATED) {
+        if (s->result == HPX_SHARD_RESULT_REPLICATED && s->hull_hi > s->hull_lo) {
             DV_TRY(stream_barrier(s));   // every owner has finished its sums
-            for (int k = 1; k < c->world; ++k) {   // start at different owners: no two ranks hammer the same peer at once
-                const int o = (me + k) % c->world;
-                const int32_t lo = std::max(s->cuts[o], s->hull_lo), hi = std::min(s->cuts[o + 1], s->hull_hi);
-                if (lo >= hi) continue;
-                DV_CUDA(launch_peer_pull<false>(main, block + static_cast<size_t>(lo) * S,
-                                                s->peer_block[static_cast<size_t>(o)] + static_cast<size_t>(lo) * S,
-                                                static_cast<size_t>(hi - lo) * S));
-            }
+            OwnerTable t{};
+            for (int r = 0; r < c->world; ++r) t.src[r] = reinterpret_cast<const float4*>(s->peer_block[static_cast<size_t>(r)]);
+            for (int r = 0; r <= c->world; ++r) t.cuts[r] = s->cuts[static_cast<size_t>(r)];
+            t.world = c->world;
+            t.me = me;
+            t.first_slab = s->hull_lo;
+            peer_gather_kernel<<<dim3(bx, static_cast<unsigned>(s->hull_hi - s->hull_lo)), 256, 0, main>>>(reinterpret_cast<float4*>(block), t, slab4);
+            DV_CUDA(cudaGetLastError());
         }
         return stream_barrier(s);        // nobody still reads this rank's block when it is cleared for the next step
     }

@@ -211,6 +211,8 @@ sample_kernel(MarchParams mp, float plan_t_near, float plan_t_far, FieldPair fie
 }
 
 // ---- K4: integrator over materialised samples (int_cpu.cpp:160-226) ---------
+// kVec: aligned blocks of four samples, like diff_kernel below (16-byte aligned arrays, checked on the host).
+template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
 integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_t n_rays, uint32_t n_samples,
                  IntegralArrays intl, bool aux_aligned, uint32_t* status) {
@@ -223,15 +225,18 @@ integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_
         atomicOr(status, kErrBadOffsets);
     } else {
         bool stopped = false;
-        for (uint32_t i = b; i < e; ++i) {
+        auto one = [&](float r, float g, float bl, float sigma, float dtv) {
             float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
             if (!stopped) {
-                const float4 v = make_float4(samp.color[3 * size_t(i)], samp.color[3 * size_t(i) + 1],
-                                             samp.color[3 * size_t(i) + 2], samp.sigma[i]);
                 float a, w, tb;
-                stopped = integrate_sample(acc, samp.dt[i], v, a, w, tb);
+                stopped = integrate_sample(acc, dtv, make_float4(r, g, bl, sigma), a, w, tb);
                 row = make_float4(a, w, tb, logf(fmaxf(tb, 1e-30f)));
             }
+            return row;
+        };
+        auto scalar = [&](uint32_t i) {
+            const float4 row = one(samp.color[3 * size_t(i)], samp.color[3 * size_t(i) + 1], samp.color[3 * size_t(i) + 2], samp.sigma[i],
+                                   samp.dt[i]);
             if (intl.aux != nullptr) {
                 if (aux_aligned) {
                     reinterpret_cast<float4*>(intl.aux)[i] = row;
@@ -240,7 +245,40 @@ integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_
                     a4[0] = row.x; a4[1] = row.y; a4[2] = row.z; a4[3] = row.w;
                 }
             }
+        };
+        uint32_t i = b;
+        if (kVec)
+            while (i < e && (i & 3u) != 0u) scalar(i++);
+        while (i + 4u <= e) {
+            float4 C0, C1, C2, SG, DT;   // colour: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+            if (kVec) {
+                const float4* c4 = reinterpret_cast<const float4*>(samp.color + 3 * size_t(i));
+                C0 = __ldcs(c4); C1 = __ldcs(c4 + 1); C2 = __ldcs(c4 + 2);
+                SG = __ldcs(reinterpret_cast<const float4*>(samp.sigma + i));
+                DT = __ldcs(reinterpret_cast<const float4*>(samp.dt + i));
+            } else {   // 4-byte aligned arrays (the reference's workspace rule): same block of four, scalar accesses
+                const float* c = samp.color + 3 * size_t(i);
+                C0 = make_float4(c[0], c[1], c[2], c[3]); C1 = make_float4(c[4], c[5], c[6], c[7]); C2 = make_float4(c[8], c[9], c[10], c[11]);
+                SG = make_float4(samp.sigma[i], samp.sigma[i + 1], samp.sigma[i + 2], samp.sigma[i + 3]);
+                DT = make_float4(samp.dt[i], samp.dt[i + 1], samp.dt[i + 2], samp.dt[i + 3]);
+            }
+            const float4 R0 = one(C0.x, C0.y, C0.z, SG.x, DT.x);
+            const float4 R1 = one(C0.w, C1.x, C1.y, SG.y, DT.y);
+            const float4 R2 = one(C1.z, C1.w, C2.x, SG.z, DT.z);
+            const float4 R3 = one(C2.y, C2.z, C2.w, SG.w, DT.w);
+            if (intl.aux != nullptr) {
+                if (aux_aligned) {
+                    float4* a4 = reinterpret_cast<float4*>(intl.aux) + i;
+                    __stcs(a4, R0); __stcs(a4 + 1, R1); __stcs(a4 + 2, R2); __stcs(a4 + 3, R3);
+                } else {
+                    float* a = intl.aux + 4 * size_t(i);
+                    a[0] = R0.x; a[1] = R0.y; a[2] = R0.z; a[3] = R0.w; a[4] = R1.x; a[5] = R1.y; a[6] = R1.z; a[7] = R1.w;
+                    a[8] = R2.x; a[9] = R2.y; a[10] = R2.z; a[11] = R2.w; a[12] = R3.x; a[13] = R3.y; a[14] = R3.z; a[15] = R3.w;
+                }
+            }
+            i += 4u;
         }
+        while (i < e) scalar(i++);
     }
     float opacity, depth;
     finish_ray(acc, plan_t_far, opacity, depth);
@@ -251,10 +289,24 @@ integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_
 }
 
 // ---- K5: per-sample backward (diff_cpu.cpp:156-195) -------------------------
+// One thread walks one ray's samples last-to-first with the reference's recurrence (the carry adj_T makes a ray
+// sequential).  A ray's samples are contiguous in every array, so the thread works in ALIGNED BLOCKS OF FOUR samples:
+// aux as 4 x 16 B, colour as 3 x 16 B (48 B), dt as 16 B in, colour gradient as 3 x 16 B and sigma gradient as 16 B out,
+// issued back to back -- every 32-byte sector that is fetched or written is used completely, where sample-at-a-time
+// scalar accesses (the reference's backward_kernel, diff_cuda.cu:11-63, and this kernel's first version) move a sector
+// per 4-byte access.  kVec needs 16-byte aligned arrays (checked on the host); ragged heads / tails are scalar.
+__device__ __forceinline__ void diff_one(float g0, float g1, float g2, float alpha, float w, float T_prev, float c0, float c1,
+                                         float c2, float dtv, float& adj_T, float& dsigma, float& o0, float& o1, float& o2) {
+    const float dot = g0 * c0 + g1 * c1 + g2 * c2;
+    adjoint_sample(dot, alpha, T_prev, dtv, adj_T, dsigma);
+    o0 = g0 * w; o1 = g1 * w; o2 = g2 * w;
+}
+
+template <bool kVec>
 __global__ void __launch_bounds__(kThreads)
 diff_kernel(const float* __restrict__ dL_dI, int64_t stride_ray, int64_t stride_c, SampleArrays samp,
-            const float* __restrict__ aux, uint32_t n_rays, uint32_t n_samples, float* grad_sigma, float* grad_color,
-            uint32_t* status) {
+            const float* __restrict__ aux, uint32_t n_rays, uint32_t n_samples, float* __restrict__ grad_sigma,
+            float* __restrict__ grad_color, uint32_t* status) {
     const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
     if (ray >= n_rays) return;
     const uint32_t b = samp.ray_offset[ray], e = samp.ray_offset[ray + 1];
@@ -265,18 +317,52 @@ diff_kernel(const float* __restrict__ dL_dI, int64_t stride_ray, int64_t stride_
     const float* gp = dL_dI + static_cast<int64_t>(ray) * stride_ray;
     const float g0 = gp[0], g1 = gp[stride_c], g2 = gp[2 * stride_c];
     float adj_T = 0.0f;
-    for (uint32_t i = e; i-- > b;) {
-        const float alpha = aux[4 * size_t(i)], w = aux[4 * size_t(i) + 1], T_prev = aux[4 * size_t(i) + 2];
-        const float c0 = samp.color[3 * size_t(i)], c1 = samp.color[3 * size_t(i) + 1],
-                    c2 = samp.color[3 * size_t(i) + 2];
-        const float dot = g0 * c0 + g1 * c1 + g2 * c2;
-        float dsigma;
-        adjoint_sample(dot, alpha, T_prev, samp.dt[i], adj_T, dsigma);
-        grad_color[3 * size_t(i)] = g0 * w;
-        grad_color[3 * size_t(i) + 1] = g1 * w;
-        grad_color[3 * size_t(i) + 2] = g2 * w;
-        grad_sigma[i] = dsigma;
+    auto scalar = [&](uint32_t i) {
+        float ds, o0, o1, o2;
+        diff_one(g0, g1, g2, aux[4 * size_t(i)], aux[4 * size_t(i) + 1], aux[4 * size_t(i) + 2], samp.color[3 * size_t(i)],
+                 samp.color[3 * size_t(i) + 1], samp.color[3 * size_t(i) + 2], samp.dt[i], adj_T, ds, o0, o1, o2);
+        grad_color[3 * size_t(i)] = o0;
+        grad_color[3 * size_t(i) + 1] = o1;
+        grad_color[3 * size_t(i) + 2] = o2;
+        grad_sigma[i] = ds;
+    };
+    uint32_t i = e;
+    if (kVec)
+        while (i > b && (i & 3u) != 0u) scalar(--i);
+    while (i >= b + 4u) {
+        i -= 4u;
+        float4 A0, A1, A2, A3, C0, C1, C2, DT;   // colour: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+        if (kVec) {
+            const float4* a4 = reinterpret_cast<const float4*>(aux) + i;
+            const float4* c4 = reinterpret_cast<const float4*>(samp.color + 3 * size_t(i));
+            A0 = __ldcs(a4); A1 = __ldcs(a4 + 1); A2 = __ldcs(a4 + 2); A3 = __ldcs(a4 + 3);
+            C0 = __ldcs(c4); C1 = __ldcs(c4 + 1); C2 = __ldcs(c4 + 2);
+            DT = __ldcs(reinterpret_cast<const float4*>(samp.dt + i));
+        } else {   // arrays that are only 4-byte aligned (the reference's workspace rule): same block, scalar accesses
+            const float* a = aux + 4 * size_t(i);
+            const float* c = samp.color + 3 * size_t(i);
+            A0 = make_float4(a[0], a[1], a[2], 0.f); A1 = make_float4(a[4], a[5], a[6], 0.f);
+            A2 = make_float4(a[8], a[9], a[10], 0.f); A3 = make_float4(a[12], a[13], a[14], 0.f);
+            C0 = make_float4(c[0], c[1], c[2], c[3]); C1 = make_float4(c[4], c[5], c[6], c[7]); C2 = make_float4(c[8], c[9], c[10], c[11]);
+            DT = make_float4(samp.dt[i], samp.dt[i + 1], samp.dt[i + 2], samp.dt[i + 3]);
+        }
+        float4 S, G0, G1, G2;
+        diff_one(g0, g1, g2, A3.x, A3.y, A3.z, C2.y, C2.z, C2.w, DT.w, adj_T, S.w, G2.y, G2.z, G2.w);
+        diff_one(g0, g1, g2, A2.x, A2.y, A2.z, C1.z, C1.w, C2.x, DT.z, adj_T, S.z, G1.z, G1.w, G2.x);
+        diff_one(g0, g1, g2, A1.x, A1.y, A1.z, C0.w, C1.x, C1.y, DT.y, adj_T, S.y, G0.w, G1.x, G1.y);
+        diff_one(g0, g1, g2, A0.x, A0.y, A0.z, C0.x, C0.y, C0.z, DT.x, adj_T, S.x, G0.x, G0.y, G0.z);
+        if (kVec) {
+            float4* o4 = reinterpret_cast<float4*>(grad_color + 3 * size_t(i));
+            __stcs(o4, G0); __stcs(o4 + 1, G1); __stcs(o4 + 2, G2);
+            __stcs(reinterpret_cast<float4*>(grad_sigma + i), S);
+        } else {
+            float* o = grad_color + 3 * size_t(i);
+            o[0] = G0.x; o[1] = G0.y; o[2] = G0.z; o[3] = G0.w; o[4] = G1.x; o[5] = G1.y; o[6] = G1.z; o[7] = G1.w;
+            o[8] = G2.x; o[9] = G2.y; o[10] = G2.z; o[11] = G2.w;
+            grad_sigma[i] = S.x; grad_sigma[i + 1] = S.y; grad_sigma[i + 2] = S.z; grad_sigma[i + 3] = S.w;
+        }
     }
+    while (i > b) scalar(--i);
 }
 
 // ---- K7: image composition (img_cpu.cpp:148-185) ----------------------------
@@ -456,9 +542,12 @@ cudaError_t launch_sample(cudaStream_t s, const MarchParams& mp, float plan_t_ne
 cudaError_t launch_integrate(cudaStream_t s, float plan_t_near, float plan_t_far, const SampleArrays& samp,
                              uint32_t n_rays, uint32_t n_samples, const IntegralArrays& intl, uint32_t* d_status) {
     if (n_rays == 0) return cudaSuccess;
-    const bool aligned = (reinterpret_cast<uintptr_t>(intl.aux) & 15u) == 0;
-    integrate_kernel<<<blocks_for(n_rays, kThreads), kThreads, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays,
-                                                                       n_samples, intl, aligned, d_status);
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0u; };
+    const bool aligned = al16(intl.aux);
+    if (al16(samp.color) && al16(samp.sigma) && al16(samp.dt))
+        integrate_kernel<true><<<blocks_for(n_rays, 64), 64, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays, n_samples, intl, aligned, d_status);
+    else
+        integrate_kernel<false><<<blocks_for(n_rays, 64), 64, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays, n_samples, intl, aligned, d_status);
     return cudaGetLastError();
 }
 
@@ -466,8 +555,13 @@ cudaError_t launch_diff(cudaStream_t s, const float* dL_dI, int64_t stride_ray, 
                         const SampleArrays& samp, const float* aux, uint32_t n_rays, uint32_t n_samples,
                         float* grad_sigma, float* grad_color, uint32_t* d_status) {
     if (n_rays == 0 || n_samples == 0) return cudaSuccess;
-    diff_kernel<<<blocks_for(n_rays, kThreads), kThreads, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays,
-                                                                  n_samples, grad_sigma, grad_color, d_status);
+    auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0u; };
+    if (aligned(aux) && aligned(samp.color) && aligned(samp.dt) && aligned(grad_sigma) && aligned(grad_color))
+        diff_kernel<true><<<blocks_for(n_rays, 64), 64, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays, n_samples, grad_sigma,
+                                                                grad_color, d_status);
+    else
+        diff_kernel<false><<<blocks_for(n_rays, 64), 64, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays, n_samples,
+                                                                 grad_sigma, grad_color, d_status);
     return cudaGetLastError();
 }
 
