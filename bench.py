@@ -244,10 +244,10 @@ def renderer_e2e(cfg, iters=5, warmup=2):
     if not os.path.exists(exe):
         return {"unavailable": "dvren_bench not built"}
     out = {}
-    for key, pin in (("pageable", 0), ("pinned_opt_in", 1)):
+    for key, pin, staged in (("pageable", 0, 0), ("pinned_opt_in", 1, 0), ("staged_path_pinned", 1, 1)):
         try:
             r = subprocess.run([exe, "bench", str(cfg["grid"]), str(cfg["width"]), str(cfg["steps"]), "1" if cfg["stratified"] else "0",
-                                str(iters), str(warmup), str(pin)], capture_output=True, text=True, timeout=600)
+                                str(iters), str(warmup), str(pin), str(staged)], capture_output=True, text=True, timeout=600)
             j = json.loads(r.stdout.strip().splitlines()[-1])
             out[key] = {"value": j["samples"] / (j["ms_per_step"] * 1e-3) / 1e6, "ms_per_step": j["ms_per_step"],
                         "forward_kernel_ms": j["forward_kernel_ms"], "forward_readback_ms": j["forward_readback_ms"],
@@ -255,7 +255,9 @@ def renderer_e2e(cfg, iters=5, warmup=2):
                         "d2h_bytes_per_step": j["d2h_bytes_per_step"], "h2d_bytes_per_step": j["h2d_bytes_per_step"]}
         except Exception as e:   # never let the side measurement kill the bench line
             out[key] = {"error": repr(e)[:200]}
-    out["what"] = "dvren::Renderer::Forward + Backward (C++ surface, host clock, every host<->device copy inside), " + cfg["workload"]
+    out["what"] = ("dvren::Renderer::Forward + Backward (C++ surface, host clock, every host<->device copy inside), " + cfg["workload"] +
+                   "; staged_path_pinned = RenderOptions::use_fused_path = false: the hp.h calls one by one on materialised samples "
+                   "(48 B per sample in HBM), the compatibility path")
     return out
 
 

@@ -2,7 +2,7 @@
 // Renderer::Forward + Backward through libdvren.so with pageable std::vector inputs and results (the shapes the
 // reference's API forces, reference src/render/renderer.cpp:376-386,441-444).  Two uses:
 //
-//   dvren_bench bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> [pin 0|1]
+//   dvren_bench bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> [pin 0|1] [staged 0|1]
 //       times Forward+Backward per step on the host clock (every host<->device copy inside) and prints ONE JSON line:
 //       bench.py reports it as e2e.renderer next to the pinned C-ABI end-to-end number.
 //   dvren_bench shard <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas> [mode]
@@ -91,7 +91,7 @@ std::vector<float> hashed_image_grad(size_t rays) {
         }                                                       \
     } while (0)
 
-int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warmup, bool pin) {
+int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warmup, bool pin, bool staged) {
     dvren::Context ctx;
     dvren::Status st = dvren::Context::Create({}, ctx);
     CHECK(st.ok(), "Context::Create: %s", st.ToString().c_str());
@@ -106,6 +106,7 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
     }
     dvren::RenderOptions opt{};
     opt.pin_result_buffers = pin;   // one set of result objects, alive for the whole loop: the opt-in's contract
+    opt.use_fused_path = !staged;   // staged: hp_ray -> hp_samp -> hp_int -> hp_img, hp_diff -> scatter on materialised samples
     dvren::Renderer renderer(ctx, plan, opt);
     const std::vector<float> dl = hashed_image_grad(static_cast<size_t>(w) * w);
     dvren::ForwardResult fwd;      // reused across steps, as a training loop does
@@ -127,10 +128,10 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
     double mass = 0.0;
     for (size_t i = 0; i < bwd.sigma.size(); i += 4099) mass += std::fabs(bwd.sigma[i]);
     const size_t pixels = static_cast<size_t>(w) * w;
-    std::printf("{\"pin_result_buffers\": %s, \"ms_per_step\": %.4f, \"samples\": %zu, \"rays\": %zu, \"live_samples\": %zu, \"forward_kernel_ms\": %.4f, "
+    std::printf("{\"pin_result_buffers\": %s, \"staged_path\": %s, \"ms_per_step\": %.4f, \"samples\": %zu, \"rays\": %zu, \"live_samples\": %zu, \"forward_kernel_ms\": %.4f, "
                 "\"forward_readback_ms\": %.4f, \"backward_kernel_ms\": %.4f, \"backward_readback_ms\": %.4f, "
                 "\"h2d_bytes_per_step\": %zu, \"d2h_bytes_per_step\": %zu, \"iters\": %d, \"warmup\": %d, \"checksum\": %.6g}\n",
-                pin ? "true" : "false", total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_read / iters,
+                pin ? "true" : "false", staged ? "true" : "false", total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_read / iters,
                 bwd_kernel / iters, bwd_read / iters, dl.size() * 4, pixels * 28 + bwd.sigma.size() * 16 + 64, iters, warmup, mass);
     return 0;
 }
@@ -392,7 +393,8 @@ int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "selftest") return run_selftest();
     if (argc >= 8 && std::string(argv[1]) == "bench")
         return run_bench(std::atoi(argv[2]), static_cast<uint32_t>(std::atoi(argv[3])), static_cast<uint32_t>(std::atoi(argv[4])),
-                         std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]), argc >= 9 && std::atoi(argv[8]) != 0);
+                         std::atoi(argv[5]) != 0, std::atoi(argv[6]), std::atoi(argv[7]), argc >= 9 && std::atoi(argv[8]) != 0,
+                         argc >= 10 && std::atoi(argv[9]) != 0);
     std::fprintf(stderr, "usage: %s selftest | bench <grid n> <width> <steps> <stratified 0|1> <iters> <warmup> [pin 0|1] | "
                          "shard <grid n> <width> <steps> <stratified> <iters> <warmup> <gpus> <groups> <reserve_sms> <max_ctas> [mode 0|1|2]\n", argv[0]);
     return 2;

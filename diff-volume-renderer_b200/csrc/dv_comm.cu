@@ -680,37 +680,26 @@ HP_API hp_status hpx_shard_create(hpx_comm* c, const hp_plan* full_plan, hpx_gri
 }
 
 
-// Owners of the slabs.  Rank o adds, for every slab it owns, the partial sums of every OTHER rank whose wedge contains the
-// slab; what a rank renders outside its own range it hands out.  The exchange is a set of concurrent point-to-point
-// transfers over NVSwitch, so its duration follows the busiest port: the cuts minimise max over ranks of max(bytes out,
-// bytes in) -- in the replicated mode including the second phase, in which every owner's sums go to all other ranks (that
-// favours equal shares; the owned mode favours cuts through the middle of the wedge overlaps).  Coordinate descent over the
-// world - 1 cuts from the mid-overlap start; every rank runs the same deterministic search on the same inputs.
-static hp_status band_assign_owners(hpx_shard* s) {
-    const int world = s->comm->world, me = s->comm->rank;
-    const int32_t n = s->n_slabs;
-    DV_CUDA(cudaStreamSynchronize(s->comm->ctx->stream));   // nothing in flight uses the old transfer lists / staging
-    cudaFree(s->staging);
-    s->staging = nullptr;
-    s->sends.clear();
-    s->recvs.clear();
+// Pure host logic of the owner search (see band_assign_owners): wedges [lo, hi) per rank, n slabs, touched hull.
+static std::vector<int32_t> choose_owner_cuts(const std::vector<std::pair<int32_t, int32_t>>& wedges, int32_t n, int32_t hull_lo,
+                                              int32_t hull_hi, bool replicated) {
+    const int world = static_cast<int>(wedges.size());
     auto overlap_len = [&](int r, int32_t lo, int32_t hi) {
-        return std::max(0, std::min(s->wedges[r].second, hi) - std::max(s->wedges[r].first, lo));
+        return std::max(0, std::min(wedges[r].second, hi) - std::max(wedges[r].first, lo));
     };
-    const bool replicated = s->result == HPX_SHARD_RESULT_REPLICATED;
     auto cost = [&](const std::vector<int32_t>& cuts) {
         double worst = 0.0, total = 0.0;
         for (int r = 0; r < world; ++r) {
             const int32_t own_lo = cuts[static_cast<size_t>(r)], own_hi = cuts[static_cast<size_t>(r) + 1];
-            double out = (s->wedges[r].second - s->wedges[r].first) - overlap_len(r, own_lo, own_hi), in = 0.0;
+            double out = (wedges[r].second - wedges[r].first) - overlap_len(r, own_lo, own_hi), in = 0.0;
             if (out < 0.0) out = 0.0;
             for (int q = 0; q < world; ++q)
                 if (q != r) in += overlap_len(q, own_lo, own_hi);
             total += out;
             if (replicated) {
-                const double own = std::max(0, std::min(own_hi, s->hull_hi) - std::max(own_lo, s->hull_lo));
+                const double own = std::max(0, std::min(own_hi, hull_hi) - std::max(own_lo, hull_lo));
                 out += own * (world - 1);
-                in += (s->hull_hi - s->hull_lo) - own;
+                in += (hull_hi - hull_lo) - own;
             }
             worst = std::max(worst, std::max(out, in));
         }
@@ -721,8 +710,8 @@ static hp_status band_assign_owners(hpx_shard* s) {
     {
         int32_t prev_hi = 0;
         for (int r = 0; r < world; ++r) {   // start: half way through the overlap (or gap) of neighbouring wedges
-            const bool empty = s->wedges[r].first >= s->wedges[r].second;
-            const int32_t lo = empty ? prev_hi : s->wedges[r].first, hi = empty ? prev_hi : s->wedges[r].second;
+            const bool empty = wedges[r].first >= wedges[r].second;
+            const int32_t lo = empty ? prev_hi : wedges[r].first, hi = empty ? prev_hi : wedges[r].second;
             if (r > 0) cuts[static_cast<size_t>(r)] = std::min(n, std::max(cuts[static_cast<size_t>(r) - 1], (lo + prev_hi) / 2));
             prev_hi = std::max(prev_hi, hi);
         }
@@ -743,7 +732,24 @@ static hp_status band_assign_owners(hpx_shard* s) {
         }
         if (!moved) break;
     }
-    s->cuts = cuts;
+    return cuts;
+}
+
+// Owners of the slabs.  Rank o adds, for every slab it owns, the partial sums of every OTHER rank whose wedge contains the
+// slab; what a rank renders outside its own range it hands out.  The exchange is a set of concurrent point-to-point
+// transfers over NVSwitch, so its duration follows the busiest port: the cuts minimise max over ranks of max(bytes out,
+// bytes in) -- in the replicated mode including the second phase, in which every owner's sums go to all other ranks (that
+// favours equal shares; the owned mode favours cuts through the middle of the wedge overlaps).  Coordinate descent over the
+// world - 1 cuts from the mid-overlap start; every rank runs the same deterministic search on the same inputs.
+static hp_status band_assign_owners(hpx_shard* s) {
+    const int world = s->comm->world, me = s->comm->rank;
+    const int32_t n = s->n_slabs;
+    DV_CUDA(cudaStreamSynchronize(s->comm->ctx->stream));   // nothing in flight uses the old transfer lists / staging
+    cudaFree(s->staging);
+    s->staging = nullptr;
+    s->sends.clear();
+    s->recvs.clear();
+    s->cuts = choose_owner_cuts(s->wedges, n, s->hull_lo, s->hull_hi, s->result == HPX_SHARD_RESULT_REPLICATED);
     auto overlap = [&](int r, int o) {   // slabs of rank r's wedge that rank o owns
         return std::pair<int32_t, int32_t>(std::max(s->wedges[r].first, s->cuts[o]), std::min(s->wedges[r].second, s->cuts[o + 1]));
     };
@@ -931,6 +937,26 @@ HP_API hp_status hpx_shard_rebalance(hpx_shard* s, int32_t* out_changed) {
     if (same) return HP_STATUS_SUCCESS;
     DV_TRY(band_configure(s));
     if (out_changed) *out_changed = 1;
+    return HP_STATUS_SUCCESS;
+}
+
+// Host-only (works without a GPU): the owner cuts hpx_shard_* chooses for the given per-rank wedges.
+HP_API hp_status hpx_plan_owner_cuts(uint32_t world, int32_t n_slabs, const int32_t* wedges, uint32_t result, int32_t* out_cuts) {
+    DV_RANGE("hpx_plan_owner_cuts");
+    if (world == 0 || world > 4096 || n_slabs <= 0 || wedges == nullptr || out_cuts == nullptr ||
+        (result != HPX_SHARD_RESULT_OWNED && result != HPX_SHARD_RESULT_REPLICATED))
+        return HP_STATUS_INVALID_ARGUMENT;
+    std::vector<std::pair<int32_t, int32_t>> w;
+    int32_t hull_lo = n_slabs, hull_hi = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+        const int32_t lo = wedges[2 * r], hi = wedges[2 * r + 1];
+        if (lo < 0 || hi > n_slabs) return HP_STATUS_INVALID_ARGUMENT;
+        w.emplace_back(lo, hi);
+        if (lo < hi) { hull_lo = std::min(hull_lo, lo); hull_hi = std::max(hull_hi, hi); }
+    }
+    if (hull_hi < hull_lo) hull_lo = hull_hi = 0;
+    const std::vector<int32_t> cuts = choose_owner_cuts(w, n_slabs, hull_lo, hull_hi, result == HPX_SHARD_RESULT_REPLICATED);
+    std::copy(cuts.begin(), cuts.end(), out_cuts);
     return HP_STATUS_SUCCESS;
 }
 

@@ -113,6 +113,7 @@ HPX_FUNCTIONS = {
     "hpx_shard_set_result": (C.c_int, [C.c_void_p, C.c_uint32]),
     "hpx_shard_rebalance": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "hpx_shard_exchange_is_direct": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "hpx_plan_owner_cuts": (C.c_int, [C.c_uint32, C.c_int32, P(C.c_int32), C.c_uint32, P(C.c_int32)]),
     "hpx_plan_balanced_bands": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_uint32), P(C.c_double)]),
     "hpx_shard_bands": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_size_t)]),
     "hpx_shard_owned": (C.c_int, [C.c_void_p, P(C.c_void_p), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_int32)]),

@@ -329,6 +329,9 @@ HP_API hp_status hpx_shard_exchange_is_direct(const hpx_shard* shard, int32_t* o
  * rows per rank, multiples of the 8-row CTA tile; out_work (may be NULL): estimated marching work per band in samples. */
 HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, uint32_t* out_row0, uint32_t* out_rows,
                                          double* out_work);
+/* Host-only: the owner cuts the shard chooses for per-rank wedges [lo, hi) (2 * world ints) over n_slabs slabs and a result
+ * mode; out_cuts: world + 1 ints, rank r owns slabs [cuts[r], cuts[r + 1]). */
+HP_API hp_status hpx_plan_owner_cuts(uint32_t world, int32_t n_slabs, const int32_t* wedges, uint32_t result, int32_t* out_cuts);
 /* Per rank (arrays of `world` entries; any pointer may be NULL): first image row inside the plan's ROI and rows of its band,
  * wedge [lo, hi) in slabs (2 * world ints), owner cuts (world + 1 ints: rank r owns slabs [cuts[r], cuts[r + 1])); floats
  * this rank sends / receives per step in the reduce-scatter part. */

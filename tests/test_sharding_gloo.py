@@ -205,3 +205,48 @@ def test_library_balanced_bands(width, height, steps, world, roi):
     if h >= 64 * world:   # enough tile rows to balance: nobody more than 6 % above the mean
         assert mine.max() <= 1.06 * mine.mean()
     plan.close(); ctx.close()
+
+
+def _exchange_volumes(wedges, cuts, replicated):
+    world = len(wedges)
+    hull = (min(w[0] for w in wedges if w[0] < w[1]), max(w[1] for w in wedges if w[0] < w[1]))
+    ov = lambda r, lo, hi: max(0, min(wedges[r][1], hi) - max(wedges[r][0], lo))
+    out, inn = [], []
+    for r in range(world):
+        lo, hi = cuts[r], cuts[r + 1]
+        o = max(0, (wedges[r][1] - wedges[r][0]) - ov(r, lo, hi))
+        i = sum(ov(q, lo, hi) for q in range(world) if q != r)
+        if replicated:
+            own = max(0, min(hi, hull[1]) - max(lo, hull[0]))
+            o, i = o + own * (world - 1), i + (hull[1] - hull[0]) - own
+        out.append(o); inn.append(i)
+    return out, inn
+
+
+@pytest.mark.parametrize("replicated", [False, True])
+@pytest.mark.parametrize("wedges,n", [
+    ([(0, 127), (0, 170), (78, 213), (164, 258), (254, 348), (299, 434), (342, 512), (385, 512)], 512),   # c3 at 8 GPUs (measured)
+    ([(0, 258), (254, 512)], 512), ([(0, 168), (74, 258), (254, 441), (345, 512)], 512),
+    ([(10, 40), (0, 0), (35, 90)], 100), ([(0, 64)], 64)])
+def test_library_owner_cuts(wedges, n, replicated):
+    """hpx_plan_owner_cuts (host-only): the cuts partition all slabs in rank order, and the busiest port (max over ranks of
+    slabs sent / received, both exchange phases in the replicated mode) is never worse than with the plain mid-overlap cuts."""
+    import dvren_b200 as D
+    lib = D.load()
+    world = len(wedges)
+    flat = (C.c_int32 * (2 * world))(*[v for w in wedges for v in w])
+    cuts = (C.c_int32 * (world + 1))()
+    D.check("hpx_plan_owner_cuts", lib.hpx_plan_owner_cuts(world, n, flat, 2 if replicated else 1, cuts))
+    cuts = list(cuts)
+    assert cuts[0] == 0 and cuts[-1] == n and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    mid, prev = [0] * (world + 1), 0
+    mid[world] = n
+    for r, (lo, hi) in enumerate(wedges):
+        if lo >= hi:
+            lo = hi = prev
+        if r:
+            mid[r] = min(n, max(mid[r - 1], (lo + prev) // 2))
+        prev = max(prev, hi)
+    worst = lambda c: max(max(v) for v in _exchange_volumes(wedges, c, replicated))
+    assert worst(cuts) <= worst(mid)
+    assert lib.hpx_plan_owner_cuts(world, n, flat, 0, (C.c_int32 * (world + 1))()) == A.HP_STATUS_INVALID_ARGUMENT
