@@ -232,39 +232,6 @@ __global__ void add_slabs_kernel(float4* __restrict__ dst, const float4* __restr
 }
 
 
-// dst[i] += src[i] / dst[i] = src[i] with src in ANOTHER GPU's memory (mapped peer pointer): 16-byte loads over NVLink,
-// four in flight per thread before the first use, so that a 148-SM grid keeps several MB of reads outstanding.
-template <bool kAdd>
-__global__ void __launch_bounds__(256) peer_pull_kernel(float4* __restrict__ dst, const float4* __restrict__ src, size_t n4) {
-    const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-    size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
-    for (; i + 3 * stride < n4; i += 4 * stride) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = src[i + k * stride];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (kAdd) {
-                float4 a = dst[i + k * stride];
-                a.x += v[k].x; a.y += v[k].y; a.z += v[k].z; a.w += v[k].w;
-                dst[i + k * stride] = a;
-            } else {
-                dst[i + k * stride] = v[k];
-            }
-        }
-    }
-    for (; i < n4; i += stride) {
-        const float4 v = src[i];
-        if (kAdd) {
-            float4 a = dst[i];
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-            dst[i] = a;
-        } else {
-            dst[i] = v;
-        }
-    }
-}
-
 // ---- exchange kernels: ONE launch per phase, all peers at once ---------------------------------------------------------
 // Reduce phase: the owner walks the slabs it owns; for every element it adds, in ascending rank order (the sum never
 // depends on timing), the partial sums of every peer whose wedge contains the slab.  The loads from the different peers
@@ -400,15 +367,6 @@ hp_status stream_barrier(hpx_shard* s) {
     hpx_comm* c = s->comm;
     DV_NCCL(nccl().AllReduce(s->d_flag, s->d_flag, 1, ncclInt32, ncclMax, c->comm, c->ctx->stream));
     return HP_STATUS_SUCCESS;
-}
-
-template <bool kAdd>
-cudaError_t launch_peer_pull(cudaStream_t stream, float* dst, const float* src, size_t floats) {
-    const size_t n4 = floats / 4;
-    if (n4 == 0) return cudaSuccess;
-    const unsigned blocks = static_cast<unsigned>(std::min<size_t>((n4 + 1023) / 1024, 148 * 8));
-    peer_pull_kernel<kAdd><<<blocks, 256, 0, stream>>>(reinterpret_cast<float4*>(dst), reinterpret_cast<const float4*>(src), n4);
-    return cudaGetLastError();
 }
 
 // Marching work of one image row, in samples: steps of its rays that lie inside the unit cube (what the kernels spend
@@ -1258,6 +1216,153 @@ HP_API hp_status hpx_shard_step(hpx_shard* s, const float* dL_dI_device, uint32_
     }
     DV_CUDA(cudaEventRecord(c->ev_side, side));
     DV_CUDA(cudaStreamWaitEvent(main, c->ev_side, 0));
+    return HP_STATUS_SUCCESS;
+}
+
+}  // extern "C"
+
+// ---- hpx_backward_streamed: the gradient read-back runs UNDER the backward kernel ----------------------------------
+// A training loop on the host (the dvren::Renderer contract, reference renderer.cpp:441-442) reads the whole gradient
+// every step: 2.1 GB at 512^3, as long over PCIe as the backward kernel itself takes.  The backward is therefore launched
+// with per-row-group completion signals (hpx_backward_signalled) on a gradient block laid out slab by slab along the
+// world axis the image rows advance along; a high-priority copy stream waits for each group (cuStreamWaitValue32: no SM
+// is occupied by the wait), un-interleaves the slabs that group finished and no later group will touch, and copies them
+// into the caller's arrays in the reference layout while the later rows still render.
+namespace {
+struct StreamPlan {
+    const hpx_grid* grid = nullptr;
+    CameraParams cam{};
+    RoiParams roi{};
+    int slow_axis = 2;
+    std::vector<uint32_t> group_end_rows;
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> runs;
+    std::vector<std::pair<int32_t, int32_t>> untouched;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+};
+
+void stream_plan_free(void* p) {
+    StreamPlan* sp = static_cast<StreamPlan*>(p);
+    if (sp == nullptr) return;
+    if (sp->side != nullptr) { cudaStreamSynchronize(sp->side); cudaStreamDestroy(sp->side); }
+    if (sp->ev_main != nullptr) cudaEventDestroy(sp->ev_main);
+    if (sp->ev_side != nullptr) cudaEventDestroy(sp->ev_side);
+    delete sp;
+}
+
+constexpr uint32_t kStreamGroups = 12;
+
+hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
+    StreamPlan* sp = static_cast<StreamPlan*>(f->stream_plan);
+    const CameraParams& cam = f->h_params.cam;
+    const RoiParams& roi = f->h_params.roi;
+    const float down[3] = {std::fabs(cam.r01), std::fabs(cam.r11), std::fabs(cam.r21)};
+    const int axis = down[0] > down[1] ? (down[0] > down[2] ? 0 : 2) : (down[1] >= down[2] ? 1 : 2);
+    if (sp != nullptr && sp->grid == g && std::memcmp(&sp->cam, &cam, sizeof(cam)) == 0 && std::memcmp(&sp->roi, &roi, sizeof(roi)) == 0 &&
+        g->grad_slow_axis == sp->slow_axis) {
+        *out = sp;
+        return HP_STATUS_SUCCESS;
+    }
+    if (sp == nullptr) {
+        sp = new (std::nothrow) StreamPlan();
+        if (sp == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+        f->stream_plan = sp;
+        f->stream_plan_free = stream_plan_free;
+        int lo = 0, hi = 0;
+        cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&sp->side, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sp->ev_main, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sp->ev_side, cudaEventDisableTiming);
+        if (e != cudaSuccess) return cuda_fail(e, "stream plan");
+    }
+    sp->grid = nullptr;   // invalid until rebuilt
+    sp->group_end_rows.clear();
+    sp->runs.clear();
+    sp->untouched.clear();
+    sp->slow_axis = axis;
+    if (g->grad_slow_axis != axis) DV_TRY(hpx_grid_set_grad_layout(g, axis, nullptr, nullptr));   // (clears the block: the caller asked for ZERO)
+    const int32_t n_slabs = axis == 0 ? g->nx : axis == 1 ? g->ny : g->nz;
+    hp_plan_desc d = f->plan->desc;
+    d.roi.x = roi.x; d.roi.y = roi.y; d.roi.width = roi.w; d.roi.height = roi.h;
+    std::vector<float> weights(kStreamGroups);
+    for (uint32_t i = 0; i < kStreamGroups; ++i) weights[i] = std::pow(0.8f, static_cast<float>(i));   // small last group: only its slabs wait for the kernel's end
+    const uint32_t tile_rows_px = kTileH * kWarpsY;
+    std::vector<std::pair<int32_t, int32_t>> ranges;
+    uint32_t owned = 0;
+    for (const RowBand& b : weighted_bands(d, weights, tile_rows_px)) {
+        if (b.rows == 0) continue;
+        int32_t box[6] = {0, 0, 0, 0, 0, 0};
+        DV_TRY(frame_rows_bounds(f, g, b.y0 - roi.y, b.rows, box));
+        ranges.emplace_back(box[3 + axis] > 0 ? box[axis] : 0, box[3 + axis] > 0 ? box[axis] + box[3 + axis] : 0);
+        owned += (b.rows + tile_rows_px - 1) / tile_rows_px;
+        sp->group_end_rows.push_back(owned);
+    }
+    if (sp->group_end_rows.empty()) return HP_STATUS_INVALID_ARGUMENT;
+    sp->runs = final_slab_runs(ranges);
+    std::vector<char> touched(static_cast<size_t>(n_slabs), 0);
+    for (const auto& r : ranges)
+        for (int32_t y = std::max(r.first, 0); y < std::min(r.second, n_slabs); ++y) touched[static_cast<size_t>(y)] = 1;
+    for (int32_t y = 0; y < n_slabs; ++y) {
+        if (touched[static_cast<size_t>(y)]) continue;
+        if (!sp->untouched.empty() && sp->untouched.back().second == y) sp->untouched.back().second = y + 1;
+        else sp->untouched.emplace_back(y, y + 1);
+    }
+    sp->cam = cam;
+    sp->roi = roi;
+    sp->grid = g;
+    *out = sp;
+    return HP_STATUS_SUCCESS;
+}
+}  // namespace
+
+extern "C" {
+
+HP_API hp_status hpx_backward_streamed(hpx_frame* f, hpx_grid* g, const float* dL_dI, hp_memspace memspace, uint32_t flags,
+                                       float* sigma_grad_host, float* color_grad_host, float* camera16_host) {
+    DV_RANGE("hpx_backward_streamed");
+    if (f == nullptr || g == nullptr || dL_dI == nullptr || f->ctx != g->ctx) return HP_STATUS_INVALID_ARGUMENT;
+    if ((flags & HPX_BACKWARD_GRID) == 0u) return HP_STATUS_INVALID_ARGUMENT;
+    const RoiParams& roi = f->h_params.roi;
+    const float down0 = std::fabs(f->h_params.cam.r01), down1 = std::fabs(f->h_params.cam.r11), down2 = std::fabs(f->h_params.cam.r21);
+    const bool x_slow = down0 > down1 && down0 > down2;
+    const bool can_stream = g->linear && !g->clamp && scatter_params(*g).unit_bbox != 0u && (flags & HPX_BACKWARD_ZERO) != 0u &&
+                            (flags & HPX_BACKWARD_DETERMINISTIC) == 0u && wait_value() != nullptr && !x_slow && roi.tile_row_stride <= 1 &&
+                            roi.tile_row_reverse == 0u && (sigma_grad_host != nullptr || color_grad_host != nullptr);
+    if (!can_stream) {   // same result, read back after the kernel
+        DV_TRY(hpx_backward(f, g, dL_dI, memspace, flags));
+        return hpx_grid_read_grad(g, sigma_grad_host, color_grad_host, camera16_host, HP_MEMSPACE_HOST);
+    }
+    DV_ENTER(f->ctx);
+    StreamPlan* sp = nullptr;
+    DV_TRY(stream_plan_build(f, g, &sp));
+    cudaStream_t main = f->ctx->stream, side = sp->side;
+    float* block = nullptr;
+    size_t floats = 0;
+    DV_TRY(hpx_grid_grad_buffer(g, &block, &floats));
+    DV_CUDA(cudaMemsetAsync(block, 0, floats * sizeof(float), main));
+    uint32_t* counters = nullptr;
+    DV_TRY(hpx_frame_reset_group_counters(f, &counters));
+    DV_CUDA(cudaEventRecord(sp->ev_main, main));   // counters cleared: the previous call's counts cannot satisfy the waits
+    uint32_t expected[16] = {};
+    const uint32_t n_groups = static_cast<uint32_t>(sp->group_end_rows.size());
+    DV_TRY(hpx_backward_signalled(f, g, dL_dI, memspace, flags & ~HPX_BACKWARD_ZERO, sp->group_end_rows.data(), n_groups, &counters, expected));
+    DV_CUDA(cudaStreamWaitEvent(side, sp->ev_main, 0));
+    const size_t slab_floats = (floats - 16) / static_cast<size_t>(sp->slow_axis == 0 ? g->nx : sp->slow_axis == 1 ? g->ny : g->nz);
+    (void)slab_floats;
+    for (uint32_t i = 0; i < n_groups; ++i) {
+        const int rc = wait_value()(side, reinterpret_cast<unsigned long long>(counters + i), expected[i], 0u /* GEQ */);
+        if (rc != 0) {
+            set_last_error("cuStreamWaitValue32 failed with driver error " + std::to_string(rc));
+            return HP_STATUS_INTERNAL_ERROR;
+        }
+        if (i == 0)
+            for (const auto& run : sp->untouched) DV_TRY(grid_slabs_to_host(g, side, run.first, run.second, sigma_grad_host, color_grad_host));
+        for (const auto& run : sp->runs[i]) DV_TRY(grid_slabs_to_host(g, side, run.first, run.second, sigma_grad_host, color_grad_host));
+    }
+    if (camera16_host != nullptr)   // (the camera reduction kernel runs after the backward kernel on the main stream)
+        DV_CUDA(cudaMemcpyAsync(camera16_host, block + floats - 16, 16 * sizeof(float), cudaMemcpyDeviceToHost, main));
+    DV_CUDA(cudaEventRecord(sp->ev_side, side));
+    DV_CUDA(cudaStreamWaitEvent(main, sp->ev_side, 0));
     return HP_STATUS_SUCCESS;
 }
 

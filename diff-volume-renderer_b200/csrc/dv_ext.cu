@@ -63,6 +63,63 @@ void set_bbox(hpx_grid* g, const float bmin[3], const float bmax[3]) {
 
 }  // namespace
 
+namespace dv {
+hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host) {
+    if (g == nullptr || lo < 0 || hi < lo) return HP_STATUS_INVALID_ARGUMENT;
+    if (hi == lo || (sigma_host == nullptr && color_host == nullptr)) return HP_STATUS_SUCCESS;
+    const int axis = g->grad_slow_axis;
+    const int32_t n_axis = axis == 0 ? g->nx : axis == 1 ? g->ny : g->nz;
+    if (hi > n_axis) return HP_STATUS_INVALID_ARGUMENT;
+    if (g->d_unpacked == nullptr || g->unpacked_voxels < g->voxels) {   // full-size staging in the reference layout
+        DV_CUDA(cudaStreamSynchronize(g->ctx->stream));
+        cudaFree(g->d_unpacked);
+        g->d_unpacked = nullptr;
+        DV_CUDA(cudaMalloc(&g->d_unpacked, std::max<size_t>(g->voxels, 1) * 16));
+        g->unpacked_voxels = g->voxels;
+    }
+    float* d_sig = g->d_unpacked;
+    float* d_col = g->d_unpacked + g->unpacked_voxels;
+    const ScatterParams lay = scatter_params(*g);
+    const uint32_t nx = static_cast<uint32_t>(g->nx), ny = static_cast<uint32_t>(g->ny), nz = static_cast<uint32_t>(g->nz);
+    DV_CUDA(launch_unpack_grad_slabs(stream, reinterpret_cast<const float4*>(g->d_grad), sigma_host ? d_sig : nullptr,
+                                     color_host ? d_col : nullptr, axis, static_cast<uint32_t>(lo), static_cast<uint32_t>(hi), nx, ny, nz,
+                                     lay.box_sx, lay.box_sy, lay.box_sz));
+    // the slabs' voxels in the reference layout [z][y][x]: axis z: one contiguous run; axis y: per z-plane one run of
+    // (hi - lo) rows; axis x: per row one run of (hi - lo) voxels -- all three are ONE pitched copy per array
+    auto copy = [&](float* host, const float* dev, size_t ch) -> cudaError_t {
+        if (axis == 2) {
+            const size_t off = static_cast<size_t>(lo) * ny * nx * ch;
+            return cudaMemcpyAsync(host + off, dev + off, static_cast<size_t>(hi - lo) * ny * nx * ch * 4, cudaMemcpyDeviceToHost, stream);
+        }
+        if (axis == 1) {
+            const size_t off = static_cast<size_t>(lo) * nx * ch, pitch = static_cast<size_t>(ny) * nx * ch * 4;
+            return cudaMemcpy2DAsync(host + off, pitch, dev + off, pitch, static_cast<size_t>(hi - lo) * nx * ch * 4, nz, cudaMemcpyDeviceToHost, stream);
+        }
+        const size_t off = static_cast<size_t>(lo) * ch, pitch = static_cast<size_t>(nx) * ch * 4;
+        return cudaMemcpy2DAsync(host + off, pitch, dev + off, pitch, static_cast<size_t>(hi - lo) * ch * 4, static_cast<size_t>(ny) * nz,
+                                 cudaMemcpyDeviceToHost, stream);
+    };
+    if (sigma_host != nullptr) DV_CUDA(copy(sigma_host, d_sig, 1));
+    if (color_host != nullptr) DV_CUDA(copy(color_host, d_col, 3));
+    return HP_STATUS_SUCCESS;
+}
+hp_status frame_rows_bounds(hpx_frame* f, const hpx_grid* g, uint32_t row0, uint32_t rows, int32_t out_box[6]) {
+    if (f == nullptr || g == nullptr || out_box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    const RoiParams saved = f->h_params.roi;
+    if (row0 >= saved.h || rows == 0) {
+        for (int i = 0; i < 6; ++i) out_box[i] = 0;
+        return HP_STATUS_SUCCESS;
+    }
+    f->h_params.roi.y = saved.y + row0;
+    f->h_params.roi.h = std::min(rows, saved.h - row0);
+    f->params_dirty = true;
+    const hp_status st = hpx_frame_bounds(f, g, out_box);
+    f->h_params.roi = saved;
+    f->params_dirty = true;
+    return st;
+}
+}  // namespace dv
+
 extern "C" {
 
 // =============================================================================
@@ -1002,6 +1059,7 @@ HP_API void hpx_frame_release(hpx_frame* f) {
         DeviceScope scope;
         scope.enter(f->ctx);
         cudaStreamSynchronize(f->ctx->stream);
+        if (f->stream_plan != nullptr && f->stream_plan_free != nullptr) f->stream_plan_free(f->stream_plan);
         if (f->graph_exec) cudaGraphExecDestroy(f->graph_exec);
         if (f->graph) cudaGraphDestroy(f->graph);
         for (void* p : f->allocations) cudaFree(p);

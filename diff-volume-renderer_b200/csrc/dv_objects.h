@@ -116,6 +116,9 @@ struct hpx_frame {
     size_t device_bytes = 0;
     uint64_t rays = 0, samples = 0;
     bool forward_done = false;
+    // hpx_backward_streamed: row groups, slab runs and the copy stream for this frame / grid / camera (dv_comm.cu)
+    void* stream_plan = nullptr;
+    void (*stream_plan_free)(void*) = nullptr;
     // captured graph
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -195,5 +198,10 @@ struct DeviceScratch {
 
 FieldPair field_pair(const hp_field* fs, const hp_field* fc);
 ScatterParams scatter_params(const hpx_grid& grid);
+// Slabs [lo, hi) of the gradient block (current layout) -> un-interleaved on `stream` and copied into the caller's HOST
+// arrays in the reference layout (sigma_grad[V], color_grad[3V]; either may be null), at their own positions there.
+hp_status grid_slabs_to_host(hpx_grid* grid, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host);
+// hpx_frame_bounds of the image rows [row0, row0 + rows) of the frame's ROI (blocks until done).
+hp_status frame_rows_bounds(hpx_frame* frame, const hpx_grid* grid, uint32_t row0, uint32_t rows, int32_t out_box[6]);
 
 }  // namespace dv

@@ -488,7 +488,33 @@ __global__ void unpack_grad_kernel(const float4* __restrict__ packed, float* __r
     }
 }
 
+// The slabs [s0, s1) along `axis` of a gradient block with arbitrary axis order (strides sx, sy, sz in voxels), un-interleaved
+// into the REFERENCE layout sigma_grad[V], color_grad[3V] (z slowest, x fastest) at their own positions there.
+__global__ void unpack_grad_slabs_kernel(const float4* __restrict__ packed, float* __restrict__ sigma_grad,
+                                         float* __restrict__ color_grad, int axis, uint32_t s0, uint32_t s1, uint32_t nx, uint32_t ny,
+                                         uint32_t nz, uint32_t sx, uint32_t sy, uint32_t sz) {
+    const uint32_t dx = axis == 0 ? s1 - s0 : nx, dy = axis == 1 ? s1 - s0 : ny, dz = axis == 2 ? s1 - s0 : nz;
+    const uint32_t ox = axis == 0 ? s0 : 0u, oy = axis == 1 ? s0 : 0u, oz = axis == 2 ? s0 : 0u;
+    const size_t total = static_cast<size_t>(dx) * dy * dz;
+    for (size_t j = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < total; j += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const uint32_t x = static_cast<uint32_t>(j % dx) + ox;
+        const size_t r = j / dx;
+        const uint32_t y = static_cast<uint32_t>(r % dy) + oy, z = static_cast<uint32_t>(r / dy) + oz;
+        const float4 v = packed[static_cast<size_t>(x) * sx + static_cast<size_t>(y) * sy + static_cast<size_t>(z) * sz];
+        const size_t ref = (static_cast<size_t>(z) * ny + y) * nx + x;
+        if (sigma_grad != nullptr) sigma_grad[ref] = v.w;
+        if (color_grad != nullptr) { color_grad[3 * ref] = v.x; color_grad[3 * ref + 1] = v.y; color_grad[3 * ref + 2] = v.z; }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_unpack_grad_slabs(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, int axis, uint32_t s0,
+                                     uint32_t s1, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t sx, uint32_t sy, uint32_t sz) {
+    if (s1 <= s0) return cudaSuccess;
+    unpack_grad_slabs_kernel<<<148 * 8, 256, 0, s>>>(packed, sigma_grad, color_grad, axis, s0, s1, nx, ny, nz, sx, sy, sz);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_rays(cudaStream_t s, const FrameParams& p, const RayArrays& out, uint32_t n_rays) {
     if (n_rays == 0) return cudaSuccess;

@@ -90,6 +90,8 @@ cudaError_t launch_pack_grid(cudaStream_t s, const float* sigma, const float* co
                              bool keep_missing);
 cudaError_t launch_pack_grid_strided(cudaStream_t s, const float* sigma, int32_t sigma_stride, const float* color,
                                      int32_t color_stride, float4* packed, size_t voxels, bool keep_missing);
+cudaError_t launch_unpack_grad_slabs(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, int axis, uint32_t s0,
+                                     uint32_t s1, uint32_t nx, uint32_t ny, uint32_t nz, uint32_t sx, uint32_t sy, uint32_t sz);
 cudaError_t launch_unpack_grad(cudaStream_t s, const float4* packed, float* sigma_grad, float* color_grad, size_t first,
                                size_t voxels, uint32_t nx, uint32_t ny, uint32_t sx, uint32_t sy, uint32_t sz);
 

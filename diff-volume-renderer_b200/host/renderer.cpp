@@ -306,18 +306,6 @@ Status Renderer::Backward(DenseGridField& field, std::span<const float> dL_dI, B
 
     const auto total0 = Clock::now();
     backward_stats_ = RenderStats{};
-    hpx_ctx_mark(impl_->ctx, kMarkBwdBegin);
-    if (last_forward_staged_) {
-        const Status st = BackwardStaged(field, dL_dI);
-        if (!st.ok()) return st;
-    } else {
-        uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
-        if (options_.camera_gradients) flags |= HPX_BACKWARD_CAMERA;
-        const hp_status hs = hpx_backward(impl_->frame, field.device_grid(), dL_dI.data(), HP_MEMSPACE_HOST, flags);
-        if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_backward");
-    }
-    hpx_ctx_mark(impl_->ctx, kMarkBwdKernels);
-    field.MarkGradientsStale();   // the field's own host mirrors are refreshed only if somebody asks for them
     // full-grid copies are what the reference's API returns (renderer.cpp:441-442): un-interleaved on the device and
     // read STRAIGHT into the caller's vectors (no intermediate host copy; page-locked once the vectors repeat)
     const size_t voxels = field.voxel_count();
@@ -326,8 +314,33 @@ Status Renderer::Backward(DenseGridField& field, std::span<const float> dL_dI, B
     impl_->PinIfRepeated(out.sigma.data(), voxels * 4);
     impl_->PinIfRepeated(out.color.data(), voxels * 12);
     std::array<float, 16> cam16{};
-    const hp_status rs = hpx_grid_read_grad(field.device_grid(), out.sigma.data(), out.color.data(), cam16.data(), HP_MEMSPACE_HOST);
-    if (rs != HP_STATUS_SUCCESS) return Fail(rs, "hpx_grid_read_grad");
+    bool read_back_done = false;
+    hpx_ctx_mark(impl_->ctx, kMarkBwdBegin);
+    if (last_forward_staged_) {
+        const Status st = BackwardStaged(field, dL_dI);
+        if (!st.ok()) return st;
+    } else {
+        uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
+        if (options_.camera_gradients) flags |= HPX_BACKWARD_CAMERA;
+        if (impl_->pin_enabled) {
+            // page-locked result vectors: the read-back runs UNDER the backward kernel (hpx_backward_streamed)
+            hp_status hs = hpx_backward_streamed(impl_->frame, field.device_grid(), dL_dI.data(), HP_MEMSPACE_HOST, flags, out.sigma.data(),
+                                                 out.color.data(), cam16.data());
+            if (hs == HP_STATUS_SUCCESS) hs = hpx_ctx_synchronize(impl_->ctx);
+            if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_backward_streamed");
+            read_back_done = true;
+            backward_stats_.notes.emplace_back("gradient_read_back=streamed_under_the_backward_kernel");
+        } else {
+            const hp_status hs = hpx_backward(impl_->frame, field.device_grid(), dL_dI.data(), HP_MEMSPACE_HOST, flags);
+            if (hs != HP_STATUS_SUCCESS) return Fail(hs, "hpx_backward");
+        }
+    }
+    hpx_ctx_mark(impl_->ctx, kMarkBwdKernels);
+    field.MarkGradientsStale();   // the field's own host mirrors are refreshed only if somebody asks for them
+    if (!read_back_done) {
+        const hp_status rs = hpx_grid_read_grad(field.device_grid(), out.sigma.data(), out.color.data(), cam16.data(), HP_MEMSPACE_HOST);
+        if (rs != HP_STATUS_SUCCESS) return Fail(rs, "hpx_grid_read_grad");
+    }
     hpx_ctx_mark(impl_->ctx, kMarkBwdRead);
     out.camera.fill(0.0f);
     intrinsics_grad_.fill(0.0f);

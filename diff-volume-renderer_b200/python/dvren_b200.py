@@ -76,6 +76,7 @@ HPX_FUNCTIONS = {
     "hpx_forward": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hpx_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32]),
     "hpx_backward_scatter": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_uint32)]),
+    "hpx_backward_streamed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "hpx_frame_set_row_order": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),

@@ -187,6 +187,18 @@ HP_API hp_status hpx_forward(hpx_frame* frame, const hpx_grid* grid);
 /* dL_dI: (rays,3) f32 per ray in plan order, HOST (copied on the stream) or DEVICE. */
 HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_dI,
                               hp_memspace memspace, uint32_t flags);
+/* hpx_backward + hpx_grid_read_grad(HOST) in one call, with the read-back running UNDER the backward kernel: the kernel
+ * signals per group of image rows, a high-priority copy stream waits for each group (no SM is occupied by the wait),
+ * un-interleaves the gradient slabs that group finished and copies them into the caller's HOST arrays in the reference
+ * layout (sigma_grad[V], color_grad[3V], camera16; any may be NULL) while later rows still render.  The gradient block is
+ * switched to the slab order of the world axis the image rows advance along (hpx_grid_set_grad_layout) and stays there.
+ * Page-lock the arrays (hpx_host_register) for the copies to be asynchronous; they are complete when the context's stream
+ * is (hpx_ctx_synchronize).  Needs HPX_BACKWARD_ZERO, a linear OOB-zero field with the unit scatter box and image rows that
+ * advance along world y or z; in every other case it runs the two plain calls (same results, blocking).
+ * dvren::Renderer::Backward uses it when RenderOptions::pin_result_buffers is set (reference renderer.cpp:415-444 copies
+ * the whole gradient after the backward has finished). */
+HP_API hp_status hpx_backward_streamed(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace, uint32_t flags,
+                                       float* sigma_grad_host, float* color_grad_host, float* camera16_host);
 /* ---- strong scaling of ONE frame over several GPUs (diff-volume-renderer_b200/python/sharding.py) ----------------
  * hpx_frame_set_interleave: this frame marches only the CTA tile rows (8 pixel rows each) t of its ROI with
  *   t % stride == phase; ray indices, pixel ids and buffers stay those of the whole ROI.  stride 1 = everything.
