@@ -269,11 +269,13 @@ __global__ void __launch_bounds__(256) peer_reduce_kernel(float4* __restrict__ b
 struct OwnerTable {
     const float4* src[kMaxPeers];   // by rank
     int32_t cuts[kMaxPeers + 1];
-    int32_t world, me, first_slab;
+    int32_t world, me, first_slab, rotate;
 };
 
 __global__ void __launch_bounds__(256) peer_gather_kernel(float4* __restrict__ block, OwnerTable t, size_t slab4) {
-    const int32_t y = t.first_slab + static_cast<int32_t>(blockIdx.y);
+    // CTAs are dispatched in blockIdx order: every rank starts behind its OWN slabs, so that at any time the ranks read from
+    // different owners (rank r from r + 1, r + 2, ...) instead of all draining one owner's outbound port after the other
+    const int32_t y = t.first_slab + static_cast<int32_t>((blockIdx.y + static_cast<uint32_t>(t.rotate)) % gridDim.y);
     int owner = 0;
     while (owner + 1 < t.world && y >= t.cuts[owner + 1]) ++owner;
     if (owner == t.me) return;
@@ -1051,6 +1053,7 @@ static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t fla
             t.world = c->world;
             t.me = me;
             t.first_slab = s->hull_lo;
+            t.rotate = std::max(0, std::min(s->cuts[me + 1], s->hull_hi) - s->hull_lo);
             peer_gather_kernel<<<dim3(bx, static_cast<unsigned>(s->hull_hi - s->hull_lo)), 256, 0, main>>>(reinterpret_cast<float4*>(block), t, slab4);
             DV_CUDA(cudaGetLastError());
         }
