@@ -197,15 +197,19 @@ std::vector<RowBand> weighted_bands(const hp_plan_desc& d, const std::vector<flo
 
 // Per group, the contiguous runs of slabs that are FINAL once that group is done: touched by it or an earlier group and
 // by no later one.  Every touched slab appears in exactly one run, so reducing the runs reduces the gradient once.
-std::vector<std::vector<std::pair<int32_t, int32_t>>> final_slab_runs(const std::vector<std::pair<int32_t, int32_t>>& ranges) {
-    std::vector<std::vector<std::pair<int32_t, int32_t>>> out;
+typedef std::vector<std::pair<int32_t, int32_t>> SlabIntervals;
+
+std::vector<SlabIntervals> final_slab_runs(const std::vector<SlabIntervals>& ranges) {
+    std::vector<SlabIntervals> out;
     std::set<int32_t> done;
     for (size_t g = 0; g < ranges.size(); ++g) {
         std::set<int32_t> touched, later;
         for (size_t i = 0; i <= g; ++i)
-            for (int32_t s = ranges[i].first; s < ranges[i].second; ++s) touched.insert(s);
+            for (const auto& r : ranges[i])
+                for (int32_t s = r.first; s < r.second; ++s) touched.insert(s);
         for (size_t i = g + 1; i < ranges.size(); ++i)
-            for (int32_t s = ranges[i].first; s < ranges[i].second; ++s) later.insert(s);
+            for (const auto& r : ranges[i])
+                for (int32_t s = r.first; s < r.second; ++s) later.insert(s);
         std::vector<std::pair<int32_t, int32_t>> runs;
         for (int32_t s : touched) {
             if (later.count(s) || done.count(s)) continue;
@@ -218,6 +222,11 @@ std::vector<std::vector<std::pair<int32_t, int32_t>>> final_slab_runs(const std:
     return out;
 }
 
+std::vector<SlabIntervals> final_slab_runs(const std::vector<std::pair<int32_t, int32_t>>& ranges) {
+    std::vector<SlabIntervals> sets;
+    for (const auto& r : ranges) sets.push_back(SlabIntervals{r});
+    return final_slab_runs(sets);
+}
 
 // ---- band mode helpers ------------------------------------------------------------------------------------------
 // dst[i] += src[i] (float4 lanes; counts are multiples of 4 floats: a slab is nx * ny * 4 floats)
@@ -1253,7 +1262,7 @@ void stream_plan_free(void* p) {
     delete sp;
 }
 
-constexpr uint32_t kStreamGroups = 12;
+constexpr uint32_t kStreamGroups = 16;   // LeanBuffers::group_end
 
 hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
     StreamPlan* sp = static_cast<StreamPlan*>(f->stream_plan);
@@ -1285,26 +1294,44 @@ hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
     sp->slow_axis = axis;
     if (g->grad_slow_axis != axis) DV_TRY(hpx_grid_set_grad_layout(g, axis, nullptr, nullptr));   // (clears the block: the caller asked for ZERO)
     const int32_t n_slabs = axis == 0 ? g->nx : axis == 1 ? g->ny : g->nz;
-    hp_plan_desc d = f->plan->desc;
-    d.roi.x = roi.x; d.roi.y = roi.y; d.roi.width = roi.w; d.roi.height = roi.h;
-    std::vector<float> weights(kStreamGroups);
-    for (uint32_t i = 0; i < kStreamGroups; ++i) weights[i] = std::pow(0.8f, static_cast<float>(i));   // small last group: only its slabs wait for the kernel's end
+    // Row groups in DISPATCH order of the centre-out row order (RoiParams::tile_row_reverse = 2): group k is the k-th ring of
+    // tile rows around the middle of the image -- one band below the centre and one above it.  With a perspective camera the
+    // rows further out can only touch slabs further out (or the far ends of the inner ones), so the slabs around the centre
+    // are final after the first group and the copy stream has work from the start.
     const uint32_t tile_rows_px = kTileH * kWarpsY;
-    std::vector<std::pair<int32_t, int32_t>> ranges;
-    uint32_t owned = 0;
-    for (const RowBand& b : weighted_bands(d, weights, tile_rows_px)) {
-        if (b.rows == 0) continue;
-        int32_t box[6] = {0, 0, 0, 0, 0, 0};
-        DV_TRY(frame_rows_bounds(f, g, b.y0 - roi.y, b.rows, box));
-        ranges.emplace_back(box[3 + axis] > 0 ? box[axis] : 0, box[3 + axis] > 0 ? box[axis] + box[3 + axis] : 0);
-        owned += (b.rows + tile_rows_px - 1) / tile_rows_px;
-        sp->group_end_rows.push_back(owned);
+    const uint32_t tile_rows = (roi.h + tile_rows_px - 1) / tile_rows_px;
+    const uint32_t groups = std::min<uint32_t>(kStreamGroups, std::max<uint32_t>(1u, tile_rows));
+    std::vector<SlabIntervals> ranges;
+    for (uint32_t k = 0; k < groups; ++k) {
+        const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(tile_rows) * k / groups);
+        const uint32_t i1 = static_cast<uint32_t>(static_cast<uint64_t>(tile_rows) * (k + 1) / groups);
+        if (i1 <= i0) continue;
+        // the dispatched rows [i0, i1) as (at most) two runs of tile rows: those below and those above the centre
+        uint32_t lo[2] = {UINT32_MAX, UINT32_MAX}, hi[2] = {0, 0};
+        const uint32_t c = tile_rows / 2u;
+        for (uint32_t i = i0; i < i1; ++i) {
+            const uint32_t r = tile_row_of(i, tile_rows, 2u);
+            const int side_of = r >= c ? 0 : 1;
+            lo[side_of] = std::min(lo[side_of], r);
+            hi[side_of] = std::max(hi[side_of], r + 1u);
+        }
+        SlabIntervals set;
+        for (int h = 0; h < 2; ++h) {
+            if (lo[h] == UINT32_MAX) continue;
+            int32_t box[6] = {0, 0, 0, 0, 0, 0};
+            const uint32_t row0 = lo[h] * tile_rows_px, rows = std::min(roi.h, hi[h] * tile_rows_px) - row0;
+            DV_TRY(frame_rows_bounds(f, g, row0, rows, box));
+            if (box[3 + axis] > 0) set.emplace_back(box[axis], box[axis] + box[3 + axis]);
+        }
+        ranges.push_back(std::move(set));
+        sp->group_end_rows.push_back(i1);
     }
     if (sp->group_end_rows.empty()) return HP_STATUS_INVALID_ARGUMENT;
     sp->runs = final_slab_runs(ranges);
     std::vector<char> touched(static_cast<size_t>(n_slabs), 0);
-    for (const auto& r : ranges)
-        for (int32_t y = std::max(r.first, 0); y < std::min(r.second, n_slabs); ++y) touched[static_cast<size_t>(y)] = 1;
+    for (const auto& set : ranges)
+        for (const auto& r : set)
+            for (int32_t y = std::max(r.first, 0); y < std::min(r.second, n_slabs); ++y) touched[static_cast<size_t>(y)] = 1;
     for (int32_t y = 0; y < n_slabs; ++y) {
         if (touched[static_cast<size_t>(y)]) continue;
         if (!sp->untouched.empty() && sp->untouched.back().second == y) sp->untouched.back().second = y + 1;
@@ -1348,7 +1375,13 @@ HP_API hp_status hpx_backward_streamed(hpx_frame* f, hpx_grid* g, const float* d
     DV_CUDA(cudaEventRecord(sp->ev_main, main));   // counters cleared: the previous call's counts cannot satisfy the waits
     uint32_t expected[16] = {};
     const uint32_t n_groups = static_cast<uint32_t>(sp->group_end_rows.size());
-    DV_TRY(hpx_backward_signalled(f, g, dL_dI, memspace, flags & ~HPX_BACKWARD_ZERO, sp->group_end_rows.data(), n_groups, &counters, expected));
+    f->h_params.roi.tile_row_reverse = 2u;   // centre-out for this launch (stream_plan_build cut the groups for it)
+    f->params_dirty = true;
+    const hp_status launched = hpx_backward_signalled(f, g, dL_dI, memspace, flags & ~HPX_BACKWARD_ZERO, sp->group_end_rows.data(),
+                                                      n_groups, &counters, expected);
+    f->h_params.roi.tile_row_reverse = 0u;
+    f->params_dirty = true;
+    DV_TRY(launched);
     DV_CUDA(cudaStreamWaitEvent(side, sp->ev_main, 0));
     const size_t slab_floats = (floats - 16) / static_cast<size_t>(sp->slow_axis == 0 ? g->nx : sp->slow_axis == 1 ? g->ny : g->nz);
     (void)slab_floats;

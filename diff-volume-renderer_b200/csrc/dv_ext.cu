@@ -728,8 +728,8 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_
 // depend on it.  Not combined with hpx_backward_signalled, whose row groups count in dispatch order.
 HP_API hp_status hpx_frame_set_row_order(hpx_frame* f, int32_t last_row_first) {
     DV_RANGE("hpx_frame_set_row_order");
-    if (f == nullptr) return HP_STATUS_INVALID_ARGUMENT;
-    f->h_params.roi.tile_row_reverse = last_row_first != 0 ? 1u : 0u;
+    if (f == nullptr || last_row_first < 0 || last_row_first > 2) return HP_STATUS_INVALID_ARGUMENT;
+    f->h_params.roi.tile_row_reverse = static_cast<uint32_t>(last_row_first);
     f->params_dirty = true;
     return HP_STATUS_SUCCESS;
 }

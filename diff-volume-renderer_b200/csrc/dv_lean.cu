@@ -38,8 +38,7 @@ struct TilePixel {
 __device__ __forceinline__ TilePixel tile_pixel(const RoiParams& roi) {
     const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
     const uint32_t tile_x = blockIdx.x % tiles_x;
-    uint32_t owned_row = blockIdx.x / tiles_x;
-    if (roi.tile_row_reverse != 0u) owned_row = gridDim.x / tiles_x - 1u - owned_row;
+    const uint32_t owned_row = tile_row_of(blockIdx.x / tiles_x, gridDim.x / tiles_x, roi.tile_row_reverse);
     const uint32_t tile_y = owned_row * roi.tile_row_stride + roi.tile_row_phase;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TilePixel p;

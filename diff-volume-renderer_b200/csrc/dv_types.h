@@ -37,11 +37,27 @@ struct RoiParams {
     // Interleaving the tile rows of one frame over the GPUs of a box gives every rank the same mix of short and long
     // rays (strong scaling, diff-volume-renderer_b200/python/sharding.py).
     uint32_t tile_row_stride, tile_row_phase;
-    // 1: CTAs take the (owned) tile rows last-to-first.  CTAs are dispatched in blockIdx order, so the rows a launch ends
-    // with decide its tail: a band of a sharded frame whose rays get LONGER towards its last row (the upper half of a
-    // perspective image) finishes with its most expensive rows and idles SMs; reversed, it finishes with the cheap ones.
+    // Order in which the CTAs (dispatched in blockIdx order) take the (owned) tile rows -- see tile_row_of():
+    // 0 first-to-last; 1 last-to-first: a band of a sharded frame whose rays get LONGER towards its last row (the upper half
+    // of a perspective image) would otherwise finish with its most expensive rows and idle SMs; 2 centre-out (middle row,
+    // one below, one above, ...): the launch ends with the cheap outer rows of a full frame AND the gradient slabs become
+    // final from the centre outwards right from the start (hpx_backward_streamed copies them while the kernel runs).
     uint32_t tile_row_reverse;
 };
+
+// Tile row taken by the i-th dispatched row of `rows` (RoiParams::tile_row_reverse = mode).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline uint32_t tile_row_of(uint32_t i, uint32_t rows, uint32_t mode) {
+    if (mode == 1u) return rows - 1u - i;
+    if (mode == 2u) {
+        const uint32_t c = rows / 2u;
+        if (i >= 2u * c) return i;                          // rows is odd: the lower half has one row more
+        return (i & 1u) ? c - 1u - (i >> 1) : c + (i >> 1);
+    }
+    return i;
+}
 
 struct FrameParams {
     CameraParams cam;

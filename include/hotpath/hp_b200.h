@@ -211,10 +211,11 @@ HP_API hp_status hpx_backward_streamed(hpx_frame* frame, hpx_grid* grid, const f
  * scatter strategy and the fused-camera choice of a captured graph are those of the view it was captured with.) */
 HP_API hp_status hpx_frame_set_interleave(hpx_frame* frame, uint32_t stride, uint32_t phase);
 HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_t out_box[6]);
-/* last_row_first != 0: the frame's launches take its tile rows last-to-first.  CTAs are dispatched in order, so the rows a
- * launch ends with decide its tail; a band whose rays get longer towards its last row should end with its first one.
- * Results do not depend on the order.  Not for hpx_backward_signalled (its row groups count in dispatch order). */
-HP_API hp_status hpx_frame_set_row_order(hpx_frame* frame, int32_t last_row_first);
+/* Order in which the frame's launches take its tile rows: 0 first-to-last, 1 last-to-first, 2 centre-out (middle row, one
+ * below, one above, ...).  CTAs are dispatched in order, so the rows a launch ends with decide its tail; a band whose rays
+ * get longer towards its last row should end with its first one.  Results do not depend on the order.  The row groups of
+ * hpx_backward_signalled count in DISPATCH order. */
+HP_API hp_status hpx_frame_set_row_order(hpx_frame* frame, int32_t order);
 HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
                                   uint32_t flags, float* box_grad, const int32_t box[6]);
 /* Axis order of the gradient block: slow_axis 0 = x, 1 = y, 2 = z (default) becomes the slowest-varying one, so that a
