@@ -1249,16 +1249,20 @@ struct StreamPlan {
     std::vector<uint32_t> group_end_rows;
     std::vector<std::vector<std::pair<int32_t, int32_t>>> runs;
     std::vector<std::pair<int32_t, int32_t>> untouched;
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    cudaStream_t side = nullptr, side2 = nullptr;   // side2: second copy engine for the colour copies
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_side2 = nullptr;
+    std::vector<cudaEvent_t> ev_unpack;              // one per slab run in flight (staging regions differ per run)
 };
 
 void stream_plan_free(void* p) {
     StreamPlan* sp = static_cast<StreamPlan*>(p);
     if (sp == nullptr) return;
     if (sp->side != nullptr) { cudaStreamSynchronize(sp->side); cudaStreamDestroy(sp->side); }
+    if (sp->side2 != nullptr) { cudaStreamSynchronize(sp->side2); cudaStreamDestroy(sp->side2); }
     if (sp->ev_main != nullptr) cudaEventDestroy(sp->ev_main);
     if (sp->ev_side != nullptr) cudaEventDestroy(sp->ev_side);
+    if (sp->ev_side2 != nullptr) cudaEventDestroy(sp->ev_side2);
+    for (cudaEvent_t e : sp->ev_unpack) cudaEventDestroy(e);
     delete sp;
 }
 
@@ -1283,8 +1287,10 @@ hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
         int lo = 0, hi = 0;
         cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&sp->side, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&sp->side2, cudaStreamNonBlocking, hi);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sp->ev_main, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sp->ev_side, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sp->ev_side2, cudaEventDisableTiming);
         if (e != cudaSuccess) return cuda_fail(e, "stream plan");
     }
     sp->grid = nullptr;   // invalid until rebuilt
@@ -1300,7 +1306,9 @@ hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
     // are final after the first group and the copy stream has work from the start.
     const uint32_t tile_rows_px = kTileH * kWarpsY;
     const uint32_t tile_rows = (roi.h + tile_rows_px - 1) / tile_rows_px;
-    const uint32_t groups = std::min<uint32_t>(kStreamGroups, std::max<uint32_t>(1u, tile_rows));
+    uint32_t want = kStreamGroups;
+    if (const char* env = std::getenv("DVREN_STREAM_GROUPS")) want = static_cast<uint32_t>(std::max(1, std::min(16, std::atoi(env))));
+    const uint32_t groups = std::min<uint32_t>(want, std::max<uint32_t>(1u, tile_rows));
     std::vector<SlabIntervals> ranges;
     for (uint32_t k = 0; k < groups; ++k) {
         const uint32_t i0 = static_cast<uint32_t>(static_cast<uint64_t>(tile_rows) * k / groups);
@@ -1385,20 +1393,31 @@ HP_API hp_status hpx_backward_streamed(hpx_frame* f, hpx_grid* g, const float* d
     DV_CUDA(cudaStreamWaitEvent(side, sp->ev_main, 0));
     const size_t slab_floats = (floats - 16) / static_cast<size_t>(sp->slow_axis == 0 ? g->nx : sp->slow_axis == 1 ? g->ny : g->nz);
     (void)slab_floats;
+    size_t run_index = 0;
     for (uint32_t i = 0; i < n_groups; ++i) {
         const int rc = wait_value()(side, reinterpret_cast<unsigned long long>(counters + i), expected[i], 0u /* GEQ */);
         if (rc != 0) {
             set_last_error("cuStreamWaitValue32 failed with driver error " + std::to_string(rc));
             return HP_STATUS_INTERNAL_ERROR;
         }
+        auto emit = [&](const std::pair<int32_t, int32_t>& run) -> hp_status {
+            if (run_index >= sp->ev_unpack.size()) {
+                cudaEvent_t e = nullptr;
+                DV_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                sp->ev_unpack.push_back(e);
+            }
+            return grid_slabs_to_host(g, side, run.first, run.second, sigma_grad_host, color_grad_host, sp->side2, sp->ev_unpack[run_index++]);
+        };
         if (i == 0)
-            for (const auto& run : sp->untouched) DV_TRY(grid_slabs_to_host(g, side, run.first, run.second, sigma_grad_host, color_grad_host));
-        for (const auto& run : sp->runs[i]) DV_TRY(grid_slabs_to_host(g, side, run.first, run.second, sigma_grad_host, color_grad_host));
+            for (const auto& run : sp->untouched) DV_TRY(emit(run));
+        for (const auto& run : sp->runs[i]) DV_TRY(emit(run));
     }
     if (camera16_host != nullptr)   // (the camera reduction kernel runs after the backward kernel on the main stream)
         DV_CUDA(cudaMemcpyAsync(camera16_host, block + floats - 16, 16 * sizeof(float), cudaMemcpyDeviceToHost, main));
     DV_CUDA(cudaEventRecord(sp->ev_side, side));
     DV_CUDA(cudaStreamWaitEvent(main, sp->ev_side, 0));
+    DV_CUDA(cudaEventRecord(sp->ev_side2, sp->side2));
+    DV_CUDA(cudaStreamWaitEvent(main, sp->ev_side2, 0));
     return HP_STATUS_SUCCESS;
 }
 

@@ -2,6 +2,7 @@
 // lean forward / backward entry points and CUDA-graph capture; plus the
 // hp_graph_* entry points of hp.h built on the same machinery.
 #include <algorithm>
+#include <cstdlib>
 #include <climits>
 #include <cstring>
 #include <new>
@@ -64,12 +65,15 @@ void set_bbox(hpx_grid* g, const float bmin[3], const float bmax[3]) {
 }  // namespace
 
 namespace dv {
-hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host) {
+hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host,
+                             cudaStream_t color_stream, cudaEvent_t ev) {
     if (g == nullptr || lo < 0 || hi < lo) return HP_STATUS_INVALID_ARGUMENT;
     if (hi == lo || (sigma_host == nullptr && color_host == nullptr)) return HP_STATUS_SUCCESS;
     const int axis = g->grad_slow_axis;
     const int32_t n_axis = axis == 0 ? g->nx : axis == 1 ? g->ny : g->nz;
     if (hi > n_axis) return HP_STATUS_INVALID_ARGUMENT;
+    // (Writing the host arrays straight from the un-interleave kernel -- zero copy over PCIe -- was measured at 29 GB/s
+    // against 40 GB/s for staging + pitched copies and 54 GB/s for one contiguous copy: profiles/README.md, round 2.)
     if (g->d_unpacked == nullptr || g->unpacked_voxels < g->voxels) {   // full-size staging in the reference layout
         DV_CUDA(cudaStreamSynchronize(g->ctx->stream));
         cudaFree(g->d_unpacked);
@@ -86,7 +90,7 @@ hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32
                                      lay.box_sx, lay.box_sy, lay.box_sz));
     // the slabs' voxels in the reference layout [z][y][x]: axis z: one contiguous run; axis y: per z-plane one run of
     // (hi - lo) rows; axis x: per row one run of (hi - lo) voxels -- all three are ONE pitched copy per array
-    auto copy = [&](float* host, const float* dev, size_t ch) -> cudaError_t {
+    auto copy = [&](float* host, const float* dev, size_t ch, cudaStream_t stream) -> cudaError_t {
         if (axis == 2) {
             const size_t off = static_cast<size_t>(lo) * ny * nx * ch;
             return cudaMemcpyAsync(host + off, dev + off, static_cast<size_t>(hi - lo) * ny * nx * ch * 4, cudaMemcpyDeviceToHost, stream);
@@ -99,8 +103,15 @@ hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32
         return cudaMemcpy2DAsync(host + off, pitch, dev + off, pitch, static_cast<size_t>(hi - lo) * ch * 4, static_cast<size_t>(ny) * nz,
                                  cudaMemcpyDeviceToHost, stream);
     };
-    if (sigma_host != nullptr) DV_CUDA(copy(sigma_host, d_sig, 1));
-    if (color_host != nullptr) DV_CUDA(copy(color_host, d_col, 3));
+    if (color_host != nullptr && color_stream != nullptr && ev != nullptr) {
+        DV_CUDA(cudaEventRecord(ev, stream));
+        DV_CUDA(cudaStreamWaitEvent(color_stream, ev, 0));
+        DV_CUDA(copy(color_host, d_col, 3, color_stream));
+        if (sigma_host != nullptr) DV_CUDA(copy(sigma_host, d_sig, 1, stream));
+        return HP_STATUS_SUCCESS;
+    }
+    if (sigma_host != nullptr) DV_CUDA(copy(sigma_host, d_sig, 1, stream));
+    if (color_host != nullptr) DV_CUDA(copy(color_host, d_col, 3, stream));
     return HP_STATUS_SUCCESS;
 }
 hp_status frame_rows_bounds(hpx_frame* f, const hpx_grid* g, uint32_t row0, uint32_t rows, int32_t out_box[6]) {

@@ -200,7 +200,10 @@ FieldPair field_pair(const hp_field* fs, const hp_field* fc);
 ScatterParams scatter_params(const hpx_grid& grid);
 // Slabs [lo, hi) of the gradient block (current layout) -> un-interleaved on `stream` and copied into the caller's HOST
 // arrays in the reference layout (sigma_grad[V], color_grad[3V]; either may be null), at their own positions there.
-hp_status grid_slabs_to_host(hpx_grid* grid, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host);
+// color_stream / ev (optional): the colour copy goes to a second stream (ordered behind the un-interleave kernel by `ev`),
+// so that the two pitched copies of a slab range can run on two copy engines at once.
+hp_status grid_slabs_to_host(hpx_grid* grid, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host,
+                             cudaStream_t color_stream = nullptr, cudaEvent_t ev = nullptr);
 // hpx_frame_bounds of the image rows [row0, row0 + rows) of the frame's ROI (blocks until done).
 hp_status frame_rows_bounds(hpx_frame* frame, const hpx_grid* grid, uint32_t row0, uint32_t rows, int32_t out_box[6]);
 
