@@ -263,7 +263,7 @@ def test_cxx_surface_selftest():
 def test_balanced_bands_sum_to_the_whole_frame(ctx):
     """What hpx_shard_create_bands gives each rank, replayed on ONE GPU: the bands of hpx_plan_balanced_bands rendered one
     after the other (ROI sub-plan, global ray-index base for the stratified jitter, every other band with its tile rows
-    taken last-to-first) reproduce the whole frame's image planes bit for bit and sum to its gradient; the voxel wedges
+    taken in another order: last-to-first, centre-out) reproduce the whole frame's image planes bit for bit and sum to its gradient; the voxel wedges
     of hpx_frame_bounds contain everything a band's backward writes."""
     W, Hh, steps, world = 96, 80, 64, 3
     desc = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=7)
@@ -285,7 +285,7 @@ def test_balanced_bands_sum_to_the_whole_frame(ctx):
         bplan = D.Plan(ctx, bd)
         frame = D.Frame(bplan)
         frame.set_view(None, desc.seed, int(row0[r]) * W)
-        D.check("hpx_frame_set_row_order", ctx.lib.hpx_frame_set_row_order(frame.handle, r % 2))
+        D.check("hpx_frame_set_row_order", ctx.lib.hpx_frame_set_row_order(frame.handle, (r + 1) % 3))   # last-to-first, centre-out, first-to-last
         box = (C.c_int32 * 6)()
         D.check("hpx_frame_bounds", ctx.lib.hpx_frame_bounds(frame.handle, grid.handle, box))
         frame.forward(grid)
