@@ -10,6 +10,8 @@
 // Compiled with -fmad=false: see dv_device.cuh.
 #include "dv_staged.h"
 
+#include <cstdlib>
+
 #include "dv_device.cuh"
 
 namespace dv {
@@ -365,6 +367,84 @@ diff_kernel(const float* __restrict__ dL_dI, int64_t stride_ray, int64_t stride_
     while (i > b) scalar(--i);
 }
 
+// ---- K5, warp-transposed: one warp = 32 rays, tiles of 16 samples through shared memory -------------------------------
+// The recurrence is sequential along a ray, so a lane must own a ray; but a thread that walks its own ray touches memory in
+// 16-64 byte pieces 4 KB away from its neighbours' (262 144 open DRAM pages at once: 0.9 TB/s).  Here the WARP loads the
+// last 32 samples of each of its 32 rays with full-line accesses (aux 512 B, colour 384 B, dt 128 B per ray, all loads of a
+// tile in flight together), transposes through shared memory, every lane runs the reference's recurrence over its ray's 32
+// samples from shared memory (row stride 33: conflict-free), and the results leave the same way.  Arithmetic and its order
+// are those of diff_kernel: the outputs are bit-identical.
+constexpr int kDiffTile = 16;
+
+__global__ void __launch_bounds__(32)
+diff_tile_kernel(const float* __restrict__ dL_dI, int64_t stride_ray, int64_t stride_c, SampleArrays samp, const float* __restrict__ aux,
+                 uint32_t n_rays, uint32_t n_samples, float* __restrict__ grad_sigma, float* __restrict__ grad_color, uint32_t* status,
+                 bool aux_aligned) {
+    __shared__ float sm[7][32][kDiffTile + 1];   // alpha, w, T_prev, c0 / out0, c1 / out1, c2 / out2, dt / d sigma
+    const uint32_t lane = threadIdx.x, ray = blockIdx.x * 32u + lane;
+    uint32_t b = 0, e = 0;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (ray < n_rays) {
+        b = samp.ray_offset[ray];
+        e = samp.ray_offset[ray + 1];
+        if (e < b || e > n_samples) {
+            atomicOr(status, kErrBadOffsets);
+            e = b;
+        }
+        const float* gp = dL_dI + static_cast<int64_t>(ray) * stride_ray;
+        g0 = gp[0]; g1 = gp[stride_c]; g2 = gp[2 * stride_c];
+    }
+    const uint32_t longest = __reduce_max_sync(0xffffffffu, e - b);
+    float adj_T = 0.0f;
+    for (uint32_t done = 0; done < longest; done += kDiffTile) {
+        // ---- load: two rays per pass (lanes 0-15 / 16-31), a lane = one sample of its ray's tile [lo, hi)
+        const uint32_t half = lane >> 4, l = lane & 15u;
+#pragma unroll 8
+        for (uint32_t rr = 0; rr < 32u; rr += 2u) {
+            const uint32_t r = rr + half;
+            const uint32_t rb = __shfl_sync(0xffffffffu, b, r), re = __shfl_sync(0xffffffffu, e, r);
+            if (re - rb <= done) continue;
+            const uint32_t hi = re - done, lo = hi - rb > kDiffTile ? hi - kDiffTile : rb, count = hi - lo;
+            if (l < count) {
+                const size_t i = static_cast<size_t>(lo) + l;
+                if (aux_aligned) {
+                    const float4 a = __ldcs(reinterpret_cast<const float4*>(aux) + i);
+                    sm[0][r][l] = a.x; sm[1][r][l] = a.y; sm[2][r][l] = a.z;
+                } else {
+                    sm[0][r][l] = aux[4 * i]; sm[1][r][l] = aux[4 * i + 1]; sm[2][r][l] = aux[4 * i + 2];
+                }
+                sm[6][r][l] = __ldcs(samp.dt + i);
+            }
+            const float* c = samp.color + 3 * static_cast<size_t>(lo);
+            for (uint32_t k = l; k < 3u * count; k += 16u) sm[3 + k % 3u][r][k / 3u] = __ldcs(c + k);
+        }
+        __syncwarp();
+        // ---- the recurrence, lane = ray, newest sample first (diff_cpu.cpp:170-194)
+        if (e - b > done) {
+            const uint32_t hi = e - done, lo = hi - b > kDiffTile ? hi - kDiffTile : b, count = hi - lo;
+            for (uint32_t j = count; j-- > 0u;) {
+                float ds, o0, o1, o2;
+                diff_one(g0, g1, g2, sm[0][lane][j], sm[1][lane][j], sm[2][lane][j], sm[3][lane][j], sm[4][lane][j], sm[5][lane][j],
+                         sm[6][lane][j], adj_T, ds, o0, o1, o2);
+                sm[3][lane][j] = o0; sm[4][lane][j] = o1; sm[5][lane][j] = o2; sm[6][lane][j] = ds;
+            }
+        }
+        __syncwarp();
+        // ---- store, two rays per pass again
+#pragma unroll 8
+        for (uint32_t rr = 0; rr < 32u; rr += 2u) {
+            const uint32_t r = rr + half;
+            const uint32_t rb = __shfl_sync(0xffffffffu, b, r), re = __shfl_sync(0xffffffffu, e, r);
+            if (re - rb <= done) continue;
+            const uint32_t hi = re - done, lo = hi - rb > kDiffTile ? hi - kDiffTile : rb, count = hi - lo;
+            if (l < count) __stcs(grad_sigma + static_cast<size_t>(lo) + l, sm[6][r][l]);
+            float* o = grad_color + 3 * static_cast<size_t>(lo);
+            for (uint32_t k = l; k < 3u * count; k += 16u) __stcs(o + k, sm[3 + k % 3u][r][k / 3u]);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- K7: image composition (img_cpu.cpp:148-185) ----------------------------
 __global__ void background_planes_kernel(ImagePlanes img, size_t pixels, float t_far) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < pixels;
@@ -582,6 +662,12 @@ cudaError_t launch_diff(cudaStream_t s, const float* dL_dI, int64_t stride_ray, 
                         float* grad_sigma, float* grad_color, uint32_t* d_status) {
     if (n_rays == 0 || n_samples == 0) return cudaSuccess;
     auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0u; };
+    static const bool per_thread = std::getenv("DVREN_DIFF_PER_THREAD") != nullptr;   // A/B timing: the thread-per-ray kernels below
+    if (!per_thread && n_samples / n_rays >= 16u) {   // long rays: the warp-transposed kernel (short rays leave its tiles mostly empty)
+        diff_tile_kernel<<<blocks_for(n_rays, 32), 32, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays, n_samples, grad_sigma,
+                                                               grad_color, d_status, aligned(aux));
+        return cudaGetLastError();
+    }
     if (aligned(aux) && aligned(samp.color) && aligned(samp.dt) && aligned(grad_sigma) && aligned(grad_color))
         diff_kernel<true><<<blocks_for(n_rays, 64), 64, 0, s>>>(dL_dI, stride_ray, stride_c, samp, aux, n_rays, n_samples, grad_sigma,
                                                                 grad_color, d_status);
