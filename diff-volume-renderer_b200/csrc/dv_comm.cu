@@ -1306,7 +1306,7 @@ hp_status stream_plan_build(hpx_frame* f, hpx_grid* g, StreamPlan** out) {
     // are final after the first group and the copy stream has work from the start.
     const uint32_t tile_rows_px = kTileH * kWarpsY;
     const uint32_t tile_rows = (roi.h + tile_rows_px - 1) / tile_rows_px;
-    uint32_t want = kStreamGroups;
+    uint32_t want = kStreamGroups;   // (DVREN_STREAM_GROUPS = 1..16 overrides it: profiles/README.md has the sweep)
     if (const char* env = std::getenv("DVREN_STREAM_GROUPS")) want = static_cast<uint32_t>(std::max(1, std::min(16, std::atoi(env))));
     const uint32_t groups = std::min<uint32_t>(want, std::max<uint32_t>(1u, tile_rows));
     std::vector<SlabIntervals> ranges;
@@ -1391,8 +1391,6 @@ HP_API hp_status hpx_backward_streamed(hpx_frame* f, hpx_grid* g, const float* d
     f->params_dirty = true;
     DV_TRY(launched);
     DV_CUDA(cudaStreamWaitEvent(side, sp->ev_main, 0));
-    const size_t slab_floats = (floats - 16) / static_cast<size_t>(sp->slow_axis == 0 ? g->nx : sp->slow_axis == 1 ? g->ny : g->nz);
-    (void)slab_floats;
     size_t run_index = 0;
     for (uint32_t i = 0; i < n_groups; ++i) {
         const int rc = wait_value()(side, reinterpret_cast<unsigned long long>(counters + i), expected[i], 0u /* GEQ */);

@@ -354,6 +354,8 @@ HP_API hp_status hpx_shard_bands(const hpx_shard* shard, uint32_t* out_row0, uin
  * hpx_grid_set_grad_layout with *out_slow_axis slowest): slabs [first, first + count) x slab_floats floats. */
 HP_API hp_status hpx_shard_owned(const hpx_shard* shard, float** out_device_ptr, int32_t* out_first_slab, int32_t* out_slabs,
                                  size_t* out_slab_floats, int32_t* out_slow_axis);
+/* Release order: a shard before its communicator, its grid and its plan's context (it keeps plain pointers to them and
+ * puts the grid's gradient block back into the default order). */
 HP_API void      hpx_shard_release(hpx_shard* shard);
 
 #ifdef __cplusplus
