@@ -687,7 +687,9 @@ def run_sharded(env, args):
                                              "single-GPU backward of the frame: config.verify_max_rel_err_vs_single_gpu"}
     if e2e is not None:
         line["e2e"] = e2e
-    line["gpu_launches"] = 2 * args.steps
+    # per rank and step: lean_forward_kernel, lean_backward_merge_kernel, peer_reduce_kernel (bands; the two barriers of the
+    # exchange are 4-byte NCCL all-reduces and not counted)
+    line["gpu_launches"] = (3 if bands else 2) * args.steps
     line["clocks"] = clocks
     if weak is not None:
         line["c2_weak"] = weak
