@@ -212,6 +212,104 @@ sample_kernel(MarchParams mp, float plan_t_near, float plan_t_far, FieldPair fie
     }
 }
 
+// ---- K2, warp-staged: the same sampler, but a warp's 32 rays buffer 16 samples each in shared memory and the warp writes
+// them out ray by ray in whole lines (positions 192 B, dt / sigma 64 B, colour 192 B, aux 256 B per ray) instead of every
+// lane poking 4-16 bytes into its own far-away region after every sample.  Arithmetic, order and results are those of
+// sample_kernel (the fused == staged bit-for-bit contract of hp_runner.cpp:1737-1760 still holds).
+constexpr int kSampTile = 16;
+
+template <bool kStratified, bool kIntegrate>
+__global__ void __launch_bounds__(32)
+sample_tile_kernel(MarchParams mp, float plan_t_near, float plan_t_far, FieldPair fields, RayArrays rays, uint32_t n_rays,
+                   SampleArrays samp, IntegralArrays intl, bool aux_aligned) {
+    __shared__ float sm[kIntegrate ? 12 : 8][32][kSampTile + 1];   // px py pz | dt | sigma | r g b | aux x4
+    const uint32_t lane = threadIdx.x, ray = blockIdx.x * 32u + lane;
+    const bool valid = ray < n_rays;
+    float ox = 0.f, oy = 0.f, oz = 0.f, dx = 0.f, dy = 0.f, dz = 0.f, tn = 0.f, tf = 0.f;
+    size_t idx = 0;
+    if (valid) {
+        ox = rays.origins[3 * ray]; oy = rays.origins[3 * ray + 1]; oz = rays.origins[3 * ray + 2];
+        dx = rays.directions[3 * ray]; dy = rays.directions[3 * ray + 1]; dz = rays.directions[3 * ray + 2];
+        tn = rays.t_near[ray]; tf = rays.t_far[ray];
+        idx = samp.ray_offset[ray];
+    }
+    const uint64_t ray_index = mp.ray_index_base + ray;
+    RayAccum acc;
+    acc.t_cursor = plan_t_near;
+    bool stopped = false, active = valid && tf > tn;
+    uint32_t cnt = 0;
+    const uint32_t half = lane >> 4, l = lane & 15u;
+    for (uint32_t step = 0;; ++step) {
+        if (active && step >= mp.max_steps) active = false;
+        if (active) {
+            float t, dtv;
+            const int r = march_step<kStratified>(tn, tf, mp.dt, mp.seed, ray_index, step, t, dtv);
+            if (r == 2) {
+                active = false;
+            } else if (r == 0) {
+                const float px = ox + dx * t, py = oy + dy * t, pz = oz + dz * t;
+                const float4 v = sample_fields(fields, px, py, pz);
+                sm[0][lane][cnt] = px; sm[1][lane][cnt] = py; sm[2][lane][cnt] = pz;
+                sm[3][lane][cnt] = dtv;
+                sm[4][lane][cnt] = v.w;
+                sm[5][lane][cnt] = v.x; sm[6][lane][cnt] = v.y; sm[7][lane][cnt] = v.z;
+                if (kIntegrate) {
+                    float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!stopped) {
+                        float a, w, tb;
+                        stopped = integrate_sample(acc, dtv, v, a, w, tb);
+                        row = make_float4(a, w, tb, logf(fmaxf(tb, 1e-30f)));
+                    }
+                    sm[8][lane][cnt] = row.x; sm[9][lane][cnt] = row.y; sm[10][lane][cnt] = row.z; sm[11][lane][cnt] = row.w;
+                }
+                ++cnt;
+            }
+        }
+        const bool any_active = __any_sync(0xffffffffu, active);
+        if (__any_sync(0xffffffffu, cnt == kSampTile) || !any_active) {
+            __syncwarp();
+            // ---- flush: two rays per pass (lanes 0-15 / 16-31), every ray's buffered samples as contiguous runs
+#pragma unroll 4
+            for (uint32_t rr = 0; rr < 32u; rr += 2u) {
+                const uint32_t r = rr + half;
+                const uint32_t n = __shfl_sync(0xffffffffu, cnt, r);
+                const unsigned long long base = __shfl_sync(0xffffffffu, static_cast<unsigned long long>(idx), r);
+                if (n == 0u) continue;
+                float* pos = samp.positions + 3 * base;
+                float* col = samp.color + 3 * base;
+                for (uint32_t k = l; k < 3u * n; k += 16u) {
+                    pos[k] = sm[k % 3u][r][k / 3u];
+                    col[k] = sm[5 + k % 3u][r][k / 3u];
+                }
+                if (l < n) {
+                    samp.dt[base + l] = sm[3][r][l];
+                    samp.sigma[base + l] = sm[4][r][l];
+                    if (kIntegrate) {
+                        if (aux_aligned) {
+                            reinterpret_cast<float4*>(intl.aux)[base + l] = make_float4(sm[8][r][l], sm[9][r][l], sm[10][r][l], sm[11][r][l]);
+                        } else {
+                            float* a4 = intl.aux + 4 * (base + l);
+                            a4[0] = sm[8][r][l]; a4[1] = sm[9][r][l]; a4[2] = sm[10][r][l]; a4[3] = sm[11][r][l];
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            idx += cnt;
+            cnt = 0;
+        }
+        if (!any_active) break;
+    }
+    if (kIntegrate && valid) {
+        float opacity, depth;
+        finish_ray(acc, plan_t_far, opacity, depth);
+        intl.radiance[3 * ray] = acc.cr; intl.radiance[3 * ray + 1] = acc.cg; intl.radiance[3 * ray + 2] = acc.cb;
+        intl.transmittance[ray] = acc.T;
+        intl.opacity[ray] = opacity;
+        intl.depth[ray] = depth;
+    }
+}
+
 // ---- K4: integrator over materialised samples (int_cpu.cpp:160-226) ---------
 // kVec: aligned blocks of four samples, like diff_kernel below (16-byte aligned arrays, checked on the host).
 template <bool kVec>
@@ -635,6 +733,18 @@ cudaError_t launch_sample(cudaStream_t s, const MarchParams& mp, float plan_t_ne
     if (n_rays == 0) return cudaSuccess;
     const uint32_t blocks = blocks_for(n_rays, kThreads);
     const bool al = (reinterpret_cast<uintptr_t>(intl.aux) & 15u) == 0;
+    static const bool per_thread = std::getenv("DVREN_SAMPLE_PER_THREAD") != nullptr;   // A/B timing: the thread-per-ray kernel
+    if (!per_thread && mp.max_steps >= 16u) {   // long rays: stage a warp's samples in shared memory, write whole lines
+        const uint32_t wb = blocks_for(n_rays, 32);
+        if (mp.stratified) {
+            if (integrate) sample_tile_kernel<true, true><<<wb, 32, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+            else           sample_tile_kernel<true, false><<<wb, 32, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+        } else {
+            if (integrate) sample_tile_kernel<false, true><<<wb, 32, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+            else           sample_tile_kernel<false, false><<<wb, 32, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
+        }
+        return cudaGetLastError();
+    }
     if (mp.stratified) {
         if (integrate) sample_kernel<true, true><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
         else           sample_kernel<true, false><<<blocks, kThreads, 0, s>>>(mp, plan_t_near, plan_t_far, fields, rays, n_rays, samp, intl, al);
