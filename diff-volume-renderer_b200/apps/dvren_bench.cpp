@@ -111,7 +111,7 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
     const std::vector<float> dl = hashed_image_grad(static_cast<size_t>(w) * w);
     dvren::ForwardResult fwd;      // reused across steps, as a training loop does
     dvren::BackwardResult bwd;
-    double fwd_kernel = 0, fwd_read = 0, bwd_kernel = 0, bwd_read = 0, total = 0;
+    double fwd_kernel = 0, fwd_read = 0, fwd_integrate = 0, bwd_kernel = 0, bwd_read = 0, total = 0;
     for (int i = 0; i < warmup + iters; ++i) {
         const auto t0 = Clock::now();
         st = renderer.Forward(field, fwd);
@@ -122,6 +122,7 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
         if (i >= warmup) {
             total += ms;
             fwd_kernel += fwd.stats.sample_ms; fwd_read += fwd.stats.compose_ms;
+            fwd_integrate += fwd.stats.integrate_ms;
             bwd_kernel += renderer.backward_stats().sample_ms; bwd_read += renderer.backward_stats().compose_ms;
         }
     }
@@ -129,9 +130,9 @@ int run_bench(int n, uint32_t w, uint32_t steps, bool strat, int iters, int warm
     for (size_t i = 0; i < bwd.sigma.size(); i += 4099) mass += std::fabs(bwd.sigma[i]);
     const size_t pixels = static_cast<size_t>(w) * w;
     std::printf("{\"pin_result_buffers\": %s, \"staged_path\": %s, \"ms_per_step\": %.4f, \"samples\": %zu, \"rays\": %zu, \"live_samples\": %zu, \"forward_kernel_ms\": %.4f, "
-                "\"forward_readback_ms\": %.4f, \"backward_kernel_ms\": %.4f, \"backward_readback_ms\": %.4f, "
+                "\"forward_integrate_ms\": %.4f, \"forward_readback_ms\": %.4f, \"backward_kernel_ms\": %.4f, \"backward_readback_ms\": %.4f, "
                 "\"h2d_bytes_per_step\": %zu, \"d2h_bytes_per_step\": %zu, \"iters\": %d, \"warmup\": %d, \"checksum\": %.6g}\n",
-                pin ? "true" : "false", staged ? "true" : "false", total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_read / iters,
+                pin ? "true" : "false", staged ? "true" : "false", total / iters, fwd.sample_count, fwd.ray_count, renderer.live_sample_count(), fwd_kernel / iters, fwd_integrate / iters, fwd_read / iters,
                 bwd_kernel / iters, bwd_read / iters, dl.size() * 4, pixels * 28 + bwd.sigma.size() * 16 + 64, iters, warmup, mass);
     return 0;
 }

@@ -388,6 +388,86 @@ integrate_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_
     intl.depth[ray] = depth;
 }
 
+// ---- K4, warp-transposed (see diff_tile_kernel below for the access pattern): tiles of 16 samples, first to last -----
+constexpr int kIntTile = 16;
+
+__global__ void __launch_bounds__(32)
+integrate_tile_kernel(float plan_t_near, float plan_t_far, SampleArrays samp, uint32_t n_rays, uint32_t n_samples, IntegralArrays intl,
+                      bool aux_aligned, uint32_t* status) {
+    __shared__ float sm[9][32][kIntTile + 1];   // r g b | sigma | dt | aux x4
+    const uint32_t lane = threadIdx.x, ray = blockIdx.x * 32u + lane;
+    const bool valid = ray < n_rays;
+    uint32_t b = 0, e = 0;
+    if (valid) {
+        b = samp.ray_offset[ray];
+        e = samp.ray_offset[ray + 1];
+        if (e < b || e > n_samples) {
+            atomicOr(status, kErrBadOffsets);
+            e = b;
+        }
+    }
+    const uint32_t longest = __reduce_max_sync(0xffffffffu, e - b);
+    RayAccum acc;
+    acc.t_cursor = plan_t_near;
+    bool stopped = false;
+    const uint32_t half = lane >> 4, l = lane & 15u;
+    for (uint32_t done = 0; done < longest; done += kIntTile) {
+#pragma unroll 8
+        for (uint32_t rr = 0; rr < 32u; rr += 2u) {
+            const uint32_t r = rr + half;
+            const uint32_t rb = __shfl_sync(0xffffffffu, b, r), re = __shfl_sync(0xffffffffu, e, r);
+            if (re - rb <= done) continue;
+            const uint32_t lo = rb + done, count = min(static_cast<uint32_t>(kIntTile), re - lo);
+            if (l < count) {
+                sm[3][r][l] = __ldcs(samp.sigma + lo + l);
+                sm[4][r][l] = __ldcs(samp.dt + lo + l);
+            }
+            const float* c = samp.color + 3 * static_cast<size_t>(lo);
+            for (uint32_t k = l; k < 3u * count; k += 16u) sm[k % 3u][r][k / 3u] = __ldcs(c + k);
+        }
+        __syncwarp();
+        if (e - b > done) {
+            const uint32_t count = min(static_cast<uint32_t>(kIntTile), e - b - done);
+            for (uint32_t j = 0; j < count; ++j) {
+                float4 row = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!stopped) {
+                    float a, w, tb;
+                    stopped = integrate_sample(acc, sm[4][lane][j], make_float4(sm[0][lane][j], sm[1][lane][j], sm[2][lane][j], sm[3][lane][j]), a, w, tb);
+                    row = make_float4(a, w, tb, logf(fmaxf(tb, 1e-30f)));
+                }
+                sm[5][lane][j] = row.x; sm[6][lane][j] = row.y; sm[7][lane][j] = row.z; sm[8][lane][j] = row.w;
+            }
+        }
+        __syncwarp();
+        if (intl.aux != nullptr) {
+#pragma unroll 8
+            for (uint32_t rr = 0; rr < 32u; rr += 2u) {
+                const uint32_t r = rr + half;
+                const uint32_t rb = __shfl_sync(0xffffffffu, b, r), re = __shfl_sync(0xffffffffu, e, r);
+                if (re - rb <= done) continue;
+                const uint32_t lo = rb + done, count = min(static_cast<uint32_t>(kIntTile), re - lo);
+                if (l < count) {
+                    if (aux_aligned) {
+                        __stcs(reinterpret_cast<float4*>(intl.aux) + lo + l, make_float4(sm[5][r][l], sm[6][r][l], sm[7][r][l], sm[8][r][l]));
+                    } else {
+                        float* a4 = intl.aux + 4 * static_cast<size_t>(lo + l);
+                        a4[0] = sm[5][r][l]; a4[1] = sm[6][r][l]; a4[2] = sm[7][r][l]; a4[3] = sm[8][r][l];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (valid) {
+        float opacity, depth;
+        finish_ray(acc, plan_t_far, opacity, depth);
+        intl.radiance[3 * ray] = acc.cr; intl.radiance[3 * ray + 1] = acc.cg; intl.radiance[3 * ray + 2] = acc.cb;
+        intl.transmittance[ray] = acc.T;
+        intl.opacity[ray] = opacity;
+        intl.depth[ray] = depth;
+    }
+}
+
 // ---- K5: per-sample backward (diff_cpu.cpp:156-195) -------------------------
 // One thread walks one ray's samples last-to-first with the reference's recurrence (the carry adj_T makes a ray
 // sequential).  A ray's samples are contiguous in every array, so the thread works in ALIGNED BLOCKS OF FOUR samples:
@@ -760,6 +840,11 @@ cudaError_t launch_integrate(cudaStream_t s, float plan_t_near, float plan_t_far
     if (n_rays == 0) return cudaSuccess;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0u; };
     const bool aligned = al16(intl.aux);
+    static const bool per_thread = std::getenv("DVREN_INT_PER_THREAD") != nullptr;   // A/B timing: the thread-per-ray kernels below
+    if (!per_thread && n_samples / n_rays >= 16u) {
+        integrate_tile_kernel<<<blocks_for(n_rays, 32), 32, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays, n_samples, intl, aligned, d_status);
+        return cudaGetLastError();
+    }
     if (al16(samp.color) && al16(samp.sigma) && al16(samp.dt))
         integrate_kernel<true><<<blocks_for(n_rays, 64), 64, 0, s>>>(plan_t_near, plan_t_far, samp, n_rays, n_samples, intl, aligned, d_status);
     else
