@@ -161,6 +161,12 @@ struct hpx_shard {
     std::vector<float*> peer_block;                                 // per rank (own entry = own block)
     std::vector<void*> ipc_opened;
     int* d_flag = nullptr;                                          // 1 int: payload of the cross-GPU barrier
+    // per rank and slab: the rows [lo, hi) inside the slab that rank's band can touch (frame_slab_rows); the direct exchange
+    // moves only those rows of a slab
+    std::vector<std::vector<int2>> slab_rows;                       // [world][n_slabs]
+    int2* d_slab_rows = nullptr;                                    // the same on the device, rank-major
+    int32_t rows_per_slab = 0;
+    size_t row_floats = 0;
     // measured rebalancing (hpx_shard_rebalance)
     hp_plan_desc full_desc{};
     FrameParams full_params{};
@@ -248,28 +254,45 @@ __global__ void add_slabs_kernel(float4* __restrict__ dst, const float4* __restr
 // the owner's own block is read and written once instead of once per peer.
 constexpr int kMaxPeers = 16;
 struct PullTable {
-    const float4* src[kMaxPeers];   // peer block (mapped into this GPU's address space)
+    const float4* src[kMaxPeers];    // peer block (mapped into this GPU's address space)
+    const int2* rows[kMaxPeers];     // per slab: the rows [x, y) of it that peer's band can touch (only those are read)
     int32_t lo[kMaxPeers], hi[kMaxPeers];   // slabs of that peer's wedge inside this rank's owned range
     int32_t n;
-    int32_t first_slab;             // blockIdx.y = 0
+    int32_t first_slab;              // blockIdx.y = 0
+    uint32_t row4;                   // float4 per row
 };
 
 __global__ void __launch_bounds__(256) peer_reduce_kernel(float4* __restrict__ block, PullTable t, size_t slab4) {
     const int32_t y = t.first_slab + static_cast<int32_t>(blockIdx.y);
     uint32_t mask = 0;
-    for (int p = 0; p < t.n; ++p)
-        if (y >= t.lo[p] && y < t.hi[p]) mask |= 1u << p;
+    int32_t r_lo[kMaxPeers], r_hi[kMaxPeers], u_lo = INT_MAX, u_hi = 0;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+        r_lo[p] = 0; r_hi[p] = 0;
+        if (p < t.n && y >= t.lo[p] && y < t.hi[p]) {
+            const int2 r = __ldg(t.rows[p] + y);
+            if (r.y > r.x) {
+                mask |= 1u << p;
+                r_lo[p] = r.x; r_hi[p] = r.y;
+                u_lo = min(u_lo, r.x); u_hi = max(u_hi, r.y);
+            }
+        }
+    }
     if (mask == 0u) return;
     const size_t base = static_cast<size_t>(y) * slab4;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < slab4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t begin = static_cast<size_t>(u_lo) * t.row4, end = static_cast<size_t>(u_hi) * t.row4;
+    for (size_t i = begin + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < end; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int32_t row = static_cast<int32_t>(i / t.row4);
+        uint32_t m = 0;
         float4 v[kMaxPeers];
 #pragma unroll
         for (int p = 0; p < kMaxPeers; ++p)
-            if (p < t.n && (mask >> p) & 1u) v[p] = t.src[p][base + i];
+            if (p < t.n && ((mask >> p) & 1u) && row >= r_lo[p] && row < r_hi[p]) { v[p] = t.src[p][base + i]; m |= 1u << p; }
+        if (m == 0u) continue;
         float4 a = block[base + i];
 #pragma unroll
         for (int p = 0; p < kMaxPeers; ++p)
-            if (p < t.n && (mask >> p) & 1u) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+            if ((m >> p) & 1u) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
         block[base + i] = a;
     }
 }
@@ -752,6 +775,13 @@ static hp_status band_configure(hpx_shard* s) {
     s->frame = nullptr;
     s->plan = nullptr;
     s->band_row0.clear(); s->band_rows.clear(); s->wedges.clear();
+    {
+        const int32_t dims[3] = {g->nx, g->ny, g->nz};
+        const int row_axis = s->slow_axis == 2 ? 1 : 2, fast_axis = s->slow_axis == 0 ? 1 : 0;
+        s->rows_per_slab = dims[row_axis];
+        s->row_floats = static_cast<size_t>(dims[fast_axis]) * 4;
+        s->slab_rows.assign(static_cast<size_t>(world), std::vector<int2>(static_cast<size_t>(s->n_slabs), make_int2(0, 0)));
+    }
     s->timed = false;
     const std::vector<RowBand> bands = partition_units(s->unit_cost, d.roi.height, static_cast<uint32_t>(world));
     hp_status st = HP_STATUS_SUCCESS;
@@ -771,6 +801,12 @@ static hp_status band_configure(hpx_shard* s) {
             st = hp_plan_create(c->ctx, &bd, &band_plan);
             if (st == HP_STATUS_SUCCESS) st = hpx_frame_create(band_plan, &frame);
             if (st == HP_STATUS_SUCCESS) st = hpx_frame_bounds(frame, g, box);
+            if (st == HP_STATUS_SUCCESS) {
+                std::vector<int32_t> lo(static_cast<size_t>(s->n_slabs)), hi(static_cast<size_t>(s->n_slabs));
+                st = frame_slab_rows(frame, g, lo.data(), hi.data());
+                for (int32_t y = 0; y < s->n_slabs && st == HP_STATUS_SUCCESS; ++y)
+                    s->slab_rows[static_cast<size_t>(r)][static_cast<size_t>(y)] = make_int2(lo[static_cast<size_t>(y)], hi[static_cast<size_t>(y)]);
+            }
             if (st == HP_STATUS_SUCCESS && r == me) {
                 // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
                 st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
@@ -798,6 +834,14 @@ static hp_status band_configure(hpx_shard* s) {
         s->hull_hi = std::max(s->hull_hi, s->wedges[r].second);
     }
     if (s->hull_hi < s->hull_lo) s->hull_lo = s->hull_hi = 0;
+    {
+        const size_t per_rank = static_cast<size_t>(s->n_slabs);
+        if (s->d_slab_rows == nullptr) DV_CUDA(cudaMalloc(&s->d_slab_rows, per_rank * world * sizeof(int2)));
+        for (int r = 0; r < world; ++r)
+            DV_CUDA(cudaMemcpyAsync(s->d_slab_rows + per_rank * r, s->slab_rows[static_cast<size_t>(r)].data(), per_rank * sizeof(int2),
+                                    cudaMemcpyHostToDevice, main));
+        DV_CUDA(cudaStreamSynchronize(main));
+    }
     return band_assign_owners(s);
 }
 
@@ -979,8 +1023,17 @@ HP_API hp_status hpx_shard_bands(const hpx_shard* s, uint32_t* out_row0, uint32_
     }
     if (out_cuts) std::copy(s->cuts.begin(), s->cuts.end(), out_cuts);
     size_t out = 0, in = 0;
-    for (const auto& x : s->sends) out += static_cast<size_t>(x.hi - x.lo) * s->slab_floats;
-    for (const auto& x : s->recvs) in += static_cast<size_t>(x.hi - x.lo) * s->slab_floats;
+    auto volume = [&](int rank, int32_t lo, int32_t hi) {   // floats of rank's partial sums inside slabs [lo, hi) that travel
+        if (!s->direct) return static_cast<size_t>(hi - lo) * s->slab_floats;
+        size_t rows = 0;
+        for (int32_t y = lo; y < hi; ++y) {
+            const int2 r = s->slab_rows[static_cast<size_t>(rank)][static_cast<size_t>(y)];
+            rows += r.y > r.x ? static_cast<size_t>(r.y - r.x) : 0;
+        }
+        return rows * s->row_floats;
+    };
+    for (const auto& x : s->sends) out += volume(s->comm->rank, x.lo, x.hi);
+    for (const auto& x : s->recvs) in += volume(x.peer, x.lo, x.hi);
     if (out_send_floats) *out_send_floats = out;
     if (out_recv_floats) *out_recv_floats = in;
     return HP_STATUS_SUCCESS;
@@ -1043,11 +1096,13 @@ static hp_status band_step(hpx_shard* s, const float* dL_dI_device, uint32_t fla
             for (const auto& x : s->recvs) {   // ascending peer order = order of the additions
                 if (t.n >= kMaxPeers) break;
                 t.src[t.n] = reinterpret_cast<const float4*>(s->peer_block[static_cast<size_t>(x.peer)]);
+                t.rows[t.n] = s->d_slab_rows + static_cast<size_t>(s->n_slabs) * static_cast<size_t>(x.peer);
                 t.lo[t.n] = x.lo;
                 t.hi[t.n] = x.hi;
                 ++t.n;
             }
             t.first_slab = s->cuts[me];
+            t.row4 = static_cast<uint32_t>(s->row_floats / 4);
             peer_reduce_kernel<<<dim3(bx, static_cast<unsigned>(s->cuts[me + 1] - s->cuts[me])), 256, 0, main>>>(
                 reinterpret_cast<float4*>(block), t, slab4);
             DV_CUDA(cudaGetLastError());
@@ -1117,6 +1172,7 @@ HP_API void hpx_shard_release(hpx_shard* s) {
         if (s->ev_zero != nullptr) cudaEventDestroy(s->ev_zero);
         cudaFree(s->staging);
         cudaFree(s->d_flag);
+        cudaFree(s->d_slab_rows);
         if (s->ev_t0 != nullptr) cudaEventDestroy(s->ev_t0);
         if (s->ev_t1 != nullptr) cudaEventDestroy(s->ev_t1);
         for (void* p : s->ipc_opened) cudaIpcCloseMemHandle(p);

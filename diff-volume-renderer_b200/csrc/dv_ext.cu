@@ -114,6 +114,33 @@ hp_status grid_slabs_to_host(hpx_grid* g, cudaStream_t stream, int32_t lo, int32
     if (color_host != nullptr) DV_CUDA(copy(color_host, d_col, 3, stream));
     return HP_STATUS_SUCCESS;
 }
+hp_status frame_slab_rows(hpx_frame* f, const hpx_grid* g, int32_t* out_lo, int32_t* out_hi) {
+    if (f == nullptr || g == nullptr || out_lo == nullptr || out_hi == nullptr || f->ctx != g->ctx) return HP_STATUS_INVALID_ARGUMENT;
+    DeviceScope scope;
+    DV_TRY(scope.enter(f->ctx));
+    DV_CUDA(launch_upload_params(f->ctx->stream, f->d_params, f->h_params));
+    f->params_dirty = false;
+    const int a = g->grad_slow_axis, b = a == 2 ? 1 : 2;   // [z][y][x] -> rows along y; [y][z][x] and [x][z][y] -> rows along z
+    const int32_t dims[3] = {g->nx, g->ny, g->nz};
+    const int32_t slabs = dims[a];
+    cudaStream_t s = f->ctx->stream;
+    DeviceScratch scratch;
+    int* d = static_cast<int*>(scratch.take(static_cast<size_t>(slabs) * 2 * sizeof(int)));
+    if (d == nullptr) return HP_STATUS_OUT_OF_MEMORY;
+    std::vector<int> init(static_cast<size_t>(slabs) * 2);
+    for (int32_t i = 0; i < slabs; ++i) { init[static_cast<size_t>(i)] = INT_MAX; init[static_cast<size_t>(slabs + i)] = INT_MIN; }
+    DV_CUDA(cudaMemcpyAsync(d, init.data(), init.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    DV_CUDA(launch_ray_slab_rows(s, f->d_params, f->h_params, g->nx, g->ny, g->nz, a, b, d, d + slabs));
+    DV_CUDA(cudaMemcpyAsync(init.data(), d, init.size() * sizeof(int), cudaMemcpyDeviceToHost, s));
+    DV_CUDA(cudaStreamSynchronize(s));
+    for (int32_t i = 0; i < slabs; ++i) {
+        const int lo = init[static_cast<size_t>(i)], hi = init[static_cast<size_t>(slabs + i)];
+        out_lo[i] = lo == INT_MAX ? 0 : lo;
+        out_hi[i] = lo == INT_MAX ? 0 : hi + 1;
+    }
+    return HP_STATUS_SUCCESS;
+}
+
 hp_status frame_rows_bounds(hpx_frame* f, const hpx_grid* g, uint32_t row0, uint32_t rows, int32_t out_box[6]) {
     if (f == nullptr || g == nullptr || out_box == nullptr) return HP_STATUS_INVALID_ARGUMENT;
     const RoiParams saved = f->h_params.roi;

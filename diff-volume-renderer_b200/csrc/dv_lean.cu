@@ -884,6 +884,74 @@ cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, 
     return cudaGetLastError();
 }
 
+// ---- rows of every slab the backward of this launch can touch ------------------------------------------------------
+namespace {
+// A gradient block laid out slab by slab along axis `a` is, inside a slab, a stack of ROWS along axis `b` (the second
+// slowest one).  Per slab: the range of rows that samples of this launch's rays can reach -- a sample at grid coordinate
+// p touches the cells floor(p), floor(p) + 1 on every axis, and along a ray p is linear in t, so the rows a ray reaches in
+// slab s are those between its positions at the two ends of the t-interval in which p_a lies within [s - 1, s + 1] (the
+// bounds below widen both intervals by one more voxel for rounding).  lo / hi: [slabs] ints pre-set to INT_MAX / INT_MIN;
+// hi is inclusive.  A sharded frame exchanges only these rows of a slab instead of the whole slab (dv_comm.cu).
+__global__ void __launch_bounds__(kLeanThreads)
+ray_slab_rows_kernel(const FrameParams* __restrict__ P, int32_t nx, int32_t ny, int32_t nz, int a, int b, int* __restrict__ lo,
+                     int* __restrict__ hi) {
+    const CameraParams cam = P->cam;
+    const MarchParams mp = P->march;
+    const RoiParams roi = P->roi;
+    const TilePixel px = tile_pixel(roi);
+    const int32_t dims[3] = {nx, ny, nz};
+    const float na = static_cast<float>(dims[a] - 1), nb = static_cast<float>(dims[b] - 1);
+    int s_lo = INT_MAX, s_hi = INT_MIN;
+    float oa = 0.f, da = 0.f, ob = 0.f, db = 0.f, ta = 0.f, tb = -1.f;
+    if (px.inside && mp.uniform_count != 0) {
+        const Ray ray = make_ray(cam, roi.x + px.lx, roi.y + px.ly);
+        float t_in, t_out;
+        cube_interval(ray, t_in, t_out);
+        const float t_last = mp.t_near + static_cast<float>(mp.uniform_count) * mp.dt;
+        ta = fmaxf(t_in, mp.t_near);
+        tb = fminf(t_out, fminf(t_last, mp.t_far));
+        if (ta <= tb) {
+            const float o[3] = {ray.ox, ray.oy, ray.oz}, d[3] = {ray.dx, ray.dy, ray.dz};
+            oa = o[a] * na; da = d[a] * na; ob = o[b] * nb; db = d[b] * nb;   // grid coordinates, linear in t
+            const float pa0 = fminf(fmaxf(oa + da * ta, 0.0f), na), pa1 = fminf(fmaxf(oa + da * tb, 0.0f), na);
+            s_lo = max(0, static_cast<int>(floorf(fminf(pa0, pa1))) - 1);
+            s_hi = min(dims[a] - 1, static_cast<int>(floorf(fmaxf(pa0, pa1))) + 2);
+        }
+    }
+    const int w_lo = __reduce_min_sync(0xffffffffu, s_lo), w_hi = __reduce_max_sync(0xffffffffu, s_hi);
+    for (int s = w_lo; s <= w_hi; ++s) {
+        int r_lo = INT_MAX, r_hi = INT_MIN;
+        if (s >= s_lo && s <= s_hi) {
+            float t0 = ta, t1 = tb;
+            if (fabsf(da) > 1e-6f) {   // t-interval in which p_a is within [s - 2, s + 2]
+                const float u = (static_cast<float>(s) - 2.0f - oa) / da, v = (static_cast<float>(s) + 2.0f - oa) / da;
+                t0 = fmaxf(ta, fminf(u, v));
+                t1 = fminf(tb, fmaxf(u, v));
+            }
+            if (t0 <= t1) {
+                const float pb0 = fminf(fmaxf(ob + db * t0, 0.0f), nb), pb1 = fminf(fmaxf(ob + db * t1, 0.0f), nb);
+                r_lo = max(0, static_cast<int>(floorf(fminf(pb0, pb1))) - 1);
+                r_hi = min(dims[b] - 1, static_cast<int>(floorf(fmaxf(pb0, pb1))) + 2);
+            }
+        }
+        r_lo = __reduce_min_sync(0xffffffffu, r_lo);
+        r_hi = __reduce_max_sync(0xffffffffu, r_hi);
+        if ((threadIdx.x & 31) == 0 && r_lo != INT_MAX) {
+            atomicMin(lo + s, r_lo);
+            atomicMax(hi + s, r_hi);
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_ray_slab_rows(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params, int32_t nx, int32_t ny,
+                                 int32_t nz, int slab_axis, int row_axis, int* d_lo, int* d_hi) {
+    const uint32_t blocks = tile_blocks(h_params.roi);
+    if (blocks == 0) return cudaSuccess;
+    ray_slab_rows_kernel<<<blocks, kLeanThreads, 0, stream>>>(d_params, nx, ny, nz, slab_axis, row_axis, d_lo, d_hi);
+    return cudaGetLastError();
+}
+
 uint32_t lean_block_count(const RoiParams& roi) { return tile_blocks(roi); }
 
 // ---- measurement helpers (bench.py roofline) ----------------------------------------------------------------------

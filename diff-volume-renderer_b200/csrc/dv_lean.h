@@ -54,6 +54,11 @@ uint32_t lean_block_count(const RoiParams& roi);
 cudaError_t launch_ray_bounds(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params, int32_t nx,
                               int32_t ny, int32_t nz, int* d_bounds);
 
+// Per slab along `slab_axis`: the inclusive range of rows (along `row_axis`) the backward of this launch can touch;
+// d_lo / d_hi: [slabs] ints pre-set to INT_MAX / INT_MIN.
+cudaError_t launch_ray_slab_rows(cudaStream_t stream, const FrameParams* d_params, const FrameParams& h_params, int32_t nx, int32_t ny,
+                                 int32_t nz, int slab_axis, int row_axis, int* d_lo, int* d_hi);
+
 // Deterministic (fixed-point) gradient accumulation, see ScatterParams::fixed.  meta = {bits of max|rgb|, bits of
 // max|dL/dI|, 1 / quantum, quantum}.
 cudaError_t launch_abs_max(cudaStream_t stream, const float* d_values, size_t n, uint32_t* d_out_bits, bool packed_rgb_only = false);

@@ -204,6 +204,9 @@ ScatterParams scatter_params(const hpx_grid& grid);
 // so that the two pitched copies of a slab range can run on two copy engines at once.
 hp_status grid_slabs_to_host(hpx_grid* grid, cudaStream_t stream, int32_t lo, int32_t hi, float* sigma_host, float* color_host,
                              cudaStream_t color_stream = nullptr, cudaEvent_t ev = nullptr);
+// Per slab of the grid's CURRENT gradient layout: rows [lo, hi) inside the slab that the frame's backward can touch
+// (lo >= hi: none).  out_lo / out_hi: [slabs] ints.  Blocks until done.
+hp_status frame_slab_rows(hpx_frame* frame, const hpx_grid* grid, int32_t* out_lo, int32_t* out_hi);
 // hpx_frame_bounds of the image rows [row0, row0 + rows) of the frame's ROI (blocks until done).
 hp_status frame_rows_bounds(hpx_frame* frame, const hpx_grid* grid, uint32_t row0, uint32_t rows, int32_t out_box[6]);
 
