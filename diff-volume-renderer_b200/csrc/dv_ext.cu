@@ -772,6 +772,14 @@ HP_API hp_status hpx_frame_set_row_order(hpx_frame* f, int32_t last_row_first) {
     return HP_STATUS_SUCCESS;
 }
 
+// Host-only: the tile row the i-th dispatched row of `rows` takes under hpx_frame_set_row_order(order) (dv_types.h tile_row_of).
+HP_API hp_status hpx_tile_row_order(uint32_t i, uint32_t rows, int32_t order, uint32_t* out_row) {
+    DV_RANGE("hpx_tile_row_order");
+    if (out_row == nullptr || i >= rows || order < 0 || order > 2) return HP_STATUS_INVALID_ARGUMENT;
+    *out_row = tile_row_of(i, rows, static_cast<uint32_t>(order));
+    return HP_STATUS_SUCCESS;
+}
+
 HP_API hp_status hpx_frame_bounds(hpx_frame* f, const hpx_grid* g, int32_t out_box[6]) {
     DV_RANGE("hpx_frame_bounds");
     DV_TRY(frame_check_grid(f, g));

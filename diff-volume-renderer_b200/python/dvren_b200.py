@@ -79,6 +79,7 @@ HPX_FUNCTIONS = {
     "hpx_backward_streamed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hpx_frame_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "hpx_frame_set_row_order": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hpx_tile_row_order": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int32, P(C.c_uint32)]),
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),

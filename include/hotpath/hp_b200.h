@@ -216,6 +216,8 @@ HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_
  * get longer towards its last row should end with its first one.  Results do not depend on the order.  The row groups of
  * hpx_backward_signalled count in DISPATCH order. */
 HP_API hp_status hpx_frame_set_row_order(hpx_frame* frame, int32_t order);
+/* Host-only: which tile row the i-th dispatched one of `rows` is under `order` (a permutation of 0 .. rows - 1). */
+HP_API hp_status hpx_tile_row_order(uint32_t i, uint32_t rows, int32_t order, uint32_t* out_row);
 HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
                                   uint32_t flags, float* box_grad, const int32_t box[6]);
 /* Axis order of the gradient block: slow_axis 0 = x, 1 = y, 2 = z (default) becomes the slowest-varying one, so that a

@@ -250,3 +250,29 @@ def test_library_owner_cuts(wedges, n, replicated):
     worst = lambda c: max(max(v) for v in _exchange_volumes(wedges, c, replicated))
     assert worst(cuts) <= worst(mid)
     assert lib.hpx_plan_owner_cuts(world, n, flat, 0, (C.c_int32 * (world + 1))()) == A.HP_STATUS_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("rows", [1, 2, 7, 8, 27, 256])
+def test_tile_row_orders_are_permutations(rows):
+    """hpx_frame_set_row_order: every order visits every tile row once; centre-out starts at the middle row and alternates
+    below / above it, so that the dispatched prefix is always one contiguous ring around the centre (hpx_backward_streamed
+    cuts its row groups from that)."""
+    import dvren_b200 as D
+    lib = D.load()
+    for order in (0, 1, 2):
+        seq = []
+        for i in range(rows):
+            out = C.c_uint32()
+            D.check("hpx_tile_row_order", lib.hpx_tile_row_order(i, rows, order, C.byref(out)))
+            seq.append(out.value)
+        assert sorted(seq) == list(range(rows)), (order, seq)
+        if order == 0:
+            assert seq == list(range(rows))
+        if order == 1:
+            assert seq == list(range(rows))[::-1]
+        if order == 2:
+            assert seq[0] == rows // 2
+            for k in range(1, rows + 1):          # every prefix is a contiguous run of rows containing the centre
+                pre = sorted(seq[:k])
+                assert pre == list(range(pre[0], pre[0] + k)) and pre[0] <= rows // 2 <= pre[-1]
+    assert lib.hpx_tile_row_order(rows, rows, 0, C.byref(C.c_uint32())) == A.HP_STATUS_INVALID_ARGUMENT
