@@ -26,8 +26,8 @@
  *   hpx_frame_set_interleave / hpx_frame_bounds / hpx_grid_set_grad_layout / hpx_backward_signalled /
  *   hpx_stream_wait_counter / hpx_backward_box / hpx_grid_add_box
  *                   building blocks for strong scaling of ONE frame over several GPUs (interleaved tile
- *                   rows, contiguous gradient slabs, device-signalled or per-group overlapped all-reduce;
- *                   orchestrated by diff-volume-renderer_b200/python/sharding.py)
+ *                   rows, contiguous gradient slabs, device-signalled row groups); hpx_comm_* / hpx_shard_* put them
+ *                   together behind the C ABI (csrc/dv_comm.cu)
  *
  * All functions return hp_status; none blocks the host unless documented.
  * Work is enqueued on the context's stream.
@@ -225,7 +225,7 @@ HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float*
  *   slow z: [z][y][x]   slow y: [y][z][x]   slow x: [x][z][y]   (x {r,g,b,sigma} floats).
  * A caller that renders one frame in groups of image rows picks the world axis the rows run along; the slabs a
  * finished group will never touch again can then be all-reduced IN PLACE while the next group is rendered
- * (sharding.PipelinedFrame).  Clears the gradient block.  hpx_grid_read_grad always returns the reference order.
+ * (hpx_shard_*, hpx_backward_streamed).  Clears the gradient block.  hpx_grid_read_grad always returns the reference order.
  * out_slab_floats: floats per slab; out_slabs: number of slabs. */
 HP_API hp_status hpx_grid_set_grad_layout(hpx_grid* grid, int32_t slow_axis, size_t* out_slab_floats, int32_t* out_slabs);
 /* grid gradient[box] += box_grad, then box_grad = 0, enqueued on the stream of `stream_ctx` (any context of the grid's
