@@ -199,7 +199,7 @@ HP_API hp_status hpx_backward(hpx_frame* frame, hpx_grid* grid, const float* dL_
  * the whole gradient after the backward has finished). */
 HP_API hp_status hpx_backward_streamed(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace, uint32_t flags,
                                        float* sigma_grad_host, float* color_grad_host, float* camera16_host);
-/* ---- strong scaling of ONE frame over several GPUs (diff-volume-renderer_b200/python/sharding.py) ----------------
+/* ---- building blocks for ONE frame over several GPUs (put together by hpx_shard_* below, csrc/dv_comm.cu) ---------
  * hpx_frame_set_interleave: this frame marches only the CTA tile rows (8 pixel rows each) t of its ROI with
  *   t % stride == phase; ray indices, pixel ids and buffers stay those of the whole ROI.  stride 1 = everything.
  * hpx_frame_bounds: box {x0, y0, z0, nx, ny, nz} of grid voxels the frame's backward can touch (blocks until done).
