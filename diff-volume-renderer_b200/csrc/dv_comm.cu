@@ -1,4 +1,4 @@
-// dv_comm.cu -- multi-GPU behind the C ABI (hp_b200.h): an NCCL communicator per context and the sharded frame step.
+// dv_comm.cu -- multi-GPU behind the C ABI (hp_b200.h) and the streamed gradient read-back.
 //
 // The reference has no multi-device support (single process, default stream).  Rays are independent,
 // so the path shards with NO forward collective; the one exchange is the sum of the packed gradient block
@@ -6,15 +6,19 @@
 //
 //   hpx_comm          one rank of an NCCL communicator bound to an hp_ctx (NCCL is loaded with dlopen: the library has no
 //                     link-time dependency on it and every other entry point works without it)
-//   hpx_grid_allreduce_grad   plain data parallelism: whole-block all-reduce behind whatever the context's stream holds
-//   hpx_shard         ONE frame rendered by all ranks (strong scaling): every rank marches the CTA tile rows t with
-//                     t % world == rank (equal mix of short and long rays), the gradient block is laid out with the world
-//                     axis the image rows advance along as its slowest axis, and the backward launch signals per row group
-//                     (hpx_backward_signalled) so that a high-priority side stream all-reduces, IN PLACE, the slabs a
-//                     finished group leaves behind while later rows are still rendering.  With hpx_ctx_ext2.reserve_sms
-//                     the rendering kernels keep a few SMs free, so the collective's CTAs start at once instead of
-//                     waiting for the rendering launch to drain (profiles/README.md, round 1: that wait exposed the
-//                     whole 2.1 GB all-reduce at 8 GPUs).
+//   hpx_grid_allreduce_grad   data parallelism over views: whole-block all-reduce behind whatever the context's stream holds
+//   hpx_shard (bands) ONE frame rendered by all ranks (strong scaling), the default: contiguous row bands cut for equal
+//                     marching work and re-cut from measured time, gradient block in slabs along the world axis the image
+//                     rows advance along, so that a band's backward touches one slab wedge; every slab has an owner, and
+//                     after a stream-ordered cross-GPU barrier each owner PULLS the rows of its slabs its neighbours' rays
+//                     can reach straight out of their gradient blocks (peer access / CUDA IPC over NVLink) and adds them
+//                     in rank order (peer_reduce_kernel).  Result: reduce-scatter (owned) or, with one more gather kernel,
+//                     the whole sum on every rank (replicated).  NCCL send/recv + broadcast is the fallback path.
+//   hpx_shard (interleaved)   round 1's design, kept for comparison: tile rows t % world == rank, ONE backward launch that
+//                     signals per row group, slab all-reduces on a priority stream behind it; optional SM reservation
+//                     through a green context (hpx_ctx_ext2.reserve_sms).  Measured slower than the bands at every N.
+//   hpx_backward_streamed     single GPU: the same per-row-group signals drive a copy stream that un-interleaves and
+//                     copies finished slabs to the caller's HOST arrays while later rows still render.
 #include <dlfcn.h>
 #include <unistd.h>
 #include <nccl.h>   // types and enumerators only; every function is resolved with dlsym
