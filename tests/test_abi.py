@@ -279,3 +279,53 @@ def test_extension_entry_points_validate_arguments_without_a_gpu():
     assert lib.hpx_stream_wait_counter(None, None, 1) == INV
     assert lib.hpx_backward_scatter(None, None, 0, C.byref(n)) == INV
     assert lib.hpx_plan_step_table(None, None, 0, C.byref(n)) == INV
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """hp_b200.h, multi-GPU / storage / read-back additions: null handles and out-of-range enumerators are rejected before
+    any device or NCCL call; the releases accept null (reference hp_*_release behaviour, hp_runtime.cpp:150-155)."""
+    import ctypes as C
+    import dvren_b200 as D
+    lib = D.load()
+    INV = A.HP_STATUS_INVALID_ARGUMENT
+    i32, u32, sz, ptr = C.c_int32(), C.c_uint32(), C.c_size_t(), C.c_void_p()
+    f32 = C.c_float()
+    assert lib.hpx_grid_set_storage(None, 1) == INV
+    assert lib.hpx_grid_build_occupancy(None, 1, C.byref(f32), C.byref(f32)) == INV
+    assert lib.hpx_grid_set_occupancy(None, 1) == INV
+    assert lib.hpx_grid_read_grad_range(None, 0, 1, None, None, None, A.HP_MEMSPACE_HOST) == INV
+    assert lib.hpx_backward_streamed(None, None, None, A.HP_MEMSPACE_DEVICE, 1, None, None, None) == INV
+    assert lib.hpx_frame_set_row_order(None, 1) == INV
+    assert lib.hpx_tile_row_order(0, 0, 0, None) == INV
+    assert lib.hpx_tile_row_order(0, 8, 3, C.byref(u32)) == INV        # order is 0, 1 or 2
+    assert lib.hpx_ctx_sm_counts(None, C.byref(u32), C.byref(u32)) == INV
+    assert lib.hpx_comm_unique_id(None) == INV
+    assert lib.hpx_comm_create(None, None, 0, 1, 0, C.byref(ptr)) == INV
+    ctx = C.c_void_p()
+    assert lib.hp_ctx_create(None, C.byref(ctx)) == 0
+    assert lib.hpx_comm_create(ctx, None, 2, 2, 0, C.byref(ptr)) == INV     # rank outside [0, world)
+    assert lib.hpx_comm_create(ctx, None, 0, 2, 0, C.byref(ptr)) == INV     # world > 1 needs a rendezvous id
+    assert lib.hpx_comm_create(ctx, None, 0, 0, 0, C.byref(ptr)) == INV
+    lib.hp_ctx_release(ctx)
+    assert lib.hpx_comm_info(None, C.byref(i32), C.byref(i32), C.byref(i32)) == INV
+    assert lib.hpx_comm_allreduce(None, None, 0) == INV
+    assert lib.hpx_grid_allreduce_grad(None, None) == INV
+    assert lib.hpx_shard_create(None, None, None, None, 1, C.byref(ptr)) == INV
+    assert lib.hpx_shard_create_bands(None, None, None, 1, C.byref(ptr)) == INV
+    assert lib.hpx_shard_step(None, None, 0) == INV
+    assert lib.hpx_shard_frame(None, C.byref(ptr)) == INV
+    assert lib.hpx_shard_set_reduce(None, 1) == INV
+    assert lib.hpx_shard_set_result(None, 1) == INV
+    assert lib.hpx_shard_rebalance(None, C.byref(i32)) == INV
+    assert lib.hpx_shard_exchange_is_direct(None, C.byref(i32)) == INV
+    assert lib.hpx_shard_layout(None, C.byref(i32), C.byref(u32), None, None) == INV
+    assert lib.hpx_shard_bands(None, None, None, None, None, C.byref(sz), C.byref(sz)) == INV
+    assert lib.hpx_shard_owned(None, C.byref(ptr), C.byref(i32), C.byref(i32), C.byref(sz), C.byref(i32)) == INV
+    wedges = (C.c_int32 * 4)(0, 4, 2, 8)
+    cuts = (C.c_int32 * 3)()
+    assert lib.hpx_plan_owner_cuts(0, 8, wedges, 1, cuts) == INV
+    assert lib.hpx_plan_owner_cuts(2, 8, wedges, 7, cuts) == INV             # result is OWNED (1) or REPLICATED (2)
+    assert lib.hpx_plan_owner_cuts(2, 4, wedges, 1, cuts) == INV             # a wedge reaches past the last slab
+    assert lib.hpx_plan_balanced_bands(None, 2, None, None, None) == INV
+    lib.hpx_comm_release(None)
+    lib.hpx_shard_release(None)
