@@ -557,6 +557,8 @@ def run_sharded(env, args):
     # stop moving -- start-up work of a training loop, like its warm-up
     rebalances = 0
     if bands:
+        step()
+        shard.tune_order(g_dev.data_ptr(), flags)   # rank-local: the band's tile dispatch order by measurement
         for _ in range(4):
             step(); step()
             if not shard.rebalance():
@@ -601,6 +603,10 @@ def run_sharded(env, args):
         rounds = layout["rebalance_rounds"]
         layout = shard.layout()        # the owner cuts of this result mode
         layout["rebalance_rounds"] = rounds
+        mine = torch.tensor([layout["tile_order"]], dtype=torch.int32, device=dev)   # hpx_frame_set_row_order value per rank
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        layout["tile_order"] = [int(t.item()) for t in every]
     total_ms = env.timed(step, k, args.warmup, sampler if rank == 0 else None)
     clocks = sampler.stop() if rank == 0 else None
     results["owned" if bands else "replicated"] = total_ms / k

@@ -201,7 +201,7 @@ struct ShardShared {
     uint8_t id[HPX_COMM_ID_BYTES];
     const dvren::DenseGridConfig* volume;
     const std::vector<float>* dl;
-    std::vector<double> ms, ms_no_reduce, send_mb, recv_mb;
+    std::vector<double> ms, ms_no_reduce, send_mb, recv_mb, tile_order;
     std::vector<int> status;
     std::vector<uint32_t> band_row0, band_rows;
     std::vector<int32_t> wedges, cuts;
@@ -255,7 +255,9 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
     SCHECK(hpx_copy_to_device(ctx, d_dl, sh.dl->data(), sh.dl->size() * 4));
     const uint32_t flags = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO;
 
-    if (a.mode != 0) {   // untimed start-up: bands re-cut from the measured per-rank time until they stop moving
+    if (a.mode != 0) {   // untimed start-up: tile dispatch order by measurement, then bands re-cut from the measured per-rank time until they stop moving
+        SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
+        if (std::getenv("DVREN_BENCH_NO_TUNE") == nullptr) SCHECK(hpx_shard_tune_order(shard, static_cast<const float*>(d_dl), flags, nullptr));
         for (int round = 0; round < 4; ++round) {
             SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
             SCHECK(hpx_shard_step(shard, static_cast<const float*>(d_dl), flags));
@@ -312,6 +314,9 @@ void shard_rank(int rank, const ShardArgs& a, ShardShared& sh, std::barrier<>& s
         hpx_shard_bands(shard, nullptr, nullptr, nullptr, nullptr, &out, &in);
         sh.send_mb[rank] = out * 4.0 / 1e6;
         sh.recv_mb[rank] = in * 4.0 / 1e6;
+        int32_t order = 0;
+        hpx_shard_tile_order(shard, &order);
+        sh.tile_order[rank] = order;
     }
     if (a.mode == 2) SCHECK(hpx_shard_set_result(shard, HPX_SHARD_RESULT_OWNED));
     for (int pass = 0; pass < 2; ++pass) {   // pass 0: the real step; pass 1: the same without its collectives
@@ -346,7 +351,7 @@ int run_shard(const ShardArgs& a) {
     sh.volume = &volume;
     sh.dl = &dl;
     sh.ms.assign(a.gpus, 0.0); sh.ms_no_reduce.assign(a.gpus, 0.0); sh.status.assign(a.gpus, 0);
-    sh.send_mb.assign(a.gpus, 0.0); sh.recv_mb.assign(a.gpus, 0.0);
+    sh.send_mb.assign(a.gpus, 0.0); sh.recv_mb.assign(a.gpus, 0.0); sh.tile_order.assign(a.gpus, 0.0);
     std::barrier<> sync(a.gpus);
     std::vector<std::thread> threads;
     for (int r = 0; r < a.gpus; ++r) threads.emplace_back([&, r] {
@@ -366,7 +371,7 @@ int run_shard(const ShardArgs& a) {
     list("ms_per_rank", sh.ms); list("ms_per_rank_without_collectives", sh.ms_no_reduce);
     if (a.mode != 0) {
         list("band_row0", sh.band_row0); list("band_rows", sh.band_rows); list("wedges", sh.wedges); list("owner_cuts", sh.cuts);
-        list("send_mb", sh.send_mb); list("recv_mb", sh.recv_mb);
+        list("send_mb", sh.send_mb); list("recv_mb", sh.recv_mb); list("tile_order", sh.tile_order);
     }
     if (a.mode != 0) std::printf("\"exchange\": \"%s\", ", sh.direct ? "own kernels over peer memory" : "nccl");
     std::printf("\"sharding\": \"%s\", ", a.mode == 0 ? "interleaved tile rows, slab all-reduces behind a signalled backward"

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <new>
 #include <set>
@@ -159,6 +160,8 @@ struct hpx_shard {
     float* staging = nullptr;
     int32_t hull_lo = 0, hull_hi = 0;                               // slabs ANY rank can touch
     size_t dl_offset_floats = 0;                                    // this rank's rows inside the frame's dL/dI
+    int tile_order = 0;                                             // hpx_frame_set_row_order of this rank's band (best_tile_order)
+    bool order_tuned = false;                                       // ... chosen by measurement (hpx_shard_tune_order)
     // direct exchange: every rank's gradient block mapped into this GPU's address space (same process: peer access;
     // other processes: CUDA IPC), read by this rank's own kernels over NVLink
     bool direct = false;
@@ -410,32 +413,88 @@ hp_status stream_barrier(hpx_shard* s) {
 // Marching work of one image row, in samples: steps of its rays that lie inside the unit cube (what the kernels spend
 // their time on; steps outside are skipped by range) plus a small constant per ray.  Host restatement of make_ray /
 // cube_interval on every 4th pixel -- an ESTIMATE that only places the band boundaries, no result depends on it.
-double row_work(const FrameParams& p, uint32_t gy, uint32_t x0, uint32_t w) {
+double pixel_work(const FrameParams& p, uint32_t px, uint32_t gy) {
     const CameraParams& c = p.cam;
     const MarchParams& m = p.march;
     const float t_last = std::min(m.t_far, m.t_near + static_cast<float>(m.uniform_count) * m.dt);
+    float qx = (static_cast<float>(px) + 0.5f - c.cx) / c.fx, qy = (static_cast<float>(gy) + 0.5f - c.cy) / c.fy;
+    if (c.ortho) qx = qy = 0.0f;
+    const float v[3] = {c.r00 * qx + c.r01 * qy + c.r02, c.r10 * qx + c.r11 * qy + c.r12, c.r20 * qx + c.r21 * qy + c.r22};
+    const float len = std::sqrt(std::max(v[0] * v[0] + v[1] * v[1] + v[2] * v[2], 1e-30f));
+    const float o[3] = {c.ox, c.oy, c.oz};
+    float t_in = m.t_near, t_out = t_last;
+    for (int i = 0; i < 3 && t_in < t_out; ++i) {
+        const float d = v[i] / len;
+        if (std::fabs(d) > 1e-12f) {
+            const float a = (0.0f - o[i]) / d, b = (1.0f - o[i]) / d;
+            t_in = std::max(t_in, std::min(a, b));
+            t_out = std::min(t_out, std::max(a, b));
+        } else if (o[i] < 0.0f || o[i] > 1.0f) {
+            t_out = t_in;
+        }
+    }
+    return 8.0 + (t_out > t_in && m.dt > 0.0f ? static_cast<double>((t_out - t_in) / m.dt) : 0.0);
+}
+
+double row_work(const FrameParams& p, uint32_t gy, uint32_t x0, uint32_t w) {
     double work = 0.0;
     uint32_t n = 0;
-    for (uint32_t px = x0; px < x0 + w; px += 4, ++n) {
-        float qx = (static_cast<float>(px) + 0.5f - c.cx) / c.fx, qy = (static_cast<float>(gy) + 0.5f - c.cy) / c.fy;
-        if (c.ortho) qx = qy = 0.0f;
-        const float v[3] = {c.r00 * qx + c.r01 * qy + c.r02, c.r10 * qx + c.r11 * qy + c.r12, c.r20 * qx + c.r21 * qy + c.r22};
-        const float len = std::sqrt(std::max(v[0] * v[0] + v[1] * v[1] + v[2] * v[2], 1e-30f));
-        const float o[3] = {c.ox, c.oy, c.oz};
-        float t_in = m.t_near, t_out = t_last;
-        for (int i = 0; i < 3 && t_in < t_out; ++i) {
-            const float d = v[i] / len;
-            if (std::fabs(d) > 1e-12f) {
-                const float a = (0.0f - o[i]) / d, b = (1.0f - o[i]) / d;
-                t_in = std::max(t_in, std::min(a, b));
-                t_out = std::min(t_out, std::max(a, b));
-            } else if (o[i] < 0.0f || o[i] > 1.0f) {
-                t_out = t_in;
-            }
-        }
-        work += 8.0 + (t_out > t_in && m.dt > 0.0f ? static_cast<double>((t_out - t_in) / m.dt) : 0.0);
-    }
+    for (uint32_t px = x0; px < x0 + w; px += 4, ++n) work += pixel_work(p, px, gy);
     return n != 0 ? work * static_cast<double>(w) / n : 0.0;
+}
+
+// Which dispatch order (hpx_frame_set_row_order) ends the launches of the band [y0, y0 + rows) of the frame soonest: the
+// CTAs of a launch are handed to free slots in blockIdx order, a CTA lasts as long as its longest ray (the warps march in
+// lock-step), and the launch is over when the last one is -- list scheduling of the tile estimates on the resident slots,
+// once per candidate order.  A band of a few tile rows is only 4-5 waves of CTAs: ending with full-length tiles leaves
+// the last wave partly empty (estimated and measured: 12 % of the launch for the middle bands of 512^3 / 8 GPUs).
+// An ESTIMATE that only orders the work; no result depends on it.
+int best_tile_order(const FrameParams& p, const hp_plan_desc& d, uint32_t y0, uint32_t rows_px, uint32_t slots, double* out_ends4 = nullptr) {
+    const uint32_t tw = kTileW * kWarpsX, th = kTileH * kWarpsY;
+    const uint32_t tiles_x = (d.roi.width + tw - 1) / tw, rows = (rows_px + th - 1) / th;
+    if (tiles_x == 0 || rows == 0 || slots == 0) return 0;
+    std::vector<double> cost(static_cast<size_t>(tiles_x) * rows, 0.0);
+    for (uint32_t r = 0; r < rows; ++r)
+        for (uint32_t cx = 0; cx < tiles_x; ++cx) {
+            double worst = 0.0;
+            for (uint32_t sy = 0; sy < 3; ++sy)
+                for (uint32_t sx = 0; sx < 3; ++sx) {
+                    const uint32_t px = std::min(d.roi.width - 1, cx * tw + sx * (tw - 1) / 2);
+                    const uint32_t py = std::min(rows_px - 1, r * th + sy * (th - 1) / 2);
+                    worst = std::max(worst, pixel_work(p, d.roi.x + px, d.roi.y + y0 + py));
+                }
+            cost[static_cast<size_t>(r) * tiles_x + cx] = worst + 32.0;   // + prologue / epilogue of a CTA, in steps
+        }
+    std::vector<double> slot_free;
+    const int candidates[4] = {0, 1, static_cast<int>(HPX_ORDER_COLUMNS), static_cast<int>(HPX_ORDER_COLUMNS) | 1};
+    double ends[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < 4; ++k) {
+        const int order = candidates[k];
+        slot_free.assign(slots, 0.0);
+        std::make_heap(slot_free.begin(), slot_free.end(), std::greater<double>());
+        double end = 0.0;
+        for (uint32_t b = 0; b < tiles_x * rows; ++b) {
+            uint32_t cx = 0, r = 0;
+            tile_of(b, tiles_x, rows, static_cast<uint32_t>(order), &cx, &r);
+            std::pop_heap(slot_free.begin(), slot_free.end(), std::greater<double>());
+            slot_free.back() += cost[static_cast<size_t>(r) * tiles_x + cx];
+            end = std::max(end, slot_free.back());
+            std::push_heap(slot_free.begin(), slot_free.end(), std::greater<double>());
+        }
+        ends[k] = end;
+        if (out_ends4 != nullptr) out_ends4[k] = end;
+    }
+    // row by row unless a column order wins by more than the estimate's noise: where the two tie in the estimate (bands of
+    // many tile rows) the row orders measured up to 2 % faster (512^3 / 2 GPUs: 28.4 vs 29.0 ms); hpx_shard_tune_order
+    // settles it by measurement
+    int best = candidates[0];
+    double best_end = ends[0];
+    for (int k : {1, 2, 3})
+        if (ends[k] < best_end * 0.995) {
+            best = candidates[k];
+            best_end = ends[k];
+        }
+    return best;
 }
 
 // Contiguous bands of CTA tile rows with (nearly) equal work.
@@ -814,10 +873,20 @@ static hp_status band_configure(hpx_shard* s) {
             if (st == HP_STATUS_SUCCESS && r == me) {
                 // stratified jitter hashes the ray's index in the WHOLE frame (reference samp_cpu.cpp:28-35)
                 st = hpx_frame_set_view(frame, nullptr, d.seed, static_cast<uint64_t>(bands[r].y0) * d.roi.width);
-                // end the launches with the band's CHEAP rows (short tail): last row first when the rays get longer downwards
-                const double first = row_work(s->full_params, d.roi.y + bands[r].y0, d.roi.x, d.roi.width);
-                const double last = row_work(s->full_params, d.roi.y + bands[r].y0 + bands[r].rows - 1, d.roi.x, d.roi.width);
-                if (st == HP_STATUS_SUCCESS) st = hpx_frame_set_row_order(frame, last > first ? 1 : 0);
+                // end the launches with the band's CHEAP tiles (short tail): rows last-to-first when the rays get longer
+                // downwards, columns centre-out when the rows cost the same and the edges of the image are cheap
+                if (!s->order_tuned)   // (a measured choice survives the small band moves of hpx_shard_rebalance)
+                    s->tile_order = best_tile_order(s->full_params, d, bands[r].y0, bands[r].rows, std::max(1u, c->ctx->usable_sms) * 5u);
+                if (const char* env = std::getenv("DVREN_SHARD_TILE_ORDER")) {   // A/B timing: "rows" = round-2 behaviour before the column order
+                    if (std::strcmp(env, "rows") == 0) {
+                        const double first = row_work(s->full_params, d.roi.y + bands[r].y0, d.roi.x, d.roi.width);
+                        const double last = row_work(s->full_params, d.roi.y + bands[r].y0 + bands[r].rows - 1, d.roi.x, d.roi.width);
+                        s->tile_order = last > first ? 1 : 0;
+                    } else if (std::strcmp(env, "columns") == 0) {
+                        s->tile_order = static_cast<int>(HPX_ORDER_COLUMNS);
+                    }
+                }
+                if (st == HP_STATUS_SUCCESS) st = hpx_frame_set_row_order(frame, s->tile_order);
                 s->plan = band_plan;
                 s->frame = frame;
                 s->dl_offset_floats = static_cast<size_t>(bands[r].y0) * d.roi.width * 3;
@@ -992,6 +1061,73 @@ HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, ui
             out_work[r] = w;
         }
     }
+    return HP_STATUS_SUCCESS;
+}
+
+// Host-only (works without a GPU): best_tile_order for a band of the plan's ROI; out_ends4 (optional): the estimated end of
+// a launch, in marching steps, under the orders {0, 1, HPX_ORDER_COLUMNS, HPX_ORDER_COLUMNS | 1}.
+HP_API hp_status hpx_plan_best_tile_order(const hp_plan* plan, uint32_t row0, uint32_t rows, uint32_t slots, int32_t* out_order,
+                                          double* out_ends4) {
+    DV_RANGE("hpx_plan_best_tile_order");
+    if (plan == nullptr || out_order == nullptr || rows == 0 || slots == 0 || slots > (1u << 20) ||
+        static_cast<uint64_t>(row0) + rows > plan->desc.roi.height)
+        return HP_STATUS_INVALID_ARGUMENT;
+    *out_order = best_tile_order(frame_params_from_plan(*plan), plan->desc, row0, rows, slots, out_ends4);
+    return HP_STATUS_SUCCESS;
+}
+
+// Rank-local (no collective): renders this rank's band -- forward + backward, no exchange -- under every candidate dispatch
+// order and keeps the fastest.  The estimate behind hpx_shard_create_bands models a CTA as lasting as long as its longest
+// ray; it knows nothing about the memory system (column order walks the slab axis with a stride; measured 0-2 % slower
+// than its estimate on bands of 50-130 tile rows), so two orders that tie in the estimate are told apart here.  The
+// backward passes ACCUMULATE into the gradient block: call it during warm-up and clear the block (HPX_BACKWARD_ZERO) on
+// the next step.  The choice survives hpx_shard_rebalance.
+HP_API hp_status hpx_shard_tune_order(hpx_shard* s, const float* dL_dI_device, uint32_t flags, int32_t* out_order) {
+    DV_RANGE("hpx_shard_tune_order");
+    if (s == nullptr || !s->bands || dL_dI_device == nullptr) return HP_STATUS_INVALID_ARGUMENT;
+    if (out_order != nullptr) *out_order = s->tile_order;
+    if (s->frame == nullptr || std::getenv("DVREN_SHARD_TILE_ORDER") != nullptr) return HP_STATUS_SUCCESS;
+    hpx_comm* c = s->comm;
+    DV_ENTER(c->ctx);
+    cudaStream_t main = c->ctx->stream;
+    const int current = s->tile_order;
+    int best = current;
+    float best_ms = 0.0f;
+    hp_status st = HP_STATUS_SUCCESS;
+    for (int order : {current, 0, 1, static_cast<int>(HPX_ORDER_COLUMNS), static_cast<int>(HPX_ORDER_COLUMNS) | 1}) {
+        if (order == current && best_ms > 0.0f) continue;   // (measured first)
+        st = hpx_frame_set_row_order(s->frame, order);
+        for (int rep = 0; rep < 3 && st == HP_STATUS_SUCCESS; ++rep) {   // one untimed, two timed
+            if (rep == 1 && cudaEventRecord(s->ev_t0, main) != cudaSuccess) st = cuda_fail(cudaGetLastError(), "tune");
+            if (st == HP_STATUS_SUCCESS) st = hpx_forward(s->frame, s->grid);
+            if (st == HP_STATUS_SUCCESS)
+                st = hpx_backward(s->frame, s->grid, dL_dI_device + s->dl_offset_floats, HP_MEMSPACE_DEVICE, flags & ~HPX_BACKWARD_ZERO);
+        }
+        float ms = 0.0f;
+        if (st == HP_STATUS_SUCCESS && (cudaEventRecord(s->ev_t1, main) != cudaSuccess || cudaStreamSynchronize(main) != cudaSuccess ||
+                                        cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1) != cudaSuccess))
+            st = cuda_fail(cudaGetLastError(), "tune");
+        if (st != HP_STATUS_SUCCESS) break;
+        if (best_ms == 0.0f || ms < best_ms * 0.995f) {   // the order in place stays unless another is measurably faster
+            best = order;
+            best_ms = ms;
+        }
+    }
+    const hp_status restored = hpx_frame_set_row_order(s->frame, st == HP_STATUS_SUCCESS ? best : current);
+    if (st != HP_STATUS_SUCCESS) return st;
+    DV_TRY(restored);
+    s->tile_order = best;
+    s->order_tuned = true;
+    s->timed = false;   // ev_t0 / ev_t1 no longer bracket a step
+    if (out_order != nullptr) *out_order = best;
+    return HP_STATUS_SUCCESS;
+}
+
+// The dispatch order (hpx_frame_set_row_order) the library chose for this rank's band.
+HP_API hp_status hpx_shard_tile_order(const hpx_shard* s, int32_t* out_order) {
+    DV_RANGE("hpx_shard_tile_order");
+    if (s == nullptr || out_order == nullptr || !s->bands) return HP_STATUS_INVALID_ARGUMENT;
+    *out_order = s->tile_order;
     return HP_STATUS_SUCCESS;
 }
 

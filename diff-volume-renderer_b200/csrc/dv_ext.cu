@@ -764,11 +764,22 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* f, uint32_t stride, uint32_
 
 // Order in which the CTAs of this frame's launches take its tile rows (RoiParams::tile_row_reverse).  Results do not
 // depend on it.  Not combined with hpx_backward_signalled, whose row groups count in dispatch order.
-HP_API hp_status hpx_frame_set_row_order(hpx_frame* f, int32_t last_row_first) {
+HP_API hp_status hpx_frame_set_row_order(hpx_frame* f, int32_t order) {
     DV_RANGE("hpx_frame_set_row_order");
-    if (f == nullptr || last_row_first < 0 || last_row_first > 2) return HP_STATUS_INVALID_ARGUMENT;
-    f->h_params.roi.tile_row_reverse = static_cast<uint32_t>(last_row_first);
+    if (f == nullptr || order < 0 || (order & ~(HPX_ORDER_COLUMNS | 3)) != 0 || (order & 3) == 3) return HP_STATUS_INVALID_ARGUMENT;
+    static_assert(HPX_ORDER_COLUMNS == kTileOrderColumns, "hp_b200.h: HPX_ORDER_COLUMNS");
+    f->h_params.roi.tile_row_reverse = static_cast<uint32_t>(order);
     f->params_dirty = true;
+    return HP_STATUS_SUCCESS;
+}
+
+// Host-only: the tile (column, row) the i-th dispatched CTA of a launch of tiles_x * rows CTAs takes under `order`.
+HP_API hp_status hpx_tile_order(uint32_t block, uint32_t tiles_x, uint32_t rows, int32_t order, uint32_t* out_col, uint32_t* out_row) {
+    DV_RANGE("hpx_tile_order");
+    if (out_col == nullptr || out_row == nullptr || tiles_x == 0 || rows == 0 || block / tiles_x >= rows || order < 0 ||
+        (order & ~(HPX_ORDER_COLUMNS | 3)) != 0 || (order & 3) == 3)
+        return HP_STATUS_INVALID_ARGUMENT;
+    tile_of(block, tiles_x, rows, static_cast<uint32_t>(order), out_col, out_row);
     return HP_STATUS_SUCCESS;
 }
 

@@ -37,8 +37,8 @@ struct TilePixel {
 
 __device__ __forceinline__ TilePixel tile_pixel(const RoiParams& roi) {
     const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
-    const uint32_t tile_x = blockIdx.x % tiles_x;
-    const uint32_t owned_row = tile_row_of(blockIdx.x / tiles_x, gridDim.x / tiles_x, roi.tile_row_reverse);
+    uint32_t tile_x, owned_row;
+    tile_of(blockIdx.x, tiles_x, gridDim.x / tiles_x, roi.tile_row_reverse, &tile_x, &owned_row);
     const uint32_t tile_y = owned_row * roi.tile_row_stride + roi.tile_row_phase;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     TilePixel p;
@@ -217,7 +217,8 @@ __device__ __forceinline__ void signal_group_done(const LeanBuffers& st, const R
     if (threadIdx.x == 0) {
         __threadfence();                   // ... and they are visible device-wide before the counter moves
         const uint32_t tiles_x = (roi.w + kTileW * kWarpsX - 1) / (kTileW * kWarpsX);
-        const uint32_t row = blockIdx.x / tiles_x;
+        // the i-th DISPATCHED row (column order: a row is complete only with the launch's last column)
+        const uint32_t row = (roi.tile_row_reverse & kTileOrderColumns) ? blockIdx.x % (gridDim.x / tiles_x) : blockIdx.x / tiles_x;
         uint32_t g = 0;
         while (g + 1 < st.group_count && row >= st.group_end[g]) ++g;
         atomicAdd(st.group_done + g, 1u);

@@ -42,8 +42,13 @@ struct RoiParams {
     // of a perspective image) would otherwise finish with its most expensive rows and idle SMs; 2 centre-out (middle row,
     // one below, one above, ...): the launch ends with the cheap outer rows of a full frame AND the gradient slabs become
     // final from the centre outwards right from the start (hpx_backward_streamed copies them while the kernel runs).
+    // + kTileOrderColumns: the CTAs walk the tiles COLUMN by column (all rows of a column, in the row order above), the
+    // columns centre-out -- a band of a few tile rows whose rows all cost the same (the middle of a sharded frame) has its
+    // cheap tiles at the left and right end of every row; taking the columns from the middle outwards ends the launch with
+    // them instead of with a last, partly empty wave of full-length tiles.
     uint32_t tile_row_reverse;
 };
+constexpr uint32_t kTileOrderColumns = 4u;
 
 // Tile row taken by the i-th dispatched row of `rows` (RoiParams::tile_row_reverse = mode).
 #if defined(__CUDACC__)
@@ -57,6 +62,20 @@ inline uint32_t tile_row_of(uint32_t i, uint32_t rows, uint32_t mode) {
         return (i & 1u) ? c - 1u - (i >> 1) : c + (i >> 1);
     }
     return i;
+}
+
+// Tile (column, owned row) the CTA `block` of a launch of tiles_x * rows CTAs takes (RoiParams::tile_row_reverse = mode).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void tile_of(uint32_t block, uint32_t tiles_x, uint32_t rows, uint32_t mode, uint32_t* out_col, uint32_t* out_row) {
+    if (mode & kTileOrderColumns) {
+        *out_col = tile_row_of(block / rows, tiles_x, 2u);
+        *out_row = tile_row_of(block % rows, rows, mode & 3u);
+    } else {
+        *out_col = block % tiles_x;
+        *out_row = tile_row_of(block / tiles_x, rows, mode & 3u);
+    }
 }
 
 struct FrameParams {

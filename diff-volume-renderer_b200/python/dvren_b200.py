@@ -24,6 +24,7 @@ HPX_CTX_EXT_MAGIC = 0x42323030
 HPX_CTX_EXT2_MAGIC = 0x42323031
 HPX_COMM_ID_BYTES = 128
 HPX_SHARD_RESULT_OWNED, HPX_SHARD_RESULT_REPLICATED = 1, 2
+HPX_ORDER_COLUMNS = 4
 HPX_BACKWARD_GRID, HPX_BACKWARD_CAMERA, HPX_BACKWARD_ZERO = 1, 2, 4
 HPX_BACKWARD_SCATTER_PER_RAY, HPX_BACKWARD_SCATTER_MERGED, HPX_BACKWARD_DETERMINISTIC = 0x10, 0x20, 0x40
 
@@ -80,6 +81,7 @@ HPX_FUNCTIONS = {
     "hpx_frame_set_interleave": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "hpx_frame_set_row_order": (C.c_int, [C.c_void_p, C.c_int32]),
     "hpx_tile_row_order": (C.c_int, [C.c_uint32, C.c_uint32, C.c_int32, P(C.c_uint32)]),
+    "hpx_tile_order": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, P(C.c_uint32), P(C.c_uint32)]),
     "hpx_frame_bounds": (C.c_int, [C.c_void_p, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_backward_box": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, P(C.c_int32 * 6)]),
     "hpx_frame_box_misses": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
@@ -115,6 +117,9 @@ HPX_FUNCTIONS = {
     "hpx_shard_set_result": (C.c_int, [C.c_void_p, C.c_uint32]),
     "hpx_shard_rebalance": (C.c_int, [C.c_void_p, P(C.c_int32)]),
     "hpx_shard_exchange_is_direct": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "hpx_shard_tile_order": (C.c_int, [C.c_void_p, P(C.c_int32)]),
+    "hpx_shard_tune_order": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, P(C.c_int32)]),
+    "hpx_plan_best_tile_order": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, P(C.c_int32), P(C.c_double)]),
     "hpx_plan_owner_cuts": (C.c_int, [C.c_uint32, C.c_int32, P(C.c_int32), C.c_uint32, P(C.c_int32)]),
     "hpx_plan_balanced_bands": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_uint32), P(C.c_uint32), P(C.c_double)]),
     "hpx_shard_bands": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_int32), P(C.c_int32), P(C.c_size_t), P(C.c_size_t)]),
@@ -490,6 +495,12 @@ class Shard:
     def step(self, dL_dI_device_ptr: int, flags: int = HPX_BACKWARD_GRID | HPX_BACKWARD_ZERO):
         check("hpx_shard_step", self.lib.hpx_shard_step(self.handle, int(dL_dI_device_ptr), flags))
 
+    def tune_order(self, dL_dI_device_ptr: int, flags: int = HPX_BACKWARD_GRID) -> int:
+        """Measured choice of the band's tile dispatch order (rank-local; the gradient block is left dirty)."""
+        order = C.c_int32()
+        check("hpx_shard_tune_order", self.lib.hpx_shard_tune_order(self.handle, int(dL_dI_device_ptr), flags, C.byref(order)))
+        return order.value
+
     def rebalance(self) -> bool:
         """Collective: re-cut the bands from the measured time of the last step; True when they moved (self.frame is then
         a new frame)."""
@@ -518,8 +529,10 @@ class Shard:
             check("hpx_shard_owned", self.lib.hpx_shard_owned(self.handle, None, None, None, None, C.byref(axis)))
             direct = C.c_int32()
             check("hpx_shard_exchange_is_direct", self.lib.hpx_shard_exchange_is_direct(self.handle, C.byref(direct)))
+            order = C.c_int32()
+            check("hpx_shard_tile_order", self.lib.hpx_shard_tile_order(self.handle, C.byref(order)))
             return {"exchange": "own kernels over mapped peer memory (NVLink)" if direct.value else "NCCL send/recv + broadcast",
-                    "slow_axis": "xyz"[axis.value], "band_row0": list(row0), "band_rows": list(rows),
+                    "slow_axis": "xyz"[axis.value], "band_row0": list(row0), "band_rows": list(rows), "tile_order": order.value,
                     "wedges": [(int(wedges[2 * i]), int(wedges[2 * i + 1])) for i in range(n)], "owner_cuts": list(cuts),
                     "send_bytes": out.value * 4, "recv_bytes": inn.value * 4}
         axis, n = C.c_int32(), C.c_uint32()

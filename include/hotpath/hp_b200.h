@@ -213,11 +213,19 @@ HP_API hp_status hpx_frame_set_interleave(hpx_frame* frame, uint32_t stride, uin
 HP_API hp_status hpx_frame_bounds(hpx_frame* frame, const hpx_grid* grid, int32_t out_box[6]);
 /* Order in which the frame's launches take its tile rows: 0 first-to-last, 1 last-to-first, 2 centre-out (middle row, one
  * below, one above, ...).  CTAs are dispatched in order, so the rows a launch ends with decide its tail; a band whose rays
- * get longer towards its last row should end with its first one.  Results do not depend on the order.  The row groups of
- * hpx_backward_signalled count in DISPATCH order. */
+ * get longer towards its last row should end with its first one.  + HPX_ORDER_COLUMNS: the tiles are taken column by
+ * column (every row of a column in the row order above), the columns from the middle of the image outwards -- for a band
+ * whose rows all cost the same but whose tiles get cheaper towards the left and right edge (the middle bands of a sharded
+ * perspective frame), so that the launch ends with cheap tiles instead of a partly empty wave of full-length ones.
+ * Results do not depend on the order.  The row groups of hpx_backward_signalled count in DISPATCH order (with
+ * HPX_ORDER_COLUMNS every group completes only with the last column). */
+#define HPX_ORDER_COLUMNS 4
 HP_API hp_status hpx_frame_set_row_order(hpx_frame* frame, int32_t order);
-/* Host-only: which tile row the i-th dispatched one of `rows` is under `order` (a permutation of 0 .. rows - 1). */
+/* Host-only: which tile row the i-th dispatched one of `rows` is under `order` 0..2 (a permutation of 0 .. rows - 1). */
 HP_API hp_status hpx_tile_row_order(uint32_t i, uint32_t rows, int32_t order, uint32_t* out_row);
+/* Host-only: the tile (column, row) the CTA `block` of a launch of tiles_x * rows CTAs takes under `order`
+ * (0..2, optionally + HPX_ORDER_COLUMNS): a permutation of the tiles. */
+HP_API hp_status hpx_tile_order(uint32_t block, uint32_t tiles_x, uint32_t rows, int32_t order, uint32_t* out_col, uint32_t* out_row);
 HP_API hp_status hpx_backward_box(hpx_frame* frame, hpx_grid* grid, const float* dL_dI, hp_memspace memspace,
                                   uint32_t flags, float* box_grad, const int32_t box[6]);
 /* Axis order of the gradient block: slow_axis 0 = x, 1 = y, 2 = z (default) becomes the slowest-varying one, so that a
@@ -340,6 +348,19 @@ HP_API hp_status hpx_shard_rebalance(hpx_shard* shard, int32_t* out_changed);
  * 0 (environment DVREN_SHARD_EXCHANGE=nccl, or mapping failed on some rank): NCCL send/recv into a staging buffer + an add
  * kernel, NCCL broadcasts for the replicated result. */
 HP_API hp_status hpx_shard_exchange_is_direct(const hpx_shard* shard, int32_t* out_direct);
+/* The dispatch order (hpx_frame_set_row_order values) the library chose for this rank's band: the one of {rows first-to-last,
+ * rows last-to-first, columns centre-out (+ either row order)} whose launches end soonest in a list-scheduling estimate of
+ * the band's CTA tiles on the GPU's resident slots.  Environment DVREN_SHARD_TILE_ORDER=rows|columns overrides the choice
+ * (timing comparisons). */
+HP_API hp_status hpx_shard_tile_order(const hpx_shard* shard, int32_t* out_order);
+/* Rank-local, no collective: settles that choice by MEASUREMENT -- this rank's band is rendered (forward + backward, no
+ * exchange) under every candidate order and the fastest is kept, also across hpx_shard_rebalance.  The backward passes
+ * accumulate into the gradient block: call it during warm-up, before hpx_shard_rebalance, and pass HPX_BACKWARD_ZERO on the
+ * next step.  dL_dI / flags as for hpx_shard_step.  out_order (optional): the order now in place. */
+HP_API hp_status hpx_shard_tune_order(hpx_shard* shard, const float* dL_dI_device, uint32_t flags, int32_t* out_order);
+/* Host-only (works without a GPU): that choice for the band [row0, row0 + rows) of the plan's ROI on `slots` resident CTAs. */
+HP_API hp_status hpx_plan_best_tile_order(const hp_plan* plan, uint32_t row0, uint32_t rows, uint32_t slots, int32_t* out_order,
+                                          double* out_ends4);
 /* Host-only (works without a GPU): the bands hpx_shard_create_bands cuts for `world` ranks -- first row inside the ROI and
  * rows per rank, multiples of the 8-row CTA tile; out_work (may be NULL): estimated marching work per band in samples. */
 HP_API hp_status hpx_plan_balanced_bands(const hp_plan* plan, uint32_t world, uint32_t* out_row0, uint32_t* out_rows,

@@ -298,6 +298,10 @@ def test_round2_entry_points_validate_arguments_without_a_gpu():
     assert lib.hpx_frame_set_row_order(None, 1) == INV
     assert lib.hpx_tile_row_order(0, 0, 0, None) == INV
     assert lib.hpx_tile_row_order(0, 8, 3, C.byref(u32)) == INV        # order is 0, 1 or 2
+    assert lib.hpx_tile_order(0, 0, 0, 0, None, None) == INV
+    assert lib.hpx_shard_tile_order(None, C.byref(i32)) == INV
+    assert lib.hpx_shard_tune_order(None, None, 1, C.byref(i32)) == INV
+    assert lib.hpx_plan_best_tile_order(None, 0, 8, 740, C.byref(i32), None) == INV
     assert lib.hpx_ctx_sm_counts(None, C.byref(u32), C.byref(u32)) == INV
     assert lib.hpx_comm_unique_id(None) == INV
     assert lib.hpx_comm_create(None, None, 0, 1, 0, C.byref(ptr)) == INV

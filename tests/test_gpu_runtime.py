@@ -262,10 +262,12 @@ def test_cxx_surface_selftest():
 
 def test_balanced_bands_sum_to_the_whole_frame(ctx):
     """What hpx_shard_create_bands gives each rank, replayed on ONE GPU: the bands of hpx_plan_balanced_bands rendered one
-    after the other (ROI sub-plan, global ray-index base for the stratified jitter, every other band with its tile rows
-    taken in another order: last-to-first, centre-out) reproduce the whole frame's image planes bit for bit and sum to its gradient; the voxel wedges
-    of hpx_frame_bounds contain everything a band's backward writes."""
-    W, Hh, steps, world = 96, 80, 64, 3
+    after the other (ROI sub-plan, global ray-index base for the stratified jitter, every band with its tiles taken in
+    another dispatch order: rows last-to-first, centre-out, column by column with each row order, first-to-last; the last tile
+    column is a partial one) reproduce the whole frame's image planes bit for bit and sum to its gradient; the voxel wedges of
+    hpx_frame_bounds contain everything a band's backward writes."""
+    W, Hh, steps, world = 104, 80, 64, 6
+    orders = [1, 2, D.HPX_ORDER_COLUMNS, D.HPX_ORDER_COLUMNS | 1, D.HPX_ORDER_COLUMNS | 2, 0]
     desc = S.bench_plan(W, Hh, steps, stratified=True, view=1, views=7)
     sig, col = S.hashed_volume(20, "dense", seed=5)
     dl = S.hashed_image_grad(W * Hh)
@@ -285,7 +287,7 @@ def test_balanced_bands_sum_to_the_whole_frame(ctx):
         bplan = D.Plan(ctx, bd)
         frame = D.Frame(bplan)
         frame.set_view(None, desc.seed, int(row0[r]) * W)
-        D.check("hpx_frame_set_row_order", ctx.lib.hpx_frame_set_row_order(frame.handle, (r + 1) % 3))   # last-to-first, centre-out, first-to-last
+        D.check("hpx_frame_set_row_order", ctx.lib.hpx_frame_set_row_order(frame.handle, orders[r]))
         box = (C.c_int32 * 6)()
         D.check("hpx_frame_bounds", ctx.lib.hpx_frame_bounds(frame.handle, grid.handle, box))
         frame.forward(grid)
@@ -322,7 +324,9 @@ def test_sharded_frame_on_two_gpus():
         pytest.skip("needs two GPUs")
     exe = os.path.join(U.REPO, "diff-volume-renderer_b200", "dvren_bench")
     assert os.path.exists(exe), f"{exe} is not built (__graft_entry__.build())"
-    for mode, env in ((0, {}), (1, {}), (2, {}), (1, {"DVREN_SHARD_EXCHANGE": "nccl"})):
+    # (the tool settles the bands' tile dispatch order by measurement, hpx_shard_tune_order; the last two runs pin it instead)
+    for mode, env in ((0, {}), (1, {}), (2, {}), (1, {"DVREN_SHARD_EXCHANGE": "nccl"}), (2, {"DVREN_SHARD_TILE_ORDER": "columns"}),
+                      (1, {"DVREN_BENCH_NO_TUNE": "1", "DVREN_SHARD_TILE_ORDER": "rows"})):
         r = subprocess.run([exe, "shard", "96", "384", "192", "1", "2", "1", "2", "3", "0", "0", str(mode)], capture_output=True,
                            text=True, timeout=300, env={**os.environ, **env})
         assert r.returncode == 0 and '"verify_max_rel_err_vs_single_gpu"' in r.stdout, (mode, env, r.stdout[-2000:], r.stderr[-2000:])

@@ -276,3 +276,73 @@ def test_tile_row_orders_are_permutations(rows):
                 pre = sorted(seq[:k])
                 assert pre == list(range(pre[0], pre[0] + k)) and pre[0] <= rows // 2 <= pre[-1]
     assert lib.hpx_tile_row_order(rows, rows, 0, C.byref(C.c_uint32())) == A.HP_STATUS_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("tiles_x,rows", [(1, 1), (1, 9), (7, 1), (6, 10), (128, 27), (13, 4)])
+def test_tile_orders_are_permutations(tiles_x, rows):
+    """hpx_frame_set_row_order with HPX_ORDER_COLUMNS: every CTA of a launch takes another tile; without the flag the tiles go
+    row by row, with it column by column from the middle column outwards, the rows of a column in the chosen row order."""
+    import dvren_b200 as D
+    lib = D.load()
+    def walk(order):
+        seq = []
+        for b in range(tiles_x * rows):
+            col, row = C.c_uint32(), C.c_uint32()
+            D.check("hpx_tile_order", lib.hpx_tile_order(b, tiles_x, rows, order, C.byref(col), C.byref(row)))
+            seq.append((col.value, row.value))
+        return seq
+    everything = sorted((c, r) for c in range(tiles_x) for r in range(rows))
+    for row_order in (0, 1, 2):
+        row_seq = []
+        for i in range(rows):
+            out = C.c_uint32()
+            D.check("hpx_tile_row_order", lib.hpx_tile_row_order(i, rows, row_order, C.byref(out)))
+            row_seq.append(out.value)
+        plain = walk(row_order)
+        assert sorted(plain) == everything
+        assert plain == [(c, r) for r in row_seq for c in range(tiles_x)]
+        cols = walk(D.HPX_ORDER_COLUMNS | row_order)
+        assert sorted(cols) == everything
+        col_seq = [cols[i * rows][0] for i in range(tiles_x)]
+        assert cols == [(c, r) for c in col_seq for r in row_seq]
+        assert col_seq[0] == tiles_x // 2
+        for k in range(1, tiles_x + 1):          # the dispatched columns are always one contiguous run around the middle
+            pre = sorted(col_seq[:k])
+            assert pre == list(range(pre[0], pre[0] + k)) and pre[0] <= tiles_x // 2 <= pre[-1]
+    bad = C.c_uint32()
+    assert lib.hpx_tile_order(tiles_x * rows, tiles_x, rows, 0, C.byref(bad), C.byref(bad)) == A.HP_STATUS_INVALID_ARGUMENT
+    assert lib.hpx_tile_order(0, tiles_x, rows, 3, C.byref(bad), C.byref(bad)) == A.HP_STATUS_INVALID_ARGUMENT
+    assert lib.hpx_tile_order(0, tiles_x, rows, 8, C.byref(bad), C.byref(bad)) == A.HP_STATUS_INVALID_ARGUMENT
+
+
+def test_best_tile_order_prefers_columns_for_the_middle_bands_of_a_sharded_frame():
+    """hpx_plan_best_tile_order (what hpx_shard_create_bands applies to its band): on BASELINE configs[2] cut for 8 GPUs the
+    middle bands -- every row equally expensive, cheap tiles at the left and right edge -- end sooner column by column,
+    the outermost bands (rows get cheaper towards the image border) row by row with the cheap rows last; the estimate of the
+    chosen order is never worse than the row orders'."""
+    import dvren_b200 as D
+    import synth as S
+    lib = D.load()
+    ctx, plan = C.c_void_p(), C.c_void_p()
+    assert lib.hp_ctx_create(None, C.byref(ctx)) == 0
+    desc = S.bench_plan(2048, 2048, 1024, stratified=False)
+    assert lib.hp_plan_create(ctx, C.byref(desc), C.byref(plan)) == 0
+    world = 8
+    row0, rows = (C.c_uint32 * world)(), (C.c_uint32 * world)()
+    D.check("hpx_plan_balanced_bands", lib.hpx_plan_balanced_bands(plan, world, row0, rows, None))
+    chosen = []
+    for r in range(world):
+        order, ends = C.c_int32(), (C.c_double * 4)()
+        D.check("hpx_plan_best_tile_order", lib.hpx_plan_best_tile_order(plan, row0[r], rows[r], 148 * 5, C.byref(order), ends))
+        table = dict(zip((0, 1, D.HPX_ORDER_COLUMNS, D.HPX_ORDER_COLUMNS | 1), ends))
+        assert table[order.value] <= min(table[0], table[1]) * 1.0001
+        if order.value & D.HPX_ORDER_COLUMNS:
+            assert table[order.value] < 0.995 * min(table[0], table[1])
+        chosen.append(order.value)
+    assert chosen[0] == 1 and chosen[-1] == 0                     # rays get longer towards the middle of the image
+    assert all(o & D.HPX_ORDER_COLUMNS for o in chosen[2:6])
+    one = C.c_int32()
+    assert lib.hpx_plan_best_tile_order(plan, 2040, 16, 740, C.byref(one), None) == A.HP_STATUS_INVALID_ARGUMENT   # past the ROI
+    assert lib.hpx_plan_best_tile_order(plan, 0, 8, 0, C.byref(one), None) == A.HP_STATUS_INVALID_ARGUMENT
+    lib.hp_plan_release(plan)
+    lib.hp_ctx_release(ctx)
