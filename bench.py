@@ -494,6 +494,35 @@ def measure_half(env, cfg, args):
     return out
 
 
+def measure_dense(env, cfg, cfg_name, args):
+    """The same frame over the DENSE hashed volume (sigma = 40u): every ray saturates and stops early (T <= 1e-4,
+    int_cpu.cpp:209-215), so the work per ray is a fraction of the thin volume's and it varies inside a warp.  `value` keeps the
+    metric's definition (samples of the plan per second); the roofline fractions count the LIVE in-cube samples only."""
+    import synth as S
+    torch, D, ctx, dev = env.torch, env.D, env.ctx, env.dev
+    n, W, steps = cfg["grid"], cfg["width"], cfg["steps"]
+    grid = make_grid(D, S, torch, ctx, n, "dense", dev)
+    plan = D.Plan(ctx, S.bench_plan(W, W, steps, stratified=cfg["stratified"]))
+    frame = D.Frame(plan)
+    g_dev = torch.from_numpy(S.hashed_image_grad(plan.n_rays)).to(dev)
+    flags = D.HPX_BACKWARD_GRID | D.HPX_BACKWARD_ZERO
+    k = args.steps
+    f = env.timed(lambda: frame.forward(grid), k, 2) / k
+    b = env.timed(lambda: frame.backward(grid, g_dev.data_ptr(), flags, device=True), k, 2) / k
+    c = frame.counts()
+    cube = frame.cube_samples(grid)
+    touched = grid.touched_voxels()
+    bwd_kernel = "lean_backward_merge_kernel" if frame.scatter_mode(grid, flags) == "merged" else "lean_backward_kernel"
+    out = {"volume": "hashed dense (sigma = 40u): early termination on every ray", "fwd_ms": f, "bwd_ms": b,
+           "value": c["samples"] / ((f + b) * 1e-3) / 1e6, "samples": c["samples"], "live_samples": c["live_samples"],
+           "in_cube_live_samples": cube, "touched_voxels": touched,
+           "live_msamples_s": c["live_samples"] / ((f + b) * 1e-3) / 1e6,
+           "roofline": roofline(cfg_name + "_dense", bwd_kernel, f, b, cube, c["live_samples"], plan.n_rays, touched, read_peaks())}
+    frame.close(); plan.close(); grid.close()
+    torch.cuda.empty_cache()
+    return out
+
+
 def base_line(env, args, cfg, value, ms_per_step, scaling):
     return {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
@@ -518,6 +547,10 @@ def run_single(env, args):
                                          "in_cube_live_samples", "touched_voxels")}
         line["c2"]["empty_space_skipping"] = measure_sparse(env, CONFIGS["c2"], args)
         line["c2"]["half_storage"] = measure_half(env, CONFIGS["c2"], args)
+        try:   # (a side measurement never takes the line down)
+            line["c2"]["dense_volume"] = measure_dense(env, CONFIGS["c2"], "c2", args)
+        except Exception as e:
+            line["c2"]["dense_volume"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(cfg, rows=args.cpu_rows, threads=1)
     emit(line)
