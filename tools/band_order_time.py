@@ -51,5 +51,5 @@ for r in range(world):
         f = timeit(lambda: frame.forward(grid))
         b = timeit(lambda: frame.backward(grid, dl, flags, device=True))
         line[f"order_{o}_ms"] = {"forward": round(f, 4), "backward": round(b, 4), "step": round(f + b, 4)}
-    print(json.dumps(line), flush=True)
+    os.write(B._REAL_STDOUT, (json.dumps(line) + "\n").encode())   # (importing bench points descriptor 1 at stderr)
     frame.close(); plan.close()

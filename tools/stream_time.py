@@ -37,4 +37,4 @@ out["plain_backward_default_layout"] = timeit(lambda: frame.backward(grid, g_dev
 out["streamed"] = timeit(lambda: D.check("s", lib.hpx_backward_streamed(frame.handle, grid.handle, g_dev.data_ptr(), A.HP_MEMSPACE_DEVICE, flags, sg.data_ptr(), cg.data_ptr(), None)))
 out["plain_backward_slab_layout"] = timeit(lambda: frame.backward(grid, g_dev.data_ptr(), flags, device=True))
 out["read_grad_host"] = timeit(lambda: D.check("r", lib.hpx_grid_read_grad(grid.handle, sg.data_ptr(), cg.data_ptr(), None, A.HP_MEMSPACE_HOST)), 3)
-print(json.dumps(out))
+os.write(B._REAL_STDOUT, (json.dumps(out) + "\n").encode())   # (importing bench points descriptor 1 at stderr)
